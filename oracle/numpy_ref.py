@@ -1,0 +1,121 @@
+"""Independent fp64 closed-form statement of the hot path (test infrastructure, NOT the product).
+
+Where ow_oracle.cpp replays the reference's literal dispatch chain in fp32, this file states WHAT that
+chain computes, in closed form and in double precision:
+
+    D_c = Re( ifft2( ifftshift( H_c(k, t) ) ) ),   c in {dy, dx, dz}
+
+It is used only by tests/ to pin the oracle (the two must agree to fp32 round-off) and to give
+size-independent properties at sizes where the scalar oracle is too slow.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+G = 9.81
+PI32 = np.float32(3.1415926535897932384626433832795)
+
+
+def wave_vectors(N: int, L: float):
+    """k for texel (iy, ix): tilde_h0_k_cs.glsl:76-77 (centred index). Returned in fp64 from fp32 inputs."""
+    idx = np.arange(N, dtype=np.float32) - np.float32(N) / np.float32(2.0)
+    k1 = ((np.float32(2.0) * PI32 * idx) / np.float32(L)).astype(np.float64)
+    kx = np.broadcast_to(k1[None, :], (N, N))
+    ky = np.broadcast_to(k1[:, None], (N, N))
+    return kx, ky
+
+
+def h0_amplitude(N, L, wind_speed, wind_dir, amplitude, suppression):
+    """sqrt(Phillips)/sqrt(2) clamped to +-4000 (tilde_h0_k_cs.glsl:42-45, 84-88); DC texel -> -4000."""
+    kx, ky = wave_vectors(N, L)
+    wd = np.asarray(wind_dir, np.float64)
+    wd = wd / np.sqrt((wd ** 2).sum())
+    km = np.sqrt(kx ** 2 + ky ** 2)
+    kmc = np.maximum(km, 1e-5)
+    k2 = kmc ** 2
+    Lp = wind_speed ** 2 / G
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore", under="ignore"):
+        d = (kx * wd[0] + ky * wd[1]) / km
+        P = amplitude * np.exp(-1.0 / (k2 * Lp * Lp)) * d * d * np.exp(-k2 * suppression ** 2) / (k2 * k2)
+        a = np.sqrt(P) / np.sqrt(2.0)
+    a = np.where(np.isnan(a), -4000.0, np.clip(a, -4000.0, 4000.0))  # fminf(fmaxf(NaN,-4000),4000) == -4000
+    return a
+
+
+def gauss_rnd(noise_u8, N):
+    """Box-Muller on the nearest-sampled noise planes (tilde_h0_k_cs.glsl:51-68). noise_u8: (4,H,W) bytes."""
+    _, H, W = noise_u8.shape
+    iy = np.floor(np.arange(N) / N * H).astype(np.int64).clip(0, H - 1)
+    ix = np.floor(np.arange(N) / N * W).astype(np.int64).clip(0, W - 1)
+    n = noise_u8[:, iy[:, None], ix[None, :]].astype(np.float64) / 255.0
+    n = np.clip(n, 0.001, 1.0)
+    u0 = 2 * np.pi * n[0]
+    v0 = np.sqrt(-2 * np.log(n[1]))
+    u1 = 2 * np.pi * n[2]
+    v1 = np.sqrt(-2 * np.log(n[3]))
+    return v0 * np.cos(u0), v0 * np.sin(u0), v1 * np.cos(u1), v1 * np.sin(u1)
+
+
+def h0_fields(N, L, wind_speed, wind_dir, amplitude, suppression, noise_u8):
+    a = h0_amplitude(N, L, wind_speed, wind_dir, amplitude, suppression)
+    r0, r1, r2, r3 = gauss_rnd(noise_u8, N)
+    return (r0 + 1j * r1) * a, (r2 + 1j * r3) * a
+
+
+def spectra(h0k, h0minusk, N, L, t):
+    """H_dy, H_dx, H_dz at time t (tilde_h0_t_cs.glsl:70-131): no conjugate on h0minusk (quirk 1)."""
+    kx, ky = wave_vectors(N, L)
+    km = np.maximum(np.sqrt(kx ** 2 + ky ** 2), 1e-5)
+    # w = sqrt(g*|k|) and the product w*t are fp32 in the shader; their fp32 rounding is part of the spec
+    # because it moves the phase by up to ulp(w*t), far above fp64 noise.
+    km32 = np.maximum(np.sqrt((kx.astype(np.float32) ** 2 + ky.astype(np.float32) ** 2).astype(np.float32)),
+                      np.float32(1e-5)).astype(np.float32)
+    w32 = np.sqrt((np.float32(G) * km32).astype(np.float32)).astype(np.float32)
+    ph = (w32 * np.float32(t)).astype(np.float32).astype(np.float64)
+    e = np.cos(ph) + 1j * np.sin(ph)
+    hdy = h0k * e + h0minusk * np.conj(e)
+    hdx = (-1j * kx / km) * hdy
+    hdz = (-1j * ky / km) * hdy
+    return hdy, hdx, hdz
+
+
+def displacement(H):
+    """What the 2*log2(N) butterfly passes + inversion compute (butterfly_cs.glsl, inversion_cs.glsl:29-36)."""
+    return np.real(np.fft.ifft2(np.fft.ifftshift(H)))
+
+
+def normal_map(h):
+    """normal_map_cs.glsl:24-54 with LINEAR+REPEAT sampling at texel corners == 4-texel box means."""
+    box = 0.25 * (h + np.roll(h, 1, 0) + np.roll(h, 1, 1) + np.roll(np.roll(h, 1, 0), 1, 1))
+
+    def z(dx, dy):
+        return np.roll(np.roll(box, -dy, 0), -dx, 1)
+
+    z0, z1, z2 = z(-1, -1), z(0, -1), z(1, -1)
+    z3, z4 = z(-1, 0), z(1, 0)
+    z5, z6, z7 = z(-1, 1), z(0, 1), z(1, 1)
+    nz = z0 + 2 * z1 + z2 - z5 - 2 * z6 - z7
+    nx = z0 + 2 * z3 + z5 - z2 - 2 * z4 - z7
+    ny = np.ones_like(nx)
+    r = 1.0 / np.sqrt(nx * nx + ny * ny + nz * nz)
+    return np.stack([nx * r, ny * r, nz * r, np.ones_like(nx)], axis=-1)
+
+
+def jacobian(dx, dz, L, lam):
+    """Extension: central differences with wrap, spacing L/N, consumer sign convention."""
+    N = dx.shape[0]
+    inv2h = N / (2.0 * L)
+    dxdx = (np.roll(dx, -1, 1) - np.roll(dx, 1, 1)) * inv2h
+    dxdz = (np.roll(dx, -1, 0) - np.roll(dx, 1, 0)) * inv2h
+    dzdx = (np.roll(dz, -1, 1) - np.roll(dz, 1, 1)) * inv2h
+    dzdz = (np.roll(dz, -1, 0) - np.roll(dz, 1, 0)) * inv2h
+    return (1 - lam * dxdx) * (1 - lam * dzdz) - (lam * dxdz) * (lam * dzdx)
+
+
+def frame_from_h0(h0k, h0minusk, N, L, t, choppiness=None):
+    hdy, hdx, hdz = spectra(h0k, h0minusk, N, L, t)
+    dy, dx, dz = displacement(hdy), displacement(hdx), displacement(hdz)
+    out = dict(dy=dy, dx=dx, dz=dz, normal=normal_map(dy))
+    if choppiness is not None:
+        out["jacobian"] = jacobian(dx, dz, L, choppiness)
+    return out
