@@ -1,0 +1,104 @@
+// ow_init_kernels.cu — one-time precompute kernels (compiled with -fmad=false so that the fp32 operation
+// order below is exactly the shader's; these run once per parameter change, not per frame).
+//
+//   ow_h0_kernel    = tilde_h0_k_cs.glsl:35-94 (Phillips spectrum x Box-Muller Gaussians), reference call
+//                     site src/main.cpp:553-583.
+//   ow_ktab_kernel  = the k-vector component of tilde_h0_t_cs.glsl:72-73, tabulated per index.
+// The reference's other two init steps (bit-reversal table main.cpp:733-744 and twiddle texture
+// twiddle_factors_cs.glsl) have no equivalent: the in-CTA FFT derives twiddles in registers.
+#include "ow_internal.h"
+
+namespace ow {
+
+namespace {
+constexpr float kPi = 3.1415926535897932384626433832795f;   // "#define M_PI" of every *_cs.glsl
+constexpr float kG = 9.81f;                                 // tilde_h0_k_cs.glsl:27
+
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+__global__ void ow_ktab_kernel(float* __restrict__ ktab, int N, float L) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) {
+        const float x = (float)i - (float)N / 2.0f;    // :72
+        ktab[i] = (2.0f * kPi * x) / L;                // :73
+    }
+}
+
+__global__ void ow_h0_kernel(float4* __restrict__ h0, const uint8_t* __restrict__ noise, int nw, int nh, int N,
+                             CascadeDev c) {
+    const int ix = blockIdx.x * blockDim.x + threadIdx.x, iy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (ix >= N || iy >= N) return;
+    const float xx = (float)ix - (float)N / 2.0f, xy = (float)iy - (float)N / 2.0f;   // :76
+    const float kx = (2.0f * kPi * xx) / c.L, ky = (2.0f * kPi * xy) / c.L;           // :77
+    const float L_philips = (c.wind_speed * c.wind_speed) / kG;                       // :78
+    float k_mag = sqrtf(kx * kx + ky * ky);                                           // :79
+    if (k_mag < 0.00001f) k_mag = 0.00001f;                                           // :81-82
+    const float k_mag_sqr = k_mag * k_mag;                                            // :84
+    const float sup = expf(-k_mag_sqr * c.suppression * c.suppression);               // :35-38
+    // philips_power_spectrum(), :42-45; normalize() acts on the unclamped k: 0 * inf = NaN at k = 0, and
+    // fminf(fmaxf(NaN, -4000), 4000) = -4000 (IEEE maxNum), which is what NVIDIA's GL compiler produces too.
+    const float rs = 1.0f / sqrtf(kx * kx + ky * ky);
+    const float base = c.amplitude * expf(-1.0f / (k_mag_sqr * L_philips * L_philips));
+    const float dp = (kx * rs) * c.wdx + (ky * rs) * c.wdy;
+    const float dm = (-kx * rs) * c.wdx + (-ky * rs) * c.wdy;
+    const float Pp = (base * (dp * dp) * sup) / (k_mag_sqr * k_mag_sqr);
+    const float Pm = (base * (dm * dm) * sup) / (k_mag_sqr * k_mag_sqr);
+    const float h0k = clampf(sqrtf(Pp) / sqrtf(2.0f), -4000.0f, 4000.0f);             // :87
+    const float h0m = clampf(sqrtf(Pm) / sqrtf(2.0f), -4000.0f, 4000.0f);             // :88
+    // gauss_rnd(), :51-68: texture(noiseJ, gid/N).r with NEAREST + CLAMP_TO_EDGE on an nw x nh RGBA8 image.
+    int tx = (int)floorf(((float)ix / (float)N) * (float)nw), ty = (int)floorf(((float)iy / (float)N) * (float)nh);
+    tx = min(tx, nw - 1);
+    ty = min(ty, nh - 1);
+    const size_t plane = (size_t)nw * nh, o = (size_t)ty * nw + tx;
+    const float n0 = clampf((float)noise[o] / 255.0f, 0.001f, 1.0f);
+    const float n1 = clampf((float)noise[plane + o] / 255.0f, 0.001f, 1.0f);
+    const float n2 = clampf((float)noise[2 * plane + o] / 255.0f, 0.001f, 1.0f);
+    const float n3 = clampf((float)noise[3 * plane + o] / 255.0f, 0.001f, 1.0f);
+    const float u0 = 2.0f * kPi * n0, v0 = sqrtf(-2.0f * logf(n1));
+    const float u1 = 2.0f * kPi * n2, v1 = sqrtf(-2.0f * logf(n3));
+    float4 out;
+    out.x = (v0 * cosf(u0)) * h0k;   // :92
+    out.y = (v0 * sinf(u0)) * h0k;
+    out.z = (v1 * cosf(u1)) * h0m;   // :93
+    out.w = (v1 * sinf(u1)) * h0m;
+    h0[(size_t)iy * N + ix] = out;
+}
+
+__global__ void ow_split_h0_kernel(const float4* __restrict__ h0, float2* __restrict__ a, float2* __restrict__ b, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float4 v = h0[i];
+        a[i] = make_float2(v.x, v.y);
+        b[i] = make_float2(v.z, v.w);
+    }
+}
+
+__global__ void ow_merge_h0_kernel(float4* __restrict__ h0, const float2* __restrict__ a, const float2* __restrict__ b, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) h0[i] = make_float4(a[i].x, a[i].y, b[i].x, b[i].y);
+}
+}  // namespace
+
+cudaError_t launch_ktab(float* ktab, int N, float L, cudaStream_t st) {
+    ow_ktab_kernel<<<(N + 255) / 256, 256, 0, st>>>(ktab, N, L);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_h0(float4* h0, const uint8_t* noise, int nw, int nh, int N, const CascadeDev& c, cudaStream_t st) {
+    ow_h0_kernel<<<dim3(N / 32, N / 8), dim3(32, 8), 0, st>>>(h0, noise, nw, nh, N, c);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_split_h0(const float4* h0, float* h0k, float* h0minusk, int n, cudaStream_t st) {
+    ow_split_h0_kernel<<<(n + 255) / 256, 256, 0, st>>>(h0, reinterpret_cast<float2*>(h0k),
+                                                        reinterpret_cast<float2*>(h0minusk), n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_merge_h0(float4* h0, const float* h0k, const float* h0minusk, int n, cudaStream_t st) {
+    ow_merge_h0_kernel<<<(n + 255) / 256, 256, 0, st>>>(h0, reinterpret_cast<const float2*>(h0k),
+                                                        reinterpret_cast<const float2*>(h0minusk), n);
+    return cudaGetLastError();
+}
+
+}  // namespace ow

@@ -1,0 +1,47 @@
+// ow_internal.h — interface between the C-ABI layer (ow_api.cu) and the kernel launchers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ow {
+
+// Per-cascade constants as the kernels want them (wind direction already normalised).
+struct CascadeDev {
+    float L, wind_speed, wdx, wdy, amplitude, suppression, choppiness, pad;
+};
+
+constexpr int kMaxGroup = 32;   // slots per launch group (slot table travels by value in the kernel params)
+
+struct SlotTable {
+    int32_t cascade[kMaxGroup];
+    float time[kMaxGroup];
+    int32_t slot[kMaxGroup];    // which output set each entry writes
+};
+
+// All device buffers of a context. Strides are in elements of the pointed-to type.
+struct FrameBuffers {
+    int N;
+    const float4* h0;      // [cascade][N][N]   (h0k.re, h0k.im, h0minusk.re, h0minusk.im)
+    const float* ktab;     // [cascade][N]      k(i) = 2*pi*(i - N/2)/L, computed with the shader's operation order
+    const CascadeDev* casc;
+    float2* inter;         // [slot][3][N/2][N] row-transformed Hermitian half spectra (dy, dx, dz)
+    float* disp;           // [slot][3][N][N]   dy, dx, dz
+    float4* normal;        // [slot][N][N]
+    float* jacobian;       // [slot][N][N] or nullptr
+};
+
+bool frame_supported(int N);
+// Launch the three frame kernels for `count` table entries. Returns number of kernels launched (<0: error).
+// ev (optional): 4 events recorded before the row kernel and after each of the three kernels.
+int launch_frame(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_jacobian, cudaStream_t st,
+                 cudaEvent_t* ev = nullptr);
+cudaError_t configure_frame_kernels(int N);   // opt-in shared memory sizes; call once per device
+
+// Init-time kernels (ow_init_kernels.cu)
+cudaError_t launch_ktab(float* ktab, int N, float L, cudaStream_t st);
+cudaError_t launch_h0(float4* h0, const uint8_t* noise, int noise_w, int noise_h, int N, const CascadeDev& c,
+                      cudaStream_t st);
+cudaError_t launch_split_h0(const float4* h0, float* h0k, float* h0minusk, int n, cudaStream_t st);
+cudaError_t launch_merge_h0(float4* h0, const float* h0k, const float* h0minusk, int n, cudaStream_t st);
+
+}  // namespace ow

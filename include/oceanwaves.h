@@ -1,0 +1,136 @@
+/* oceanwaves.h — C ABI of the B200-native Tessendorf hot path (liboceanwaves.so).
+ *
+ * Drop-in boundary for the per-frame ocean simulation of diharaw/fft-ocean-waves. The reference has no
+ * library/FFI surface: the seam is a group of private member functions of `FFTOceanWaves`
+ * (reference src/main.cpp) that communicate through member textures. Each entry point below names the
+ * reference code it replaces. All functions return an ow_status (0 = OK), never throw, never abort, keep no
+ * global state; one context is single-threaded (externally synchronised); contexts on different devices are
+ * independent. No torch / C++ types cross this boundary: plain pointers and sizes only.
+ *
+ * Texel (x, y) <-> gl_GlobalInvocationID.xy; all images are row-major [y][x], first row first in memory,
+ * exactly the layout of the reference's GL textures (src/main.cpp:1089-1099).
+ */
+#ifndef OCEANWAVES_H
+#define OCEANWAVES_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OW_VERSION 100
+
+typedef enum ow_status {
+    OW_OK = 0,
+    OW_ERR_INVALID = 1,   /* bad argument (N not a supported power of two, null pointer, index out of range) */
+    OW_ERR_CUDA = 2,      /* a CUDA runtime call failed; see ow_last_error() */
+    OW_ERR_STATE = 3,     /* call order violated (e.g. ow_step before ow_init_spectrum) */
+    OW_ERR_NO_GL = 4,     /* GL interop requested but no current GL context / registration failed */
+    OW_ERR_NOMEM = 5
+} ow_status;
+
+/* Simulation parameters of ONE cascade (patch). Reference: FFTOceanWaves members, src/main.cpp:1640-1646
+ * (m_wind_speed 80, m_amplitude 2, m_suppression_factor 0.1, m_wind_direction (1,1), m_N 256, m_L 1000) and
+ * :1632-1633 (m_choppiness). wind_dir need not be normalised (the library normalises it like
+ * glm::normalize at src/main.cpp:555). L is float here; the reference's u_L is an int uniform. */
+typedef struct ow_params {
+    float L;            /* patch size in metres (u_L) */
+    float wind_speed;   /* u_WindSpeed */
+    float wind_dir[2];  /* u_WindDirection before normalisation */
+    float amplitude;    /* u_Amplitude */
+    float suppression;  /* u_SuppressFactor */
+    float choppiness;   /* lambda; only used by the Jacobian (the consumer applies it to dx/dz, grid_tes.glsl:61-62) */
+} ow_params;
+
+#define OW_FLAG_JACOBIAN 0x1u   /* also produce the Jacobian/foam map (extension; not in the reference) */
+
+typedef struct ow_ctx ow_ctx;
+
+/* Device pointers to one output set ("slot"); library-owned, valid until ow_destroy. Written by ow_step*.
+ * Replaces the reference's output textures m_dy/m_dx/m_dz (R32F) and m_normal_map (RGBA32F),
+ * src/main.cpp:1096-1099. */
+typedef struct ow_outputs {
+    int32_t N;
+    float* dy;         /* [N*N]   height displacement            */
+    float* dx;         /* [N*N]   choppy displacement along x    */
+    float* dz;         /* [N*N]   choppy displacement along z    */
+    float* normal;     /* [N*N*4] unit normal xyz, w = 1         */
+    float* jacobian;   /* [N*N]   NULL unless OW_FLAG_JACOBIAN   */
+} ow_outputs;
+
+typedef enum ow_image {
+    OW_IMG_DY = 0, OW_IMG_DX = 1, OW_IMG_DZ = 2, OW_IMG_NORMAL = 3, OW_IMG_JACOBIAN = 4,
+    OW_IMG_H0K = 5,        /* [N*N*2] tilde_h0k        (index = cascade, not slot) */
+    OW_IMG_H0MINUSK = 6    /* [N*N*2] tilde_h0minusk   (index = cascade, not slot) */
+} ow_image;
+
+/* ---- lifecycle: replaces create_textures() (src/main.cpp:1083-1145) for the sim resources ------------- */
+
+/* n_cascades independent patches of size N x N (N a power of two in [256, 4096]); n_slots >= n_cascades
+ * output sets (extra slots let one cascade be evaluated at several times per launch, see ow_step_multi).
+ * device = CUDA ordinal. */
+int ow_create(int32_t N, int32_t n_cascades, int32_t n_slots, const ow_params* cascades, int32_t device,
+              uint32_t flags, ow_ctx** out);
+void ow_destroy(ow_ctx* ctx);
+/* Last error text of this context (or of the calling thread's last failed ow_create when ctx == NULL). */
+const char* ow_last_error(const ow_ctx* ctx);
+
+/* ---- init: replaces tilde_h0_k(), generate_bit_reversed_indices(), generate_twiddle_factors()
+ *      (src/main.cpp:218-220, 553-583, 711-744) ------------------------------------------------------- */
+
+/* Change one cascade's parameters; takes effect at the next ow_init_spectrum (the reference never
+ * re-runs tilde_h0_k after its GUI edits, SURVEY.md quirk 8 — this API makes it explicit). */
+int ow_set_params(ow_ctx* ctx, int32_t cascade, const ow_params* p);
+/* Uniform noise for the Box-Muller draw: 4 planes of w*h bytes (the R channel of the reference's
+ * data/noise/LDR_LLL1_{0..3}.png, w = h = 256), HOST pointers. cascade = -1 sets every cascade.
+ * Lookup rule is the shader's NEAREST/CLAMP fetch at gid/N (tilde_h0_k_cs.glsl:53-58). */
+int ow_set_noise(ow_ctx* ctx, int32_t cascade, const uint8_t* const planes[4], int32_t w, int32_t h);
+/* = tilde_h0_k_cs.glsl for every cascade. Re-callable. Synchronous (like the reference's glFinish). */
+int ow_init_spectrum(ow_ctx* ctx);
+/* Overwrite / read back a cascade's initial spectrum (HOST pointers, N*N*2 floats each). */
+int ow_set_h0(ow_ctx* ctx, int32_t cascade, const float* h0k, const float* h0minusk);
+
+/* ---- per frame: replaces tilde_h0_t(); butterfly_fft() x3; generate_normal_map()
+ *      (src/main.cpp:240-244, 587-707) ---------------------------------------------------------------- */
+
+/* Slot i <- cascade i at time t, for every cascade. Asynchronous on `stream` (a cudaStream_t passed as
+ * void*; NULL = the context's own stream). t replaces float(glfwGetTime()) (src/main.cpp:599). */
+int ow_step(ow_ctx* ctx, float t, void* stream);
+/* Slot i <- cascade cascade_of_slot[i] at time time_of_slot[i], i < count <= n_slots (HOST arrays). */
+int ow_step_multi(ow_ctx* ctx, int32_t count, const int32_t* cascade_of_slot, const float* time_of_slot, void* stream);
+/* Same as ow_step_multi but synchronous, with CUDA events around each kernel on `stream`: kernel_ms[0..2] receive
+ * the summed durations (ms) of the row-IFFT, column-IFFT and normal/Jacobian kernels. For bench.py's roofline. */
+int ow_step_multi_timed(ow_ctx* ctx, int32_t count, const int32_t* cascade_of_slot, const float* time_of_slot, void* stream,
+                        float* kernel_ms);
+/* Block until everything queued by this context on `stream` has finished. */
+int ow_sync(ow_ctx* ctx, void* stream);
+
+int ow_get_outputs(ow_ctx* ctx, int32_t slot, ow_outputs* out);
+/* Copy one image to HOST memory (synchronous w.r.t. `stream`). bytes must equal the image size. */
+int ow_download(ow_ctx* ctx, int32_t index, int32_t which /* ow_image */, void* host, size_t bytes, void* stream);
+/* Asynchronous variant of ow_download of a slot's dy,dx,dz,normal[,jacobian] into ONE pinned host block
+ * laid out in that order; used by the headless end-to-end path. */
+int ow_download_frame_async(ow_ctx* ctx, int32_t slot, void* pinned_host, size_t bytes, void* stream);
+size_t ow_frame_bytes(const ow_ctx* ctx);
+
+/* Tuning: how many slots share one row/column/normal launch group (keeps the 12 B/texel intermediate of a
+ * group resident in L2). 0 = automatic. */
+int ow_set_group_size(ow_ctx* ctx, int32_t slots_per_group);
+/* Number of kernels the last ow_step/ow_step_multi launched (for launch accounting in bench.py). */
+int ow_last_launch_count(const ow_ctx* ctx);
+
+/* ---- CUDA-GL interop: replaces the renderer's texture binds (src/main.cpp:477-487) ------------------- */
+
+/* Register the caller's GL textures (R32F dy,dx,dz; RGBA32F normal) via cudaGraphicsGLRegisterImage. The
+ * caller's GL context must be current on the calling thread. Returns OW_ERR_NO_GL when that fails. */
+int ow_gl_register(ow_ctx* ctx, uint32_t tex_dy, uint32_t tex_dx, uint32_t tex_dz, uint32_t tex_normal);
+/* ow_step for slot 0 and copy the results into the registered textures (map -> copy -> unmap). */
+int ow_gl_step(ow_ctx* ctx, float t);
+int ow_gl_unregister(ow_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCEANWAVES_H */

@@ -1,0 +1,172 @@
+// ow_emu.cu — CPU emulation of the frame kernels' index logic (TEST INFRASTRUCTURE, never a product path).
+//
+// Compiles the very same per-thread phase functions the CUDA kernels run (csrc/ow_kernels.cuh) as host code
+// and executes them thread by thread, phase by phase, CTA by CTA. It exists so that index-algebra mistakes
+// (digit maps, Hermitian mirroring, paddings) are caught on the CPU-only build box, and to count
+// shared-memory bank conflicts of each access pattern. Nothing in the product loads this library.
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <vector>
+
+#include "../../fft-ocean-waves_b200/csrc/ow_config.cuh"
+#include "../../fft-ocean-waves_b200/csrc/ow_kernels.cuh"
+
+using namespace ow;
+
+namespace {
+
+// Records every shared-memory access of one phase: seq[tid] = list of element addresses in program order.
+struct Recorder {
+    std::vector<std::vector<int>> seq;
+    long requests = 0, wavefronts = 0;
+    void begin(int nthreads) { seq.assign(nthreads, {}); }
+    // 8-byte accesses are served per half-warp; a bank pair is (element address mod 16).
+    void end() {
+        const int nt = (int)seq.size();
+        for (int h = 0; h < nt; h += 16) {
+            size_t len = 0;
+            for (int t = h; t < h + 16 && t < nt; ++t) len = std::max(len, seq[t].size());
+            for (size_t i = 0; i < len; ++i) {
+                std::map<int, std::vector<int>> banks;
+                for (int t = h; t < h + 16 && t < nt; ++t) {
+                    if (i >= seq[t].size()) continue;
+                    auto& v = banks[seq[t][i] & 15];
+                    bool dup = false;
+                    for (int a : v) dup |= (a == seq[t][i]);
+                    if (!dup) v.push_back(seq[t][i]);
+                }
+                size_t worst = 0;
+                for (auto& kv : banks) worst = std::max(worst, kv.second.size());
+                if (worst) { requests += 1; wavefronts += (long)worst; }
+            }
+        }
+    }
+};
+
+struct SmemEmu {
+    float2* p;
+    std::vector<int>* log;
+    OW_HD float2 ld(int i) const {
+#ifndef __CUDA_ARCH__
+        log->push_back(i);
+#endif
+        return p[i];
+    }
+    OW_HD void st(int i, float2 v) const {
+#ifndef __CUDA_ARCH__
+        log->push_back(i);
+#endif
+        p[i] = v;
+    }
+};
+
+struct Stats {
+    long req[6] = {0, 0, 0, 0, 0, 0}, wf[6] = {0, 0, 0, 0, 0, 0};   // row phase 0..2, col phase 0..2
+};
+
+template <int N>
+void emu_rows(const float4* h0, const float* ktab, float t, float2* inter, Stats& st) {
+    using C = Cfg<N>;
+    using P = typename C::Row;
+    constexpr int PAIRS = C::ROW_PAIRS, NT = P::T * PAIRS;
+    std::vector<float2> smem((size_t)PAIRS * 3 * P::LINE);
+    Recorder rec;
+    for (int blk = 0; blk < N / 2 / PAIRS; ++blk) {
+        for (int phase = 0; phase < 3; ++phase) {
+            rec.begin(NT);
+            for (int tid = 0; tid < NT; ++tid) {
+                const int ft = tid % P::T, g = tid / P::T, p = blk * PAIRS + g;
+                const SmemEmu sm{smem.data() + (size_t)g * 3 * P::LINE, &rec.seq[tid]};
+                if (phase == 0) row_phase0<P>(sm, ft, p, h0, ktab, t);
+                if (phase == 1) row_phase1<P>(sm, ft);
+                if (phase == 2) row_phase2<P>(sm, ft, p, inter);
+            }
+            if (blk < 2) { rec.requests = rec.wavefronts = 0; rec.end(); st.req[phase] += rec.requests; st.wf[phase] += rec.wavefronts; }
+        }
+    }
+}
+
+template <int N>
+void emu_cols(const float2* inter, float* disp, Stats& st) {
+    using C = Cfg<N>;
+    using P = typename C::Col;
+    constexpr int G = C::COL_G, NT = P::T * G;
+    using LY = ColLayout<P, G>;
+    std::vector<float2> smem((size_t)G * LY::SJ);
+    const float scale = 0.5f / ((float)N * (float)N);
+    Recorder rec;
+    for (int f = 0; f < 3; ++f)
+        for (int blk = 0; blk < N / (2 * G); ++blk) {
+            for (int phase = 0; phase < 3; ++phase) {
+                rec.begin(NT);
+                for (int tid = 0; tid < NT; ++tid) {
+                    const int job = tid % G, ft = tid / G, x = 2 * (blk * G + job);
+                    const SmemEmu sm{smem.data(), &rec.seq[tid]};
+                    const int base = job * LY::SJ;
+                    const float2* src = inter + (size_t)f * (N / 2) * N + x;
+                    float* dst = disp + (size_t)f * N * N + x;
+                    if (phase == 0) for (int j = ft; j < P::M / 2; j += P::T) col_phase0<P>(sm, base, j, src);
+                    if (phase == 1) col_phase1<P>(sm, base, ft);
+                    if (phase == 2) col_phase2<P>(sm, base, ft, dst, scale);
+                }
+                if (f == 0 && blk < 2) { rec.requests = rec.wavefronts = 0; rec.end(); st.req[3 + phase] += rec.requests; st.wf[3 + phase] += rec.wavefronts; }
+            }
+        }
+}
+
+template <int N>
+void emu_normals(const float* disp, float4* normal, float* jac, float lambda, float L) {
+    const WrapFetch<N> hy{disp}, hx{disp + (size_t)N * N}, hz{disp + (size_t)2 * N * N};
+    for (int y = 0; y < N; ++y)
+        for (int x = 0; x < N; ++x) {
+            normal[(size_t)y * N + x] = normal_at(hy, x, y);
+            if (jac) jac[(size_t)y * N + x] = jacobian_at(hx, hz, x, y, lambda, (float)N / (2.0f * L));
+        }
+}
+
+template <int N>
+int emu_frame_n(const float* h0k, const float* h0minusk, float L, float t, float lambda, float* inter_out, float* disp,
+                float* normal, float* jac, long* stats) {
+    std::vector<float4> h0((size_t)N * N);
+    for (size_t i = 0; i < (size_t)N * N; ++i) h0[i] = make_float4(h0k[2 * i], h0k[2 * i + 1], h0minusk[2 * i], h0minusk[2 * i + 1]);
+    std::vector<float> ktab(N);
+    const float pi = 3.1415926535897932384626433832795f;
+    for (int i = 0; i < N; ++i) ktab[i] = (2.0f * pi * ((float)i - (float)N / 2.0f)) / L;
+    std::vector<float2> inter((size_t)3 * (N / 2) * N);
+    Stats st;
+    emu_rows<N>(h0.data(), ktab.data(), t, inter.data(), st);
+    emu_cols<N>(inter.data(), disp, st);
+    emu_normals<N>(disp, reinterpret_cast<float4*>(normal), jac, lambda, L);
+    if (inter_out) std::memcpy(inter_out, inter.data(), inter.size() * sizeof(float2));
+    if (stats) for (int i = 0; i < 6; ++i) { stats[2 * i] = st.req[i]; stats[2 * i + 1] = st.wf[i]; }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int emu_frame(int N, const float* h0k, const float* h0minusk, float L, float t, float lambda, float* inter_out,
+                         float* disp, float* normal, float* jac, long* stats) {
+    switch (N) {
+        case 256: return emu_frame_n<256>(h0k, h0minusk, L, t, lambda, inter_out, disp, normal, jac, stats);
+        case 512: return emu_frame_n<512>(h0k, h0minusk, L, t, lambda, inter_out, disp, normal, jac, stats);
+        case 1024: return emu_frame_n<1024>(h0k, h0minusk, L, t, lambda, inter_out, disp, normal, jac, stats);
+        case 2048: return emu_frame_n<2048>(h0k, h0minusk, L, t, lambda, inter_out, disp, normal, jac, stats);
+        case 4096: return emu_frame_n<4096>(h0k, h0minusk, L, t, lambda, inter_out, disp, normal, jac, stats);
+    }
+    return -1;
+}
+
+// In-register DFT self-test: out[k] = dft<R>(in), for R in {2,4,8,16}.
+extern "C" int emu_dft(int R, const float* in, float* out) {
+    float2 v2[2], v4[4], v8[8], v16[16];
+    auto load = [&](float2* v) { for (int i = 0; i < R; ++i) v[i] = make_float2(in[2 * i], in[2 * i + 1]); };
+    auto store = [&](float2* v) { for (int i = 0; i < R; ++i) { out[2 * i] = v[i].x; out[2 * i + 1] = v[i].y; } };
+    switch (R) {
+        case 2: load(v2); Dft<2>::run(v2); store(v2); return 0;
+        case 4: load(v4); Dft<4>::run(v4); store(v4); return 0;
+        case 8: load(v8); Dft<8>::run(v8); store(v8); return 0;
+        case 16: load(v16); Dft<16>::run(v16); store(v16); return 0;
+    }
+    return -1;
+}

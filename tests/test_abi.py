@@ -1,0 +1,74 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads, exports every symbol include/oceanwaves.h
+declares, and fails loudly (no CPU fallback) when no CUDA device is present. No compute calls here."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+import fft_ocean_waves_b200 as fow
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "oceanwaves.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(ow_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_declares_the_documented_surface():
+    syms = header_symbols()
+    assert sorted(fow.EXPORTED_SYMBOLS) == syms
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(fow.lib_path()), "build with: python fft-ocean-waves_b200/build.py"
+    lib = C.CDLL(fow.lib_path())
+    for s in header_symbols():
+        assert hasattr(lib, s), s
+
+
+def test_header_compiles_as_plain_c(tmp_path):
+    src = tmp_path / "t.c"
+    src.write_text('#include "oceanwaves.h"\nint main(void){ ow_params p; ow_outputs o; (void)p; (void)o; return OW_OK; }\n')
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           "-c", str(src), "-o", str(tmp_path / "t.o")])
+
+
+def test_library_contains_sm100a_code():
+    cuobjdump = "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-lelf", fow.lib_path()], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out
+
+
+def test_invalid_arguments_are_rejected_without_a_gpu():
+    lib = fow.load_library()
+    h = C.c_void_p()
+    p = fow.OceanParams().to_c()
+    assert lib.ow_create(300, 1, 1, C.byref(p), 0, 0, C.byref(h)) == 1          # N not supported -> OW_ERR_INVALID
+    assert b"N must be" in lib.ow_last_error(None)
+    assert lib.ow_create(256, 2, 1, C.byref(p), 0, 0, C.byref(h)) == 1          # n_slots < n_cascades
+    assert lib.ow_step(None, 0.0, None) == 1
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device creating a simulation must raise; with one it must succeed."""
+    import torch
+    if torch.cuda.is_available():
+        fow.FFTOceanWaves(N=256).close()
+    else:
+        with pytest.raises(fow.OceanWavesError):
+            fow.FFTOceanWaves(N=256)
+
+
+def test_product_does_not_reference_the_oracle():
+    pkg = os.path.join(ROOT, "fft-ocean-waves_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "oracle" not in txt.lower() or f in ("ow_kernels.cuh",) and "import" not in txt, f

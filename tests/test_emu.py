@@ -1,0 +1,70 @@
+"""CPU check of the CUDA kernels' index algebra: the product's per-thread phase functions
+(fft-ocean-waves_b200/csrc/ow_kernels.cuh) compiled as host code and run thread by thread (tests/emu),
+compared with the oracle. Also asserts that every shared-memory access pattern is bank-conflict free.
+This does not replace the GPU parity tests (tests/test_gpu_parity.py); it keeps index bugs off the GPU box."""
+import numpy as np
+import pytest
+
+from oracle import numpy_ref as R
+from oracle.oracle import OracleSim
+from tests.emu import emu
+
+REL_TOL = 1e-4   # north star: max abs error <= 1e-4 x peak displacement; the emulator lands near 1e-6
+
+
+@pytest.mark.parametrize("R_", [2, 4, 8, 16])
+def test_register_dft(R_):
+    rng = np.random.default_rng(R_)
+    x = (rng.standard_normal(R_) + 1j * rng.standard_normal(R_)).astype(np.complex64)
+    ref = np.fft.ifft(x.astype(np.complex128)) * R_     # e^{+2 pi i nk/R}: the reference's inverse sign
+    assert np.abs(emu.dft(x) - ref).max() < 2e-6 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("N,t", [(256, 0.0), (256, 1.0), (256, 10.0), (512, 599.0 / 60.0), (1024, 1.0)])
+def test_emulated_frame_matches_oracle(noise, N, t):
+    s = OracleSim(N, 1000.0, 40.0, (1.0, 1.0), 2.0, 0.1, noise, threads=8)
+    a, b = s.h0()
+    ref = s.frame(t, choppiness=1.0)
+    got = emu.frame(N, a, b, 1000.0, t, 1.0)
+    for k in ("dy", "dx", "dz"):
+        peak = np.abs(ref[k]).max()
+        assert np.abs(got[k] - ref[k]).max() <= REL_TOL * peak, k
+        assert np.abs(got[k] - ref[k]).max() <= 5e-6 * peak, k          # what fp32 actually delivers
+    assert np.abs(got["normal"] - ref["normal"]).max() < 1e-4
+    assert np.abs(got["jacobian"] - ref["jacobian"]).max() < 1e-4
+    for phase, (req, wf) in got["conflicts"].items():
+        assert req > 0 and wf == req, f"{phase}: {wf} wavefronts for {req} requests (bank conflicts)"
+
+
+def test_emulated_2048_matches_fp64(noise):
+    """Full-size C3 grid: compare with the fp64 closed form (the scalar oracle would also do, but slower)."""
+    N = 2048
+    rngn = np.random.default_rng(2048).integers(0, 256, (4, N, N), dtype=np.uint8)
+    ak, bk = R.h0_fields(N, 1000.0, 40.0, (1, 1), 2.0, 0.1, rngn)
+    a = np.stack([ak.real, ak.imag], -1).astype(np.float32)
+    b = np.stack([bk.real, bk.imag], -1).astype(np.float32)
+    ref = R.frame_from_h0(a[..., 0] + 1j * a[..., 1].astype(np.float64), b[..., 0] + 1j * b[..., 1].astype(np.float64),
+                          N, 1000.0, 1.0, 1.0)
+    got = emu.frame(N, a, b, 1000.0, 1.0, 1.0)
+    for k in ("dy", "dx", "dz"):
+        assert np.abs(got[k] - ref[k]).max() <= 5e-6 * np.abs(ref[k]).max(), k
+    assert np.abs(got["normal"] - ref["normal"]).max() < 1e-5
+    for phase, (req, wf) in got["conflicts"].items():
+        assert wf == req, phase
+
+
+def test_intermediate_is_row_transform_of_hermitian_part(noise):
+    """The row kernel's output is the row IFFT of S = H + conj(H(-k)) for rows 0..N/2-1 (row 0 packs rows 0, N/2)."""
+    N, t = 256, 1.0
+    s = OracleSim(N, 1000.0, 40.0, (1.0, 1.0), 2.0, 0.1, noise, threads=4)
+    a, b = s.h0()
+    got = emu.frame(N, a, b, 1000.0, t, 1.0, want_inter=True)["inter"]
+    H = R.spectra(a[..., 0] + 1j * a[..., 1].astype(np.float64), b[..., 0] + 1j * b[..., 1].astype(np.float64), N, 1000.0, t)
+    idx = (-np.arange(N)) % N
+    for c in range(3):
+        S = H[c] + np.conj(H[c][idx][:, idx])
+        rows = np.fft.ifft(S, axis=1) * N
+        ref = rows[:N // 2].copy()
+        ref[0] = rows[0].real + 1j * rows[N // 2].real
+        g = got[c][..., 0] + 1j * got[c][..., 1]
+        assert np.abs(g - ref).max() < 5e-6 * np.abs(ref).max()
