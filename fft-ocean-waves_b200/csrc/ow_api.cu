@@ -1,6 +1,7 @@
 // ow_api.cu — the C ABI declared in include/oceanwaves.h: context, buffers, launch sequencing.
 // Host side of the drop-in: what FFTOceanWaves::init()/update() do for the sim (reference
 // src/main.cpp:199-255, 553-744, 1083-1145) minus windowing, rendering and GL plumbing.
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -247,12 +248,16 @@ static int step_impl(ow_ctx* c, int32_t count, const int32_t* cascade_of_slot, c
     for (int base = 0; base < count; base += group) {
         const int n = count - base < group ? count - base : group;
         SlotTable tab{};
+        bool fast = (c->flags & OW_FLAG_EXACT_SINCOS) == 0;
         for (int i = 0; i < n; ++i) {
             tab.cascade[i] = cascade_of_slot[base + i];
             tab.time[i] = time_of_slot[base + i];
             tab.slot[i] = base + i;
+            // largest phase of this cascade: w_max = sqrt(g*|k|max), |k|max = sqrt(2)*pi*N/L
+            const float kmax = 1.41421356f * 3.14159265f * (float)c->N / c->params[tab.cascade[i]].L;
+            if (!(sqrtf(9.81f * kmax) * fabsf(tab.time[i]) < kFastPhaseLimit)) fast = false;
         }
-        const int k = launch_frame(fb, tab, n, (c->flags & OW_FLAG_JACOBIAN) != 0, st, kernel_ms ? ev : nullptr);
+        const int k = launch_frame(fb, tab, n, (c->flags & OW_FLAG_JACOBIAN) != 0, fast, st, kernel_ms ? ev : nullptr);
         if (k < 0) return cuda_fail(c, cudaGetLastError(), "launch_frame");
         launches += k;
         if (kernel_ms) {

@@ -171,16 +171,20 @@ struct SmemDirect {
     OW_HD void st(int i, float2 v) const { p[i] = v; }
 };
 
-// Stage 1 for butterfly id q of one line (base = line offset inside the accessor).
+// Stage 1 for butterfly id q of one line (base = line offset inside the accessor). tw = powers of
+// e^{2 pi i d2/(R1*R2)} (stage1_twiddles), shared by every line the thread transforms at this q.
+template <class P>
+OW_HD void stage1_twiddles(int q, float2 (&tw)[P::R1]) {
+    twiddle_powers<P::R1>(unit_root(q % P::R2, P::R1 * P::R2), tw);
+}
+
 template <class P, class Smem>
-OW_HD void stage1(const Smem& sm, int base, int q) {
+OW_HD void stage1(const Smem& sm, int base, int q, const float2 (&tw)[P::R1]) {
     const int d2 = q % P::R2, k0 = q / P::R2;
     float2 v[P::R1];
 #pragma unroll
     for (int d1 = 0; d1 < P::R1; ++d1) v[d1] = sm.ld(base + P::addr(k0, d1, d2));
     Dft<P::R1>::run(v);
-    float2 tw[P::R1];
-    twiddle_powers<P::R1>(unit_root(d2, P::R1 * P::R2), tw);
 #pragma unroll
     for (int k1 = 1; k1 < P::R1; ++k1) v[k1] = cmul(v[k1], tw[k1]);
 #pragma unroll

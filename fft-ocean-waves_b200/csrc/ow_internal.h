@@ -33,8 +33,10 @@ struct FrameBuffers {
 bool frame_supported(int N);
 // Launch the three frame kernels for `count` table entries. Returns number of kernels launched (<0: error).
 // ev (optional): 4 events recorded before the row kernel and after each of the three kernels.
-int launch_frame(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_jacobian, cudaStream_t st,
-                 cudaEvent_t* ev = nullptr);
+// fast_phase: every |w*t| of this launch is below kFastPhaseLimit, so the SFU sin/cos path is accurate enough.
+int launch_frame(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_jacobian, bool fast_phase,
+                 cudaStream_t st, cudaEvent_t* ev = nullptr);
+constexpr float kFastPhaseLimit = 2.0e4f;
 cudaError_t configure_frame_kernels(int N);   // opt-in shared memory sizes; call once per device
 
 // Init-time kernels (ow_init_kernels.cu)

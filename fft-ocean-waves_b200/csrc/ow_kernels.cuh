@@ -49,19 +49,53 @@ struct Sym3 {
     float2 y, x, z;
 };
 
+// sin/cos of the phase w*t. FAST: two-constant Cody-Waite reduction by 2*pi + the SFU's sin/cos (absolute
+// error ~5e-7 for |x| < 2e4; the launcher only selects it when max |w*t| of the cascade is below that);
+// otherwise libdevice sincosf (full-range Payne-Hanek).
+template <bool FAST>
+OW_HD void phase_sincos(float x, float* s, float* c) {
+#ifdef __CUDA_ARCH__
+    if (FAST) {
+        const float n = rintf(x * 0.15915494309189535f);
+        float r = fmaf(n, -6.2831854820251465f, x);
+        r = fmaf(n, 1.7484555314695172e-7f, r);
+        *s = __sinf(r);
+        *c = __cosf(r);
+        return;
+    }
+#endif
+    sincosf(x, s, c);
+}
+
+// Raw inputs of one texel pair; loading is split from the arithmetic so a thread can put all the loads of a
+// butterfly in flight before the first use (the sincos code otherwise serialises them: one DRAM round trip each).
+struct TexelPair {
+    float4 A, B;   // h0 at (u, v) and at the mirror texel (N-u, N-v)
+    float kx;      // k_x at u
+};
+
 template <int N>
-OW_HD Sym3 spectrum_sym(const float4* __restrict__ h0, const float* __restrict__ ktab, float t, int u, int v, int mv) {
+OW_HD TexelPair load_pair(const float4* __restrict__ h0, const float* __restrict__ ktab, int u, int v, int mv) {
     const int mu = (N - u) & (N - 1);
-    const float4 A = OW_LDG(h0 + (size_t)v * N + u);
-    const float4 B = OW_LDG(h0 + (size_t)mv * N + mu);
-    const float kx = OW_LDG(ktab + u), ky = OW_LDG(ktab + v);
-    const float kxm = OW_LDG(ktab + mu), kym = OW_LDG(ktab + mv);
+    TexelPair tp;
+    tp.A = OW_LDG(h0 + (size_t)v * N + u);
+    tp.B = OW_LDG(h0 + (size_t)mv * N + mu);
+    tp.kx = OW_LDG(ktab + u);
+    return tp;
+}
+
+template <bool FAST>
+OW_HD Sym3 spectrum_sym(const TexelPair& tp, int u, float ky, bool self_row, float t) {
+    const float4 A = tp.A, B = tp.B;
+    const float kx = tp.kx;
+    // k at the mirror texel is -k, except on the Nyquist row/column (index 0) whose mirror is itself
+    const float kxm = (u == 0) ? kx : -kx, kym = self_row ? ky : -ky;
     // tilde_h0_t_cs.glsl:74-79 — same operation order as the shader so w*t matches to the bit.
     float km = OW_SQRT(OW_ADD(OW_MUL(kx, kx), OW_MUL(ky, ky)));
     if (km < 0.00001f) km = 0.00001f;
     const float w = OW_SQRT(OW_MUL(kGravity, km));
     float s, c;
-    sincosf(OW_MUL(w, t), &s, &c);                                  // :96-97
+    phase_sincos<FAST>(OW_MUL(w, t), &s, &c);                       // :96-97
     // :110  h = h0k * e^{iwt} + h0minusk * e^{-iwt}   (conjugate() is a no-op in the shader, :42-48)
     const float2 H  = make_float2((A.x * c - A.y * s) + (A.z * c + A.w * s), (A.x * s + A.y * c) + (A.w * c - A.z * s));
     const float2 Hm = make_float2((B.x * c - B.y * s) + (B.z * c + B.w * s), (B.x * s + B.y * c) + (B.w * c - B.z * s));
@@ -80,36 +114,48 @@ OW_HD Sym3 spectrum_sym(const float4* __restrict__ h0, const float* __restrict__
 // the three channels. Shared memory per group: 3 lines of P::LINE float2 (dy, dx, dz).
 // Output: inter[c][p][x] (float2), c in {dy,dx,dz}, p < N/2, x < N — the row transform of S_c(., p).
 // ---------------------------------------------------------------------------------------------------
-template <class P, class Smem>
+template <class P, bool FAST, class Smem>
 OW_HD void row_phase0(const Smem& sm, int ft, int p, const float4* __restrict__ h0, const float* __restrict__ ktab,
                       float t) {
-    constexpr int N = P::N;
+    constexpr int N = P::N, R0 = P::R0;
 #pragma unroll 1
     for (int c = 0; c < P::C0; ++c) {
         const int b = ft + P::T * c;
         if (b >= P::M) break;
-        float2 vy[P::R0], vx[P::R0], vz[P::R0];
+        float2 vy[R0], vx[R0], vz[R0];
+        TexelPair tp[R0];
         if (p != 0) {
+            const float ky = OW_LDG(ktab + p);
 #pragma unroll
-            for (int d0 = 0; d0 < P::R0; ++d0) {
-                const Sym3 s = spectrum_sym<N>(h0, ktab, t, d0 * P::M + b, p, N - p);
+            for (int d0 = 0; d0 < R0; ++d0) tp[d0] = load_pair<N>(h0, ktab, d0 * P::M + b, p, N - p);
+#pragma unroll
+            for (int d0 = 0; d0 < R0; ++d0) {
+                const Sym3 s = spectrum_sym<FAST>(tp[d0], d0 * P::M + b, ky, false, t);
                 vy[d0] = s.y; vx[d0] = s.x; vz[d0] = s.z;
             }
         } else {
             // rows 0 (Nyquist) and N/2 (DC) mirror onto themselves; both row transforms are real, so they
             // travel as one complex line: Z = S(.,0) + i*S(.,N/2).
+            const float ky0 = OW_LDG(ktab), kyh = OW_LDG(ktab + N / 2);
 #pragma unroll
-            for (int d0 = 0; d0 < P::R0; ++d0) {
-                const int u = d0 * P::M + b;
-                const Sym3 a = spectrum_sym<N>(h0, ktab, t, u, 0, 0);
-                const Sym3 q = spectrum_sym<N>(h0, ktab, t, u, N / 2, N / 2);
-                vy[d0] = make_float2(a.y.x - q.y.y, a.y.y + q.y.x);
-                vx[d0] = make_float2(a.x.x - q.x.y, a.x.y + q.x.x);
-                vz[d0] = make_float2(a.z.x - q.z.y, a.z.y + q.z.x);
+            for (int d0 = 0; d0 < R0; ++d0) tp[d0] = load_pair<N>(h0, ktab, d0 * P::M + b, 0, 0);
+#pragma unroll
+            for (int d0 = 0; d0 < R0; ++d0) {
+                const Sym3 a = spectrum_sym<FAST>(tp[d0], d0 * P::M + b, ky0, true, t);
+                vy[d0] = a.y; vx[d0] = a.x; vz[d0] = a.z;
+            }
+#pragma unroll
+            for (int d0 = 0; d0 < R0; ++d0) tp[d0] = load_pair<N>(h0, ktab, d0 * P::M + b, N / 2, N / 2);
+#pragma unroll
+            for (int d0 = 0; d0 < R0; ++d0) {
+                const Sym3 q = spectrum_sym<FAST>(tp[d0], d0 * P::M + b, kyh, true, t);
+                vy[d0] = make_float2(vy[d0].x - q.y.y, vy[d0].y + q.y.x);
+                vx[d0] = make_float2(vx[d0].x - q.x.y, vx[d0].y + q.x.x);
+                vz[d0] = make_float2(vz[d0].x - q.z.y, vz[d0].y + q.z.x);
             }
         }
-        float2 tw[P::R0];
-        twiddle_powers<P::R0>(unit_root(b, N), tw);
+        float2 tw[R0];
+        twiddle_powers<R0>(unit_root(b, N), tw);
         stage0_finish<P>(sm, 0 * P::LINE, b, vy, tw);
         stage0_finish<P>(sm, 1 * P::LINE, b, vx, tw);
         stage0_finish<P>(sm, 2 * P::LINE, b, vz, tw);
@@ -122,8 +168,10 @@ OW_HD void row_phase1(const Smem& sm, int ft) {
     for (int c = 0; c < P::C1; ++c) {
         const int q = ft + P::T * c;
         if (q >= P::B1) break;
+        float2 tw[P::R1];
+        stage1_twiddles<P>(q, tw);
 #pragma unroll 1
-        for (int f = 0; f < 3; ++f) stage1<P>(sm, f * P::LINE, q);
+        for (int f = 0; f < 3; ++f) stage1<P>(sm, f * P::LINE, q, tw);
     }
 }
 
@@ -197,7 +245,9 @@ OW_HD void col_phase1(const Smem& sm, int base, int ft) {
     for (int c = 0; c < P::C1; ++c) {
         const int q = ft + P::T * c;
         if (q >= P::B1) break;
-        stage1<P>(sm, base, q);
+        float2 tw[P::R1];
+        stage1_twiddles<P>(q, tw);
+        stage1<P>(sm, base, q, tw);
     }
 }
 
@@ -221,44 +271,65 @@ OW_HD void col_phase2(const Smem& sm, int base, int ft, float* __restrict__ dst 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// NORMAL (+ JACOBIAN) for texel (x, y).  normal_map_cs.glsl:24-54: the eight texture() taps sit on texel
-// corners, so with LINEAR+REPEAT each is the mean of a 2x2 block; the stencil covers columns x-2..x+1 and
-// rows y-2..y+1 with wrap-around.
+// NORMAL (+ JACOBIAN).  normal_map_cs.glsl:24-54: the eight texture() taps sit on texel corners, so with
+// LINEAR+REPEAT each tap is the mean of a 2x2 block ("box"); the stencil covers columns x-2..x+1 and rows
+// y-2..y+1 with wrap-around. One thread owns column x and walks down RY output rows keeping a sliding window:
+//   hs(r)[c]  = h[r][x+c-2] + h[r][x+c-1]          c = 0,1,2   (horizontal pair sums, 4 loads per row)
+//   box(r)[c] = (hs(r-1)[c] + hs(r)[c]) / 4        = taps at (x-1, x, x+1) of tap-row r
+//   sx(r)  = box[0] + 2 box[1] + box[2],   dxb(r) = box[0] - box[2]
+//   n.z(j) = sx(j-1) - sx(j+1)                     (:49)     n.x(j) = dxb(j-1) + 2 dxb(j) + dxb(j+1)   (:50)
+// so each texel costs 4 loads instead of 16. Lanes run along x: every load and the float4 store are coalesced.
+// The Jacobian (extension) rides the same walk:
+//   J = (1 - l*dDx/dx)(1 - l*dDz/dz) - l^2 (dDx/dz)(dDz/dx), central differences with wrap, spacing L/N.
 // ---------------------------------------------------------------------------------------------------
-template <class Fetch>
-OW_HD float4 normal_at(const Fetch& h, int x, int y) {
-    float t[4][4];   // t[a][b] = h(x - 2 + b, y - 2 + a)
+template <int N, int RY, bool JAC>
+OW_HD void normal_column_walk(const float* __restrict__ disp /* dy,dx,dz planes */, float4* __restrict__ normal,
+                              float* __restrict__ jac, int x, int y0, float lambda, float inv2h) {
+    constexpr int MSK = N - 1;
+    const int c0 = (x - 2) & MSK, c1 = (x - 1) & MSK, c3 = (x + 1) & MSK;
+    const float* hy = disp;
+    const float* hx = disp + (size_t)N * N;
+    const float* hz = disp + (size_t)2 * N * N;
+    float hs_prev[3], sx_m1 = 0.f, sx_0 = 0.f, dxb_m1 = 0.f, dxb_0 = 0.f;   // window state
+    float xc_m1 = 0.f, xc_0 = 0.f, zc_m1 = 0.f, zc_0 = 0.f, ddx_0 = 0.f, ddz_0 = 0.f;
+    {
+        const float* r = hy + (size_t)((y0 - 2) & MSK) * N;
+        const float a = OW_LDG(r + c0), b = OW_LDG(r + c1), c = OW_LDG(r + x), d = OW_LDG(r + c3);
+        hs_prev[0] = a + b; hs_prev[1] = b + c; hs_prev[2] = c + d;
+    }
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) t[a][b] = h(x - 2 + b, y - 2 + a);
-    float z[3][3];   // z[dj+1][di+1] = bilinear tap at (x+di, y+dj)/N = mean of texels (x+di-1..x+di, y+dj-1..y+dj)
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-#pragma unroll
-        for (int b = 0; b < 3; ++b) z[a][b] = ((t[a][b] + t[a][b + 1]) * 0.5f) * 0.5f + ((t[a + 1][b] + t[a + 1][b + 1]) * 0.5f) * 0.5f;
-    const float z0 = z[0][0], z1 = z[0][1], z2 = z[0][2], z3 = z[1][0], z4 = z[1][2], z5 = z[2][0], z6 = z[2][1], z7 = z[2][2];
-    const float nz = z0 + 2.0f * z1 + z2 - z5 - 2.0f * z6 - z7;   // :49
-    const float nx = z0 + 2.0f * z3 + z5 - z2 - 2.0f * z4 - z7;   // :50
-    const float r = rsqrtf(nx * nx + 1.0f + nz * nz);
-    return make_float4(nx * r, r, nz * r, 1.0f);                  // :53
+    for (int i = -1; i <= RY; ++i) {              // tap-row r = y0 + i ; emits output row r - 1 once i >= 1
+        const int rr = (y0 + i) & MSK;
+        const float* r = hy + (size_t)rr * N;
+        const float a = OW_LDG(r + c0), b = OW_LDG(r + c1), c = OW_LDG(r + x), d = OW_LDG(r + c3);
+        const float h0 = a + b, h1 = b + c, h2 = c + d;
+        const float b0 = (hs_prev[0] + h0) * 0.25f, b1 = (hs_prev[1] + h1) * 0.25f, b2 = (hs_prev[2] + h2) * 0.25f;
+        hs_prev[0] = h0; hs_prev[1] = h1; hs_prev[2] = h2;
+        const float sx = b0 + 2.0f * b1 + b2, dxb = b0 - b2;
+        float xc = 0.f, zc = 0.f, ddx = 0.f, ddz = 0.f;
+        if (JAC) {
+            const float* rx = hx + (size_t)rr * N;
+            const float* rz = hz + (size_t)rr * N;
+            xc = OW_LDG(rx + x); zc = OW_LDG(rz + x);
+            if (i >= 0 && i < RY) {
+                ddx = OW_LDG(rx + c3) - OW_LDG(rx + c1);      // dDx/dx * 2h at row r
+                ddz = OW_LDG(rz + c3) - OW_LDG(rz + c1);      // dDz/dx * 2h at row r
+            }
+        }
+        if (i >= 1) {
+            const int j = y0 + i - 1;             // output row: taps j-1 (.._m1), j (.._0), j+1 (current)
+            const float nz = sx_m1 - sx, nx = dxb_m1 + 2.0f * dxb_0 + dxb;
+            const float rinv = rsqrtf(nx * nx + 1.0f + nz * nz);
+            normal[(size_t)j * N + x] = make_float4(nx * rinv, rinv, nz * rinv, 1.0f);   // :53
+            if (JAC) {
+                const float dxdx = ddx_0 * inv2h, dzdx = ddz_0 * inv2h;
+                const float dxdz = (xc - xc_m1) * inv2h, dzdz = (zc - zc_m1) * inv2h;
+                jac[(size_t)j * N + x] = (1.0f - lambda * dxdx) * (1.0f - lambda * dzdz) - (lambda * dxdz) * (lambda * dzdx);
+            }
+        }
+        sx_m1 = sx_0; sx_0 = sx; dxb_m1 = dxb_0; dxb_0 = dxb;
+        xc_m1 = xc_0; xc_0 = xc; zc_m1 = zc_0; zc_0 = zc; ddx_0 = ddx; ddz_0 = ddz;
+    }
 }
-
-// Extension: J = (1 - l*dDx/dx)(1 - l*dDz/dz) - l^2 (dDx/dz)(dDz/dx), central differences
-// with wrap, grid spacing L/N  (inv2h = N / (2L)).
-template <class Fetch>
-OW_HD float jacobian_at(const Fetch& dx, const Fetch& dz, int x, int y, float lambda, float inv2h) {
-    const float dxdx = (dx(x + 1, y) - dx(x - 1, y)) * inv2h;
-    const float dxdz = (dx(x, y + 1) - dx(x, y - 1)) * inv2h;
-    const float dzdx = (dz(x + 1, y) - dz(x - 1, y)) * inv2h;
-    const float dzdz = (dz(x, y + 1) - dz(x, y - 1)) * inv2h;
-    return (1.0f - lambda * dxdx) * (1.0f - lambda * dzdz) - (lambda * dxdz) * (lambda * dzdx);
-}
-
-template <int N>
-struct WrapFetch {
-    const float* __restrict__ p;
-    OW_HD float operator()(int x, int y) const { return OW_LDG(p + (size_t)(y & (N - 1)) * N + (x & (N - 1))); }
-};
 
 }  // namespace ow

@@ -45,6 +45,8 @@ typedef struct ow_params {
 } ow_params;
 
 #define OW_FLAG_JACOBIAN 0x1u   /* also produce the Jacobian/foam map (extension; not in the reference) */
+#define OW_FLAG_EXACT_SINCOS 0x2u /* always use full-range sincosf for e^{iwt} (default: SFU sin/cos after an exact
+                                    2*pi reduction whenever max|w*t| < 2e4, absolute error ~5e-7) */
 
 typedef struct ow_ctx ow_ctx;
 

@@ -78,7 +78,7 @@ void emu_rows(const float4* h0, const float* ktab, float t, float2* inter, Stats
             for (int tid = 0; tid < NT; ++tid) {
                 const int ft = tid % P::T, g = tid / P::T, p = blk * PAIRS + g;
                 const SmemEmu sm{smem.data() + (size_t)g * 3 * P::LINE, &rec.seq[tid]};
-                if (phase == 0) row_phase0<P>(sm, ft, p, h0, ktab, t);
+                if (phase == 0) row_phase0<P, false>(sm, ft, p, h0, ktab, t);
                 if (phase == 1) row_phase1<P>(sm, ft);
                 if (phase == 2) row_phase2<P>(sm, ft, p, inter);
             }
@@ -117,11 +117,11 @@ void emu_cols(const float2* inter, float* disp, Stats& st) {
 
 template <int N>
 void emu_normals(const float* disp, float4* normal, float* jac, float lambda, float L) {
-    const WrapFetch<N> hy{disp}, hx{disp + (size_t)N * N}, hz{disp + (size_t)2 * N * N};
-    for (int y = 0; y < N; ++y)
+    constexpr int RY = 8;
+    for (int y0 = 0; y0 < N; y0 += RY)
         for (int x = 0; x < N; ++x) {
-            normal[(size_t)y * N + x] = normal_at(hy, x, y);
-            if (jac) jac[(size_t)y * N + x] = jacobian_at(hx, hz, x, y, lambda, (float)N / (2.0f * L));
+            if (jac) normal_column_walk<N, RY, true>(disp, normal, jac, x, y0, lambda, (float)N / (2.0f * L));
+            else normal_column_walk<N, RY, false>(disp, normal, nullptr, x, y0, lambda, 0.f);
         }
 }
 

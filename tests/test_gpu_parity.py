@@ -228,6 +228,23 @@ def test_multi_slot_time_sweep_equals_single_steps(noise):
             assert np.array_equal(sim.download("dy", i), singles[i])
 
 
+def test_exact_and_fast_phase_paths(noise):
+    """e^{iwt}: SFU sin/cos after an exact 2*pi reduction (default for |w t| < 2e4) vs full-range sincosf
+    (OW_FLAG_EXACT_SINCOS, and automatically for huge t). Both must sit inside the parity tolerance."""
+    N = 512
+    orc = oracle_for(N, noise)
+    for t in (9.98, 300.0):
+        ref = orc.frame(np.float32(t))
+        for exact in (False, True):
+            with fow.FFTOceanWaves(N=N, cascades=[params()], exact_sincos=exact) as sim:
+                sim.init(noise)
+                check_frame(sim.frame(t), ref, f"t={t} exact={exact} ")
+    t = 40000.0      # max |w t| ~ 2.7e5 > 2e4: the launcher must fall back to sincosf on its own
+    with fow.FFTOceanWaves(N=N, cascades=[params()]) as sim:
+        sim.init(noise)
+        check_frame(sim.frame(t), orc.frame(np.float32(t)), "t=4e4 ")
+
+
 def test_api_errors(noise):
     with fow.FFTOceanWaves(N=256, cascades=[params()]) as sim:
         with pytest.raises(fow.OceanWavesError):
