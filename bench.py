@@ -255,6 +255,9 @@ def run_ours(args):
         total_ms = float(tt.item())
     value = world * frames * args.steps / (total_ms * 1e-3)
 
+    if args.profile:
+        sim.close()
+        return
     # ---- per-kernel durations (CUDA events around each kernel, same stream, same workload) -> roofline ----
     kms = np.zeros(3)
     prof_sweeps = 2
@@ -372,8 +375,10 @@ def main():
     ap.add_argument("--slots", type=int, default=32, help="frames evaluated per ow_step_multi call")
     ap.add_argument("--group", type=int, default=0, help="slots per launch group (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--profile", action="store_true",
+                    help="profiler mode (ncu): run warm-up + timed sweeps only and exit without printing a bench line")
     args = ap.parse_args()
-    if args.warmup < 3 and args.impl == "ours":
+    if args.warmup < 3 and args.impl == "ours" and not args.profile:
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)

@@ -72,3 +72,26 @@ def test_product_does_not_reference_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oracle" not in txt.lower() or f in ("ow_kernels.cuh",) and "import" not in txt, f
+
+
+def test_cpp_wrapper_compiles_and_links_and_fails_loudly_without_gpu(tmp_path):
+    """include/oceanwaves.hpp (the C++ host mirror of FFTOceanWaves' sim methods) builds against the library; on a
+    GPU-less box create() returns false with an error text instead of computing anything."""
+    import torch
+    src = tmp_path / "t.cpp"
+    src.write_text(
+        '#include <cstdio>\n#include "oceanwaves.hpp"\n'
+        "int main(){ ow::OceanSim s; ow::OceanSim::Params p; p.wind_speed = 40.f;\n"
+        "  if(!s.create(256, p)){ std::printf(\"ERR %s\\n\", s.last_error().c_str()); return 3; }\n"
+        "  s.generate_bit_reversed_indices(); s.generate_twiddle_factors();\n"
+        "  if(s.update(0.f)) return 4;   /* ow_step before tilde_h0_k must be refused */\n"
+        "  std::printf(\"OK %d\\n\", s.N()); return 0; }\n")
+    exe = tmp_path / "t"
+    libdir = os.path.dirname(fow.lib_path())
+    subprocess.check_call(["/usr/bin/g++", "-std=c++14", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                           "-o", str(exe), "-L", libdir, "-loceanwaves", f"-Wl,-rpath,{libdir}"])
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and r.stdout.startswith("OK 256"), r.stdout + r.stderr
+    else:
+        assert r.returncode == 3 and r.stdout.startswith("ERR "), r.stdout + r.stderr
