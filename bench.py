@@ -207,6 +207,8 @@ def run_ours(args):
     sim.tilde_h0_k()
     if args.group:
         sim.set_group_size(args.group)
+    if args.streams:
+        sim.set_streams(args.streams)
     # A dedicated non-default stream: its handle is what the C ABI launches on, and the torch events below are
     # recorded on the same stream (handle 0 would mean "the context's own stream" to ow_step*).
     stream = torch.cuda.Stream()
@@ -374,6 +376,7 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
     ap.add_argument("--slots", type=int, default=32, help="frames evaluated per ow_step_multi call")
     ap.add_argument("--group", type=int, default=0, help="slots per launch group (0 = library default)")
+    ap.add_argument("--streams", type=int, default=0, help="internal streams the launch groups are spread over (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--profile", action="store_true",
                     help="profiler mode (ncu): run warm-up + timed sweeps only and exit without printing a bench line")

@@ -23,7 +23,7 @@ SOURCES = [
     ("ow_init_kernels.cu", ["-fmad=false"]),
     ("ow_api.cu", []),
 ]
-HEADERS = ["ow_fft.cuh", "ow_kernels.cuh", "ow_config.cuh", "ow_internal.h", os.path.join("..", "..", "include", "oceanwaves.h")]
+HEADERS = ["ow_fft.cuh", "ow_kernels.cuh", "ow_config.cuh", "ow_frame_kernels.cuh", "ow_internal.h", os.path.join("..", "..", "include", "oceanwaves.h")]
 
 
 def _nvcc() -> str:

@@ -31,6 +31,12 @@ struct ow_ctx {
     float* d_jac = nullptr;
     float* d_tmp = nullptr;       // 2 * N*N*2 floats staging for h0 split/merge
     cudaStream_t stream = nullptr;
+    // Launch groups of one ow_step_multi call are independent frames: they are spread round-robin over these
+    // auxiliary streams (fork/join around the caller's stream) so one group's tail overlaps the next group's head.
+    static constexpr int kMaxAux = 4;
+    cudaStream_t aux[kMaxAux] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[kMaxAux] = {nullptr, nullptr, nullptr, nullptr};
+    int n_streams = 3;
     bool spectrum_ready = false;
     int group_size = 0;
     int last_launches = 0;
@@ -82,14 +88,25 @@ FrameBuffers buffers(const ow_ctx* c) {
     return fb;
 }
 
-int auto_group(const ow_ctx* c) {
-    if (c->group_size > 0) return c->group_size < kMaxGroup ? c->group_size : kMaxGroup;
-    // keep the group's 12 B/texel intermediate (plus its outputs in flight) inside the ~126 MB L2
-    const double inter_bytes = 12.0 * c->N * (double)c->N;
-    int g = (int)(48.0e6 / inter_bytes);
-    if (g < 1) g = 1;
-    if (g > kMaxGroup) g = kMaxGroup;
-    return g;
+// Slots per launch group. Upper bound: a group's 12 B/texel intermediate should not exceed ~100 MB (measured on
+// B200: launch count and tail efficiency matter more than keeping the intermediate strictly inside the 126 MB L2).
+// Then the slots are split evenly (32 -> 11+11+10, not 15+15+2) into at least n_streams groups, so that the
+// independent groups can overlap on the auxiliary streams.
+int pick_group(const ow_ctx* c, int count) {
+    int gmax;
+    if (c->group_size > 0) {
+        gmax = c->group_size;
+    } else {
+        gmax = (int)(100.0e6 / (12.0 * c->N * (double)c->N));
+        if (gmax < 1) gmax = 1;
+    }
+    if (gmax > kMaxGroup) gmax = kMaxGroup;
+    int ngroups = (count + gmax - 1) / gmax;
+    if (c->group_size <= 0) {
+        const int want = c->n_streams < count ? c->n_streams : count;
+        if (ngroups < want) ngroups = want;
+    }
+    return (count + ngroups - 1) / ngroups;
 }
 
 void release(ow_ctx* c) {
@@ -99,6 +116,9 @@ void release(ow_ctx* c) {
     cudaFree(c->d_noise); cudaFree(c->d_h0); cudaFree(c->d_ktab); cudaFree(c->d_casc); cudaFree(c->d_inter);
     cudaFree(c->d_disp); cudaFree(c->d_normal); cudaFree(c->d_jac); cudaFree(c->d_tmp);
     if (c->stream) cudaStreamDestroy(c->stream);
+    for (auto& s : c->aux) if (s) cudaStreamDestroy(s);
+    for (auto& e : c->ev_join) if (e) cudaEventDestroy(e);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     delete c;
 }
 
@@ -132,6 +152,11 @@ int ow_create(int32_t N, int32_t n_cascades, int32_t n_slots, const ow_params* c
     } while (0)
     OW_TRY(cudaSetDevice(device));
     OW_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < ow_ctx::kMaxAux; ++i) {
+        OW_TRY(cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
+        OW_TRY(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+    }
+    OW_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     OW_TRY(cudaMalloc(&c->d_h0, nn * n_cascades * sizeof(float4)));
     OW_TRY(cudaMalloc(&c->d_ktab, (size_t)N * n_cascades * sizeof(float)));
     OW_TRY(cudaMalloc(&c->d_casc, n_cascades * sizeof(CascadeDev)));
@@ -238,15 +263,23 @@ static int step_impl(ow_ctx* c, int32_t count, const int32_t* cascade_of_slot, c
     OW_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = pick(c, stream);
     const FrameBuffers fb = buffers(c);
-    const int group = auto_group(c);
+    const int group = pick_group(c, count);
     int launches = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     if (kernel_ms) {
         kernel_ms[0] = kernel_ms[1] = kernel_ms[2] = 0.0f;
         for (auto& e : ev) OW_CUDA(c, cudaEventCreate(&e));
     }
-    for (int base = 0; base < count; base += group) {
+    const int ngroups = (count + group - 1) / group;
+    const int nfan = (kernel_ms || ngroups < 2 || c->n_streams < 2) ? 0 : (ngroups < c->n_streams ? ngroups : c->n_streams);
+    if (nfan) {
+        OW_CUDA(c, cudaEventRecord(c->ev_fork, st));
+        for (int i = 0; i < nfan; ++i) OW_CUDA(c, cudaStreamWaitEvent(c->aux[i], c->ev_fork, 0));
+    }
+    int gi = 0;
+    for (int base = 0; base < count; base += group, ++gi) {
         const int n = count - base < group ? count - base : group;
+        cudaStream_t gst = nfan ? c->aux[gi % nfan] : st;
         SlotTable tab{};
         bool fast = (c->flags & OW_FLAG_EXACT_SINCOS) == 0;
         for (int i = 0; i < n; ++i) {
@@ -257,7 +290,7 @@ static int step_impl(ow_ctx* c, int32_t count, const int32_t* cascade_of_slot, c
             const float kmax = 1.41421356f * 3.14159265f * (float)c->N / c->params[tab.cascade[i]].L;
             if (!(sqrtf(9.81f * kmax) * fabsf(tab.time[i]) < kFastPhaseLimit)) fast = false;
         }
-        const int k = launch_frame(fb, tab, n, (c->flags & OW_FLAG_JACOBIAN) != 0, fast, st, kernel_ms ? ev : nullptr);
+        const int k = launch_frame(fb, tab, n, (c->flags & OW_FLAG_JACOBIAN) != 0, fast, gst, kernel_ms ? ev : nullptr);
         if (k < 0) return cuda_fail(c, cudaGetLastError(), "launch_frame");
         launches += k;
         if (kernel_ms) {
@@ -268,6 +301,10 @@ static int step_impl(ow_ctx* c, int32_t count, const int32_t* cascade_of_slot, c
                 kernel_ms[i] += ms;
             }
         }
+    }
+    for (int i = 0; i < nfan; ++i) {
+        OW_CUDA(c, cudaEventRecord(c->ev_join[i], c->aux[i]));
+        OW_CUDA(c, cudaStreamWaitEvent(st, c->ev_join[i], 0));
     }
     if (kernel_ms) for (auto& e : ev) cudaEventDestroy(e);
     c->last_launches = launches;
@@ -368,6 +405,12 @@ int ow_download_frame_async(ow_ctx* c, int32_t slot, void* host, size_t bytes, v
 int ow_set_group_size(ow_ctx* c, int32_t g) {
     if (!c || g < 0) return OW_ERR_INVALID;
     c->group_size = g;
+    return OW_OK;
+}
+
+int ow_set_streams(ow_ctx* c, int32_t n) {
+    if (!c || n < 1 || n > ow_ctx::kMaxAux) return c ? fail(c, OW_ERR_INVALID, "ow_set_streams: n must be in [1, 4]") : OW_ERR_INVALID;
+    c->n_streams = n;
     return OW_OK;
 }
 

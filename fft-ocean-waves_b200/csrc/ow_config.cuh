@@ -7,6 +7,7 @@ namespace ow {
 // ---------------------------------------------------------------------------------------------------
 // Per-N configuration. Row plans have R2 = 16 so that 16 consecutive butterfly ids of stages 0 and 1 walk
 // the unit-stride digit; pads (P1,P0) make stage 2 conflict-free for 8-byte accesses (16-lane phases).
+// Normal kernel: NRM_RY output rows per thread walk, NRM_WARPS warps per CTA, NRM_MINB resident CTAs per SM.
 // Column plans interleave G jobs in the lane index, need S0 odd and a job stride == 16/G (mod 16).
 // ---------------------------------------------------------------------------------------------------
 template <int N>
@@ -17,28 +18,32 @@ struct Cfg<256> {
     using Row = Plan<256, 4, 4, 16, 32, 1, 0>;
     static constexpr int ROW_PAIRS = 4, ROW_MINB = 4;
     using Col = Plan<256, 4, 4, 16, 32, 0, 1>;
-    static constexpr int COL_G = 4, COL_MINB = 4;
+    static constexpr int COL_G = 8, COL_MINB = 2;
+    static constexpr int NRM_RY = 8, NRM_WARPS = 4, NRM_MINB = 4;
 };
 template <>
 struct Cfg<512> {
     using Row = Plan<512, 8, 4, 16, 32, 1, 14>;
     static constexpr int ROW_PAIRS = 4, ROW_MINB = 3;
     using Col = Plan<512, 8, 4, 16, 32, 0, 1>;
-    static constexpr int COL_G = 4, COL_MINB = 4;
+    static constexpr int COL_G = 8, COL_MINB = 2;
+    static constexpr int NRM_RY = 8, NRM_WARPS = 4, NRM_MINB = 4;
 };
 template <>
 struct Cfg<1024> {
     using Row = Plan<1024, 8, 8, 16, 64, 1, 10>;
     static constexpr int ROW_PAIRS = 2, ROW_MINB = 3;
     using Col = Plan<1024, 8, 8, 16, 64, 0, 1>;
-    static constexpr int COL_G = 4, COL_MINB = 3;
+    static constexpr int COL_G = 8, COL_MINB = 2;
+    static constexpr int NRM_RY = 8, NRM_WARPS = 4, NRM_MINB = 4;
 };
 template <>
 struct Cfg<2048> {
     using Row = Plan<2048, 8, 16, 16, 128, 1, 2>;
-    static constexpr int ROW_PAIRS = 1, ROW_MINB = 4;
+    static constexpr int ROW_PAIRS = 1, ROW_MINB = 3;
     using Col = Plan<2048, 8, 16, 16, 64, 0, 1>;
-    static constexpr int COL_G = 4, COL_MINB = 3;
+    static constexpr int COL_G = 8, COL_MINB = 1;
+    static constexpr int NRM_RY = 8, NRM_WARPS = 4, NRM_MINB = 4;
 };
 template <>
 struct Cfg<4096> {
@@ -46,6 +51,7 @@ struct Cfg<4096> {
     static constexpr int ROW_PAIRS = 1, ROW_MINB = 1;
     using Col = Plan<4096, 16, 16, 16, 128, 0, 1>;
     static constexpr int COL_G = 4, COL_MINB = 1;
+    static constexpr int NRM_RY = 8, NRM_WARPS = 4, NRM_MINB = 4;
 };
 
 template <class P, int G>

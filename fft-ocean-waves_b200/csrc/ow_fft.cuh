@@ -117,6 +117,24 @@ struct Dft<16> {
     }
 };
 
+// e^{2 pi i k/R} as compile-time constants (R in {2,4,8,16}); get(k) folds to immediates when k is unrolled.
+template <int R>
+struct RootsOfUnity {
+    static OW_HD float2 get(int k) {
+        // quarter-wave table in sixteenths of a turn: cos(2 pi m/16), m = 0..4
+        const float c16[5] = {1.0f, 0.92387953251128675613f, 0.70710678118654752440f, 0.38268343236508977173f, 0.0f};
+        const int m = (k * (16 / R)) & 15;           // angle in sixteenths
+        const int q = m >> 2, r = m & 3;             // quadrant, remainder
+        const float c = c16[r], s = c16[4 - r];      // cos, sin of the remainder angle
+        switch (q) {
+            case 0: return make_float2(c, s);
+            case 1: return make_float2(-s, c);
+            case 2: return make_float2(-c, -s);
+            default: return make_float2(s, -c);
+        }
+    }
+};
+
 // tw[k] = w^k for k in [0,R) with multiplication depth <= 4 (keeps the error at a few ulp).
 template <int R>
 OW_HD void twiddle_powers(float2 w, float2 (&tw)[R]) {

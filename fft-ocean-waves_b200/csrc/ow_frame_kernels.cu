@@ -1,71 +1,8 @@
 // ow_frame_kernels.cu — __global__ wrappers and launchers of the per-frame kernels (sm_100a).
 // Kernel bodies live in ow_kernels.cuh (shared with the CPU emulator used by the tests).
-#include "ow_internal.h"
-#include "ow_kernels.cuh"
-#include "ow_config.cuh"
+#include "ow_frame_kernels.cuh"
 
 namespace ow {
-
-// ---------------------------------------------------------------------------------------------------
-template <class P, int PAIRS, int MINB, bool FAST>
-__global__ void __launch_bounds__(P::T* PAIRS, MINB) ow_row_kernel(FrameBuffers fb, SlotTable tab) {
-    extern __shared__ __align__(16) float2 smem[];
-    constexpr int N = P::N;
-    const int ft = threadIdx.x % P::T, g = threadIdx.x / P::T;
-    const int p = blockIdx.x * PAIRS + g;
-    const int e = blockIdx.y;
-    const int cascade = tab.cascade[e];
-    const float t = tab.time[e];
-    const int slot = tab.slot[e];
-    const SmemDirect sm{smem + (size_t)g * 3 * P::LINE};
-    const float4* h0 = fb.h0 + (size_t)cascade * N * N;
-    const float* ktab = fb.ktab + (size_t)cascade * N;
-    float2* inter = fb.inter + (size_t)slot * 3 * (N / 2) * N;
-    row_phase0<P, FAST>(sm, ft, p, h0, ktab, t);
-    __syncthreads();
-    row_phase1<P>(sm, ft);
-    __syncthreads();
-    row_phase2<P>(sm, ft, p, inter);
-}
-
-template <class P, int G, int MINB>
-__global__ void __launch_bounds__(P::T* G, MINB) ow_col_kernel(FrameBuffers fb, SlotTable tab, float scale) {
-    extern __shared__ __align__(16) float2 smem[];
-    constexpr int N = P::N;
-    using LY = ColLayout<P, G>;
-    const int job = threadIdx.x % G, ft = threadIdx.x / G;
-    const int x = 2 * (blockIdx.x * G + job);
-    const int f = blockIdx.y;
-    const int slot = tab.slot[blockIdx.z];
-    const SmemDirect sm{smem};
-    const int base = job * LY::SJ;
-    const float2* src = fb.inter + ((size_t)slot * 3 + f) * (N / 2) * N + x;
-    float* dst = fb.disp + ((size_t)slot * 3 + f) * N * N + x;
-#pragma unroll 1
-    for (int j = ft; j < P::M / 2; j += P::T) col_phase0<P>(sm, base, j, src);
-    __syncthreads();
-    col_phase1<P>(sm, base, ft);
-    __syncthreads();
-    col_phase2<P>(sm, base, ft, dst, scale);
-}
-
-constexpr int kNormalRows = 8;   // output rows per thread of the normal kernel's column walk
-
-template <int N, bool JAC>
-__global__ void __launch_bounds__(256) ow_normal_kernel(FrameBuffers fb, SlotTable tab) {
-    const int x = blockIdx.x * 32 + threadIdx.x, y0 = (blockIdx.y * 8 + threadIdx.y) * kNormalRows;
-    const int e = blockIdx.z;
-    const int slot = tab.slot[e];
-    const float* disp = fb.disp + (size_t)slot * 3 * N * N;
-    float lambda = 0.f, inv2h = 0.f;
-    if (JAC) {
-        const CascadeDev c = fb.casc[tab.cascade[e]];
-        lambda = c.choppiness;
-        inv2h = (float)N / (2.0f * c.L);
-    }
-    normal_column_walk<N, kNormalRows, JAC>(disp, fb.normal + (size_t)slot * N * N,
-                                            JAC ? fb.jacobian + (size_t)slot * N * N : nullptr, x, y0, lambda, inv2h);
-}
 
 // ---------------------------------------------------------------------------------------------------
 template <int N>
@@ -99,9 +36,9 @@ int launch_n(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_
     ow_col_kernel<K, C::COL_G, C::COL_MINB>
         <<<dim3(N / (2 * C::COL_G), 3, count), K::T * C::COL_G, ColLayout<K, C::COL_G>::SMEM, st>>>(fb, tab, scale);
     if (ev) cudaEventRecord(ev[2], st);
-    const dim3 ngrid(N / 32, N / (8 * kNormalRows), count);
-    if (with_jac) ow_normal_kernel<N, true><<<ngrid, dim3(32, 8), 0, st>>>(fb, tab);
-    else ow_normal_kernel<N, false><<<ngrid, dim3(32, 8), 0, st>>>(fb, tab);
+    const dim3 ngrid(N / 128, N / (C::NRM_WARPS * C::NRM_RY), count);
+    if (with_jac) ow_normal_kernel<N, true, C::NRM_RY, C::NRM_WARPS, C::NRM_MINB><<<ngrid, dim3(32, C::NRM_WARPS), 0, st>>>(fb, tab);
+    else ow_normal_kernel<N, false, C::NRM_RY, C::NRM_WARPS, C::NRM_MINB><<<ngrid, dim3(32, C::NRM_WARPS), 0, st>>>(fb, tab);
     if (ev) cudaEventRecord(ev[3], st);
     return cudaGetLastError() == cudaSuccess ? 3 : -1;
 }

@@ -39,6 +39,12 @@ namespace ow {
 
 constexpr float kGravity = 9.81f;   // tilde_h0_t_cs.glsl:58
 
+// Ablation hooks for tools/tune only (never defined in the library build): bit 0 = no h0/ktab loads, bit 1 = no
+// dispersion/sincos math, bit 2 = skip FFT stages 1 and 2 of the row kernel, bit 3 = row kernel stores suppressed.
+#ifndef OW_ABLATE
+#define OW_ABLATE 0
+#endif
+
 // ---------------------------------------------------------------------------------------------------
 // Spectrum at one texel pair: (u,v) and its mirror (mu,mv) = (-k).  Returns the Hermitian parts
 //   Sy = Hdy(u,v) + conj(Hdy(mu,mv)),  Sx, Sz likewise with the texels' OWN choppy multipliers
@@ -78,6 +84,10 @@ template <int N>
 OW_HD TexelPair load_pair(const float4* __restrict__ h0, const float* __restrict__ ktab, int u, int v, int mv) {
     const int mu = (N - u) & (N - 1);
     TexelPair tp;
+#if OW_ABLATE & 1
+    tp.A = make_float4(u * 1e-3f, v * 1e-3f, mu * 1e-3f, 1.0f); tp.B = make_float4(mv * 1e-3f, 0.5f, u * 2e-3f, 0.25f); tp.kx = (u - N / 2) * 6.28e-3f;
+    return tp;
+#endif
     tp.A = OW_LDG(h0 + (size_t)v * N + u);
     tp.B = OW_LDG(h0 + (size_t)mv * N + mu);
     tp.kx = OW_LDG(ktab + u);
@@ -95,7 +105,11 @@ OW_HD Sym3 spectrum_sym(const TexelPair& tp, int u, float ky, bool self_row, flo
     if (km < 0.00001f) km = 0.00001f;
     const float w = OW_SQRT(OW_MUL(kGravity, km));
     float s, c;
+#if OW_ABLATE & 2
+    s = w * t; c = 1.0f - s; km = 1.0f + kx;
+#else
     phase_sincos<FAST>(OW_MUL(w, t), &s, &c);                       // :96-97
+#endif
     // :110  h = h0k * e^{iwt} + h0minusk * e^{-iwt}   (conjugate() is a no-op in the shader, :42-48)
     const float2 H  = make_float2((A.x * c - A.y * s) + (A.z * c + A.w * s), (A.x * s + A.y * c) + (A.w * c - A.z * s));
     const float2 Hm = make_float2((B.x * c - B.y * s) + (B.z * c + B.w * s), (B.x * s + B.y * c) + (B.w * c - B.z * s));
@@ -164,12 +178,18 @@ OW_HD void row_phase0(const Smem& sm, int ft, int p, const float4* __restrict__ 
 
 template <class P, class Smem>
 OW_HD void row_phase1(const Smem& sm, int ft) {
+#if OW_ABLATE & 4
+    return;
+#endif
+    // d2 = q % R2 is the same for every butterfly q = ft + T*c of this thread when R2 divides T
+    constexpr bool kSameTw = (P::T % P::R2 == 0);
+    float2 tw[P::R1];
+    if (kSameTw) stage1_twiddles<P>(ft, tw);
 #pragma unroll 1
     for (int c = 0; c < P::C1; ++c) {
         const int q = ft + P::T * c;
         if (q >= P::B1) break;
-        float2 tw[P::R1];
-        stage1_twiddles<P>(q, tw);
+        if (!kSameTw) stage1_twiddles<P>(q, tw);
 #pragma unroll 1
         for (int f = 0; f < 3; ++f) stage1<P>(sm, f * P::LINE, q, tw);
     }
@@ -185,10 +205,20 @@ OW_HD void row_phase2(const Smem& sm, int ft, int p, float2* __restrict__ inter)
 #pragma unroll 1
         for (int f = 0; f < 3; ++f) {
             float2 v[P::R2];
+#if OW_ABLATE & 4
+#pragma unroll
+            for (int d2 = 0; d2 < P::R2; ++d2) v[d2] = sm.ld(f * P::LINE + P::addr(bp % P::R0, bp / P::R0, d2));
+#else
             stage2<P>(sm, f * P::LINE, bp, v);
+#endif
             float2* dst = inter + ((size_t)f * (N / 2) + p) * N + bp;
+#if OW_ABLATE & 8
+#pragma unroll
+            for (int k2 = 0; k2 < P::R2; ++k2) if (v[k2].x == 12345.678f) dst[k2 * P::B2] = v[k2];
+#else
 #pragma unroll
             for (int k2 = 0; k2 < P::R2; ++k2) dst[k2 * P::B2] = v[k2];
+#endif
         }
     }
 }
@@ -235,18 +265,26 @@ OW_HD void col_phase0(const Smem& sm, int base, int j /* pair id in [0, M/2) */,
     float2 tw[R0];
     twiddle_powers<R0>(unit_root(bA, N), tw);
     stage0_finish<P>(sm, base, bA, qa, tw);
-    twiddle_powers<R0>(unit_root(bB, N), tw);
+    if (j != 0) {
+        // bB = M - bA:  e^{2 pi i k0 (M - bA)/N} = e^{2 pi i k0/R0} * conj(e^{2 pi i k0 bA/N})  (R0-th roots are constants)
+#pragma unroll
+        for (int k0 = 1; k0 < R0; ++k0) tw[k0] = cmul(RootsOfUnity<R0>::get(k0), cconj(tw[k0]));
+    } else {
+        twiddle_powers<R0>(unit_root(bB, N), tw);
+    }
     stage0_finish<P>(sm, base, bB, qb, tw);
 }
 
 template <class P, class Smem>
 OW_HD void col_phase1(const Smem& sm, int base, int ft) {
+    constexpr bool kSameTw = (P::T % P::R2 == 0);
+    float2 tw[P::R1];
+    if (kSameTw) stage1_twiddles<P>(ft, tw);
 #pragma unroll 1
     for (int c = 0; c < P::C1; ++c) {
         const int q = ft + P::T * c;
         if (q >= P::B1) break;
-        float2 tw[P::R1];
-        stage1_twiddles<P>(q, tw);
+        if (!kSameTw) stage1_twiddles<P>(q, tw);
         stage1<P>(sm, base, q, tw);
     }
 }
@@ -273,63 +311,125 @@ OW_HD void col_phase2(const Smem& sm, int base, int ft, float* __restrict__ dst 
 // ---------------------------------------------------------------------------------------------------
 // NORMAL (+ JACOBIAN).  normal_map_cs.glsl:24-54: the eight texture() taps sit on texel corners, so with
 // LINEAR+REPEAT each tap is the mean of a 2x2 block ("box"); the stencil covers columns x-2..x+1 and rows
-// y-2..y+1 with wrap-around. One thread owns column x and walks down RY output rows keeping a sliding window:
-//   hs(r)[c]  = h[r][x+c-2] + h[r][x+c-1]          c = 0,1,2   (horizontal pair sums, 4 loads per row)
-//   box(r)[c] = (hs(r-1)[c] + hs(r)[c]) / 4        = taps at (x-1, x, x+1) of tap-row r
-//   sx(r)  = box[0] + 2 box[1] + box[2],   dxb(r) = box[0] - box[2]
-//   n.z(j) = sx(j-1) - sx(j+1)                     (:49)     n.x(j) = dxb(j-1) + 2 dxb(j) + dxb(j+1)   (:50)
-// so each texel costs 4 loads instead of 16. Lanes run along x: every load and the float4 store are coalesced.
-// The Jacobian (extension) rides the same walk:
-//   J = (1 - l*dDx/dx)(1 - l*dDz/dz) - l^2 (dDx/dz)(dDz/dx), central differences with wrap, spacing L/N.
+// y-2..y+1 with wrap-around. One thread owns FOUR adjacent columns x0..x0+3 and walks down RY output rows with
+// a sliding window (all sums are kept unscaled, V = 4*box; the 1/4 is applied once to nx, nz):
+//   hs(r)[c] = h[r][x0+c-2] + h[r][x0+c-1]          c = 0..5   (7 loaded values: one float4, one float2, one float)
+//   V(r)[c]  = hs(r-1)[c] + hs(r)[c]                = 4 * box at tap-row r, tap-columns x0-1 .. x0+4
+//   sx(r)[j] = V[j] + 2 V[j+1] + V[j+2],   dxb(r)[j] = V[j] - V[j+2]          j = 0..3 (column x0+j)
+//   n.z(y) = (sx(y-1) - sx(y+1)) / 4     (:49)      n.x(y) = (dxb(y-1) + 2 dxb(y) + dxb(y+1)) / 4     (:50)
+// which costs ~20 instructions per texel instead of 16 texture taps. Lanes run along x (a warp covers 128
+// columns), every global access is a coalesced 16/8/4-byte-per-lane request; the normals of a row are handed to
+// `emit`, which on the device transposes them through shared memory so each store instruction writes 512
+// contiguous bytes. The Jacobian (extension) rides the same walk:
+//   J = (1 - l*dDx/dx)(1 - l*dDz/dz) - l^2 (dDx/dz)(dDz/dx), central differences with wrap, spacing L/N;
+//   s = l * N / (2 L) is folded into each difference.
 // ---------------------------------------------------------------------------------------------------
-template <int N, int RY, bool JAC>
-OW_HD void normal_column_walk(const float* __restrict__ disp /* dy,dx,dz planes */, float4* __restrict__ normal,
-                              float* __restrict__ jac, int x, int y0, float lambda, float inv2h) {
+// Everything one walk iteration needs from global memory (h row r): loaded one iteration AHEAD of its use, so
+// the L2 round trip overlaps the previous row's arithmetic and staged stores (which contain warp barriers the
+// compiler will not move loads across).
+struct NormalRowIn {
+    float2 l;            // dy[x0-2], dy[x0-1]
+    float4 m;            // dy[x0 .. x0+3]
+    float e;             // dy[x0+4]
+    float4 a, b;         // Dx[x0 .. x0+3], Dz[x0 .. x0+3]
+    float al, ar, bl, br;   // Dx[x0-1], Dx[x0+4], Dz[x0-1], Dz[x0+4]
+};
+
+template <int N, bool JAC>
+OW_HD NormalRowIn normal_row_load(const float* __restrict__ disp, int x0, int rr, bool want_xz, bool want_dd) {
     constexpr int MSK = N - 1;
-    const int c0 = (x - 2) & MSK, c1 = (x - 1) & MSK, c3 = (x + 1) & MSK;
-    const float* hy = disp;
-    const float* hx = disp + (size_t)N * N;
-    const float* hz = disp + (size_t)2 * N * N;
-    float hs_prev[3], sx_m1 = 0.f, sx_0 = 0.f, dxb_m1 = 0.f, dxb_0 = 0.f;   // window state
-    float xc_m1 = 0.f, xc_0 = 0.f, zc_m1 = 0.f, zc_0 = 0.f, ddx_0 = 0.f, ddz_0 = 0.f;
-    {
-        const float* r = hy + (size_t)((y0 - 2) & MSK) * N;
-        const float a = OW_LDG(r + c0), b = OW_LDG(r + c1), c = OW_LDG(r + x), d = OW_LDG(r + c3);
-        hs_prev[0] = a + b; hs_prev[1] = b + c; hs_prev[2] = c + d;
+    const int xl2 = (x0 - 2) & MSK, xl1 = (x0 - 1) & MSK, xr = (x0 + 4) & MSK;
+    const float* r = disp + (size_t)rr * N;
+    NormalRowIn in;
+    in.l = OW_LDG(reinterpret_cast<const float2*>(r + xl2));
+    in.m = OW_LDG(reinterpret_cast<const float4*>(r + x0));
+    in.e = OW_LDG(r + xr);
+    in.a = in.b = make_float4(0.f, 0.f, 0.f, 0.f);
+    in.al = in.ar = in.bl = in.br = 0.f;
+    if (JAC && want_xz) {
+        const float* rx = r + (size_t)N * N;
+        const float* rz = r + (size_t)2 * N * N;
+        in.a = OW_LDG(reinterpret_cast<const float4*>(rx + x0));
+        in.b = OW_LDG(reinterpret_cast<const float4*>(rz + x0));
+        if (want_dd) {
+            in.al = OW_LDG(rx + xl1); in.ar = OW_LDG(rx + xr);
+            in.bl = OW_LDG(rz + xl1); in.br = OW_LDG(rz + xr);
+        }
+    }
+    return in;
+}
+
+template <int N, int RY, bool JAC, class Emit>
+OW_HD void normal_quad_walk(const float* __restrict__ disp /* dy,dx,dz planes */, int x0, int y0, float s, const Emit& emit) {
+    constexpr int MSK = N - 1;
+    float hs_prev[6], sx_m1[4], sx_0[4], dxb_m1[4], dxb_0[4];
+    float xc_m1[4], xc_0[4], zc_m1[4], zc_0[4], ddx_0[4], ddz_0[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        sx_m1[j] = sx_0[j] = dxb_m1[j] = dxb_0[j] = 0.f;
+        xc_m1[j] = xc_0[j] = zc_m1[j] = zc_0[j] = ddx_0[j] = ddz_0[j] = 0.f;
     }
 #pragma unroll
-    for (int i = -1; i <= RY; ++i) {              // tap-row r = y0 + i ; emits output row r - 1 once i >= 1
-        const int rr = (y0 + i) & MSK;
-        const float* r = hy + (size_t)rr * N;
-        const float a = OW_LDG(r + c0), b = OW_LDG(r + c1), c = OW_LDG(r + x), d = OW_LDG(r + c3);
-        const float h0 = a + b, h1 = b + c, h2 = c + d;
-        const float b0 = (hs_prev[0] + h0) * 0.25f, b1 = (hs_prev[1] + h1) * 0.25f, b2 = (hs_prev[2] + h2) * 0.25f;
-        hs_prev[0] = h0; hs_prev[1] = h1; hs_prev[2] = h2;
-        const float sx = b0 + 2.0f * b1 + b2, dxb = b0 - b2;
-        float xc = 0.f, zc = 0.f, ddx = 0.f, ddz = 0.f;
-        if (JAC) {
-            const float* rx = hx + (size_t)rr * N;
-            const float* rz = hz + (size_t)rr * N;
-            xc = OW_LDG(rx + x); zc = OW_LDG(rz + x);
-            if (i >= 0 && i < RY) {
-                ddx = OW_LDG(rx + c3) - OW_LDG(rx + c1);      // dDx/dx * 2h at row r
-                ddz = OW_LDG(rz + c3) - OW_LDG(rz + c1);      // dDz/dx * 2h at row r
+    for (int c = 0; c < 6; ++c) hs_prev[c] = 0.f;
+    NormalRowIn nxt = normal_row_load<N, JAC>(disp, x0, (y0 - 2) & MSK, false, false);
+#pragma unroll
+    for (int i = -2; i <= RY; ++i) {              // h row r = y0 + i ; emits output row r - 1 once i >= 1
+        const NormalRowIn in = nxt;
+        if (i < RY) nxt = normal_row_load<N, JAC>(disp, x0, (y0 + i + 1) & MSK, i + 1 >= -1, i + 1 >= 0 && i + 1 < RY);
+        const float4 m = in.m;
+        const float hs[6] = {in.l.x + in.l.y, in.l.y + m.x, m.x + m.y, m.y + m.z, m.z + m.w, m.w + in.e};
+        float sx[4] = {0.f, 0.f, 0.f, 0.f}, dxb[4] = {0.f, 0.f, 0.f, 0.f};
+        if (i >= -1) {
+            float V[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) V[c] = hs_prev[c] + hs[c];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                sx[j] = fmaf(2.0f, V[j + 1], V[j] + V[j + 2]);
+                dxb[j] = V[j] - V[j + 2];
             }
         }
+#pragma unroll
+        for (int c = 0; c < 6; ++c) hs_prev[c] = hs[c];
+        const float4 a = in.a, b = in.b;
+        const float xc[4] = {a.x, a.y, a.z, a.w}, zc[4] = {b.x, b.y, b.z, b.w};
+        // x differences of Dx and Dz at row r (only meaningful for 0 <= i < RY; otherwise unused)
+        const float ddx[4] = {a.y - in.al, a.z - a.x, a.w - a.y, in.ar - a.z};
+        const float ddz[4] = {b.y - in.bl, b.z - b.x, b.w - b.y, in.br - b.z};
         if (i >= 1) {
-            const int j = y0 + i - 1;             // output row: taps j-1 (.._m1), j (.._0), j+1 (current)
-            const float nz = sx_m1 - sx, nx = dxb_m1 + 2.0f * dxb_0 + dxb;
-            const float rinv = rsqrtf(nx * nx + 1.0f + nz * nz);
-            normal[(size_t)j * N + x] = make_float4(nx * rinv, rinv, nz * rinv, 1.0f);   // :53
-            if (JAC) {
-                const float dxdx = ddx_0 * inv2h, dzdx = ddz_0 * inv2h;
-                const float dxdz = (xc - xc_m1) * inv2h, dzdz = (zc - zc_m1) * inv2h;
-                jac[(size_t)j * N + x] = (1.0f - lambda * dxdx) * (1.0f - lambda * dzdz) - (lambda * dxdz) * (lambda * dzdx);
+            float4 n[4];
+            float J[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {         // output row y = y0+i-1: taps y-1 (.._m1), y (.._0), y+1 (current)
+                const float nz = 0.25f * (sx_m1[j] - sx[j]);
+                const float nx = 0.25f * (dxb_m1[j] + 2.0f * dxb_0[j] + dxb[j]);
+                const float rinv = rsqrtf(fmaf(nx, nx, fmaf(nz, nz, 1.0f)));
+                n[j] = make_float4(nx * rinv, rinv, nz * rinv, 1.0f);   // :53
+                if (JAC)
+                    J[j] = fmaf(-s, ddx_0[j], 1.0f) * fmaf(-s, zc[j] - zc_m1[j], 1.0f) - (s * (xc[j] - xc_m1[j])) * (s * ddz_0[j]);
             }
+            emit(y0 + i - 1, n, make_float4(J[0], J[1], J[2], J[3]));
         }
-        sx_m1 = sx_0; sx_0 = sx; dxb_m1 = dxb_0; dxb_0 = dxb;
-        xc_m1 = xc_0; xc_0 = xc; zc_m1 = zc_0; zc_0 = zc; ddx_0 = ddx; ddz_0 = ddz;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            sx_m1[j] = sx_0[j]; sx_0[j] = sx[j]; dxb_m1[j] = dxb_0[j]; dxb_0[j] = dxb[j];
+            xc_m1[j] = xc_0[j]; xc_0[j] = xc[j]; zc_m1[j] = zc_0[j]; zc_0[j] = zc[j]; ddx_0[j] = ddx[j]; ddz_0[j] = ddz[j];
+        }
     }
 }
+
+// Plain (un-staged) emit: each thread stores its own four normals; used by the CPU emulator.
+template <int N, bool JAC>
+struct EmitDirect {
+    float4* normal;
+    float* jac;
+    int x0;
+    OW_HD void operator()(int y, const float4 (&n)[4], float4 J) const {
+        float4* d = normal + (size_t)y * N + x0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d[j] = n[j];
+        if (JAC) *reinterpret_cast<float4*>(jac + (size_t)y * N + x0) = J;
+    }
+};
 
 }  // namespace ow

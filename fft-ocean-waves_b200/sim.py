@@ -29,7 +29,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 EXPORTED_SYMBOLS = [
     "ow_create", "ow_destroy", "ow_last_error", "ow_set_params", "ow_set_noise", "ow_init_spectrum", "ow_set_h0",
     "ow_step", "ow_step_multi", "ow_step_multi_timed", "ow_sync", "ow_get_outputs", "ow_download", "ow_download_frame_async",
-    "ow_frame_bytes", "ow_set_group_size", "ow_last_launch_count", "ow_gl_register", "ow_gl_step", "ow_gl_unregister",
+    "ow_frame_bytes", "ow_set_group_size", "ow_set_streams", "ow_last_launch_count", "ow_gl_register", "ow_gl_step", "ow_gl_unregister",
 ]
 
 OW_FLAG_JACOBIAN = 0x1
@@ -106,6 +106,7 @@ def load_library():
     L.ow_frame_bytes.argtypes = [vp]
     L.ow_frame_bytes.restype = C.c_size_t
     L.ow_set_group_size.argtypes = [vp, i32]
+    L.ow_set_streams.argtypes = [vp, i32]
     L.ow_last_launch_count.argtypes = [vp]
     L.ow_gl_register.argtypes = [vp, u32, u32, u32, u32]
     L.ow_gl_step.argtypes = [vp, f32]
@@ -212,6 +213,9 @@ class FFTOceanWaves:
 
     def set_group_size(self, g: int):
         self._check(self._lib.ow_set_group_size(self._h, int(g)), "ow_set_group_size")
+
+    def set_streams(self, n: int):
+        self._check(self._lib.ow_set_streams(self._h, int(n)), "ow_set_streams")
 
     def last_launch_count(self) -> int:
         return int(self._lib.ow_last_launch_count(self._h))

@@ -117,9 +117,13 @@ int ow_download(ow_ctx* ctx, int32_t index, int32_t which /* ow_image */, void* 
 int ow_download_frame_async(ow_ctx* ctx, int32_t slot, void* pinned_host, size_t bytes, void* stream);
 size_t ow_frame_bytes(const ow_ctx* ctx);
 
-/* Tuning: how many slots share one row/column/normal launch group (keeps the 12 B/texel intermediate of a
- * group resident in L2). 0 = automatic. */
+/* Tuning: upper bound on the slots that share one row/column/normal launch group. 0 = automatic (the group's
+ * 12 B/texel intermediate <= ~100 MB, slots split evenly into at least as many groups as there are streams). */
 int ow_set_group_size(ow_ctx* ctx, int32_t slots_per_group);
+/* Tuning: independent launch groups of one ow_step_multi call are spread over n internal streams (forked from and
+ * joined back into the caller's stream), so one group's tail overlaps the next group's head. 1 = strictly serial.
+ * Default 3; n in [1, 4]. Results do not depend on it. */
+int ow_set_streams(ow_ctx* ctx, int32_t n);
 /* Number of kernels the last ow_step/ow_step_multi launched (for launch accounting in bench.py). */
 int ow_last_launch_count(const ow_ctx* ctx);
 

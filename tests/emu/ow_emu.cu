@@ -118,10 +118,11 @@ void emu_cols(const float2* inter, float* disp, Stats& st) {
 template <int N>
 void emu_normals(const float* disp, float4* normal, float* jac, float lambda, float L) {
     constexpr int RY = 8;
+    const float s = lambda * ((float)N / (2.0f * L));
     for (int y0 = 0; y0 < N; y0 += RY)
-        for (int x = 0; x < N; ++x) {
-            if (jac) normal_column_walk<N, RY, true>(disp, normal, jac, x, y0, lambda, (float)N / (2.0f * L));
-            else normal_column_walk<N, RY, false>(disp, normal, nullptr, x, y0, lambda, 0.f);
+        for (int x0 = 0; x0 < N; x0 += 4) {
+            if (jac) normal_quad_walk<N, RY, true>(disp, x0, y0, s, EmitDirect<N, true>{normal, jac, x0});
+            else normal_quad_walk<N, RY, false>(disp, x0, y0, 0.f, EmitDirect<N, false>{normal, nullptr, x0});
         }
 }
 
