@@ -9,6 +9,8 @@ The directory name has a hyphen; import it through the alias module at the repo 
 
     import fft_ocean_waves_b200 as fow
     sim = fow.FFTOceanWaves(N=512); sim.init(); sim.update(t=1.0); dy = sim.download("dy")
+
+One grid over several GPUs (torchrun, one process per GPU): `fow.SlabOcean` (slab.py).
 """
 from __future__ import annotations
 
@@ -21,6 +23,7 @@ from .sim import (  # noqa: F401
     lib_path,
     load_library,
 )
+from .slab import SlabOcean, slab_plan  # noqa: F401
 
 __all__ = ["FFTOceanWaves", "OceanParams", "OceanWavesError", "default_noise", "lib_path", "load_library",
-           "EXPORTED_SYMBOLS"]
+           "EXPORTED_SYMBOLS", "SlabOcean", "slab_plan"]

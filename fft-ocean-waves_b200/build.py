@@ -22,6 +22,7 @@ SOURCES = [
     ("ow_frame_kernels.cu", []),
     ("ow_init_kernels.cu", ["-fmad=false"]),
     ("ow_api.cu", []),
+    ("ow_slab.cu", []),
 ]
 HEADERS = ["ow_fft.cuh", "ow_kernels.cuh", "ow_config.cuh", "ow_frame_kernels.cuh", "ow_internal.h", os.path.join("..", "..", "include", "oceanwaves.h")]
 

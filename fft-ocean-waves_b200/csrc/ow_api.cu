@@ -1,6 +1,7 @@
 // ow_api.cu — the C ABI declared in include/oceanwaves.h: context, buffers, launch sequencing.
 // Host side of the drop-in: what FFTOceanWaves::init()/update() do for the sim (reference
 // src/main.cpp:199-255, 553-744, 1083-1145) minus windowing, rendering and GL plumbing.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -207,6 +208,31 @@ int ow_set_noise(ow_ctx* c, int32_t cascade, const uint8_t* const planes[4], int
         c->noise_set[i] = 1;
     }
     OW_CUDA(c, cudaStreamSynchronize(c->stream));   // host planes may be freed by the caller on return
+    c->spectrum_ready = false;
+    return OW_OK;
+}
+
+int ow_set_noise_seed(ow_ctx* c, int32_t cascade, uint64_t seed) {
+    if (!c) return OW_ERR_INVALID;
+    if (cascade < -1 || cascade >= c->n_cascades) return fail(c, OW_ERR_INVALID, "ow_set_noise_seed: cascade out of range");
+    OW_CUDA(c, cudaSetDevice(c->device));
+    const int N = c->N;
+    const size_t plane = (size_t)N * N;
+    if (c->d_noise && (c->noise_w != N || c->noise_h != N)) {
+        OW_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_noise); c->d_noise = nullptr;
+        std::fill(c->noise_set.begin(), c->noise_set.end(), 0);
+    }
+    if (!c->d_noise) {
+        OW_CUDA(c, cudaMalloc(&c->d_noise, plane * 4 * c->n_cascades));
+        c->noise_w = N; c->noise_h = N;
+    }
+    const int lo = cascade < 0 ? 0 : cascade, hi = cascade < 0 ? c->n_cascades : cascade + 1;
+    for (int i = lo; i < hi; ++i) {
+        OW_CUDA(c, launch_noise_seed(c->d_noise + (size_t)i * 4 * plane, N, seed, c->stream));
+        c->noise_set[i] = 1;
+    }
+    OW_CUDA(c, cudaStreamSynchronize(c->stream));
     c->spectrum_ready = false;
     return OW_OK;
 }

@@ -15,9 +15,60 @@ cudaError_t configure_n() {
     e = cudaFuncSetAttribute(ow_row_kernel<typename C::Row, C::ROW_PAIRS, C::ROW_MINB, true>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<typename C::Row, C::ROW_PAIRS>());
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(ow_col_kernel<typename C::Col, C::COL_G, C::COL_MINB>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)ColLayout<typename C::Col, C::COL_G>::SMEM);
+    e = cudaFuncSetAttribute(ow_col_kernel<typename C::Col, C::COL_G, C::COL_MINB>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ColLayout<typename C::Col, C::COL_G>::SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(ow_row_slab_kernel<typename C::Row, C::ROW_PAIRS, C::ROW_MINB, false>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<typename C::Row, C::ROW_PAIRS>());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(ow_row_slab_kernel<typename C::Row, C::ROW_PAIRS, C::ROW_MINB, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<typename C::Row, C::ROW_PAIRS>());
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(ow_col_slab_kernel<typename C::Col, C::COL_G, C::COL_MINB>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ColLayout<typename C::Col, C::COL_G>::SMEM);
+}
+
+template <int N>
+bool slab_ok(int world) {
+    using C = Cfg<N>;
+    if (world < 1 || world > kMaxWorld || (N / 2) % world) return false;
+    const int PL = N / 2 / world, XL = N / world, XH = XL + 2 * kHalo;
+    return PL % C::ROW_PAIRS == 0 && XH % (2 * C::COL_G) == 0 && XL % 128 == 0 && (XL & (XL - 1)) == 0;
+}
+
+template <int N>
+int slab_rows_n(const SlabGeom& g, const float4* h0_loc, const float* ktab, float2* const sink_base[kSlabMaxWorld], float t,
+                bool fast_phase, cudaStream_t st) {
+    using C = Cfg<N>;
+    using R = typename C::Row;
+    SlabRows<N> rows{h0_loc, g.rank * g.PL, g.PL};
+    SlabSink<N> sink{};
+    for (int h = 0; h < g.world; ++h) sink.base[h] = sink_base[h];
+    sink.world = g.world; sink.p0 = g.rank * g.PL; sink.XL = g.XL; sink.XH = g.XH;
+    sink.xl_shift = 0;
+    while ((1 << sink.xl_shift) < g.XL) ++sink.xl_shift;
+    const dim3 grid(g.PL / C::ROW_PAIRS);
+    if (fast_phase)
+        ow_row_slab_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true><<<grid, R::T * C::ROW_PAIRS, row_smem<R, C::ROW_PAIRS>(), st>>>(rows, ktab, sink, t);
+    else
+        ow_row_slab_kernel<R, C::ROW_PAIRS, C::ROW_MINB, false><<<grid, R::T * C::ROW_PAIRS, row_smem<R, C::ROW_PAIRS>(), st>>>(rows, ktab, sink, t);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+template <int N>
+int slab_cols_n(const SlabGeom& g, const float2* recv, float* disp_loc, float4* normal_loc, float* jac_loc, float jac_scale,
+                cudaStream_t st) {
+    using C = Cfg<N>;
+    using K = typename C::Col;
+    const float scale = 0.5f / ((float)N * (float)N);
+    ow_col_slab_kernel<K, C::COL_G, C::COL_MINB>
+        <<<dim3(g.XH / (2 * C::COL_G), 3), K::T * C::COL_G, ColLayout<K, C::COL_G>::SMEM, st>>>(recv, disp_loc, g.XH, scale);
+    const dim3 ngrid(g.XL / 128, N / (C::NRM_WARPS * C::NRM_RY));
+    if (jac_loc)
+        ow_normal_slab_kernel<N, true, C::NRM_RY, C::NRM_WARPS, C::NRM_MINB><<<ngrid, dim3(32, C::NRM_WARPS), 0, st>>>(disp_loc, normal_loc, jac_loc, g.XL, g.XH, jac_scale);
+    else
+        ow_normal_slab_kernel<N, false, C::NRM_RY, C::NRM_WARPS, C::NRM_MINB><<<ngrid, dim3(32, C::NRM_WARPS), 0, st>>>(disp_loc, normal_loc, nullptr, g.XL, g.XH, 0.f);
+    return cudaGetLastError() == cudaSuccess ? 2 : -1;
 }
 
 template <int N>
@@ -54,6 +105,41 @@ cudaError_t configure_frame_kernels(int N) {
         case 4096: return configure_n<4096>();
     }
     return cudaErrorInvalidValue;
+}
+
+bool slab_supported(int N, int world) {
+    switch (N) {
+        case 256: return slab_ok<256>(world);
+        case 512: return slab_ok<512>(world);
+        case 1024: return slab_ok<1024>(world);
+        case 2048: return slab_ok<2048>(world);
+        case 4096: return slab_ok<4096>(world);
+    }
+    return false;
+}
+
+int launch_slab_rows(const SlabGeom& g, const float4* h0_loc, const float* ktab, float2* const sink_base[kSlabMaxWorld], float t,
+                     bool fast_phase, cudaStream_t st) {
+    switch (g.N) {
+        case 256: return slab_rows_n<256>(g, h0_loc, ktab, sink_base, t, fast_phase, st);
+        case 512: return slab_rows_n<512>(g, h0_loc, ktab, sink_base, t, fast_phase, st);
+        case 1024: return slab_rows_n<1024>(g, h0_loc, ktab, sink_base, t, fast_phase, st);
+        case 2048: return slab_rows_n<2048>(g, h0_loc, ktab, sink_base, t, fast_phase, st);
+        case 4096: return slab_rows_n<4096>(g, h0_loc, ktab, sink_base, t, fast_phase, st);
+    }
+    return -1;
+}
+
+int launch_slab_cols(const SlabGeom& g, const float2* recv, float* disp_loc, float4* normal_loc, float* jac_loc, float jac_scale,
+                     cudaStream_t st) {
+    switch (g.N) {
+        case 256: return slab_cols_n<256>(g, recv, disp_loc, normal_loc, jac_loc, jac_scale, st);
+        case 512: return slab_cols_n<512>(g, recv, disp_loc, normal_loc, jac_loc, jac_scale, st);
+        case 1024: return slab_cols_n<1024>(g, recv, disp_loc, normal_loc, jac_loc, jac_scale, st);
+        case 2048: return slab_cols_n<2048>(g, recv, disp_loc, normal_loc, jac_loc, jac_scale, st);
+        case 4096: return slab_cols_n<4096>(g, recv, disp_loc, normal_loc, jac_loc, jac_scale, st);
+    }
+    return -1;
 }
 
 int launch_frame(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_jac, bool fast_phase, cudaStream_t st, cudaEvent_t* ev) {

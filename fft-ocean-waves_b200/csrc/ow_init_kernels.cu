@@ -24,10 +24,8 @@ __global__ void ow_ktab_kernel(float* __restrict__ ktab, int N, float L) {
     }
 }
 
-__global__ void ow_h0_kernel(float4* __restrict__ h0, const uint8_t* __restrict__ noise, int nw, int nh, int N,
-                             CascadeDev c) {
-    const int ix = blockIdx.x * blockDim.x + threadIdx.x, iy = blockIdx.y * blockDim.y + threadIdx.y;
-    if (ix >= N || iy >= N) return;
+// tilde_h0_k_cs.glsl:70-94 for texel (ix, iy) given its four uniform noise bytes.
+__device__ __forceinline__ float4 h0_texel(int ix, int iy, int N, const CascadeDev& c, uint8_t b0, uint8_t b1, uint8_t b2, uint8_t b3) {
     const float xx = (float)ix - (float)N / 2.0f, xy = (float)iy - (float)N / 2.0f;   // :76
     const float kx = (2.0f * kPi * xx) / c.L, ky = (2.0f * kPi * xy) / c.L;           // :77
     const float L_philips = (c.wind_speed * c.wind_speed) / kG;                       // :78
@@ -45,23 +43,64 @@ __global__ void ow_h0_kernel(float4* __restrict__ h0, const uint8_t* __restrict_
     const float Pm = (base * (dm * dm) * sup) / (k_mag_sqr * k_mag_sqr);
     const float h0k = clampf(sqrtf(Pp) / sqrtf(2.0f), -4000.0f, 4000.0f);             // :87
     const float h0m = clampf(sqrtf(Pm) / sqrtf(2.0f), -4000.0f, 4000.0f);             // :88
-    // gauss_rnd(), :51-68: texture(noiseJ, gid/N).r with NEAREST + CLAMP_TO_EDGE on an nw x nh RGBA8 image.
-    int tx = (int)floorf(((float)ix / (float)N) * (float)nw), ty = (int)floorf(((float)iy / (float)N) * (float)nh);
-    tx = min(tx, nw - 1);
-    ty = min(ty, nh - 1);
-    const size_t plane = (size_t)nw * nh, o = (size_t)ty * nw + tx;
-    const float n0 = clampf((float)noise[o] / 255.0f, 0.001f, 1.0f);
-    const float n1 = clampf((float)noise[plane + o] / 255.0f, 0.001f, 1.0f);
-    const float n2 = clampf((float)noise[2 * plane + o] / 255.0f, 0.001f, 1.0f);
-    const float n3 = clampf((float)noise[3 * plane + o] / 255.0f, 0.001f, 1.0f);
-    const float u0 = 2.0f * kPi * n0, v0 = sqrtf(-2.0f * logf(n1));
+    const float n0 = clampf((float)b0 / 255.0f, 0.001f, 1.0f);                        // :53-58
+    const float n1 = clampf((float)b1 / 255.0f, 0.001f, 1.0f);
+    const float n2 = clampf((float)b2 / 255.0f, 0.001f, 1.0f);
+    const float n3 = clampf((float)b3 / 255.0f, 0.001f, 1.0f);
+    const float u0 = 2.0f * kPi * n0, v0 = sqrtf(-2.0f * logf(n1));                   // :60-63
     const float u1 = 2.0f * kPi * n2, v1 = sqrtf(-2.0f * logf(n3));
     float4 out;
     out.x = (v0 * cosf(u0)) * h0k;   // :92
     out.y = (v0 * sinf(u0)) * h0k;
     out.z = (v1 * cosf(u1)) * h0m;   // :93
     out.w = (v1 * sinf(u1)) * h0m;
-    h0[(size_t)iy * N + ix] = out;
+    return out;
+}
+
+__global__ void ow_h0_kernel(float4* __restrict__ h0, const uint8_t* __restrict__ noise, int nw, int nh, int N,
+                             CascadeDev c) {
+    const int ix = blockIdx.x * blockDim.x + threadIdx.x, iy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (ix >= N || iy >= N) return;
+    // gauss_rnd(), :51-68: texture(noiseJ, gid/N).r with NEAREST + CLAMP_TO_EDGE on an nw x nh RGBA8 image.
+    int tx = (int)floorf(((float)ix / (float)N) * (float)nw), ty = (int)floorf(((float)iy / (float)N) * (float)nh);
+    tx = min(tx, nw - 1);
+    ty = min(ty, nh - 1);
+    const size_t plane = (size_t)nw * nh, o = (size_t)ty * nw + tx;
+    h0[(size_t)iy * N + ix] = h0_texel(ix, iy, N, c, noise[o], noise[plane + o], noise[2 * plane + o], noise[3 * plane + o]);
+}
+
+// Counter-based uniform noise for grids too large to ship noise images for (BASELINE config C5): Philox4x32-10
+// (Salmon et al., SC'11) with counter (ix, iy, 0, 0) and key (seed lo, seed hi); plane j's byte for texel
+// (ix, iy) is the low byte of output word j. One N x N "noise image" per plane, looked up 1:1.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+
+__global__ void ow_noise_seed_kernel(uint8_t* __restrict__ noise /* [4][N][N] */, int N, uint64_t seed) {
+    const int ix = blockIdx.x * blockDim.x + threadIdx.x, iy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (ix >= N || iy >= N) return;
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)ix, (uint32_t)iy, 0u, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const size_t plane = (size_t)N * N, o = (size_t)iy * N + ix;
+    noise[o] = (uint8_t)r.x; noise[plane + o] = (uint8_t)r.y; noise[2 * plane + o] = (uint8_t)r.z; noise[3 * plane + o] = (uint8_t)r.w;
+}
+
+// Slab-local initial spectrum: local row lr of h0_loc[2*PL][N] holds global row v (see SlabRows in ow_kernels.cuh):
+// lr < PL -> v = p0 + lr; otherwise pair j = p0 + lr - PL -> v = N - j (pair 0: N/2). Noise straight from Philox.
+__global__ void ow_h0_slab_kernel(float4* __restrict__ h0, int N, int p0, int PL, uint64_t seed, CascadeDev c) {
+    const int ix = blockIdx.x * blockDim.x + threadIdx.x, lr = blockIdx.y * blockDim.y + threadIdx.y;
+    if (ix >= N || lr >= 2 * PL) return;
+    const int j = p0 + lr - PL;
+    const int iy = lr < PL ? p0 + lr : (j == 0 ? N / 2 : N - j);
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)ix, (uint32_t)iy, 0u, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    h0[(size_t)lr * N + ix] = h0_texel(ix, iy, N, c, (uint8_t)r.x, (uint8_t)r.y, (uint8_t)r.z, (uint8_t)r.w);
 }
 
 __global__ void ow_split_h0_kernel(const float4* __restrict__ h0, float2* __restrict__ a, float2* __restrict__ b, int n) {
@@ -86,6 +125,16 @@ cudaError_t launch_ktab(float* ktab, int N, float L, cudaStream_t st) {
 
 cudaError_t launch_h0(float4* h0, const uint8_t* noise, int nw, int nh, int N, const CascadeDev& c, cudaStream_t st) {
     ow_h0_kernel<<<dim3(N / 32, N / 8), dim3(32, 8), 0, st>>>(h0, noise, nw, nh, N, c);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_noise_seed(uint8_t* noise, int N, uint64_t seed, cudaStream_t st) {
+    ow_noise_seed_kernel<<<dim3(N / 32, N / 8), dim3(32, 8), 0, st>>>(noise, N, seed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_h0_slab(float4* h0, int N, int p0, int PL, uint64_t seed, const CascadeDev& c, cudaStream_t st) {
+    ow_h0_slab_kernel<<<dim3(N / 32, (2 * PL + 7) / 8), dim3(32, 8), 0, st>>>(h0, N, p0, PL, seed, c);
     return cudaGetLastError();
 }
 

@@ -39,7 +39,27 @@ int launch_frame(const FrameBuffers& fb, const SlotTable& tab, int count, bool w
 constexpr float kFastPhaseLimit = 2.0e4f;
 cudaError_t configure_frame_kernels(int N);   // opt-in shared memory sizes; call once per device
 
+// ---- slab decomposition of one grid over `world` GPUs (layouts: SlabRows/SlabSink in ow_kernels.cuh) ----
+constexpr int kSlabHalo = 8;       // == ow::kHalo
+constexpr int kSlabMaxWorld = 8;   // == ow::kMaxWorld
+struct SlabGeom {
+    int N, world, rank;
+    int PL;   // row pairs per rank   = N / 2 / world
+    int XL;   // columns per rank     = N / world
+    int XH;   // padded columns       = XL + 2 * kSlabHalo
+};
+bool slab_supported(int N, int world);
+// Row kernel for this rank's pairs; block h of the result goes to sink_base[h] ([PL][3][XH] float2 each).
+int launch_slab_rows(const SlabGeom& g, const float4* h0_loc, const float* ktab, float2* const sink_base[kSlabMaxWorld], float t,
+                     bool fast_phase, cudaStream_t st);
+// Column kernel on recv[N/2][3][XH] -> disp_loc[3][N][XH], then normals (+ Jacobian when jac != nullptr) for the XL
+// interior columns -> normal_loc[N][XL], jac_loc[N][XL]. jac_scale = choppiness * N / (2 L).
+int launch_slab_cols(const SlabGeom& g, const float2* recv, float* disp_loc, float4* normal_loc, float* jac_loc, float jac_scale,
+                     cudaStream_t st);
+
 // Init-time kernels (ow_init_kernels.cu)
+cudaError_t launch_noise_seed(uint8_t* noise /* [4][N][N] */, int N, uint64_t seed, cudaStream_t st);
+cudaError_t launch_h0_slab(float4* h0_loc, int N, int p0, int PL, uint64_t seed, const CascadeDev& c, cudaStream_t st);
 cudaError_t launch_ktab(float* ktab, int N, float L, cudaStream_t st);
 cudaError_t launch_h0(float4* h0, const uint8_t* noise, int noise_w, int noise_h, int N, const CascadeDev& c,
                       cudaStream_t st);

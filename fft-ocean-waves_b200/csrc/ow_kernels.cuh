@@ -80,19 +80,82 @@ struct TexelPair {
     float kx;      // k_x at u
 };
 
+// rowA = base of h0 row v, rowB = base of the mirror row (N - v) mod N (see the row maps below).
 template <int N>
-OW_HD TexelPair load_pair(const float4* __restrict__ h0, const float* __restrict__ ktab, int u, int v, int mv) {
+OW_HD TexelPair load_pair(const float4* __restrict__ rowA, const float4* __restrict__ rowB, const float* __restrict__ ktab, int u) {
     const int mu = (N - u) & (N - 1);
     TexelPair tp;
 #if OW_ABLATE & 1
-    tp.A = make_float4(u * 1e-3f, v * 1e-3f, mu * 1e-3f, 1.0f); tp.B = make_float4(mv * 1e-3f, 0.5f, u * 2e-3f, 0.25f); tp.kx = (u - N / 2) * 6.28e-3f;
+    tp.A = make_float4(u * 1e-3f, 1e-3f, mu * 1e-3f, 1.0f); tp.B = make_float4(2e-3f, 0.5f, u * 2e-3f, 0.25f); tp.kx = (u - N / 2) * 6.28e-3f;
     return tp;
 #endif
-    tp.A = OW_LDG(h0 + (size_t)v * N + u);
-    tp.B = OW_LDG(h0 + (size_t)mv * N + mu);
+    tp.A = OW_LDG(rowA + u);
+    tp.B = OW_LDG(rowB + mu);
     tp.kx = OW_LDG(ktab + u);
     return tp;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Where the rows of h0 live and where the row-transformed lines go.
+//   FullRows/FullSink : one GPU owns the whole grid: h0[v][u], inter[c][p][x]  (FrameBuffers layout).
+//   SlabRows/SlabSink : slab decomposition of ONE grid over `world` GPUs. Rank r owns the row
+//     pairs p in [p0, p0 + PL), PL = N/2/world, i.e. rows p and N-p (pair 0: rows 0 and N/2), stored locally as
+//     h0_loc[2*PL][N]: row v < N/2 at index v - p0, row v >= N/2 at index PL + ((N-v) mod N/2) - p0. The sink is the
+//     transpose: column x belongs to rank h = x / XL (XL = N/world); rank h's receive buffer is laid out
+//     [p][c][XH] with XH = XL + 2*kHalo columns, column x at index kHalo + (x mod XL); the kHalo columns either
+//     side are copies of the neighbours' edge columns (wrap-around), so the normal/Jacobian stencil of a column
+//     slab needs no second exchange. base[h] points at THIS rank's [PL][3][XH] block inside rank h's buffer (a peer
+//     mapping for direct NVLink stores, or a slice of the local send buffer for the NCCL all-to-all).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kHalo = 8;          // halo columns either side of a column slab (stencil needs 2 left, 1 right; 8 keeps
+                                  // 16-column CTA tiles and float4 alignment)
+constexpr int kMaxWorld = 8;
+
+template <int N>
+struct FullRows {
+    const float4* h0;
+    OW_HD const float4* row(int v) const { return h0 + (size_t)v * N; }
+};
+
+template <int N>
+struct FullSink {
+    float2* inter;
+    OW_HD void put(int c, int p, int x, float2 v) const { inter[((size_t)c * (N / 2) + p) * N + x] = v; }
+};
+
+template <int N>
+struct SlabRows {
+    const float4* h0;   // [2*PL][N]
+    int p0, PL;
+    OW_HD int local(int v) const { return (v < N / 2 ? v : PL + ((N - v) & (N / 2 - 1))) - p0; }
+    OW_HD const float4* row(int v) const { return h0 + (size_t)local(v) * N; }
+};
+
+template <int N>
+struct SlabSink {
+    float2* base[kMaxWorld];
+    int world, p0, XL, XH, xl_shift;      // XL = 1 << xl_shift
+    OW_HD void put(int c, int p, int x, float2 v) const {
+        const int h = x >> xl_shift, xl = x & (XL - 1);
+        const size_t line = ((size_t)(p - p0) * 3 + c) * XH;
+        base[h][line + kHalo + xl] = v;
+        if (xl < kHalo) base[h == 0 ? world - 1 : h - 1][line + kHalo + XL + xl] = v;          // right halo of the left neighbour
+        if (xl >= XL - kHalo) base[h == world - 1 ? 0 : h + 1][line + xl - (XL - kHalo)] = v;   // left halo of the right neighbour
+    }
+};
+
+// Row strides of the column kernel's source (float2 elements between consecutive pair rows p of one channel) and
+// destination (floats between output rows y).
+template <int N>
+struct FullColGeom {
+    OW_HD size_t src_stride() const { return N; }
+    OW_HD size_t dst_stride() const { return N; }
+};
+struct SlabColGeom {
+    size_t ss, ds;
+    OW_HD size_t src_stride() const { return ss; }
+    OW_HD size_t dst_stride() const { return ds; }
+};
 
 template <bool FAST>
 OW_HD Sym3 spectrum_sym(const TexelPair& tp, int u, float ky, bool self_row, float t) {
@@ -128,8 +191,8 @@ OW_HD Sym3 spectrum_sym(const TexelPair& tp, int u, float ky, bool self_row, flo
 // the three channels. Shared memory per group: 3 lines of P::LINE float2 (dy, dx, dz).
 // Output: inter[c][p][x] (float2), c in {dy,dx,dz}, p < N/2, x < N — the row transform of S_c(., p).
 // ---------------------------------------------------------------------------------------------------
-template <class P, bool FAST, class Smem>
-OW_HD void row_phase0(const Smem& sm, int ft, int p, const float4* __restrict__ h0, const float* __restrict__ ktab,
+template <class P, bool FAST, class Smem, class Rows>
+OW_HD void row_phase0(const Smem& sm, int ft, int p, const Rows& rows, const float* __restrict__ ktab,
                       float t) {
     constexpr int N = P::N, R0 = P::R0;
 #pragma unroll 1
@@ -140,8 +203,10 @@ OW_HD void row_phase0(const Smem& sm, int ft, int p, const float4* __restrict__ 
         TexelPair tp[R0];
         if (p != 0) {
             const float ky = OW_LDG(ktab + p);
+            const float4* rowA = rows.row(p);
+            const float4* rowB = rows.row(N - p);
 #pragma unroll
-            for (int d0 = 0; d0 < R0; ++d0) tp[d0] = load_pair<N>(h0, ktab, d0 * P::M + b, p, N - p);
+            for (int d0 = 0; d0 < R0; ++d0) tp[d0] = load_pair<N>(rowA, rowB, ktab, d0 * P::M + b);
 #pragma unroll
             for (int d0 = 0; d0 < R0; ++d0) {
                 const Sym3 s = spectrum_sym<FAST>(tp[d0], d0 * P::M + b, ky, false, t);
@@ -151,15 +216,17 @@ OW_HD void row_phase0(const Smem& sm, int ft, int p, const float4* __restrict__ 
             // rows 0 (Nyquist) and N/2 (DC) mirror onto themselves; both row transforms are real, so they
             // travel as one complex line: Z = S(.,0) + i*S(.,N/2).
             const float ky0 = OW_LDG(ktab), kyh = OW_LDG(ktab + N / 2);
+            const float4* row0 = rows.row(0);
+            const float4* rowh = rows.row(N / 2);
 #pragma unroll
-            for (int d0 = 0; d0 < R0; ++d0) tp[d0] = load_pair<N>(h0, ktab, d0 * P::M + b, 0, 0);
+            for (int d0 = 0; d0 < R0; ++d0) tp[d0] = load_pair<N>(row0, row0, ktab, d0 * P::M + b);
 #pragma unroll
             for (int d0 = 0; d0 < R0; ++d0) {
                 const Sym3 a = spectrum_sym<FAST>(tp[d0], d0 * P::M + b, ky0, true, t);
                 vy[d0] = a.y; vx[d0] = a.x; vz[d0] = a.z;
             }
 #pragma unroll
-            for (int d0 = 0; d0 < R0; ++d0) tp[d0] = load_pair<N>(h0, ktab, d0 * P::M + b, N / 2, N / 2);
+            for (int d0 = 0; d0 < R0; ++d0) tp[d0] = load_pair<N>(rowh, rowh, ktab, d0 * P::M + b);
 #pragma unroll
             for (int d0 = 0; d0 < R0; ++d0) {
                 const Sym3 q = spectrum_sym<FAST>(tp[d0], d0 * P::M + b, kyh, true, t);
@@ -195,9 +262,8 @@ OW_HD void row_phase1(const Smem& sm, int ft) {
     }
 }
 
-template <class P, class Smem>
-OW_HD void row_phase2(const Smem& sm, int ft, int p, float2* __restrict__ inter) {
-    constexpr int N = P::N;
+template <class P, class Smem, class Sink>
+OW_HD void row_phase2(const Smem& sm, int ft, int p, const Sink& sink) {
 #pragma unroll 1
     for (int c = 0; c < P::C2; ++c) {
         const int bp = ft + P::T * c;
@@ -211,13 +277,12 @@ OW_HD void row_phase2(const Smem& sm, int ft, int p, float2* __restrict__ inter)
 #else
             stage2<P>(sm, f * P::LINE, bp, v);
 #endif
-            float2* dst = inter + ((size_t)f * (N / 2) + p) * N + bp;
 #if OW_ABLATE & 8
 #pragma unroll
-            for (int k2 = 0; k2 < P::R2; ++k2) if (v[k2].x == 12345.678f) dst[k2 * P::B2] = v[k2];
+            for (int k2 = 0; k2 < P::R2; ++k2) if (v[k2].x == 12345.678f) sink.put(f, p, bp + k2 * P::B2, v[k2]);
 #else
 #pragma unroll
-            for (int k2 = 0; k2 < P::R2; ++k2) dst[k2 * P::B2] = v[k2];
+            for (int k2 = 0; k2 < P::R2; ++k2) sink.put(f, p, bp + k2 * P::B2, v[k2]);
 #endif
         }
     }
@@ -237,16 +302,18 @@ OW_HD void row_phase2(const Smem& sm, int ft, int p, float2* __restrict__ inter)
 OW_HD float2 pack_fwd(float4 r) { return make_float2(r.x - r.w, r.y + r.z); }   // P1 + i*P2
 OW_HD float2 pack_cnj(float4 r) { return make_float2(r.x + r.w, r.z - r.y); }   // conj(P1) + i*conj(P2)
 
-template <class P, class Smem>
-OW_HD void col_phase0(const Smem& sm, int base, int j /* pair id in [0, M/2) */, const float2* __restrict__ src /* inter[c] + x */) {
+template <class P, class Smem, class Geom>
+OW_HD void col_phase0(const Smem& sm, int base, int j /* pair id in [0, M/2) */, const float2* __restrict__ src /* inter[c] + x */,
+                      const Geom& geom) {
     constexpr int N = P::N, R0 = P::R0, M = P::M, H = R0 / 2;
+    const size_t ss = geom.src_stride();
     const int bA = j, bB = (j == 0) ? M / 2 : M - j;
     float2 qa[R0], qb[R0];
     float4 la[H], lb[H];
 #pragma unroll
     for (int i = 0; i < H; ++i) {
-        la[i] = OW_LDG(reinterpret_cast<const float4*>(src + (size_t)(i * M + bA) * N));
-        lb[i] = OW_LDG(reinterpret_cast<const float4*>(src + (size_t)(i * M + bB) * N));
+        la[i] = OW_LDG(reinterpret_cast<const float4*>(src + (size_t)(i * M + bA) * ss));
+        lb[i] = OW_LDG(reinterpret_cast<const float4*>(src + (size_t)(i * M + bB) * ss));
     }
     if (j != 0) {
 #pragma unroll
@@ -289,9 +356,9 @@ OW_HD void col_phase1(const Smem& sm, int base, int ft) {
     }
 }
 
-template <class P, class Smem>
-OW_HD void col_phase2(const Smem& sm, int base, int ft, float* __restrict__ dst /* out[c] + x */, float scale) {
-    constexpr int N = P::N;
+template <class P, class Smem, class Geom>
+OW_HD void col_phase2(const Smem& sm, int base, int ft, float* __restrict__ dst /* out[c] + x */, float scale, const Geom& geom) {
+    const size_t ds = geom.dst_stride();
 #pragma unroll 1
     for (int c = 0; c < P::C2; ++c) {
         const int bp = ft + P::T * c;
@@ -303,7 +370,7 @@ OW_HD void col_phase2(const Smem& sm, int base, int ft, float* __restrict__ dst 
 #pragma unroll
         for (int k2 = 0; k2 < P::R2; ++k2) {
             const int y = bp + P::B2 * k2;
-            *reinterpret_cast<float2*>(dst + (size_t)y * N) = make_float2(sg * v[k2].x, -sg * v[k2].y);
+            *reinterpret_cast<float2*>(dst + (size_t)y * ds) = make_float2(sg * v[k2].x, -sg * v[k2].y);
         }
     }
 }
@@ -335,11 +402,26 @@ struct NormalRowIn {
     float al, ar, bl, br;   // Dx[x0-1], Dx[x0+4], Dz[x0-1], Dz[x0+4]
 };
 
-template <int N, bool JAC>
-OW_HD NormalRowIn normal_row_load(const float* __restrict__ disp, int x0, int rr, bool want_xz, bool want_dd) {
-    constexpr int MSK = N - 1;
+// Geometry of the displacement planes the stencil reads. Full grid: [3][N][N], x wraps with mask N-1. Column slab:
+// [3][N][XH] with halo columns present, so x never wraps (mask = -1) and x0 is an index into the padded row.
+template <int N>
+struct FullNrmGeom {
+    OW_HD size_t row_stride() const { return N; }
+    OW_HD size_t plane_stride() const { return (size_t)N * N; }
+    OW_HD int xmask() const { return N - 1; }
+};
+struct SlabNrmGeom {
+    size_t rs, ps;
+    OW_HD size_t row_stride() const { return rs; }
+    OW_HD size_t plane_stride() const { return ps; }
+    OW_HD int xmask() const { return -1; }
+};
+
+template <int N, bool JAC, class Geom>
+OW_HD NormalRowIn normal_row_load(const float* __restrict__ disp, const Geom& geom, int x0, int rr, bool want_xz, bool want_dd) {
+    const int MSK = geom.xmask();
     const int xl2 = (x0 - 2) & MSK, xl1 = (x0 - 1) & MSK, xr = (x0 + 4) & MSK;
-    const float* r = disp + (size_t)rr * N;
+    const float* r = disp + (size_t)rr * geom.row_stride();
     NormalRowIn in;
     in.l = OW_LDG(reinterpret_cast<const float2*>(r + xl2));
     in.m = OW_LDG(reinterpret_cast<const float4*>(r + x0));
@@ -347,8 +429,8 @@ OW_HD NormalRowIn normal_row_load(const float* __restrict__ disp, int x0, int rr
     in.a = in.b = make_float4(0.f, 0.f, 0.f, 0.f);
     in.al = in.ar = in.bl = in.br = 0.f;
     if (JAC && want_xz) {
-        const float* rx = r + (size_t)N * N;
-        const float* rz = r + (size_t)2 * N * N;
+        const float* rx = r + geom.plane_stride();
+        const float* rz = r + 2 * geom.plane_stride();
         in.a = OW_LDG(reinterpret_cast<const float4*>(rx + x0));
         in.b = OW_LDG(reinterpret_cast<const float4*>(rz + x0));
         if (want_dd) {
@@ -359,8 +441,8 @@ OW_HD NormalRowIn normal_row_load(const float* __restrict__ disp, int x0, int rr
     return in;
 }
 
-template <int N, int RY, bool JAC, class Emit>
-OW_HD void normal_quad_walk(const float* __restrict__ disp /* dy,dx,dz planes */, int x0, int y0, float s, const Emit& emit) {
+template <int N, int RY, bool JAC, class Geom, class Emit>
+OW_HD void normal_quad_walk(const float* __restrict__ disp /* dy,dx,dz planes */, const Geom& geom, int x0, int y0, float s, const Emit& emit) {
     constexpr int MSK = N - 1;
     float hs_prev[6], sx_m1[4], sx_0[4], dxb_m1[4], dxb_0[4];
     float xc_m1[4], xc_0[4], zc_m1[4], zc_0[4], ddx_0[4], ddz_0[4];
@@ -371,11 +453,11 @@ OW_HD void normal_quad_walk(const float* __restrict__ disp /* dy,dx,dz planes */
     }
 #pragma unroll
     for (int c = 0; c < 6; ++c) hs_prev[c] = 0.f;
-    NormalRowIn nxt = normal_row_load<N, JAC>(disp, x0, (y0 - 2) & MSK, false, false);
+    NormalRowIn nxt = normal_row_load<N, JAC>(disp, geom, x0, (y0 - 2) & MSK, false, false);
 #pragma unroll
     for (int i = -2; i <= RY; ++i) {              // h row r = y0 + i ; emits output row r - 1 once i >= 1
         const NormalRowIn in = nxt;
-        if (i < RY) nxt = normal_row_load<N, JAC>(disp, x0, (y0 + i + 1) & MSK, i + 1 >= -1, i + 1 >= 0 && i + 1 < RY);
+        if (i < RY) nxt = normal_row_load<N, JAC>(disp, geom, x0, (y0 + i + 1) & MSK, i + 1 >= -1, i + 1 >= 0 && i + 1 < RY);
         const float4 m = in.m;
         const float hs[6] = {in.l.x + in.l.y, in.l.y + m.x, m.x + m.y, m.y + m.z, m.z + m.w, m.w + in.e};
         float sx[4] = {0.f, 0.f, 0.f, 0.f}, dxb[4] = {0.f, 0.f, 0.f, 0.f};
@@ -419,16 +501,17 @@ OW_HD void normal_quad_walk(const float* __restrict__ disp /* dy,dx,dz planes */
 }
 
 // Plain (un-staged) emit: each thread stores its own four normals; used by the CPU emulator.
-template <int N, bool JAC>
+template <bool JAC>
 struct EmitDirect {
     float4* normal;
     float* jac;
-    int x0;
+    size_t ostride;   // elements between output rows
+    int xout;         // first of the four output columns
     OW_HD void operator()(int y, const float4 (&n)[4], float4 J) const {
-        float4* d = normal + (size_t)y * N + x0;
+        float4* d = normal + (size_t)y * ostride + xout;
 #pragma unroll
         for (int j = 0; j < 4; ++j) d[j] = n[j];
-        if (JAC) *reinterpret_cast<float4*>(jac + (size_t)y * N + x0) = J;
+        if (JAC) *reinterpret_cast<float4*>(jac + (size_t)y * ostride + xout) = J;
     }
 };
 

@@ -1,0 +1,260 @@
+// ow_slab.cu — C ABI of the slab-decomposed frame: ONE N x N grid spread over the GPUs of a box
+// (BASELINE config C5). One process per GPU; every process creates an ow_slab for its rank.
+//
+//   rank r owns   row pairs  p in [r*PL, (r+1)*PL), PL = N/2/world   (rows p and N-p: the Hermitian mirror is local)
+//          and    columns    x in [r*XL, (r+1)*XL), XL = N/world
+//   ow_slab_rows : h0 -> h(k,t) -> row IFFT of this rank's pairs (the reference's tilde_h0_t + horizontal butterfly passes,
+//                  src/main.cpp:587-643), each result stored where its COLUMN owner wants it: the transpose of the
+//                  distributed 2-D IFFT is the row kernel's store pattern. Two transports:
+//                    OW_SLAB_PEER_STORES  straight into the owners' receive buffers over NVLink (peer mappings opened
+//                                         from CUDA IPC handles the host exchanged once); the host only has to order
+//                                         "all rows done" before "columns start" (a barrier).
+//                    OW_SLAB_SEND_BUFFER  into a local send buffer [dest][PL][3][XH]; the host moves it with ONE equal-split
+//                                         all-to-all (NCCL over NVLink) into the owners' receive buffers.
+//   ow_slab_cols : receive buffer [N/2][3][XH] -> column IFFT + inversion (src/main.cpp:645-682) -> normals (+Jacobian)
+//                  (:687-707) for this rank's columns. Outputs stay column-slabbed: dy/dx/dz [N][XL], normal [N][XL][4].
+// Each block carries kSlabHalo wrap-around halo columns either side, so the stencils need no second exchange.
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/oceanwaves.h"
+#include "ow_internal.h"
+
+using namespace ow;
+
+struct ow_slab {
+    SlabGeom g{};
+    int device = 0;
+    uint32_t flags = 0;
+    ow_params params{};
+    CascadeDev casc{};
+    float4* d_h0 = nullptr;       // [2*PL][N]
+    float* d_ktab = nullptr;      // [N]
+    float2* d_send = nullptr;     // [world][PL][3][XH]
+    float2* d_recv = nullptr;     // [N/2][3][XH] = [world][PL][3][XH]
+    float* d_disp = nullptr;      // [3][N][XH]
+    float4* d_normal = nullptr;   // [N][XL]
+    float* d_jac = nullptr;       // [N][XL]
+    float2* peer_recv[kSlabMaxWorld] = {};   // peer mappings of every rank's d_recv (own entry = d_recv)
+    bool peers_open = false;
+    bool spectrum_ready = false;
+    cudaStream_t stream = nullptr;
+    std::string err;
+};
+
+static thread_local std::string g_slab_create_error;
+
+namespace {
+
+int sfail(ow_slab* s, int code, const std::string& msg) {
+    if (s) s->err = msg; else g_slab_create_error = msg;
+    return code;
+}
+int scuda(ow_slab* s, cudaError_t e, const char* what) { return sfail(s, OW_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e)); }
+
+#define OWS_CUDA(s, call)                                            \
+    do {                                                             \
+        cudaError_t e__ = (call);                                    \
+        if (e__ != cudaSuccess) return scuda((s), e__, #call);       \
+    } while (0)
+
+size_t block_elems(const SlabGeom& g) { return (size_t)g.PL * 3 * g.XH; }   // float2 elements one rank sends to one rank
+
+void srelease(ow_slab* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->peers_open)
+        for (int h = 0; h < s->g.world; ++h)
+            if (h != s->g.rank && s->peer_recv[h]) cudaIpcCloseMemHandle(s->peer_recv[h]);
+    cudaFree(s->d_h0); cudaFree(s->d_ktab); cudaFree(s->d_send); cudaFree(s->d_recv); cudaFree(s->d_disp);
+    cudaFree(s->d_normal); cudaFree(s->d_jac);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+cudaStream_t spick(ow_slab* s, void* st) { return st ? static_cast<cudaStream_t>(st) : s->stream; }
+
+}  // namespace
+
+extern "C" {
+
+int ow_slab_create(int32_t N, int32_t world, int32_t rank, const ow_params* p, int32_t device, uint32_t flags, ow_slab** out) {
+    if (!out) return sfail(nullptr, OW_ERR_INVALID, "ow_slab_create: out is NULL");
+    *out = nullptr;
+    if (!p) return sfail(nullptr, OW_ERR_INVALID, "ow_slab_create: params is NULL");
+    if (!frame_supported(N) || !slab_supported(N, world))
+        return sfail(nullptr, OW_ERR_INVALID, "ow_slab_create: unsupported (N, world): N in {256..4096}, world in {1,2,4,8} with N/world >= 128");
+    if (rank < 0 || rank >= world) return sfail(nullptr, OW_ERR_INVALID, "ow_slab_create: rank out of range");
+    if (!(p->L > 0.0f) || !(p->wind_speed > 0.0f) || (p->wind_dir[0] == 0.0f && p->wind_dir[1] == 0.0f))
+        return sfail(nullptr, OW_ERR_INVALID, "ow_slab_create: invalid parameters");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess) return scuda(nullptr, e, "cudaGetDeviceCount (no usable CUDA device; there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return sfail(nullptr, OW_ERR_INVALID, "ow_slab_create: device ordinal out of range");
+    ow_slab* s = new (std::nothrow) ow_slab();
+    if (!s) return sfail(nullptr, OW_ERR_NOMEM, "ow_slab_create: out of host memory");
+    s->g.N = N; s->g.world = world; s->g.rank = rank;
+    s->g.PL = N / 2 / world; s->g.XL = N / world; s->g.XH = s->g.XL + 2 * kSlabHalo;
+    s->device = device; s->flags = flags; s->params = *p;
+    s->casc.L = p->L; s->casc.wind_speed = p->wind_speed; s->casc.amplitude = p->amplitude; s->casc.suppression = p->suppression;
+    s->casc.choppiness = p->choppiness;
+    const float inv = 1.0f / sqrtf(p->wind_dir[0] * p->wind_dir[0] + p->wind_dir[1] * p->wind_dir[1]);   // glm::normalize, src/main.cpp:555
+    s->casc.wdx = p->wind_dir[0] * inv; s->casc.wdy = p->wind_dir[1] * inv;
+    const SlabGeom& g = s->g;
+#define OWS_TRY(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess) { int r__ = scuda(nullptr, e__, #call); srelease(s); return r__; }      \
+    } while (0)
+    OWS_TRY(cudaSetDevice(device));
+    OWS_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    OWS_TRY(cudaMalloc(&s->d_h0, (size_t)2 * g.PL * N * sizeof(float4)));
+    OWS_TRY(cudaMalloc(&s->d_ktab, (size_t)N * sizeof(float)));
+    OWS_TRY(cudaMalloc(&s->d_send, block_elems(g) * world * sizeof(float2)));
+    OWS_TRY(cudaMalloc(&s->d_recv, block_elems(g) * world * sizeof(float2)));
+    OWS_TRY(cudaMalloc(&s->d_disp, (size_t)3 * N * g.XH * sizeof(float)));
+    OWS_TRY(cudaMalloc(&s->d_normal, (size_t)N * g.XL * sizeof(float4)));
+    if (flags & OW_FLAG_JACOBIAN) OWS_TRY(cudaMalloc(&s->d_jac, (size_t)N * g.XL * sizeof(float)));
+    OWS_TRY(configure_frame_kernels(N));
+#undef OWS_TRY
+    s->peer_recv[rank] = s->d_recv;
+    *out = s;
+    return OW_OK;
+}
+
+void ow_slab_destroy(ow_slab* s) { srelease(s); }
+
+const char* ow_slab_last_error(const ow_slab* s) { return s ? s->err.c_str() : g_slab_create_error.c_str(); }
+
+int ow_slab_get_info(const ow_slab* s, ow_slab_info* info) {
+    if (!s || !info) return OW_ERR_INVALID;
+    const SlabGeom& g = s->g;
+    info->N = g.N; info->world = g.world; info->rank = g.rank;
+    info->pairs_per_rank = g.PL; info->cols_per_rank = g.XL; info->padded_cols = g.XH; info->halo = kSlabHalo;
+    info->block_bytes = block_elems(g) * sizeof(float2);
+    info->send = s->d_send; info->recv = s->d_recv;
+    info->dy = s->d_disp; info->dx = s->d_disp + (size_t)g.N * g.XH; info->dz = s->d_disp + (size_t)2 * g.N * g.XH;
+    info->normal = reinterpret_cast<float*>(s->d_normal); info->jacobian = s->d_jac;
+    return OW_OK;
+}
+
+int ow_slab_init_spectrum_seeded(ow_slab* s, uint64_t seed) {
+    if (!s) return OW_ERR_INVALID;
+    OWS_CUDA(s, cudaSetDevice(s->device));
+    const SlabGeom& g = s->g;
+    OWS_CUDA(s, launch_ktab(s->d_ktab, g.N, s->params.L, s->stream));
+    OWS_CUDA(s, launch_h0_slab(s->d_h0, g.N, g.rank * g.PL, g.PL, seed, s->casc, s->stream));
+    OWS_CUDA(s, cudaStreamSynchronize(s->stream));   // like the reference's glFinish after tilde_h0_k (src/main.cpp:582)
+    s->spectrum_ready = true;
+    return OW_OK;
+}
+
+int ow_slab_ipc_handle(ow_slab* s, void* handle, size_t bytes) {
+    if (!s || !handle) return OW_ERR_INVALID;
+    if (bytes != sizeof(cudaIpcMemHandle_t)) return sfail(s, OW_ERR_INVALID, "ow_slab_ipc_handle: handle buffer must be OW_SLAB_IPC_HANDLE_BYTES");
+    OWS_CUDA(s, cudaSetDevice(s->device));
+    cudaIpcMemHandle_t h;
+    OWS_CUDA(s, cudaIpcGetMemHandle(&h, s->d_recv));
+    std::memcpy(handle, &h, sizeof(h));
+    return OW_OK;
+}
+
+int ow_slab_open_peers(ow_slab* s, const void* handles, size_t bytes) {
+    if (!s || !handles) return OW_ERR_INVALID;
+    const SlabGeom& g = s->g;
+    if (bytes != sizeof(cudaIpcMemHandle_t) * (size_t)g.world) return sfail(s, OW_ERR_INVALID, "ow_slab_open_peers: need world handles");
+    if (s->peers_open) return OW_OK;
+    OWS_CUDA(s, cudaSetDevice(s->device));
+    const char* hb = static_cast<const char*>(handles);
+    for (int h = 0; h < g.world; ++h) {
+        if (h == g.rank) continue;
+        cudaIpcMemHandle_t mh;
+        std::memcpy(&mh, hb + (size_t)h * sizeof(mh), sizeof(mh));
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            for (int k = 0; k < h; ++k) if (k != g.rank && s->peer_recv[k]) { cudaIpcCloseMemHandle(s->peer_recv[k]); s->peer_recv[k] = nullptr; }
+            cudaGetLastError();
+            return scuda(s, e, "cudaIpcOpenMemHandle (peer access between the GPUs of this box is required for OW_SLAB_PEER_STORES)");
+        }
+        s->peer_recv[h] = static_cast<float2*>(ptr);
+    }
+    s->peers_open = true;
+    return OW_OK;
+}
+
+int ow_slab_rows(ow_slab* s, float t, int32_t transport, void* stream) {
+    if (!s) return OW_ERR_INVALID;
+    if (!s->spectrum_ready) return sfail(s, OW_ERR_STATE, "ow_slab_rows: call ow_slab_init_spectrum_seeded first");
+    const SlabGeom& g = s->g;
+    float2* base[kSlabMaxWorld] = {};
+    if (transport == OW_SLAB_PEER_STORES) {
+        if (g.world > 1 && !s->peers_open) return sfail(s, OW_ERR_STATE, "ow_slab_rows: OW_SLAB_PEER_STORES needs ow_slab_open_peers");
+        for (int h = 0; h < g.world; ++h) base[h] = s->peer_recv[h] + (size_t)g.rank * block_elems(g);
+    } else if (transport == OW_SLAB_SEND_BUFFER) {
+        for (int h = 0; h < g.world; ++h) base[h] = s->d_send + (size_t)h * block_elems(g);
+    } else {
+        return sfail(s, OW_ERR_INVALID, "ow_slab_rows: unknown transport");
+    }
+    OWS_CUDA(s, cudaSetDevice(s->device));
+    bool fast = (s->flags & OW_FLAG_EXACT_SINCOS) == 0;
+    const float kmax = 1.41421356f * 3.14159265f * (float)g.N / s->params.L;
+    if (!(sqrtf(9.81f * kmax) * fabsf(t) < kFastPhaseLimit)) fast = false;
+    if (launch_slab_rows(g, s->d_h0, s->d_ktab, base, t, fast, spick(s, stream)) < 0) return scuda(s, cudaGetLastError(), "launch_slab_rows");
+    return OW_OK;
+}
+
+int ow_slab_cols(ow_slab* s, void* stream) {
+    if (!s) return OW_ERR_INVALID;
+    if (!s->spectrum_ready) return sfail(s, OW_ERR_STATE, "ow_slab_cols: call ow_slab_init_spectrum_seeded first");
+    OWS_CUDA(s, cudaSetDevice(s->device));
+    const SlabGeom& g = s->g;
+    const float js = s->casc.choppiness * ((float)g.N / (2.0f * s->casc.L));
+    if (launch_slab_cols(g, s->d_recv, s->d_disp, s->d_normal, s->d_jac, js, spick(s, stream)) < 0)
+        return scuda(s, cudaGetLastError(), "launch_slab_cols");
+    return OW_OK;
+}
+
+int ow_slab_sync(ow_slab* s, void* stream) {
+    if (!s) return OW_ERR_INVALID;
+    OWS_CUDA(s, cudaSetDevice(s->device));
+    OWS_CUDA(s, cudaStreamSynchronize(spick(s, stream)));
+    return OW_OK;
+}
+
+int ow_slab_download(ow_slab* s, int32_t which, void* host, size_t bytes, void* stream) {
+    if (!s || !host) return OW_ERR_INVALID;
+    OWS_CUDA(s, cudaSetDevice(s->device));
+    const SlabGeom& g = s->g;
+    cudaStream_t st = spick(s, stream);
+    if (which == OW_IMG_DY || which == OW_IMG_DX || which == OW_IMG_DZ) {
+        if (bytes != (size_t)g.N * g.XL * sizeof(float)) return sfail(s, OW_ERR_INVALID, "ow_slab_download: size mismatch");
+        const float* src = s->d_disp + (size_t)which * g.N * g.XH + kSlabHalo;   // strip the halo columns
+        OWS_CUDA(s, cudaMemcpy2DAsync(host, (size_t)g.XL * sizeof(float), src, (size_t)g.XH * sizeof(float), (size_t)g.XL * sizeof(float), g.N,
+                                      cudaMemcpyDeviceToHost, st));
+    } else if (which == OW_IMG_NORMAL) {
+        if (bytes != (size_t)g.N * g.XL * sizeof(float4)) return sfail(s, OW_ERR_INVALID, "ow_slab_download: size mismatch");
+        OWS_CUDA(s, cudaMemcpyAsync(host, s->d_normal, bytes, cudaMemcpyDeviceToHost, st));
+    } else if (which == OW_IMG_JACOBIAN) {
+        if (!s->d_jac) return sfail(s, OW_ERR_STATE, "ow_slab_download: created without OW_FLAG_JACOBIAN");
+        if (bytes != (size_t)g.N * g.XL * sizeof(float)) return sfail(s, OW_ERR_INVALID, "ow_slab_download: size mismatch");
+        OWS_CUDA(s, cudaMemcpyAsync(host, s->d_jac, bytes, cudaMemcpyDeviceToHost, st));
+    } else {
+        return sfail(s, OW_ERR_INVALID, "ow_slab_download: unknown image");
+    }
+    OWS_CUDA(s, cudaStreamSynchronize(st));
+    return OW_OK;
+}
+
+// Single-process transport for world == 1 (and for tests): what the all-to-all does when there is nobody else.
+int ow_slab_local_exchange(ow_slab* s, void* stream) {
+    if (!s) return OW_ERR_INVALID;
+    if (s->g.world != 1) return sfail(s, OW_ERR_STATE, "ow_slab_local_exchange: only for world == 1 (use an all-to-all otherwise)");
+    OWS_CUDA(s, cudaSetDevice(s->device));
+    OWS_CUDA(s, cudaMemcpyAsync(s->d_recv, s->d_send, block_elems(s->g) * sizeof(float2), cudaMemcpyDeviceToDevice, spick(s, stream)));
+    return OW_OK;
+}
+
+}  // extern "C"

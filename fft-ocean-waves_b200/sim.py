@@ -30,6 +30,9 @@ EXPORTED_SYMBOLS = [
     "ow_create", "ow_destroy", "ow_last_error", "ow_set_params", "ow_set_noise", "ow_init_spectrum", "ow_set_h0",
     "ow_step", "ow_step_multi", "ow_step_multi_timed", "ow_sync", "ow_get_outputs", "ow_download", "ow_download_frame_async",
     "ow_frame_bytes", "ow_set_group_size", "ow_set_streams", "ow_last_launch_count", "ow_gl_register", "ow_gl_step", "ow_gl_unregister",
+    "ow_set_noise_seed",
+    "ow_slab_create", "ow_slab_destroy", "ow_slab_last_error", "ow_slab_get_info", "ow_slab_init_spectrum_seeded", "ow_slab_ipc_handle",
+    "ow_slab_open_peers", "ow_slab_rows", "ow_slab_cols", "ow_slab_local_exchange", "ow_slab_sync", "ow_slab_download",
 ]
 
 OW_FLAG_JACOBIAN = 0x1
@@ -49,6 +52,13 @@ class _Params(C.Structure):
 class _Outputs(C.Structure):
     _fields_ = [("N", C.c_int32), ("dy", C.c_void_p), ("dx", C.c_void_p), ("dz", C.c_void_p), ("normal", C.c_void_p),
                 ("jacobian", C.c_void_p)]
+
+
+class _SlabInfo(C.Structure):
+    _fields_ = [("N", C.c_int32), ("world", C.c_int32), ("rank", C.c_int32), ("pairs_per_rank", C.c_int32),
+                ("cols_per_rank", C.c_int32), ("padded_cols", C.c_int32), ("halo", C.c_int32), ("block_bytes", C.c_size_t),
+                ("send", C.c_void_p), ("recv", C.c_void_p), ("dy", C.c_void_p), ("dx", C.c_void_p), ("dz", C.c_void_p),
+                ("normal", C.c_void_p), ("jacobian", C.c_void_p)]
 
 
 @dataclass
@@ -111,6 +121,21 @@ def load_library():
     L.ow_gl_register.argtypes = [vp, u32, u32, u32, u32]
     L.ow_gl_step.argtypes = [vp, f32]
     L.ow_gl_unregister.argtypes = [vp]
+    L.ow_set_noise_seed.argtypes = [vp, i32, C.c_uint64]
+    L.ow_slab_create.argtypes = [i32, i32, i32, C.POINTER(_Params), i32, u32, C.POINTER(vp)]
+    L.ow_slab_destroy.argtypes = [vp]
+    L.ow_slab_destroy.restype = None
+    L.ow_slab_last_error.argtypes = [vp]
+    L.ow_slab_last_error.restype = C.c_char_p
+    L.ow_slab_get_info.argtypes = [vp, C.POINTER(_SlabInfo)]
+    L.ow_slab_init_spectrum_seeded.argtypes = [vp, C.c_uint64]
+    L.ow_slab_ipc_handle.argtypes = [vp, vp, C.c_size_t]
+    L.ow_slab_open_peers.argtypes = [vp, vp, C.c_size_t]
+    L.ow_slab_rows.argtypes = [vp, f32, i32, vp]
+    L.ow_slab_cols.argtypes = [vp, vp]
+    L.ow_slab_local_exchange.argtypes = [vp, vp]
+    L.ow_slab_sync.argtypes = [vp, vp]
+    L.ow_slab_download.argtypes = [vp, i32, vp, C.c_size_t, vp]
     _lib = L
     return L
 
@@ -170,6 +195,10 @@ class FFTOceanWaves:
             raise ValueError("noise must have shape (4, h, w)")
         ptrs = (C.c_void_p * 4)(*[noise[j].ctypes.data for j in range(4)])
         self._check(self._lib.ow_set_noise(self._h, int(cascade), ptrs, noise.shape[2], noise.shape[1]), "ow_set_noise")
+
+    def set_noise_seed(self, seed: int, cascade: int = -1):
+        """Device-generated Philox noise (BASELINE config C5), identical to what the slab path draws."""
+        self._check(self._lib.ow_set_noise_seed(self._h, int(cascade), C.c_uint64(int(seed))), "ow_set_noise_seed")
 
     def tilde_h0_k(self):
         self._check(self._lib.ow_init_spectrum(self._h), "ow_init_spectrum")

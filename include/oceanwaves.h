@@ -89,6 +89,11 @@ int ow_set_params(ow_ctx* ctx, int32_t cascade, const ow_params* p);
  * data/noise/LDR_LLL1_{0..3}.png, w = h = 256), HOST pointers. cascade = -1 sets every cascade.
  * Lookup rule is the shader's NEAREST/CLAMP fetch at gid/N (tilde_h0_k_cs.glsl:53-58). */
 int ow_set_noise(ow_ctx* ctx, int32_t cascade, const uint8_t* const planes[4], int32_t w, int32_t h);
+/* Counter-based noise for grids with no noise image to ship (BASELINE config C5): the four N x N byte planes are
+ * generated ON THE DEVICE with Philox4x32-10 (counter (ix, iy, 0, 0), key = seed; plane j = low byte of output word j)
+ * and looked up 1:1; everything downstream (Box-Muller, Phillips) is the same tilde_h0_k_cs.glsl path. The slab
+ * context (ow_slab_init_spectrum_seeded) draws from the same function, so both paths see identical h0. */
+int ow_set_noise_seed(ow_ctx* ctx, int32_t cascade, uint64_t seed);
 /* = tilde_h0_k_cs.glsl for every cascade. Re-callable. Synchronous (like the reference's glFinish). */
 int ow_init_spectrum(ow_ctx* ctx);
 /* Overwrite / read back a cascade's initial spectrum (HOST pointers, N*N*2 floats each). */
@@ -135,6 +140,56 @@ int ow_gl_register(ow_ctx* ctx, uint32_t tex_dy, uint32_t tex_dx, uint32_t tex_d
 /* ow_step for slot 0 and copy the results into the registered textures (map -> copy -> unmap). */
 int ow_gl_step(ow_ctx* ctx, float t);
 int ow_gl_unregister(ow_ctx* ctx);
+
+/* ---- one grid over several GPUs (BASELINE config C5): slab-decomposed 2-D IFFT --------------------------
+ * Replaces the same reference functions as ow_step (tilde_h0_t; butterfly_fft x3; generate_normal_map,
+ * src/main.cpp:240-244) for a grid too large or too slow for one GPU. One process per GPU, one ow_slab per process.
+ * Rank r owns row pairs [r*PL, (r+1)*PL) (rows p and N-p, PL = N/2/world) for the row pass and columns
+ * [r*XL, (r+1)*XL) (XL = N/world) for the column pass; the transpose between them is the row kernel's store pattern
+ * (see ow_slab_rows). Outputs stay column-slabbed. N in [256, 4096] this round (N = 32768 needs a four-step line
+ * FFT: not built yet). */
+typedef struct ow_slab ow_slab;
+
+#define OW_SLAB_IPC_HANDLE_BYTES 64
+enum { OW_SLAB_SEND_BUFFER = 0, OW_SLAB_PEER_STORES = 1 };
+
+typedef struct ow_slab_info {
+    int32_t N, world, rank;
+    int32_t pairs_per_rank;   /* PL */
+    int32_t cols_per_rank;    /* XL */
+    int32_t padded_cols;      /* XH = XL + 2*halo: row length of recv / dy / dx / dz */
+    int32_t halo;
+    size_t block_bytes;       /* bytes one rank sends to one rank per frame: PL*3*XH*8; send and recv hold `world` blocks */
+    void* send;               /* device: [world][PL][3][XH] float2, filled by ow_slab_rows(OW_SLAB_SEND_BUFFER) */
+    void* recv;               /* device: [world][PL][3][XH] float2 = [N/2][3][XH], read by ow_slab_cols */
+    float *dy, *dx, *dz;      /* device: [N][XH] each; this rank's columns start at index `halo` of every row */
+    float* normal;            /* device: [N][XL][4] */
+    float* jacobian;          /* device: [N][XL] or NULL */
+} ow_slab_info;
+
+int ow_slab_create(int32_t N, int32_t world, int32_t rank, const ow_params* p, int32_t device, uint32_t flags, ow_slab** out);
+void ow_slab_destroy(ow_slab* s);
+const char* ow_slab_last_error(const ow_slab* s);
+int ow_slab_get_info(const ow_slab* s, ow_slab_info* info);
+/* tilde_h0_k for the rows this rank owns, noise from Philox (see ow_set_noise_seed). */
+int ow_slab_init_spectrum_seeded(ow_slab* s, uint64_t seed);
+/* CUDA IPC handle of this rank's receive buffer (OW_SLAB_IPC_HANDLE_BYTES bytes); the host all-gathers them once. */
+int ow_slab_ipc_handle(ow_slab* s, void* handle, size_t bytes);
+/* handles: world x OW_SLAB_IPC_HANDLE_BYTES, rank order. Maps every peer's receive buffer into this process. */
+int ow_slab_open_peers(ow_slab* s, const void* handles, size_t bytes);
+/* Spectrum at time t + row IFFT of this rank's row pairs. transport OW_SLAB_PEER_STORES: results are stored straight
+ * into the column owners' receive buffers over NVLink (the caller must order every rank's ow_slab_rows before any
+ * rank's ow_slab_cols, and the previous frame's ow_slab_cols before the next ow_slab_rows: two barriers per frame).
+ * OW_SLAB_SEND_BUFFER: results go to info.send; the caller then runs one equal-split all-to-all send -> recv
+ * (block_bytes per pair of ranks), e.g. ncclSend/ncclRecv grouped or torch.distributed.all_to_all_single. */
+int ow_slab_rows(ow_slab* s, float t, int32_t transport, void* stream);
+/* Column IFFT + inversion + normals (+ Jacobian) on the receive buffer. */
+int ow_slab_cols(ow_slab* s, void* stream);
+/* world == 1 stand-in for the all-to-all (send -> recv device copy). */
+int ow_slab_local_exchange(ow_slab* s, void* stream);
+int ow_slab_sync(ow_slab* s, void* stream);
+/* which = OW_IMG_DY/DX/DZ ([N][XL] floats, halo stripped), OW_IMG_NORMAL ([N][XL][4]), OW_IMG_JACOBIAN ([N][XL]). */
+int ow_slab_download(ow_slab* s, int32_t which, void* host, size_t bytes, void* stream);
 
 #ifdef __cplusplus
 }

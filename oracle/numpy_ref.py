@@ -119,3 +119,28 @@ def frame_from_h0(h0k, h0minusk, N, L, t, choppiness=None):
     if choppiness is not None:
         out["jacobian"] = jacobian(dx, dz, L, choppiness)
     return out
+
+
+def philox4x32_10(ctr, key):
+    """Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11), vectorised.
+    ctr: (..., 4) uint32, key: (2,) uint32 -> (..., 4) uint32. Restates ow_init_kernels.cu:philox4x32_10 (config C5 noise)."""
+    c = [np.asarray(ctr[..., i], np.uint64) for i in range(4)]
+    k0, k1 = np.uint64(key[0]), np.uint64(key[1])
+    M0, M1, MASK = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & MASK, p1 >> np.uint64(32), p1 & MASK
+        c = [hi1 ^ c[1] ^ k0, lo1, hi0 ^ c[3] ^ k1, lo0]
+        k0 = (k0 + np.uint64(0x9E3779B9)) & MASK
+        k1 = (k1 + np.uint64(0xBB67AE85)) & MASK
+    return np.stack(c, -1).astype(np.uint32)
+
+
+def philox_noise(seed: int, N: int) -> np.ndarray:
+    """The four N x N noise byte planes ow_set_noise_seed / ow_slab_init_spectrum_seeded generate on the device:
+    counter (ix, iy, 0, 0), key (seed lo, seed hi), plane j = low byte of output word j."""
+    ctr = np.zeros((N, N, 4), np.uint32)
+    ctr[..., 0] = np.arange(N, dtype=np.uint32)[None, :]
+    ctr[..., 1] = np.arange(N, dtype=np.uint32)[:, None]
+    out = philox4x32_10(ctr, (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF))
+    return np.ascontiguousarray(np.moveaxis(out & np.uint32(0xFF), -1, 0).astype(np.uint8))

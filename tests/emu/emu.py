@@ -33,6 +33,7 @@ def lib():
         fp = C.POINTER(C.c_float)
         L.emu_frame.argtypes = [C.c_int, fp, fp, C.c_float, C.c_float, C.c_float, fp, fp, fp, fp, C.POINTER(C.c_long)]
         L.emu_dft.argtypes = [C.c_int, fp, fp]
+        L.emu_slab_frame.argtypes = [C.c_int, C.c_int, fp, fp, C.c_float, C.c_float, C.c_float, fp, fp, fp]
         _lib = L
     return _lib
 
@@ -67,3 +68,15 @@ def frame(N, h0k, h0minusk, L, t, choppiness=1.0, want_inter=False):
     if want_inter:
         out["inter"] = inter
     return out
+
+
+def slab_frame(N, world, h0k, h0minusk, L, t, choppiness=1.0):
+    """The slab-decomposed frame with `world` emulated ranks (row pairs -> peer stores -> column slabs), re-assembled."""
+    a = np.ascontiguousarray(h0k, np.float32)
+    b = np.ascontiguousarray(h0minusk, np.float32)
+    disp = np.empty((3, N, N), np.float32)
+    nm = np.empty((N, N, 4), np.float32)
+    jac = np.empty((N, N), np.float32)
+    rc = lib().emu_slab_frame(N, int(world), _p(a), _p(b), float(L), float(t), float(choppiness), _p(disp), _p(nm), _p(jac))
+    assert rc == 0, rc
+    return dict(dy=disp[0], dx=disp[1], dz=disp[2], normal=nm, jacobian=jac)

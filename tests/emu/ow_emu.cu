@@ -65,30 +65,32 @@ struct Stats {
     long req[6] = {0, 0, 0, 0, 0, 0}, wf[6] = {0, 0, 0, 0, 0, 0};   // row phase 0..2, col phase 0..2
 };
 
-template <int N>
-void emu_rows(const float4* h0, const float* ktab, float t, float2* inter, Stats& st) {
+// Row kernel of the CTAs [blk0, blk0 + nblk): pairs p = pbase + blk * PAIRS + g (pbase = first pair of a slab, 0 for the full grid).
+template <int N, class Rows, class Sink>
+void emu_rows(const Rows& rows, const float* ktab, float t, const Sink& sink, int pbase, int npairs, Stats& st) {
     using C = Cfg<N>;
     using P = typename C::Row;
     constexpr int PAIRS = C::ROW_PAIRS, NT = P::T * PAIRS;
     std::vector<float2> smem((size_t)PAIRS * 3 * P::LINE);
     Recorder rec;
-    for (int blk = 0; blk < N / 2 / PAIRS; ++blk) {
+    for (int blk = 0; blk < npairs / PAIRS; ++blk) {
         for (int phase = 0; phase < 3; ++phase) {
             rec.begin(NT);
             for (int tid = 0; tid < NT; ++tid) {
-                const int ft = tid % P::T, g = tid / P::T, p = blk * PAIRS + g;
+                const int ft = tid % P::T, g = tid / P::T, p = pbase + blk * PAIRS + g;
                 const SmemEmu sm{smem.data() + (size_t)g * 3 * P::LINE, &rec.seq[tid]};
-                if (phase == 0) row_phase0<P, false>(sm, ft, p, h0, ktab, t);
+                if (phase == 0) row_phase0<P, false>(sm, ft, p, rows, ktab, t);
                 if (phase == 1) row_phase1<P>(sm, ft);
-                if (phase == 2) row_phase2<P>(sm, ft, p, inter);
+                if (phase == 2) row_phase2<P>(sm, ft, p, sink);
             }
             if (blk < 2) { rec.requests = rec.wavefronts = 0; rec.end(); st.req[phase] += rec.requests; st.wf[phase] += rec.wavefronts; }
         }
     }
 }
 
-template <int N>
-void emu_cols(const float2* inter, float* disp, Stats& st) {
+// Column kernel over `ncols` columns: src0/dst0 = channel-0 bases, channel f at src0 + f*src_chan, dst0 + f*dst_chan.
+template <int N, class Geom>
+void emu_cols(const float2* src0, size_t src_chan, float* dst0, size_t dst_chan, int ncols, const Geom& geom, Stats& st) {
     using C = Cfg<N>;
     using P = typename C::Col;
     constexpr int G = C::COL_G, NT = P::T * G;
@@ -97,32 +99,33 @@ void emu_cols(const float2* inter, float* disp, Stats& st) {
     const float scale = 0.5f / ((float)N * (float)N);
     Recorder rec;
     for (int f = 0; f < 3; ++f)
-        for (int blk = 0; blk < N / (2 * G); ++blk) {
+        for (int blk = 0; blk < ncols / (2 * G); ++blk) {
             for (int phase = 0; phase < 3; ++phase) {
                 rec.begin(NT);
                 for (int tid = 0; tid < NT; ++tid) {
                     const int job = tid % G, ft = tid / G, x = 2 * (blk * G + job);
                     const SmemEmu sm{smem.data(), &rec.seq[tid]};
                     const int base = job * LY::SJ;
-                    const float2* src = inter + (size_t)f * (N / 2) * N + x;
-                    float* dst = disp + (size_t)f * N * N + x;
-                    if (phase == 0) for (int j = ft; j < P::M / 2; j += P::T) col_phase0<P>(sm, base, j, src);
+                    const float2* src = src0 + (size_t)f * src_chan + x;
+                    float* dst = dst0 + (size_t)f * dst_chan + x;
+                    if (phase == 0) for (int j = ft; j < P::M / 2; j += P::T) col_phase0<P>(sm, base, j, src, geom);
                     if (phase == 1) col_phase1<P>(sm, base, ft);
-                    if (phase == 2) col_phase2<P>(sm, base, ft, dst, scale);
+                    if (phase == 2) col_phase2<P>(sm, base, ft, dst, scale, geom);
                 }
                 if (f == 0 && blk < 2) { rec.requests = rec.wavefronts = 0; rec.end(); st.req[3 + phase] += rec.requests; st.wf[3 + phase] += rec.wavefronts; }
             }
         }
 }
 
-template <int N>
-void emu_normals(const float* disp, float4* normal, float* jac, float lambda, float L) {
+// Normal/Jacobian walk over output columns [0, ncols); xin0 = index of output column 0 inside a row of `disp`.
+template <int N, class Geom>
+void emu_normals(const float* disp, const Geom& geom, int xin0, int ncols, float4* normal, float* jac, size_t ostride, float lambda, float L) {
     constexpr int RY = 8;
     const float s = lambda * ((float)N / (2.0f * L));
     for (int y0 = 0; y0 < N; y0 += RY)
-        for (int x0 = 0; x0 < N; x0 += 4) {
-            if (jac) normal_quad_walk<N, RY, true>(disp, x0, y0, s, EmitDirect<N, true>{normal, jac, x0});
-            else normal_quad_walk<N, RY, false>(disp, x0, y0, 0.f, EmitDirect<N, false>{normal, nullptr, x0});
+        for (int x0 = 0; x0 < ncols; x0 += 4) {
+            if (jac) normal_quad_walk<N, RY, true>(disp, geom, xin0 + x0, y0, s, EmitDirect<true>{normal, jac, ostride, x0});
+            else normal_quad_walk<N, RY, false>(disp, geom, xin0 + x0, y0, 0.f, EmitDirect<false>{normal, nullptr, ostride, x0});
         }
 }
 
@@ -136,11 +139,63 @@ int emu_frame_n(const float* h0k, const float* h0minusk, float L, float t, float
     for (int i = 0; i < N; ++i) ktab[i] = (2.0f * pi * ((float)i - (float)N / 2.0f)) / L;
     std::vector<float2> inter((size_t)3 * (N / 2) * N);
     Stats st;
-    emu_rows<N>(h0.data(), ktab.data(), t, inter.data(), st);
-    emu_cols<N>(inter.data(), disp, st);
-    emu_normals<N>(disp, reinterpret_cast<float4*>(normal), jac, lambda, L);
+    emu_rows<N>(FullRows<N>{h0.data()}, ktab.data(), t, FullSink<N>{inter.data()}, 0, N / 2, st);
+    emu_cols<N>(inter.data(), (size_t)(N / 2) * N, disp, (size_t)N * N, N, FullColGeom<N>{}, st);
+    emu_normals<N>(disp, FullNrmGeom<N>{}, 0, N, reinterpret_cast<float4*>(normal), jac, N, lambda, L);
     if (inter_out) std::memcpy(inter_out, inter.data(), inter.size() * sizeof(float2));
     if (stats) for (int i = 0; i < 6; ++i) { stats[2 * i] = st.req[i]; stats[2 * i + 1] = st.wf[i]; }
+    return 0;
+}
+
+// The slab-decomposed frame with `world` emulated ranks run one after the other: every rank's row
+// kernel stores through SlabSink straight into the owners' receive buffers (what the peer-store mode does over
+// NVLink), then every rank runs the column + normal kernels on its padded column slab. Outputs are re-assembled into
+// full [N][N] images so the test can compare them bit for bit with emu_frame.
+template <int N>
+int emu_slab_frame_n(int world, const float* h0k, const float* h0minusk, float L, float t, float lambda, float* disp,
+                     float* normal, float* jac) {
+    if (world < 1 || world > kMaxWorld || (N / 2) % world) return -2;
+    const int PL = N / 2 / world, XL = N / world, XH = XL + 2 * kHalo;
+    if (PL % Cfg<N>::ROW_PAIRS || XH % (2 * Cfg<N>::COL_G) || XL % 128) return -3;
+    int shift = 0;
+    while ((1 << shift) < XL) ++shift;
+    std::vector<float> ktab(N);
+    const float pi = 3.1415926535897932384626433832795f;
+    for (int i = 0; i < N; ++i) ktab[i] = (2.0f * pi * ((float)i - (float)N / 2.0f)) / L;
+    std::vector<std::vector<float2>> recv(world, std::vector<float2>((size_t)(N / 2) * 3 * XH));
+    Stats st;
+    for (int r = 0; r < world; ++r) {
+        SlabRows<N> rows{nullptr, r * PL, PL};
+        std::vector<float4> h0((size_t)2 * PL * N);
+        for (int v = 0; v < N; ++v) {
+            const int pair = (v < N / 2) ? v : ((N - v) & (N / 2 - 1));
+            if (pair < r * PL || pair >= (r + 1) * PL) continue;
+            float4* dst = h0.data() + (size_t)rows.local(v) * N;
+            for (int u = 0; u < N; ++u) {
+                const size_t i = (size_t)v * N + u;
+                dst[u] = make_float4(h0k[2 * i], h0k[2 * i + 1], h0minusk[2 * i], h0minusk[2 * i + 1]);
+            }
+        }
+        rows.h0 = h0.data();
+        SlabSink<N> sink{};
+        for (int h = 0; h < world; ++h) sink.base[h] = recv[h].data() + (size_t)r * PL * 3 * XH;
+        sink.world = world; sink.p0 = r * PL; sink.XL = XL; sink.XH = XH; sink.xl_shift = shift;
+        emu_rows<N>(rows, ktab.data(), t, sink, r * PL, PL, st);
+    }
+    for (int r = 0; r < world; ++r) {
+        std::vector<float> dloc((size_t)3 * N * XH);
+        emu_cols<N>(recv[r].data(), (size_t)XH, dloc.data(), (size_t)N * XH, XH, SlabColGeom{(size_t)3 * XH, (size_t)XH}, st);
+        std::vector<float4> nloc((size_t)N * XL);
+        std::vector<float> jloc(jac ? (size_t)N * XL : 0);
+        emu_normals<N>(dloc.data(), SlabNrmGeom{(size_t)XH, (size_t)N * XH}, kHalo, XL, nloc.data(), jac ? jloc.data() : nullptr, XL, lambda, L);
+        for (int f = 0; f < 3; ++f)
+            for (int y = 0; y < N; ++y)
+                std::memcpy(disp + ((size_t)f * N + y) * N + (size_t)r * XL, dloc.data() + ((size_t)f * N + y) * XH + kHalo, XL * sizeof(float));
+        for (int y = 0; y < N; ++y) {
+            std::memcpy(normal + ((size_t)y * N + (size_t)r * XL) * 4, nloc.data() + (size_t)y * XL, XL * sizeof(float4));
+            if (jac) std::memcpy(jac + (size_t)y * N + (size_t)r * XL, jloc.data() + (size_t)y * XL, XL * sizeof(float));
+        }
+    }
     return 0;
 }
 
@@ -154,6 +209,18 @@ extern "C" int emu_frame(int N, const float* h0k, const float* h0minusk, float L
         case 1024: return emu_frame_n<1024>(h0k, h0minusk, L, t, lambda, inter_out, disp, normal, jac, stats);
         case 2048: return emu_frame_n<2048>(h0k, h0minusk, L, t, lambda, inter_out, disp, normal, jac, stats);
         case 4096: return emu_frame_n<4096>(h0k, h0minusk, L, t, lambda, inter_out, disp, normal, jac, stats);
+    }
+    return -1;
+}
+
+extern "C" int emu_slab_frame(int N, int world, const float* h0k, const float* h0minusk, float L, float t, float lambda,
+                              float* disp, float* normal, float* jac) {
+    switch (N) {
+        case 256: return emu_slab_frame_n<256>(world, h0k, h0minusk, L, t, lambda, disp, normal, jac);
+        case 512: return emu_slab_frame_n<512>(world, h0k, h0minusk, L, t, lambda, disp, normal, jac);
+        case 1024: return emu_slab_frame_n<1024>(world, h0k, h0minusk, L, t, lambda, disp, normal, jac);
+        case 2048: return emu_slab_frame_n<2048>(world, h0k, h0minusk, L, t, lambda, disp, normal, jac);
+        case 4096: return emu_slab_frame_n<4096>(world, h0k, h0minusk, L, t, lambda, disp, normal, jac);
     }
     return -1;
 }

@@ -1,0 +1,57 @@
+"""torchrun worker for the multi-GPU slab tests: every rank runs SlabOcean over NCCL; rank 0 also runs the single-GPU
+path on the same Philox seed and compares the gathered column slabs with it (they run the same kernels' arithmetic, so
+the comparison is bit for bit).   torchrun --nproc-per-node P tests/slab_worker.py N [frames]"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import fft_ocean_waves_b200 as fow
+
+    N = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    p = fow.OceanParams(L=1000.0, wind_speed=40.0, wind_dir=(1.0, 1.0), amplitude=2.0, suppression=0.1, choppiness=1.0)
+    seed, times = 32768, (0.5, 1.0)
+    ref = None
+    if rank == 0:
+        with fow.FFTOceanWaves(N=N, cascades=[p], jacobian=True, device=local) as one:
+            one.set_noise_seed(seed)
+            one.tilde_h0_k()
+            ref = one.frame(times[-1])
+    ok = True
+    for transport in ("peer", "alltoall"):
+        with fow.SlabOcean(N=N, params=p, device=local, jacobian=True, transport=transport) as sim:
+            sim.init(seed)
+            assert sim.transport == transport
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                for t in times:                      # two frames back to back: exercises the buffer-reuse ordering
+                    sim.update(t)
+                sim.sync()
+                full = {k: sim.gather(k) for k in ("dy", "dx", "dz", "normal", "jacobian")}
+            if rank == 0:
+                for k, v in full.items():
+                    same = np.array_equal(v, ref[k])
+                    print(f"[slab N={N} world={world} {transport}] {k}: {'bit-exact' if same else 'MISMATCH max ' + str(np.abs(v - ref[k]).max())}", flush=True)
+                    ok &= same
+    flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("SLAB OK" if ok else "SLAB FAILED", flush=True)
+    sys.exit(0 if flag.item() == 1.0 else 1)
+
+
+if __name__ == "__main__":
+    main()
