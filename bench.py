@@ -46,6 +46,10 @@ WORKLOADS = {
     "c2": (512, 600, "C2: N=512 single patch, 600-frame sweep t=f/60, L=1000 wind 40 A=2 lambda=1, PNG noise, dy/dx/dz+normal", False),
     "c3": (2048, 64, "C3: N=2048 single patch + Jacobian, 64-frame sweep t=f/60, L=1000 wind 40 A=2, rng(2048) noise", True),
     "c4": (1024, 64, "C4: 64 cascades N=1024 (L=100*1.08^c, wind 10+0.5c, dir 2*pi*c/64), one frame each at t=1", False),
+    # C5 is quoted on N=32768; this round's in-CTA line FFT stops at N=4096, so the slab path is measured on the
+    # down-scaled grid SURVEY.md §8 d2 names for its parity check (identical code path; strong scaling over the ranks).
+    "c5": (4096, 32, "C5 (down-scaled to N=4096): ONE grid, slab-decomposed 2-D IFFT over the ranks, Philox(32768) noise, "
+                     "32-frame sweep t=f/60, dy/dx/dz+normal+Jacobian left column-slabbed", True),
 }
 
 
@@ -63,7 +67,10 @@ def workload_setup(name):
         times = [1.0] * 64
     else:
         casc = [fow.OceanParams(L=1000.0, wind_speed=40.0, wind_dir=(1.0, 1.0), amplitude=2.0, suppression=0.1, choppiness=1.0)]
-        noise = [fow.default_noise() if name == "c2" else np.random.default_rng(2048).integers(0, 256, (4, N, N), dtype=np.uint8)]
+        if name == "c5":
+            noise = [_philox_noise(32768, N)]
+        else:
+            noise = [fow.default_noise() if name == "c2" else np.random.default_rng(2048).integers(0, 256, (4, N, N), dtype=np.uint8)]
         cascade_of = [0] * frames
         times = [float(np.float32(f / 60.0)) for f in range(frames)]
     return dict(N=N, frames=frames, desc=desc, jacobian=jac, cascades=casc, noise=noise, cascade_of=cascade_of, times=times)
@@ -181,6 +188,168 @@ def cpu_baseline(w, seconds=10.0):
             break
     return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"first {n} frames of the sweep ({dt:.1f} s), oracle/ow_oracle.cpp with OpenMP over rows"}
+
+
+def run_slab(args):
+    """--workload c5: one grid over all ranks (strong scaling). A step = one 32-frame sweep of SlabOcean.update."""
+    import torch
+    import fft_ocean_waves_b200 as fow
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    N, frames, desc, jac = WORKLOADS["c5"]
+    p = fow.OceanParams(L=1000.0, wind_speed=40.0, wind_dir=(1.0, 1.0), amplitude=2.0, suppression=0.1, choppiness=1.0)
+    times = [float(np.float32(f / 60.0)) for f in range(frames)]
+    sim = fow.SlabOcean(N=N, params=p, device=local, jacobian=jac, transport=args.transport)
+    sim.init(32768)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def sweep():
+        for t in times:
+            sim.update(t)
+
+    for _ in range(args.warmup):
+        flush.zero_()
+        sweep()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = []
+    for _ in range(args.steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        sweep()
+        b.record(stream)
+        evs.append((a, b))
+    barrier()
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    if dist is not None:
+        tt = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+    value = frames * args.steps / (total_ms * 1e-3)
+    if args.profile:
+        sim.close()
+        return
+    # per-phase durations: events around ow_slab_rows (1 kernel) and ow_slab_cols (column + normal kernels)
+    b_ = sim.backend
+    st = b_.current_stream()
+    kms = np.zeros(2)
+    for t in times:
+        if sim.transport == "peer":
+            sim._barrier()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        e[0].record(stream)
+        b_.rows(t, 1 if sim.transport == "peer" else 0, st)
+        e[1].record(stream)
+        if sim.transport == "peer":
+            sim._barrier()
+        elif world == 1:
+            b_.local_exchange(st)
+        else:
+            send, recv = b_.exchange_tensors()
+            dist.all_to_all_single(recv, send)
+        e[2].record(stream)
+        b_.cols(st)
+        e[3].record(stream)
+        torch.cuda.synchronize()
+        kms += np.array([e[0].elapsed_time(e[1]), e[2].elapsed_time(e[3])])
+    if dist is not None:
+        tt = torch.tensor(kms, device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        kms = tt.cpu().numpy()
+    clocks = sampler.stop() if rank == 0 else None
+    peak, peak_src = measured_peak()
+    texels_rank = float(N) * N / world
+    kb = {"ow_row_slab_kernel": 16 + 12, "ow_col_slab_kernel+ow_normal_slab_kernel": 12 + 12 + 4 + 8 + 16 + 4}
+    per_kernel = []
+    for i, k in enumerate(kb):
+        gbs = kb[k] * texels_rank * frames / (kms[i] * 1e-3) / 1e9
+        per_kernel.append({"kernel": k, "ms_per_launch": kms[i] / frames, "share": kms[i] / kms.sum(), "bytes_per_texel": kb[k],
+                           "achieved_gbs": gbs, "frac": gbs / peak})
+    dom = int(np.argmax(kms))
+    frame_gbs = 48 * texels_rank * value / 1e9
+    xbytes = sim.exchange_bytes_per_frame()
+    roofline = {"bound": "hbm", "kernel": per_kernel[dom]["kernel"], "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": per_kernel[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "bytes_per_launch": per_kernel[dom]["bytes_per_texel"] * texels_rank, "kernels": per_kernel,
+                "frame": {"algorithmic_bytes_per_texel": 48, "achieved": frame_gbs, "frac": frame_gbs / peak,
+                          "note": "per GPU: 48 B/texel x N^2/world texels x frames/s"},
+                "nvlink": {"bytes_per_frame_per_gpu_per_direction": xbytes, "achieved_gbs": xbytes * value / 1e9, "peak_gbs": 770.0,
+                           "frac": xbytes * value / 1e9 / 770.0,
+                           "note": "12 B/texel Hermitian-packed intermediate x (world-1)/world of this rank's texels (+ halo columns); "
+                                   "peak = measured peer copy 770 GB/s per direction (B200_PROFILING.md)"}}
+    # ---- end to end: seed in, every frame's column slab copied to pinned host memory ---------------------------------
+    outs = b_.output_tensors()
+    host = {k: torch.empty(v.shape, dtype=torch.float32, pin_memory=True) for k, v in outs.items()}
+    fbytes = sum(h.numel() * 4 for h in host.values())
+
+    def e2e_step():
+        sim.init(32768)
+        for t in times:
+            sim.update(t)
+            for k, v in outs.items():
+                host[k].copy_(v, non_blocking=True)
+        torch.cuda.synchronize()
+        return float(host["dy"][0, 0])
+
+    e2e_step()
+    barrier()
+    e2e_steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_t = time.perf_counter() - t0
+    if dist is not None:
+        tt = torch.tensor([e2e_t], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_t = float(tt.item())
+    e2e = {"value": frames * e2e_steps / e2e_t, "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": int(frames * fbytes * world),
+           "steps": e2e_steps, "what": "ow_slab_init_spectrum_seeded (8-byte seed) + SlabOcean.update + every rank's column slab "
+                                       "(dy,dx,dz,normal,J) copied to pinned host memory every frame"}
+    line = None
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": desc, "N": N, "frames_per_step": frames, "transport": sim.transport,
+                           "l2": "flushed between timed steps (256 MiB memset outside the event pair); a frame's working set "
+                                 f"({(16 + 12 + 12 + 20) * N * N / world / 1e6:.0f} MB per GPU) exceeds L2 at world <= 4",
+                           "parallelism": f"slab{world}: row pairs -> transpose (peer stores / all-to-all over NVLink) -> column slabs"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(3 * frames * args.steps), "roofline": roofline}
+        if world == 1 and not args.no_cpu:
+            w = dict(N=N, frames=frames, jacobian=True, cascades=[p], noise=[_philox_noise(32768, N)], times=times)
+            line["cpu_baseline"] = cpu_baseline(w)
+    sim.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def _philox_noise(seed, N):
+    from oracle.numpy_ref import philox_noise
+    return philox_noise(seed, N)
 
 
 def run_ours(args):
@@ -378,6 +547,7 @@ def main():
     ap.add_argument("--group", type=int, default=0, help="slots per launch group (0 = library default)")
     ap.add_argument("--streams", type=int, default=0, help="internal streams the launch groups are spread over (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--transport", choices=["auto", "peer", "alltoall"], default="auto", help="c5 only: how the transpose crosses GPUs")
     ap.add_argument("--profile", action="store_true",
                     help="profiler mode (ncu): run warm-up + timed sweeps only and exit without printing a bench line")
     args = ap.parse_args()
@@ -385,6 +555,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c5":
+        run_slab(args)
     else:
         run_ours(args)
 

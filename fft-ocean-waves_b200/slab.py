@@ -126,6 +126,20 @@ class LibSlabBackend:
             self._views = (send, recv)
         return self._views
 
+    def output_tensors(self) -> dict:
+        """torch views of this rank's output slabs (halo columns cut off): dy/dx/dz [N][XL] (row stride XH), normal
+        [N][XL][4], jacobian [N][XL]. Valid until close(); for stream-ordered D2H copies without extra staging."""
+        import torch
+        i, dev = self.info, f"cuda:{self.device}"
+        out = {}
+        for k, ptr in (("dy", i.dy), ("dx", i.dx), ("dz", i.dz)):
+            full = torch.as_tensor(_DeviceBytes(ptr, i.N * i.padded_cols * 4), device=dev).view(torch.float32).view(i.N, i.padded_cols)
+            out[k] = full[:, i.halo:i.halo + i.cols_per_rank]
+        out["normal"] = torch.as_tensor(_DeviceBytes(i.normal, i.N * i.cols_per_rank * 16), device=dev).view(torch.float32).view(i.N, i.cols_per_rank, 4)
+        if i.jacobian:
+            out["jacobian"] = torch.as_tensor(_DeviceBytes(i.jacobian, i.N * i.cols_per_rank * 4), device=dev).view(torch.float32).view(i.N, i.cols_per_rank)
+        return out
+
     def barrier_token(self):
         import torch
         return torch.zeros(1, device=f"cuda:{self.device}")
