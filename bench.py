@@ -369,7 +369,7 @@ def run_ours(args):
 
     w = workload_setup(args.workload)
     N, frames = w["N"], w["frames"]
-    slots = min(args.slots, frames) if args.workload != "c4" else 64
+    slots = min(args.slots or (128 if N <= 512 else 32), frames) if args.workload != "c4" else 64
     sim = fow.FFTOceanWaves(N=N, cascades=w["cascades"], n_slots=max(slots, len(w["cascades"])), device=local, jacobian=w["jacobian"])
     for i, nz in enumerate(w["noise"]):
         sim.set_noise(nz, cascade=i)
@@ -543,7 +543,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
-    ap.add_argument("--slots", type=int, default=32, help="frames evaluated per ow_step_multi call")
+    ap.add_argument("--slots", type=int, default=0, help="frames evaluated per ow_step_multi call (0 = 128 for c2, 32 for c3, 64 for c4)")
     ap.add_argument("--group", type=int, default=0, help="slots per launch group (0 = library default)")
     ap.add_argument("--streams", type=int, default=0, help="internal streams the launch groups are spread over (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -24,6 +24,8 @@ struct ow_ctx {
     int noise_w = 0, noise_h = 0;
     std::vector<char> noise_set;
     float4* d_h0 = nullptr;
+    float4* d_hp = nullptr;       // [cascade][N/2][N] folded texel pairs (what the row kernel streams)
+    float4* d_nyq = nullptr;      // [cascade][N/2]
     float* d_ktab = nullptr;
     CascadeDev* d_casc = nullptr;
     float2* d_inter = nullptr;
@@ -84,7 +86,7 @@ cudaStream_t pick(ow_ctx* c, void* s) { return s ? static_cast<cudaStream_t>(s) 
 
 FrameBuffers buffers(const ow_ctx* c) {
     FrameBuffers fb{};
-    fb.N = c->N; fb.h0 = c->d_h0; fb.ktab = c->d_ktab; fb.casc = c->d_casc; fb.inter = c->d_inter;
+    fb.N = c->N; fb.h0 = c->d_h0; fb.hp = c->d_hp; fb.nyq = c->d_nyq; fb.ktab = c->d_ktab; fb.casc = c->d_casc; fb.inter = c->d_inter;
     fb.disp = c->d_disp; fb.normal = c->d_normal; fb.jacobian = c->d_jac;
     return fb;
 }
@@ -98,7 +100,9 @@ int pick_group(const ow_ctx* c, int count) {
     if (c->group_size > 0) {
         gmax = c->group_size;
     } else {
-        gmax = (int)(100.0e6 / (12.0 * c->N * (double)c->N));
+        // small grids: a launch has to be long enough to amortise its ramp-up and tail (measured at N=512: 11 frames per
+        // group 301 k fps, 21 per group 326 k fps), so the budget is larger there
+        gmax = (int)((c->N <= 512 ? 400.0e6 : 100.0e6) / (12.0 * c->N * (double)c->N));
         if (gmax < 1) gmax = 1;
     }
     if (gmax > kMaxGroup) gmax = kMaxGroup;
@@ -114,7 +118,7 @@ void release(ow_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->gl_registered) for (auto& r : c->gl_res) if (r) cudaGraphicsUnregisterResource(r);
-    cudaFree(c->d_noise); cudaFree(c->d_h0); cudaFree(c->d_ktab); cudaFree(c->d_casc); cudaFree(c->d_inter);
+    cudaFree(c->d_noise); cudaFree(c->d_h0); cudaFree(c->d_hp); cudaFree(c->d_nyq); cudaFree(c->d_ktab); cudaFree(c->d_casc); cudaFree(c->d_inter);
     cudaFree(c->d_disp); cudaFree(c->d_normal); cudaFree(c->d_jac); cudaFree(c->d_tmp);
     if (c->stream) cudaStreamDestroy(c->stream);
     for (auto& s : c->aux) if (s) cudaStreamDestroy(s);
@@ -159,6 +163,10 @@ int ow_create(int32_t N, int32_t n_cascades, int32_t n_slots, const ow_params* c
     }
     OW_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     OW_TRY(cudaMalloc(&c->d_h0, nn * n_cascades * sizeof(float4)));
+    OW_TRY(cudaMalloc(&c->d_hp, nn / 2 * n_cascades * sizeof(float4)));
+    OW_TRY(cudaMalloc(&c->d_nyq, (size_t)(N / 2) * n_cascades * sizeof(float4)));
+    OW_TRY(cudaMemsetAsync(c->d_hp, 0, nn / 2 * n_cascades * sizeof(float4), c->stream));
+    OW_TRY(cudaMemsetAsync(c->d_nyq, 0, (size_t)(N / 2) * n_cascades * sizeof(float4), c->stream));
     OW_TRY(cudaMalloc(&c->d_ktab, (size_t)N * n_cascades * sizeof(float)));
     OW_TRY(cudaMalloc(&c->d_casc, n_cascades * sizeof(CascadeDev)));
     OW_TRY(cudaMalloc(&c->d_inter, nn / 2 * 3 * n_slots * sizeof(float2)));
@@ -249,6 +257,7 @@ int ow_init_spectrum(ow_ctx* c) {
         OW_CUDA(c, launch_ktab(c->d_ktab + (size_t)i * c->N, c->N, c->params[i].L, c->stream));
         OW_CUDA(c, launch_h0(c->d_h0 + (size_t)i * nn, c->d_noise + (size_t)i * 4 * plane, c->noise_w, c->noise_h, c->N,
                              c->casc_host[i], c->stream));
+        OW_CUDA(c, launch_fold(c->d_h0 + (size_t)i * nn, c->d_hp + (size_t)i * (nn / 2), c->d_nyq + (size_t)i * (c->N / 2), c->N, c->stream));
     }
     OW_CUDA(c, cudaMemcpyAsync(c->d_casc, c->casc_host.data(), c->n_cascades * sizeof(CascadeDev), cudaMemcpyHostToDevice, c->stream));
     OW_CUDA(c, cudaStreamSynchronize(c->stream));   // the reference ends tilde_h0_k() with glFinish (main.cpp:582)
@@ -264,6 +273,7 @@ int ow_set_h0(ow_ctx* c, int32_t cascade, const float* h0k, const float* h0minus
     OW_CUDA(c, cudaMemcpyAsync(c->d_tmp, h0k, nn * 2 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     OW_CUDA(c, cudaMemcpyAsync(c->d_tmp + nn * 2, h0minusk, nn * 2 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     OW_CUDA(c, launch_merge_h0(c->d_h0 + (size_t)cascade * nn, c->d_tmp, c->d_tmp + nn * 2, (int)nn, c->stream));
+    OW_CUDA(c, launch_fold(c->d_h0 + (size_t)cascade * nn, c->d_hp + (size_t)cascade * (nn / 2), c->d_nyq + (size_t)cascade * (c->N / 2), c->N, c->stream));
     if (!c->spectrum_ready) {
         // k table and cascade constants are needed even when h0 is supplied directly
         c->casc_host.resize(c->n_cascades);

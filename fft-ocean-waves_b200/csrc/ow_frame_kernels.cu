@@ -1,13 +1,46 @@
 // ow_frame_kernels.cu — __global__ wrappers and launchers of the per-frame kernels (sm_100a).
 // Kernel bodies live in ow_kernels.cuh (shared with the CPU emulator used by the tests).
+#include <cstdlib>
+
 #include "ow_frame_kernels.cuh"
 
 namespace ow {
 
 // ---------------------------------------------------------------------------------------------------
+// CTAs of the persistent row kernel that fit one SM (queried once per N and variant).
+template <int N>
+int g_row_pipe_ctas_per_sm[2] = {0, 0};
+static int g_sm_count = 148;
+static int g_row_classic = -1;   // OW_ROW_KERNEL=classic selects the one-pair-per-CTA kernel (A/B runs, tools)
+static int g_skip = 0;           // OW_SKIP=[r][c][n]: development switch, leaves kernels out to study their overlap (results invalid)
+
 template <int N>
 cudaError_t configure_n() {
     using C = Cfg<N>;
+    {
+        using R = typename C::Row;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        cudaError_t e0 = cudaFuncSetAttribute(ow_row_pipe_kernel<R, C::ROW_PAIRS, C::ROW_MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)row_smem<R, C::ROW_PAIRS>());
+        if (e0 != cudaSuccess) return e0;
+        e0 = cudaFuncSetAttribute(ow_row_pipe_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)row_smem<R, C::ROW_PAIRS>());
+        if (e0 != cudaSuccess) return e0;
+        e0 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_row_pipe_ctas_per_sm<N>[0], ow_row_pipe_kernel<R, C::ROW_PAIRS, C::ROW_MINB, false>,
+                                                           R::T * C::ROW_PAIRS, row_smem<R, C::ROW_PAIRS>());
+        if (e0 != cudaSuccess) return e0;
+        e0 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_row_pipe_ctas_per_sm<N>[1], ow_row_pipe_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true>,
+                                                           R::T * C::ROW_PAIRS, row_smem<R, C::ROW_PAIRS>());
+        if (e0 != cudaSuccess) return e0;
+        if (g_row_classic < 0) {
+            const char* v = getenv("OW_ROW_KERNEL");
+            g_row_classic = (v && v[0] == 'c') ? 1 : 0;
+            const char* k = getenv("OW_SKIP");
+            for (; k && *k; ++k) g_skip |= (*k == 'r') ? 1 : (*k == 'c') ? 2 : (*k == 'n') ? 4 : 0;
+        }
+    }
     cudaError_t e = cudaFuncSetAttribute(ow_row_kernel<typename C::Row, C::ROW_PAIRS, C::ROW_MINB, false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)row_smem<typename C::Row, C::ROW_PAIRS>());
@@ -37,11 +70,11 @@ bool slab_ok(int world) {
 }
 
 template <int N>
-int slab_rows_n(const SlabGeom& g, const float4* h0_loc, const float* ktab, float2* const sink_base[kSlabMaxWorld], float t,
-                bool fast_phase, cudaStream_t st) {
+int slab_rows_n(const SlabGeom& g, const float4* h0_loc, const float4* hp_loc, const float4* nyq_loc, const float* ktab,
+                float2* const sink_base[kSlabMaxWorld], float t, bool fast_phase, cudaStream_t st) {
     using C = Cfg<N>;
     using R = typename C::Row;
-    SlabRows<N> rows{h0_loc, g.rank * g.PL, g.PL};
+    SlabRows<N> rows{h0_loc, hp_loc, nyq_loc, g.rank * g.PL, g.PL};
     SlabSink<N> sink{};
     for (int h = 0; h < g.world; ++h) sink.base[h] = sink_base[h];
     sink.world = g.world; sink.p0 = g.rank * g.PL; sink.XL = g.XL; sink.XH = g.XH;
@@ -77,18 +110,31 @@ int launch_n(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_
     using R = typename C::Row;
     using K = typename C::Col;
     if (ev) cudaEventRecord(ev[0], st);
-    const dim3 rgrid(N / 2 / C::ROW_PAIRS, count);
-    if (fast_phase)
-        ow_row_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true><<<rgrid, R::T * C::ROW_PAIRS, row_smem<R, C::ROW_PAIRS>(), st>>>(fb, tab);
-    else
-        ow_row_kernel<R, C::ROW_PAIRS, C::ROW_MINB, false><<<rgrid, R::T * C::ROW_PAIRS, row_smem<R, C::ROW_PAIRS>(), st>>>(fb, tab);
+    if (g_skip & 1) {
+    } else if (g_row_classic == 1) {
+        const dim3 rgrid(N / 2 / C::ROW_PAIRS, count);
+        if (fast_phase)
+            ow_row_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true><<<rgrid, R::T * C::ROW_PAIRS, row_smem<R, C::ROW_PAIRS>(), st>>>(fb, tab);
+        else
+            ow_row_kernel<R, C::ROW_PAIRS, C::ROW_MINB, false><<<rgrid, R::T * C::ROW_PAIRS, row_smem<R, C::ROW_PAIRS>(), st>>>(fb, tab);
+    } else {
+        const int n_cta_items = count * (N / 2 / C::ROW_PAIRS);
+        const int resident = g_sm_count * (g_row_pipe_ctas_per_sm<N>[fast_phase ? 1 : 0] > 0 ? g_row_pipe_ctas_per_sm<N>[fast_phase ? 1 : 0] : 1);
+        const int grid = n_cta_items < resident ? n_cta_items : resident;
+        if (fast_phase)
+            ow_row_pipe_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true><<<grid, R::T * C::ROW_PAIRS, row_smem<R, C::ROW_PAIRS>(), st>>>(fb, tab, n_cta_items);
+        else
+            ow_row_pipe_kernel<R, C::ROW_PAIRS, C::ROW_MINB, false><<<grid, R::T * C::ROW_PAIRS, row_smem<R, C::ROW_PAIRS>(), st>>>(fb, tab, n_cta_items);
+    }
     if (ev) cudaEventRecord(ev[1], st);
     const float scale = 0.5f / ((float)N * (float)N);   // 1/2 from the Hermitian split, 1/N^2 from inversion_cs.glsl:36
+    if (!(g_skip & 2))
     ow_col_kernel<K, C::COL_G, C::COL_MINB>
         <<<dim3(N / (2 * C::COL_G), 3, count), K::T * C::COL_G, ColLayout<K, C::COL_G>::SMEM, st>>>(fb, tab, scale);
     if (ev) cudaEventRecord(ev[2], st);
     const dim3 ngrid(N / 128, N / (C::NRM_WARPS * C::NRM_RY), count);
-    if (with_jac) ow_normal_kernel<N, true, C::NRM_RY, C::NRM_WARPS, C::NRM_MINB><<<ngrid, dim3(32, C::NRM_WARPS), 0, st>>>(fb, tab);
+    if (g_skip & 4) {
+    } else if (with_jac) ow_normal_kernel<N, true, C::NRM_RY, C::NRM_WARPS, C::NRM_MINB><<<ngrid, dim3(32, C::NRM_WARPS), 0, st>>>(fb, tab);
     else ow_normal_kernel<N, false, C::NRM_RY, C::NRM_WARPS, C::NRM_MINB><<<ngrid, dim3(32, C::NRM_WARPS), 0, st>>>(fb, tab);
     if (ev) cudaEventRecord(ev[3], st);
     return cudaGetLastError() == cudaSuccess ? 3 : -1;
@@ -118,14 +164,14 @@ bool slab_supported(int N, int world) {
     return false;
 }
 
-int launch_slab_rows(const SlabGeom& g, const float4* h0_loc, const float* ktab, float2* const sink_base[kSlabMaxWorld], float t,
-                     bool fast_phase, cudaStream_t st) {
+int launch_slab_rows(const SlabGeom& g, const float4* h0_loc, const float4* hp_loc, const float4* nyq_loc, const float* ktab,
+                     float2* const sink_base[kSlabMaxWorld], float t, bool fast_phase, cudaStream_t st) {
     switch (g.N) {
-        case 256: return slab_rows_n<256>(g, h0_loc, ktab, sink_base, t, fast_phase, st);
-        case 512: return slab_rows_n<512>(g, h0_loc, ktab, sink_base, t, fast_phase, st);
-        case 1024: return slab_rows_n<1024>(g, h0_loc, ktab, sink_base, t, fast_phase, st);
-        case 2048: return slab_rows_n<2048>(g, h0_loc, ktab, sink_base, t, fast_phase, st);
-        case 4096: return slab_rows_n<4096>(g, h0_loc, ktab, sink_base, t, fast_phase, st);
+        case 256: return slab_rows_n<256>(g, h0_loc, hp_loc, nyq_loc, ktab, sink_base, t, fast_phase, st);
+        case 512: return slab_rows_n<512>(g, h0_loc, hp_loc, nyq_loc, ktab, sink_base, t, fast_phase, st);
+        case 1024: return slab_rows_n<1024>(g, h0_loc, hp_loc, nyq_loc, ktab, sink_base, t, fast_phase, st);
+        case 2048: return slab_rows_n<2048>(g, h0_loc, hp_loc, nyq_loc, ktab, sink_base, t, fast_phase, st);
+        case 4096: return slab_rows_n<4096>(g, h0_loc, hp_loc, nyq_loc, ktab, sink_base, t, fast_phase, st);
     }
     return -1;
 }

@@ -8,6 +8,24 @@
 
 namespace ow {
 
+// Per-CTA timeline for tools/tune (never defined in the library build): thread 0 stamps clock64 + globaltimer + smid at
+// the phase boundaries into g_ow_trace[cta][8].
+#ifdef OW_TRACE
+__device__ unsigned long long* g_ow_trace;
+__device__ __forceinline__ void ow_stamp(int cta, int i) {
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        unsigned long long gt; unsigned sm;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+        asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
+        g_ow_trace[(size_t)cta * 8 + i] = (i == 0) ? ((gt << 8) | sm) : (unsigned long long)clock64();
+        if (i == 1) g_ow_trace[(size_t)cta * 8 + 7] = gt;
+    }
+}
+#define OW_STAMP(cta, i) ow_stamp(cta, i)
+#else
+#define OW_STAMP(cta, i)
+#endif
+
 // ---------------------------------------------------------------------------------------------------
 template <class P, int PAIRS, int MINB, bool FAST>
 __global__ void __launch_bounds__(P::T* PAIRS, MINB) ow_row_kernel(FrameBuffers fb, SlotTable tab) {
@@ -20,14 +38,107 @@ __global__ void __launch_bounds__(P::T* PAIRS, MINB) ow_row_kernel(FrameBuffers 
     const float t = tab.time[e];
     const int slot = tab.slot[e];
     const SmemDirect sm{smem + (size_t)g * 3 * P::LINE};
-    const float4* h0 = fb.h0 + (size_t)cascade * N * N;
+    const FullRows<N> rows{fb.h0 + (size_t)cascade * N * N, fb.hp + (size_t)cascade * (N / 2) * N, fb.nyq + (size_t)cascade * (N / 2)};
     const float* ktab = fb.ktab + (size_t)cascade * N;
     float2* inter = fb.inter + (size_t)slot * 3 * (N / 2) * N;
-    row_phase0<P, FAST>(sm, ft, p, FullRows<N>{h0}, ktab, t);
+    OW_STAMP(blockIdx.x, 0); OW_STAMP(blockIdx.x, 1);
+    row_phase0<P, FAST>(sm, ft, p, rows, ktab, t);
+    OW_STAMP(blockIdx.x, 2);
     __syncthreads();
+    OW_STAMP(blockIdx.x, 3);
     row_phase1<P>(sm, ft);
+    OW_STAMP(blockIdx.x, 4);
     __syncthreads();
+    OW_STAMP(blockIdx.x, 5);
     row_phase2<P>(sm, ft, p, FullSink<N>{inter});
+    OW_STAMP(blockIdx.x, 6);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Persistent, software-pipelined row kernel. The per-CTA timeline of ow_row_kernel (tools/tune/trace.cu) shows a CTA
+// spending two thirds of its life in phase 0, and a third of that waiting on the h0 loads of each stage-0 batch
+// (issue 16 LDG.128 -> wait a DRAM round trip -> compute, C0 times, with nothing in flight in between). Here a CTA
+// walks over many row pairs ("items", (slot entry, pair) flattened) and always has the NEXT batch's loads in flight:
+// they are issued right after the spectrum of the current batch has consumed its registers, so the DRAM round trip
+// overlaps the stage-0 butterflies of this batch or, across items, all of stages 1 and 2 and their stores.
+// Pair 0 (rows 0 and N/2, two batches per butterfly) takes the plain path.
+// ---------------------------------------------------------------------------------------------------
+template <int N>
+struct RowItem {
+    FullRows<N> rows;
+    const float4* prow;   // folded pair row of this item
+    const float* ktab;
+    float2* inter;
+    float t;
+    int p;
+};
+
+template <class P, int PAIRS, int MINB, bool FAST>
+__global__ void __launch_bounds__(P::T* PAIRS, MINB) ow_row_pipe_kernel(FrameBuffers fb, SlotTable tab, int n_cta_items) {
+    extern __shared__ __align__(16) float2 smem[];
+    constexpr int N = P::N, R0 = P::R0, HP = N / 2, C0 = P::C0;
+    static_assert(P::M % P::T == 0, "pipelined row kernel needs whole stage-0 batches");
+    const int ft = threadIdx.x % P::T, g = threadIdx.x / P::T;
+    const SmemDirect sm{smem + (size_t)g * 3 * P::LINE};
+
+    auto item_of = [&](int ci) {
+        const int item = ci * PAIRS + g, e = item / HP;
+        RowItem<N> it;
+        it.p = item - e * HP;
+        const int cascade = tab.cascade[e];
+        it.rows = FullRows<N>{fb.h0 + (size_t)cascade * N * N, fb.hp + (size_t)cascade * HP * N, fb.nyq + (size_t)cascade * HP};
+        it.prow = it.rows.pair_row(it.p);
+        it.ktab = fb.ktab + (size_t)cascade * N;
+        it.inter = fb.inter + (size_t)tab.slot[e] * 3 * HP * N;
+        it.t = tab.time[e];
+        return it;
+    };
+    auto issue = [&](const RowItem<N>& it, int c, FoldedPair (&fp)[R0]) {
+        const int b = ft + P::T * c;
+#pragma unroll
+        for (int d0 = 0; d0 < R0; ++d0) fp[d0] = load_folded(it.prow, it.ktab, d0 * P::M + b);
+    };
+
+    FoldedPair nxt[R0];
+    int ci = blockIdx.x;
+    if (ci >= n_cta_items) return;
+    RowItem<N> cur = item_of(ci);
+    if (cur.p != 0) issue(cur, 0, nxt);
+    for (; ci < n_cta_items; ci += gridDim.x) {
+        const int cn = ci + gridDim.x;
+        const bool has_next = cn < n_cta_items;
+        RowItem<N> nx = cur;
+        if (has_next) nx = item_of(cn);
+        if (cur.p == 0) {
+            row_phase0_pair0<P, FAST>(sm, ft, cur.rows, cur.ktab, cur.t);
+            if (has_next && nx.p != 0) issue(nx, 0, nxt);
+        } else {
+            const float ky = OW_LDG(cur.ktab + cur.p);
+#pragma unroll
+            for (int c = 0; c < C0; ++c) {
+                const int b = ft + P::T * c;
+                float2 vy[R0], vx[R0], vz[R0];
+#pragma unroll
+                for (int d0 = 0; d0 < R0; ++d0) {
+                    const Sym3 s = spectrum_folded<FAST>(nxt[d0], ky, cur.t, (d0 == 0 && b == 0) ? cur.rows.nyq_of(cur.p) : nullptr);
+                    vy[d0] = s.y; vx[d0] = s.x; vz[d0] = s.z;
+                }
+                if (c + 1 < C0) issue(cur, c + 1, nxt);                       // next batch of this pair
+                else if (has_next && nx.p != 0) issue(nx, 0, nxt);            // first batch of the next pair
+                float2 tw[R0];
+                twiddle_powers<R0>(unit_root(b, N), tw);
+                stage0_finish<P>(sm, 0 * P::LINE, b, vy, tw);
+                stage0_finish<P>(sm, 1 * P::LINE, b, vx, tw);
+                stage0_finish<P>(sm, 2 * P::LINE, b, vz, tw);
+            }
+        }
+        __syncthreads();
+        row_phase1<P>(sm, ft);
+        __syncthreads();
+        row_phase2<P>(sm, ft, cur.p, FullSink<N>{cur.inter});
+        __syncthreads();          // the next pair's stage-0 stores reuse the lines
+        cur = nx;
+    }
 }
 
 // Slab variant (one grid over several GPUs): this rank's row pairs [p0, p0 + PL), results stored straight into the

@@ -7,6 +7,7 @@
 // The reference's other two init steps (bit-reversal table main.cpp:733-744 and twiddle texture
 // twiddle_factors_cs.glsl) have no equivalent: the in-CTA FFT derives twiddles in registers.
 #include "ow_internal.h"
+#include "ow_kernels.cuh"
 
 namespace ow {
 
@@ -103,6 +104,19 @@ __global__ void ow_h0_slab_kernel(float4* __restrict__ h0, int N, int p0, int PL
     h0[(size_t)lr * N + ix] = h0_texel(ix, iy, N, c, (uint8_t)r.x, (uint8_t)r.y, (uint8_t)r.z, (uint8_t)r.w);
 }
 
+// hp[pl][u] = fold_pair(h0 at (u, p), h0 at the mirror texel); rowsA/rowsB = first "primary"/"mirror" row of the block,
+// mirror rows advance by mirror_step (-N for the full grid where row N-p follows row N-p+1 downwards, +N in a slab).
+__global__ void ow_fold_kernel(const float4* __restrict__ rowsA, const float4* __restrict__ rowsB, long long mirror_step,
+                               float4* __restrict__ hp, float4* __restrict__ nyq, int N, int npairs, int first_pair) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x, pl = blockIdx.y;
+    if (u >= N || pl >= npairs) return;
+    if (first_pair + pl == 0) return;      // pair 0 (rows 0 and N/2) keeps the unfolded path
+    const float4 A = rowsA[(size_t)pl * N + u];
+    const float4 B = (rowsB + (long long)pl * mirror_step)[(N - u) & (N - 1)];
+    hp[(size_t)pl * N + u] = fold_pair(A, B);
+    if (u == 0) nyq[pl] = fold_pair_nyq(A, B);
+}
+
 __global__ void ow_split_h0_kernel(const float4* __restrict__ h0, float2* __restrict__ a, float2* __restrict__ b, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
@@ -135,6 +149,17 @@ cudaError_t launch_noise_seed(uint8_t* noise, int N, uint64_t seed, cudaStream_t
 
 cudaError_t launch_h0_slab(float4* h0, int N, int p0, int PL, uint64_t seed, const CascadeDev& c, cudaStream_t st) {
     ow_h0_slab_kernel<<<dim3(N / 32, (2 * PL + 7) / 8), dim3(32, 8), 0, st>>>(h0, N, p0, PL, seed, c);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fold(const float4* h0, float4* hp, float4* nyq, int N, cudaStream_t st) {
+    // pair p: rows p and N-p; block starts at pair 0 (skipped), mirror of pair pl is row N - pl = rowsB - pl*N with rowsB = row N
+    ow_fold_kernel<<<dim3((N + 255) / 256, N / 2), 256, 0, st>>>(h0, h0 + (size_t)N * N, -(long long)N, hp, nyq, N, N / 2, 0);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fold_slab(const float4* h0_loc, float4* hp_loc, float4* nyq_loc, int N, int first_pair, int PL, cudaStream_t st) {
+    ow_fold_kernel<<<dim3((N + 255) / 256, PL), 256, 0, st>>>(h0_loc, h0_loc + (size_t)PL * N, (long long)N, hp_loc, nyq_loc, N, PL, first_pair);
     return cudaGetLastError();
 }
 

@@ -10,7 +10,7 @@ struct CascadeDev {
     float L, wind_speed, wdx, wdy, amplitude, suppression, choppiness, pad;
 };
 
-constexpr int kMaxGroup = 32;   // slots per launch group (slot table travels by value in the kernel params)
+constexpr int kMaxGroup = 128;  // slots per launch group (slot table travels by value in the kernel params: 1.5 KB of the 4 KB)
 
 struct SlotTable {
     int32_t cascade[kMaxGroup];
@@ -22,6 +22,8 @@ struct SlotTable {
 struct FrameBuffers {
     int N;
     const float4* h0;      // [cascade][N][N]   (h0k.re, h0k.im, h0minusk.re, h0minusk.im)
+    const float4* hp;      // [cascade][N/2][N] folded texel pairs (fold_pair in ow_kernels.cuh); what the row kernel streams
+    const float4* nyq;     // [cascade][N/2]    Nyquist-column extras (fold_pair_nyq)
     const float* ktab;     // [cascade][N]      k(i) = 2*pi*(i - N/2)/L, computed with the shader's operation order
     const CascadeDev* casc;
     float2* inter;         // [slot][3][N/2][N] row-transformed Hermitian half spectra (dy, dx, dz)
@@ -50,8 +52,8 @@ struct SlabGeom {
 };
 bool slab_supported(int N, int world);
 // Row kernel for this rank's pairs; block h of the result goes to sink_base[h] ([PL][3][XH] float2 each).
-int launch_slab_rows(const SlabGeom& g, const float4* h0_loc, const float* ktab, float2* const sink_base[kSlabMaxWorld], float t,
-                     bool fast_phase, cudaStream_t st);
+int launch_slab_rows(const SlabGeom& g, const float4* h0_loc, const float4* hp_loc, const float4* nyq_loc, const float* ktab,
+                     float2* const sink_base[kSlabMaxWorld], float t, bool fast_phase, cudaStream_t st);
 // Column kernel on recv[N/2][3][XH] -> disp_loc[3][N][XH], then normals (+ Jacobian when jac != nullptr) for the XL
 // interior columns -> normal_loc[N][XL], jac_loc[N][XL]. jac_scale = choppiness * N / (2 L).
 int launch_slab_cols(const SlabGeom& g, const float2* recv, float* disp_loc, float4* normal_loc, float* jac_loc, float jac_scale,
@@ -63,6 +65,10 @@ cudaError_t launch_h0_slab(float4* h0_loc, int N, int p0, int PL, uint64_t seed,
 cudaError_t launch_ktab(float* ktab, int N, float L, cudaStream_t st);
 cudaError_t launch_h0(float4* h0, const uint8_t* noise, int noise_w, int noise_h, int N, const CascadeDev& c,
                       cudaStream_t st);
+// Fold h0 into the per-pair coefficients the row kernel streams. Full grid: pair p uses rows p and N-p of h0[N][N];
+// slab: local rows pl and PL+pl of h0_loc[2*PL][N] (first_pair = rank*PL; pair 0 is skipped in both).
+cudaError_t launch_fold(const float4* h0, float4* hp, float4* nyq, int N, cudaStream_t st);
+cudaError_t launch_fold_slab(const float4* h0_loc, float4* hp_loc, float4* nyq_loc, int N, int first_pair, int PL, cudaStream_t st);
 cudaError_t launch_split_h0(const float4* h0, float* h0k, float* h0minusk, int n, cudaStream_t st);
 cudaError_t launch_merge_h0(float4* h0, const float* h0k, const float* h0minusk, int n, cudaStream_t st);
 

@@ -113,8 +113,12 @@ constexpr int kMaxWorld = 8;
 
 template <int N>
 struct FullRows {
-    const float4* h0;
+    const float4* h0;     // [N][N]    full initial spectrum (pair 0 and downloads)
+    const float4* hp;     // [N/2][N]  folded pairs, row p (row 0 unused)
+    const float4* nyq;    // [N/2]     Nyquist-column extras
     OW_HD const float4* row(int v) const { return h0 + (size_t)v * N; }
+    OW_HD const float4* pair_row(int p) const { return hp + (size_t)p * N; }
+    OW_HD const float4* nyq_of(int p) const { return nyq + p; }
 };
 
 template <int N>
@@ -126,9 +130,13 @@ struct FullSink {
 template <int N>
 struct SlabRows {
     const float4* h0;   // [2*PL][N]
+    const float4* hp;   // [PL][N]   folded pairs of this rank (local pair index p - p0)
+    const float4* nyq;  // [PL]
     int p0, PL;
     OW_HD int local(int v) const { return (v < N / 2 ? v : PL + ((N - v) & (N / 2 - 1))) - p0; }
     OW_HD const float4* row(int v) const { return h0 + (size_t)local(v) * N; }
+    OW_HD const float4* pair_row(int p) const { return hp + (size_t)(p - p0) * N; }
+    OW_HD const float4* nyq_of(int p) const { return nyq + (p - p0); }
 };
 
 template <int N>
@@ -187,53 +195,130 @@ OW_HD Sym3 spectrum_sym(const TexelPair& tp, int u, float ky, bool self_row, flo
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Folded initial spectrum. With e = e^{iwt}, A = h0 at (u,v), B = h0 at the mirror texel, the Hermitian part of dy is
+//   S_y = H + conj(Hm) = (f0 c + f1 s,  f2 s + f3 c),   f = fold_pair(A, B)              (c = cos wt, s = sin wt)
+// which depends on the EIGHT h0 floats of the pair only through FOUR time-independent sums. They are formed once at
+// init (ow_fold_kernel), so the row kernel reads 16 B per texel PAIR instead of 32 and forms S_y in 4 flops. Away from
+// the Nyquist column/row the mirror's wave vector is -k, hence S_x = -i (kx/|k|) S_y and S_z = -i (ky/|k|) S_y. On the
+// Nyquist column (u = 0, where the shader's k is NOT negated by mirroring) S_x needs D = H - conj(Hm) instead:
+//   D = (g0 c + g1 s, g2 s + g3 c),  g = fold_pair_nyq(A, B),   S_x = -i (kx/|k|) D       (one float4 per row pair)
+// Pair 0 (rows 0 and N/2, their own mirrors) keeps the unfolded path (spectrum_sym) on the full h0 rows.
+// ---------------------------------------------------------------------------------------------------
+OW_HD float4 fold_pair(float4 A, float4 B) {
+    return make_float4(((A.x + A.z) + B.x) + B.z, ((A.w + B.w) - A.y) - B.y, ((A.x - A.z) - B.x) + B.z, ((A.y + A.w) - B.y) - B.w);
+}
+OW_HD float4 fold_pair_nyq(float4 A, float4 B) {
+    return make_float4(((A.x + A.z) - B.x) - B.z, ((A.w - A.y) - B.w) + B.y, ((A.x - A.z) + B.x) - B.z, ((A.y + A.w) + B.y) + B.w);
+}
+
+// Folded texel pair as loaded: f at (u, p), k_x at u. g (Nyquist column only) is loaded by the one thread that owns u = 0.
+struct FoldedPair {
+    float4 f;
+    float kx;
+};
+
+OW_HD FoldedPair load_folded(const float4* __restrict__ prow, const float* __restrict__ ktab, int u) {
+    FoldedPair fp;
+#if OW_ABLATE & 1
+    fp.f = make_float4(u * 1e-3f, 1e-3f, u * 2e-3f, 1.0f); fp.kx = (u - 512) * 6.28e-3f;
+    return fp;
+#endif
+    fp.f = OW_LDG(prow + u);
+    fp.kx = OW_LDG(ktab + u);
+    return fp;
+}
+
+template <bool FAST>
+OW_HD Sym3 spectrum_folded(const FoldedPair& fp, float ky, float t, const float4* __restrict__ nyq_g /* non-null iff u == 0 */) {
+    const float kx = fp.kx;
+    // tilde_h0_t_cs.glsl:74-79 — same operation order as the shader so w*t matches to the bit.
+    float km = OW_SQRT(OW_ADD(OW_MUL(kx, kx), OW_MUL(ky, ky)));
+    if (km < 0.00001f) km = 0.00001f;
+    const float w = OW_SQRT(OW_MUL(kGravity, km));
+    float s, c;
+#if OW_ABLATE & 2
+    s = w * t; c = 1.0f - s; km = 1.0f + kx;
+#else
+    phase_sincos<FAST>(OW_MUL(w, t), &s, &c);                       // :96-97
+#endif
+    const float4 f = fp.f;
+    const float ik = OW_RCP(km);
+    const float rx = kx * ik, rz = ky * ik;
+    Sym3 o;
+    o.y = make_float2(f.x * c + f.y * s, f.z * s + f.w * c);
+    o.x = make_float2(rx * o.y.y, -rx * o.y.x);                     // :113-126 folded: -i (kx/|k|) S_y
+    o.z = make_float2(rz * o.y.y, -rz * o.y.x);
+    if (nyq_g) {
+        const float4 g = OW_LDG(nyq_g);
+        const float2 D = make_float2(g.x * c + g.y * s, g.z * s + g.w * c);
+        o.x = make_float2(rx * D.y, -rx * D.x);
+    }
+    return o;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // ROW KERNEL.  One group of P::T threads transforms row pair p (rows p and N-p; p==0: rows 0 and N/2) for
 // the three channels. Shared memory per group: 3 lines of P::LINE float2 (dy, dx, dz).
 // Output: inter[c][p][x] (float2), c in {dy,dx,dz}, p < N/2, x < N — the row transform of S_c(., p).
 // ---------------------------------------------------------------------------------------------------
+// Pair 0: rows 0 (Nyquist) and N/2 (DC) mirror onto themselves; both row transforms are real, so they travel as one
+// complex line Z = S(.,0) + i*S(.,N/2). It is ONE row pair in N/2, so this path is written for a small register
+// footprint, not speed (rolled loops, the butterfly inputs parked in local memory, out of line): the hot path's
+// register budget — and with it the occupancy of the whole kernel — must not be set by it.
+template <class P, bool FAST, class Smem, class Rows>
+__host__ __device__ __noinline__ void row_phase0_pair0(const Smem& sm, int ft, const Rows& rows, const float* __restrict__ ktab, float t) {
+    constexpr int N = P::N, R0 = P::R0;
+    const float ky0 = OW_LDG(ktab), kyh = OW_LDG(ktab + N / 2);
+    const float4* row0 = rows.row(0);
+    const float4* rowh = rows.row(N / 2);
+#pragma unroll 1
+    for (int c = 0; c < P::C0; ++c) {
+        const int b = ft + P::T * c;
+        if (b >= P::M) break;
+        float2 v[3][R0];
+#pragma unroll 1
+        for (int d0 = 0; d0 < R0; ++d0) {
+            const int u = d0 * P::M + b;
+            const Sym3 a = spectrum_sym<FAST>(load_pair<N>(row0, row0, ktab, u), u, ky0, true, t);
+            const Sym3 q = spectrum_sym<FAST>(load_pair<N>(rowh, rowh, ktab, u), u, kyh, true, t);
+            v[0][d0] = make_float2(a.y.x - q.y.y, a.y.y + q.y.x);
+            v[1][d0] = make_float2(a.x.x - q.x.y, a.x.y + q.x.x);
+            v[2][d0] = make_float2(a.z.x - q.z.y, a.z.y + q.z.x);
+        }
+        float2 tw[R0];
+        twiddle_powers<R0>(unit_root(b, N), tw);
+#pragma unroll 1
+        for (int f = 0; f < 3; ++f) {
+            float2 w[R0];
+#pragma unroll
+            for (int d0 = 0; d0 < R0; ++d0) w[d0] = v[f][d0];
+            stage0_finish<P>(sm, f * P::LINE, b, w, tw);
+        }
+    }
+}
+
 template <class P, bool FAST, class Smem, class Rows>
 OW_HD void row_phase0(const Smem& sm, int ft, int p, const Rows& rows, const float* __restrict__ ktab,
                       float t) {
     constexpr int N = P::N, R0 = P::R0;
+    if (p == 0) {
+        row_phase0_pair0<P, FAST>(sm, ft, rows, ktab, t);
+        return;
+    }
+    const float ky = OW_LDG(ktab + p);
+    const float4* prow = rows.pair_row(p);
 #pragma unroll 1
     for (int c = 0; c < P::C0; ++c) {
         const int b = ft + P::T * c;
         if (b >= P::M) break;
         float2 vy[R0], vx[R0], vz[R0];
-        TexelPair tp[R0];
-        if (p != 0) {
-            const float ky = OW_LDG(ktab + p);
-            const float4* rowA = rows.row(p);
-            const float4* rowB = rows.row(N - p);
+        FoldedPair fp[R0];
 #pragma unroll
-            for (int d0 = 0; d0 < R0; ++d0) tp[d0] = load_pair<N>(rowA, rowB, ktab, d0 * P::M + b);
+        for (int d0 = 0; d0 < R0; ++d0) fp[d0] = load_folded(prow, ktab, d0 * P::M + b);
 #pragma unroll
-            for (int d0 = 0; d0 < R0; ++d0) {
-                const Sym3 s = spectrum_sym<FAST>(tp[d0], d0 * P::M + b, ky, false, t);
-                vy[d0] = s.y; vx[d0] = s.x; vz[d0] = s.z;
-            }
-        } else {
-            // rows 0 (Nyquist) and N/2 (DC) mirror onto themselves; both row transforms are real, so they
-            // travel as one complex line: Z = S(.,0) + i*S(.,N/2).
-            const float ky0 = OW_LDG(ktab), kyh = OW_LDG(ktab + N / 2);
-            const float4* row0 = rows.row(0);
-            const float4* rowh = rows.row(N / 2);
-#pragma unroll
-            for (int d0 = 0; d0 < R0; ++d0) tp[d0] = load_pair<N>(row0, row0, ktab, d0 * P::M + b);
-#pragma unroll
-            for (int d0 = 0; d0 < R0; ++d0) {
-                const Sym3 a = spectrum_sym<FAST>(tp[d0], d0 * P::M + b, ky0, true, t);
-                vy[d0] = a.y; vx[d0] = a.x; vz[d0] = a.z;
-            }
-#pragma unroll
-            for (int d0 = 0; d0 < R0; ++d0) tp[d0] = load_pair<N>(rowh, rowh, ktab, d0 * P::M + b);
-#pragma unroll
-            for (int d0 = 0; d0 < R0; ++d0) {
-                const Sym3 q = spectrum_sym<FAST>(tp[d0], d0 * P::M + b, kyh, true, t);
-                vy[d0] = make_float2(vy[d0].x - q.y.y, vy[d0].y + q.y.x);
-                vx[d0] = make_float2(vx[d0].x - q.x.y, vx[d0].y + q.x.x);
-                vz[d0] = make_float2(vz[d0].x - q.z.y, vz[d0].y + q.z.x);
-            }
+        for (int d0 = 0; d0 < R0; ++d0) {
+            const Sym3 s = spectrum_folded<FAST>(fp[d0], ky, t, (d0 == 0 && b == 0) ? rows.nyq_of(p) : nullptr);
+            vy[d0] = s.y; vx[d0] = s.x; vz[d0] = s.z;
         }
         float2 tw[R0];
         twiddle_powers<R0>(unit_root(b, N), tw);

@@ -31,6 +31,8 @@ struct ow_slab {
     ow_params params{};
     CascadeDev casc{};
     float4* d_h0 = nullptr;       // [2*PL][N]
+    float4* d_hp = nullptr;       // [PL][N] folded pairs
+    float4* d_nyq = nullptr;      // [PL]
     float* d_ktab = nullptr;      // [N]
     float2* d_send = nullptr;     // [world][PL][3][XH]
     float2* d_recv = nullptr;     // [N/2][3][XH] = [world][PL][3][XH]
@@ -68,7 +70,7 @@ void srelease(ow_slab* s) {
     if (s->peers_open)
         for (int h = 0; h < s->g.world; ++h)
             if (h != s->g.rank && s->peer_recv[h]) cudaIpcCloseMemHandle(s->peer_recv[h]);
-    cudaFree(s->d_h0); cudaFree(s->d_ktab); cudaFree(s->d_send); cudaFree(s->d_recv); cudaFree(s->d_disp);
+    cudaFree(s->d_h0); cudaFree(s->d_hp); cudaFree(s->d_nyq); cudaFree(s->d_ktab); cudaFree(s->d_send); cudaFree(s->d_recv); cudaFree(s->d_disp);
     cudaFree(s->d_normal); cudaFree(s->d_jac);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
@@ -111,6 +113,10 @@ int ow_slab_create(int32_t N, int32_t world, int32_t rank, const ow_params* p, i
     OWS_TRY(cudaSetDevice(device));
     OWS_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     OWS_TRY(cudaMalloc(&s->d_h0, (size_t)2 * g.PL * N * sizeof(float4)));
+    OWS_TRY(cudaMalloc(&s->d_hp, (size_t)g.PL * N * sizeof(float4)));
+    OWS_TRY(cudaMalloc(&s->d_nyq, (size_t)g.PL * sizeof(float4)));
+    OWS_TRY(cudaMemsetAsync(s->d_hp, 0, (size_t)g.PL * N * sizeof(float4), s->stream));
+    OWS_TRY(cudaMemsetAsync(s->d_nyq, 0, (size_t)g.PL * sizeof(float4), s->stream));
     OWS_TRY(cudaMalloc(&s->d_ktab, (size_t)N * sizeof(float)));
     OWS_TRY(cudaMalloc(&s->d_send, block_elems(g) * world * sizeof(float2)));
     OWS_TRY(cudaMalloc(&s->d_recv, block_elems(g) * world * sizeof(float2)));
@@ -146,6 +152,7 @@ int ow_slab_init_spectrum_seeded(ow_slab* s, uint64_t seed) {
     const SlabGeom& g = s->g;
     OWS_CUDA(s, launch_ktab(s->d_ktab, g.N, s->params.L, s->stream));
     OWS_CUDA(s, launch_h0_slab(s->d_h0, g.N, g.rank * g.PL, g.PL, seed, s->casc, s->stream));
+    OWS_CUDA(s, launch_fold_slab(s->d_h0, s->d_hp, s->d_nyq, g.N, g.rank * g.PL, g.PL, s->stream));
     OWS_CUDA(s, cudaStreamSynchronize(s->stream));   // like the reference's glFinish after tilde_h0_k (src/main.cpp:582)
     s->spectrum_ready = true;
     return OW_OK;
@@ -202,7 +209,7 @@ int ow_slab_rows(ow_slab* s, float t, int32_t transport, void* stream) {
     bool fast = (s->flags & OW_FLAG_EXACT_SINCOS) == 0;
     const float kmax = 1.41421356f * 3.14159265f * (float)g.N / s->params.L;
     if (!(sqrtf(9.81f * kmax) * fabsf(t) < kFastPhaseLimit)) fast = false;
-    if (launch_slab_rows(g, s->d_h0, s->d_ktab, base, t, fast, spick(s, stream)) < 0) return scuda(s, cudaGetLastError(), "launch_slab_rows");
+    if (launch_slab_rows(g, s->d_h0, s->d_hp, s->d_nyq, s->d_ktab, base, t, fast, spick(s, stream)) < 0) return scuda(s, cudaGetLastError(), "launch_slab_rows");
     return OW_OK;
 }
 

@@ -61,6 +61,19 @@ struct SmemEmu {
     }
 };
 
+// Host restatement of ow_fold_kernel (ow_init_kernels.cu): hp[p][u] = fold_pair(h0[p][u], h0[N-p][(N-u) mod N]).
+template <int N>
+void fold_full(const std::vector<float4>& h0, std::vector<float4>& hp, std::vector<float4>& nyq) {
+    hp.assign((size_t)(N / 2) * N, make_float4(0, 0, 0, 0));
+    nyq.assign(N / 2, make_float4(0, 0, 0, 0));
+    for (int p = 1; p < N / 2; ++p)
+        for (int u = 0; u < N; ++u) {
+            const float4 A = h0[(size_t)p * N + u], B = h0[(size_t)(N - p) * N + ((N - u) & (N - 1))];
+            hp[(size_t)p * N + u] = fold_pair(A, B);
+            if (u == 0) nyq[p] = fold_pair_nyq(A, B);
+        }
+}
+
 struct Stats {
     long req[6] = {0, 0, 0, 0, 0, 0}, wf[6] = {0, 0, 0, 0, 0, 0};   // row phase 0..2, col phase 0..2
 };
@@ -139,7 +152,9 @@ int emu_frame_n(const float* h0k, const float* h0minusk, float L, float t, float
     for (int i = 0; i < N; ++i) ktab[i] = (2.0f * pi * ((float)i - (float)N / 2.0f)) / L;
     std::vector<float2> inter((size_t)3 * (N / 2) * N);
     Stats st;
-    emu_rows<N>(FullRows<N>{h0.data()}, ktab.data(), t, FullSink<N>{inter.data()}, 0, N / 2, st);
+    std::vector<float4> hp, nyq;
+    fold_full<N>(h0, hp, nyq);
+    emu_rows<N>(FullRows<N>{h0.data(), hp.data(), nyq.data()}, ktab.data(), t, FullSink<N>{inter.data()}, 0, N / 2, st);
     emu_cols<N>(inter.data(), (size_t)(N / 2) * N, disp, (size_t)N * N, N, FullColGeom<N>{}, st);
     emu_normals<N>(disp, FullNrmGeom<N>{}, 0, N, reinterpret_cast<float4*>(normal), jac, N, lambda, L);
     if (inter_out) std::memcpy(inter_out, inter.data(), inter.size() * sizeof(float2));
@@ -165,7 +180,7 @@ int emu_slab_frame_n(int world, const float* h0k, const float* h0minusk, float L
     std::vector<std::vector<float2>> recv(world, std::vector<float2>((size_t)(N / 2) * 3 * XH));
     Stats st;
     for (int r = 0; r < world; ++r) {
-        SlabRows<N> rows{nullptr, r * PL, PL};
+        SlabRows<N> rows{nullptr, nullptr, nullptr, r * PL, PL};
         std::vector<float4> h0((size_t)2 * PL * N);
         for (int v = 0; v < N; ++v) {
             const int pair = (v < N / 2) ? v : ((N - v) & (N / 2 - 1));
@@ -177,6 +192,17 @@ int emu_slab_frame_n(int world, const float* h0k, const float* h0minusk, float L
             }
         }
         rows.h0 = h0.data();
+        // ow_fold_kernel on the slab-local layout: primary row pl, mirror row PL + pl
+        std::vector<float4> hp((size_t)PL * N, make_float4(0, 0, 0, 0)), nyq(PL, make_float4(0, 0, 0, 0));
+        for (int pl = 0; pl < PL; ++pl) {
+            if (r * PL + pl == 0) continue;
+            for (int u = 0; u < N; ++u) {
+                const float4 A = h0[(size_t)pl * N + u], B = h0[(size_t)(PL + pl) * N + ((N - u) & (N - 1))];
+                hp[(size_t)pl * N + u] = fold_pair(A, B);
+                if (u == 0) nyq[pl] = fold_pair_nyq(A, B);
+            }
+        }
+        rows.hp = hp.data(); rows.nyq = nyq.data();
         SlabSink<N> sink{};
         for (int h = 0; h < world; ++h) sink.base[h] = recv[h].data() + (size_t)r * PL * 3 * XH;
         sink.world = world; sink.p0 = r * PL; sink.XL = XL; sink.XH = XH; sink.xl_shift = shift;

@@ -1,6 +1,6 @@
 """torchrun worker for the multi-GPU slab tests: every rank runs SlabOcean over NCCL; rank 0 also runs the single-GPU
-path on the same Philox seed and compares the gathered column slabs with it (they run the same kernels' arithmetic, so
-the comparison is bit for bit).   torchrun --nproc-per-node P tests/slab_worker.py N [frames]"""
+path on the same Philox seed and compares the gathered column slabs with it (same phase functions; agreement to fp32
+round-off, 1e-6 of peak — the single-GPU row kernel is the pipelined variant, so FMA contraction may differ).   torchrun --nproc-per-node P tests/slab_worker.py N [frames]"""
 import os
 import sys
 
@@ -41,8 +41,10 @@ def main():
                 full = {k: sim.gather(k) for k in ("dy", "dx", "dz", "normal", "jacobian")}
             if rank == 0:
                 for k, v in full.items():
-                    same = np.array_equal(v, ref[k])
-                    print(f"[slab N={N} world={world} {transport}] {k}: {'bit-exact' if same else 'MISMATCH max ' + str(np.abs(v - ref[k]).max())}", flush=True)
+                    err = float(np.abs(v - ref[k]).max())
+                    tol = 1e-6 * float(np.abs(ref[k]).max()) + (2e-6 if k in ("normal", "jacobian") else 0.0)
+                    same = err <= tol
+                    print(f"[slab N={N} world={world} {transport}] {k}: max err {err:.3e} (tol {tol:.3e}) {'ok' if same else 'MISMATCH'}", flush=True)
                     ok &= same
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
