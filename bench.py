@@ -35,7 +35,7 @@ METRIC = "ocean frames/sec (spectrum+IFFT+normals)"
 UNIT = "frames/s"
 ALG_BYTES_PER_TEXEL = 44            # read h0k+h0minusk 16 B, write dy,dx,dz 12 B + normal 16 B
 KERNEL_BYTES_PER_TEXEL = {          # compulsory bytes of each kernel of the 3-kernel frame
-    "ow_row_kernel": 16 + 12,       # read h0 (16) -> write Hermitian half-spectra after the row IFFT (12)
+    "ow_row_kernel": 8 + 12,        # read the folded initial spectrum (16 B per texel PAIR) -> write Hermitian half-spectra (12)
     "ow_col_kernel": 12 + 12,       # read intermediate (12) -> write dy,dx,dz (12)
     "ow_normal_kernel": 4 + 16,     # read dy (4) -> write normal (16)
 }
@@ -369,7 +369,19 @@ def run_ours(args):
 
     w = workload_setup(args.workload)
     N, frames = w["N"], w["frames"]
-    slots = min(args.slots or (128 if N <= 512 else 32), frames) if args.workload != "c4" else 64
+    # C4 (BASELINE.json configs[3]): the 64 cascades are SHARDED, a contiguous block of 64/world per GPU,
+    # no data-path collective -> strong scaling (total work fixed). Every other workload replicates per GPU (weak).
+    sharded = args.workload == "c4" and world > 1
+    if sharded:
+        if 64 % world:
+            raise SystemExit("bench.py: c4 shards 64 cascades; --gpus must divide 64")
+        per = 64 // world
+        lo = rank * per
+        w["cascades"], w["noise"] = w["cascades"][lo:lo + per], w["noise"][lo:lo + per]
+        w["cascade_of"], w["times"] = list(range(per)), w["times"][lo:lo + per]
+        frames = w["frames"] = per
+    job_frames = 64 if sharded else world * frames            # frames the WHOLE job produces per step
+    slots = min(args.slots or (128 if N <= 512 else 32), frames) if args.workload != "c4" else frames
     sim = fow.FFTOceanWaves(N=N, cascades=w["cascades"], n_slots=max(slots, len(w["cascades"])), device=local, jacobian=w["jacobian"])
     for i, nz in enumerate(w["noise"]):
         sim.set_noise(nz, cascade=i)
@@ -424,7 +436,7 @@ def run_ours(args):
         tt = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         total_ms = float(tt.item())
-    value = world * frames * args.steps / (total_ms * 1e-3)
+    value = job_frames * args.steps / (total_ms * 1e-3)
 
     if args.profile:
         sim.close()
@@ -463,7 +475,7 @@ def run_ours(args):
                 "bytes_per_launch": kb[KERNELS[dom]] * texels * frames / groups_per_sweep,
                 "kernels": per_kernel,
                 "frame": {"algorithmic_bytes_per_texel": alg, "achieved": frame_gbs, "frac": frame_gbs / peak,
-                          "note": "whole frame on 44 B/texel (48 with Jacobian), per GPU; the 3-kernel design moves 72 B/texel"}}
+                          "note": "whole frame on SURVEY.md's 44 B/texel (48 with Jacobian), per GPU; the 3-kernel design moves 64 B/texel (8+12, 12+12, 4+16) of which 36 are compulsory since the h0 fold"}}
 
     # ---- end to end through the C ABI with HOST buffers --------------------------------------------------
     fbytes = sim.frame_bytes()
@@ -495,7 +507,7 @@ def run_ours(args):
         tt = torch.tensor([e2e_t], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_t = float(tt.item())
-    e2e = {"value": world * frames * e2e_steps / e2e_t, "unit": UNIT,
+    e2e = {"value": job_frames * e2e_steps / e2e_t, "unit": UNIT,
            "h2d_bytes_per_step": int(sum(nz.numel() for nz in pinned_noise)), "d2h_bytes_per_step": int(frames * fbytes),
            "steps": e2e_steps,
            "what": "ow_set_noise + ow_init_spectrum + ow_step_multi + ow_download_frame_async of every frame into pinned host memory"}
@@ -517,13 +529,14 @@ def run_ours(args):
     if rank == 0:
         cpu = cpu_baseline(w) if world == 1 and not args.no_cpu else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": w["desc"], "N": N, "frames_per_step": frames, "slots_per_launch": slots,
+                "config": {"workload": w["desc"], "N": N, "frames_per_step": job_frames if sharded else frames, "slots_per_launch": slots,
                            "launch_groups_per_step": groups_per_sweep,
                            "l2": "flushed between timed steps (256 MiB memset outside the event pair); within a step the outputs "
                                  f"({frames * fbytes / 1e9:.2f} GB) stream through L2, h0 ({16 * texels * len(w['cascades']) / 1e6:.1f} MB) is re-read every frame as in the reference",
-                           "parallelism": f"{world} x independent patch per GPU, no communication",
+                           "parallelism": (f"64 cascades sharded {frames} per GPU over {world} GPUs, no communication" if sharded
+                                           else f"{world} x independent patch per GPU, no communication"),
                            "single_slot_sequential_fps": seq_fps, "wall_s_timed_region": t_wall},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(timed_launches), "roofline": roofline}
         if cpu is not None:

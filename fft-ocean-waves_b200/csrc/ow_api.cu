@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -88,6 +89,10 @@ FrameBuffers buffers(const ow_ctx* c) {
     FrameBuffers fb{};
     fb.N = c->N; fb.h0 = c->d_h0; fb.hp = c->d_hp; fb.nyq = c->d_nyq; fb.ktab = c->d_ktab; fb.casc = c->d_casc; fb.inter = c->d_inter;
     fb.disp = c->d_disp; fb.normal = c->d_normal; fb.jacobian = c->d_jac;
+    // Measured on B200 (profiles/r01d_discard_ab.txt): dropping the consumed intermediate from L2 changes nothing — the
+    // frame is not bound by DRAM write-back — so it stays off; OW_DISCARD=1 turns it on for experiments.
+    static const int discard = getenv("OW_DISCARD") ? 1 : 0;
+    fb.discard_inter = discard;
     return fb;
 }
 

@@ -11,7 +11,7 @@ namespace ow {
 template <int N>
 int g_row_pipe_ctas_per_sm[2] = {0, 0};
 static int g_sm_count = 148;
-static int g_row_classic = -1;   // OW_ROW_KERNEL=classic selects the one-pair-per-CTA kernel (A/B runs, tools)
+static int g_row_classic = -1;   // OW_ROW_KERNEL=classic|pipe overrides the per-N choice Cfg<N>::ROW_PIPE (A/B runs, tools)
 static int g_skip = 0;           // OW_SKIP=[r][c][n]: development switch, leaves kernels out to study their overlap (results invalid)
 
 template <int N>
@@ -36,7 +36,7 @@ cudaError_t configure_n() {
         if (e0 != cudaSuccess) return e0;
         if (g_row_classic < 0) {
             const char* v = getenv("OW_ROW_KERNEL");
-            g_row_classic = (v && v[0] == 'c') ? 1 : 0;
+            g_row_classic = (v && v[0] == 'c') ? 1 : (v && v[0] == 'p') ? 0 : 2;
             const char* k = getenv("OW_SKIP");
             for (; k && *k; ++k) g_skip |= (*k == 'r') ? 1 : (*k == 'c') ? 2 : (*k == 'n') ? 4 : 0;
         }
@@ -111,7 +111,7 @@ int launch_n(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_
     using K = typename C::Col;
     if (ev) cudaEventRecord(ev[0], st);
     if (g_skip & 1) {
-    } else if (g_row_classic == 1) {
+    } else if (g_row_classic == 1 || (g_row_classic == 2 && !C::ROW_PIPE)) {
         const dim3 rgrid(N / 2 / C::ROW_PAIRS, count);
         if (fast_phase)
             ow_row_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true><<<rgrid, R::T * C::ROW_PAIRS, row_smem<R, C::ROW_PAIRS>(), st>>>(fb, tab);

@@ -171,8 +171,10 @@ __global__ void __launch_bounds__(P::T* G, MINB) ow_col_kernel(FrameBuffers fb, 
     const float2* src = fb.inter + ((size_t)slot * 3 + f) * (N / 2) * N + x;
     float* dst = fb.disp + ((size_t)slot * 3 + f) * N * N + x;
     const FullColGeom<N> geom{};
+    // a G=8 tile reads whole 128-byte lines of the intermediate (8 jobs x 16 B): job 0 drops them from L2 after use
+    const bool discard = (G == 8) && job == 0 && fb.discard_inter;
 #pragma unroll 1
-    for (int j = ft; j < P::M / 2; j += P::T) col_phase0<P>(sm, base, j, src, geom);
+    for (int j = ft; j < P::M / 2; j += P::T) col_phase0<P>(sm, base, j, src, geom, discard);
     __syncthreads();
     col_phase1<P>(sm, base, ft);
     __syncthreads();
@@ -223,8 +225,8 @@ struct EmitStaged {
         __syncwarp();
         float4* d = normal + (size_t)y * ostride + xw + lane;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) d[32 * k] = tile[swz(32 * k + lane)];
-        if (JAC) *reinterpret_cast<float4*>(jac + (size_t)y * ostride + xw + 4 * lane) = J;
+        for (int k = 0; k < 4; ++k) __stcs(&d[32 * k], tile[swz(32 * k + lane)]);      // streaming: never re-read on the device
+        if (JAC) __stcs(reinterpret_cast<float4*>(jac + (size_t)y * ostride + xw + 4 * lane), J);
     }
 };
 

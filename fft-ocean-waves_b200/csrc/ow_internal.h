@@ -30,6 +30,7 @@ struct FrameBuffers {
     float* disp;           // [slot][3][N][N]   dy, dx, dz
     float4* normal;        // [slot][N][N]
     float* jacobian;       // [slot][N][N] or nullptr
+    int discard_inter;     // column kernel drops the intermediate's lines from L2 after reading them (no DRAM write-back)
 };
 
 bool frame_supported(int N);

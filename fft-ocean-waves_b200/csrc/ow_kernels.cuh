@@ -29,7 +29,12 @@ namespace ow {
 #define OW_SQRT(a) __fsqrt_rn((a))
 #define OW_RCP(a) __fdividef(1.0f, (a))
 #define OW_LDG(p) __ldg(p)
+// Drop a 128-byte line from L2 WITHOUT writing it back (its contents become undefined). Used on the row->column
+// intermediate once the column kernel has consumed it: nobody reads it again before the next frame's row kernel
+// rewrites the whole line, so the dirty data never has to travel to DRAM.
+#define OW_DISCARD_L2(p) asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory")
 #else
+#define OW_DISCARD_L2(p) ((void)(p))
 #define OW_MUL(a, b) ((a) * (b))
 #define OW_ADD(a, b) ((a) + (b))
 #define OW_SQRT(a) sqrtf((a))
@@ -389,7 +394,7 @@ OW_HD float2 pack_cnj(float4 r) { return make_float2(r.x + r.w, r.z - r.y); }   
 
 template <class P, class Smem, class Geom>
 OW_HD void col_phase0(const Smem& sm, int base, int j /* pair id in [0, M/2) */, const float2* __restrict__ src /* inter[c] + x */,
-                      const Geom& geom) {
+                      const Geom& geom, bool discard_line = false /* this thread drops the 128-B lines it read (job 0 of a G=8 tile) */) {
     constexpr int N = P::N, R0 = P::R0, M = P::M, H = R0 / 2;
     const size_t ss = geom.src_stride();
     const int bA = j, bB = (j == 0) ? M / 2 : M - j;
@@ -413,6 +418,13 @@ OW_HD void col_phase0(const Smem& sm, int base, int j /* pair id in [0, M/2) */,
         for (int i = 1; i < H; ++i) { qa[i] = pack_fwd(la[i]); qa[R0 - i] = pack_cnj(la[i]); }       // v = i*M ; N-v = (R0-i)*M
 #pragma unroll
         for (int i = 0; i < H; ++i) { qb[i] = pack_fwd(lb[i]); qb[R0 - 1 - i] = pack_cnj(lb[i]); }   // v = i*M+M/2
+    }
+    if (discard_line) {     // after the first use of the loaded values: every lane's piece of these lines has arrived
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+            OW_DISCARD_L2(src + (size_t)(i * M + bA) * ss);
+            OW_DISCARD_L2(src + (size_t)(i * M + bB) * ss);
+        }
     }
     float2 tw[R0];
     twiddle_powers<R0>(unit_root(bA, N), tw);

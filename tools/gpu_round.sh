@@ -8,11 +8,11 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > $
 ( timeout 1500 python -m pytest tests -m gpu -x -q > $O/pytest_$TAG.log 2>&1; echo "pytest exit $?" >> $O/pytest_$TAG.log )
 tail -3 $O/pytest_$TAG.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke_$TAG.log 2>&1; tail -2 $O/smoke_$TAG.log
-for w in c2 c3 c4; do
+for w in c2 c3 c4 c5; do
   timeout 600 python bench.py --workload $w > $O/b_$w.json 2> $O/b_$w.err; echo "bench $w exit $?"
 done
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $O/b_ref.json 2> $O/b_ref.err
-python tools/summ.py c2 c3 c4
+python tools/summ.py c2 c3 c4 c5
 # ncu: launch list (shares) for the default workload and C3, then full captures of each kernel at C3
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/launches_c2_$TAG.csv \
     python bench.py --workload c2 --profile --steps 1 --warmup 1 > $O/ncu_c2.log 2>&1

@@ -28,7 +28,11 @@ void run() {
     CK(cudaMemcpyToSymbol(g_ow_trace, &tr, sizeof(tr)));
     fill_h0<<<(unsigned)((nn + 255) / 256), 256>>>(h0, nn);
     fill_ktab<<<(N + 255) / 256, 256>>>(ktab, N, 1000.0f);
-    FrameBuffers fb{N, h0, ktab, nullptr, inter, nullptr, nullptr, nullptr};
+    float4 *hp, *nyq;
+    CK(cudaMalloc(&hp, nn / 2 * 16)); CK(cudaMalloc(&nyq, (size_t)(N / 2) * 16));
+    fill_h0<<<(unsigned)((nn / 2 + 255) / 256), 256>>>(hp, nn / 2);
+    fill_h0<<<(unsigned)((N / 2 + 255) / 256), 256>>>(nyq, N / 2);
+    FrameBuffers fb{N, h0, hp, nyq, ktab, nullptr, inter, nullptr, nullptr, nullptr, 0};
     SlotTable tab{};
     auto k = ow_row_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true>;
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<R, C::ROW_PAIRS>()));

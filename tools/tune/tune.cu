@@ -5,6 +5,7 @@
 // caches are in the steady state of a multi-frame sweep (previous frames' outputs draining from L2).
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -I../../fft-ocean-waves_b200/csrc -o tune tune.cu
 //   ./tune N count [reps]
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <functional>
@@ -22,6 +23,7 @@ struct Ctx {
     FrameBuffers fb;
     SlotTable tab[8];      // rotating output sets: rep r writes set r % nsets, like consecutive frames of a sweep
     mutable int cur = 0;
+    mutable cudaStream_t st = nullptr;   // stream the next launches go to
     cudaEvent_t ev[4];
 };
 
@@ -43,31 +45,45 @@ template <int N> Launch default_row() {
     using C = Cfg<N>; using R = typename C::Row;
     auto k = ow_row_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true>;
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<R, C::ROW_PAIRS>()));
-    return [k](const Ctx& c) { k<<<dim3(N / 2 / C::ROW_PAIRS, c.count), R::T * C::ROW_PAIRS, row_smem<R, C::ROW_PAIRS>()>>>(c.fb, c.tab[c.cur]); };
+    return [k](const Ctx& c) { k<<<dim3(N / 2 / C::ROW_PAIRS, c.count), R::T * C::ROW_PAIRS, row_smem<R, C::ROW_PAIRS>(), c.st>>>(c.fb, c.tab[c.cur]); };
 }
 template <class R, int PAIRS, int MINB> Launch row_variant() {
     auto k = ow_row_kernel<R, PAIRS, MINB, true>;
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<R, PAIRS>()));
-    return [k](const Ctx& c) { k<<<dim3(R::N / 2 / PAIRS, c.count), R::T * PAIRS, row_smem<R, PAIRS>()>>>(c.fb, c.tab[c.cur]); };
+    return [k](const Ctx& c) { k<<<dim3(R::N / 2 / PAIRS, c.count), R::T * PAIRS, row_smem<R, PAIRS>(), c.st>>>(c.fb, c.tab[c.cur]); };
+}
+// persistent pipelined row kernel: grid = min(items, SMs x resident CTAs)
+template <class R, int PAIRS, int MINB> Launch row_pipe_variant() {
+    auto k = ow_row_pipe_kernel<R, PAIRS, MINB, true>;
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<R, PAIRS>()));
+    int per_sm = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, R::T * PAIRS, row_smem<R, PAIRS>()));
+    cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k));
+    printf("    [row pipe PAIRS=%d minb=%d: %d regs, %d CTAs/SM, %zu B local]\n", PAIRS, MINB, fa.numRegs, per_sm, fa.localSizeBytes);
+    return [k, per_sm](const Ctx& c) {
+        const int items = c.count * (R::N / 2 / PAIRS);
+        const int grid = items < 148 * per_sm ? items : 148 * per_sm;
+        k<<<grid, R::T * PAIRS, row_smem<R, PAIRS>(), c.st>>>(c.fb, c.tab[c.cur], items);
+    };
 }
 template <int N> Launch default_col() {
     using C = Cfg<N>; using K = typename C::Col;
     auto k = ow_col_kernel<K, C::COL_G, C::COL_MINB>;
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ColLayout<K, C::COL_G>::SMEM));
     return [k](const Ctx& c) {
-        k<<<dim3(N / (2 * C::COL_G), 3, c.count), K::T * C::COL_G, ColLayout<K, C::COL_G>::SMEM>>>(c.fb, c.tab[c.cur], 0.5f / ((float)N * N));
+        k<<<dim3(N / (2 * C::COL_G), 3, c.count), K::T * C::COL_G, ColLayout<K, C::COL_G>::SMEM, c.st>>>(c.fb, c.tab[c.cur], 0.5f / ((float)N * N));
     };
 }
 template <class K, int G, int MINB> Launch col_variant() {
     auto k = ow_col_kernel<K, G, MINB>;
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ColLayout<K, G>::SMEM));
     return [k](const Ctx& c) {
-        k<<<dim3(K::N / (2 * G), 3, c.count), K::T * G, ColLayout<K, G>::SMEM>>>(c.fb, c.tab[c.cur], 0.5f / ((float)K::N * K::N));
+        k<<<dim3(K::N / (2 * G), 3, c.count), K::T * G, ColLayout<K, G>::SMEM, c.st>>>(c.fb, c.tab[c.cur], 0.5f / ((float)K::N * K::N));
     };
 }
 template <int N, bool JAC, int RY, int WARPS, int MINB> Launch nrm_variant() {
     auto k = ow_normal_kernel<N, JAC, RY, WARPS, MINB>;
-    return [k](const Ctx& c) { k<<<dim3(N / 128, N / (WARPS * RY), c.count), dim3(32, WARPS)>>>(c.fb, c.tab[c.cur]); };
+    return [k](const Ctx& c) { k<<<dim3(N / 128, N / (WARPS * RY), c.count), dim3(32, WARPS), 0, c.st>>>(c.fb, c.tab[c.cur]); };
 }
 
 // Runs the sequence `reps` times and returns the mean duration (us) of each of the three kernels.
@@ -89,6 +105,88 @@ void time_seq(const Ctx& c, const Launch& row, const Launch& col, const Launch& 
     }
 }
 
+// Throughput mode, like ow_step_multi: the output sets are independent frame groups, spread round-robin over 3 streams.
+double time_sweep(const Ctx& c, const Launch& row, const Launch& col, const Launch& nrm) {
+    static cudaStream_t ss[3] = {nullptr, nullptr, nullptr};
+    if (!ss[0]) for (auto& s : ss) CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    double best = 1e30;
+    for (int r = -1; r < 3; ++r) {
+        CK(cudaDeviceSynchronize());
+        cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+        CK(cudaEventRecord(a, ss[0]));
+        CK(cudaStreamWaitEvent(ss[1], a, 0)); CK(cudaStreamWaitEvent(ss[2], a, 0));
+        const int groups = 8 * c.nsets;
+        for (int g = 0; g < groups; ++g) {
+            c.cur = g % c.nsets; c.st = ss[g % 3];
+            row(c); col(c); nrm(c);
+        }
+        cudaEvent_t j1, j2; cudaEventCreate(&j1); cudaEventCreate(&j2);
+        CK(cudaEventRecord(j1, ss[1])); CK(cudaEventRecord(j2, ss[2]));
+        CK(cudaStreamWaitEvent(ss[0], j1, 0)); CK(cudaStreamWaitEvent(ss[0], j2, 0));
+        CK(cudaEventRecord(b, ss[0]));
+        CK(cudaEventSynchronize(b));
+        CK(cudaGetLastError());
+        float ms; CK(cudaEventElapsedTime(&ms, a, b));
+        if (r >= 0) best = std::min(best, (double)ms * 1e3 / (groups * c.count));
+        cudaEventDestroy(a); cudaEventDestroy(b); cudaEventDestroy(j1); cudaEventDestroy(j2);
+    }
+    c.st = nullptr;
+    return best;   // us per frame
+}
+
+#ifdef TUNE_SWEEP
+template <int N>
+void sweep(Ctx& c) {
+    using C = Cfg<N>; using R = typename C::Row; using K = typename C::Col;
+    const Launch rowc = default_row<N>(), col0 = default_col<N>();
+    const Launch nrm0 = nrm_variant<N, true, C::NRM_RY, C::NRM_WARPS, C::NRM_MINB>();
+    const Launch nrm1 = nrm_variant<N, false, C::NRM_RY, C::NRM_WARPS, C::NRM_MINB>();
+    const Launch none = [](const Ctx&) {};
+    auto rep = [&](const char* what, const Launch& r, const Launch& k, const Launch& n) {
+        printf("%-54s %8.2f us/frame\n", what, time_sweep(c, r, k, n)); fflush(stdout);
+    };
+    const Launch rowp = row_pipe_variant<R, C::ROW_PAIRS, C::ROW_MINB>();
+    rep("all: classic row, default col, normal+J", rowc, col0, nrm0);
+    rep("all: pipe row,    default col, normal+J", rowp, col0, nrm0);
+    rep("all: pipe row,    default col, normal (no J)", rowp, col0, nrm1);
+#ifdef TUNE_SWEEP_BRIEF
+    rep("col only: default", none, col0, none);
+    return;
+#endif
+    rep("row only: classic", rowc, none, none);
+    rep("row only: pipe (config)", rowp, none, none);
+#define RP(PAIRS, MB) rep("row only: pipe PAIRS=" #PAIRS " minb=" #MB, row_pipe_variant<R, PAIRS, MB>(), none, none);
+#define RC(PAIRS, MB) rep("row only: classic PAIRS=" #PAIRS " minb=" #MB, row_variant<R, PAIRS, MB>(), none, none);
+    RP(1, 2) RP(1, 3) RP(1, 4) RP(1, 5) RP(2, 2) RP(2, 3)
+    RC(1, 3) RC(1, 4) RC(1, 5) RC(1, 6) RC(2, 2) RC(2, 3)
+    if (N <= 1024) { RP(4, 1) RP(4, 2) RP(4, 3) RP(4, 4) RC(4, 3) RC(4, 4) }
+    {   // twice the threads per line (half the work per thread)
+        using R2x = Plan<N, R::R0, R::R1, R::R2, 2 * R::T, R::S1 - R::R2, R::S0 - R::R1 * R::S1>;
+#define RC2(PAIRS, MB) rep("row only: classic 2xT PAIRS=" #PAIRS " minb=" #MB, row_variant<R2x, PAIRS, MB>(), none, none);
+#define RP2(PAIRS, MB) rep("row only: pipe 2xT PAIRS=" #PAIRS " minb=" #MB, row_pipe_variant<R2x, PAIRS, MB>(), none, none);
+        RC2(1, 2) RC2(1, 3) RC2(1, 4) RC2(2, 2) RC2(2, 3) RP2(1, 2) RP2(1, 3) RP2(2, 2)
+        if (N <= 1024) { RC2(4, 1) RC2(4, 2) RC2(1, 8) RC2(2, 4) }
+        using K2x = Plan<N, K::R0, K::R1, K::R2, 2 * K::T, K::S1 - K::R2, K::S0 - K::R1 * K::S1>;
+        rep("all: classic 2xT P1 minb3 row, default col, normal", row_variant<R2x, 1, 3>(), col0, nrm1);
+        rep("all: classic P1 minb4 row, default col, normal", row_variant<R, 1, 4>(), col0, nrm1);
+        rep("all: classic cfg row, default col, normal", rowc, col0, nrm1);
+        rep("all: pipe cfg row, default col, normal", rowp, col0, nrm1);
+        rep("all: pipe P1 minb4 row, default col, normal", row_pipe_variant<R, 1, 4>(), col0, nrm1);
+        rep("all: pipe cfg row, 2xT G8 col, normal", rowp, col_variant<K2x, 8, 1>(), nrm1);
+        rep("all: classic P1 minb4 row, 2xT G8 col, normal", row_variant<R, 1, 4>(), col_variant<K2x, 8, 1>(), nrm1);
+    }
+    rep("col only: default", none, col0, none);
+#define CV(G, MB) rep("col only: G=" #G " minb=" #MB, none, col_variant<K, G, MB>(), none);
+    CV(8, 1) CV(8, 2) CV(4, 1) CV(4, 2) CV(4, 3) CV(4, 4)
+    {
+        using K2x = Plan<N, K::R0, K::R1, K::R2, 2 * K::T, K::S1 - K::R2, K::S0 - K::R1 * K::S1>;
+#define CV2(G, MB) rep("col only: 2xT G=" #G " minb=" #MB, none, col_variant<K2x, G, MB>(), none);
+        CV2(8, 1) CV2(4, 1) CV2(4, 2)
+    }
+    rep("normal+J only", none, none, nrm0);
+    rep("normal only", none, none, nrm1);
+}
+#else
 template <int N>
 void sweep(Ctx& c) {
     const Launch row0 = default_row<N>(), col0 = default_col<N>();
@@ -135,6 +233,8 @@ void sweep(Ctx& c) {
     COLV(4, 1) COLV(4, 2) COLV(4, 3) COLV(4, 4) COLV(2, 2) COLV(2, 4) COLV(2, 6) COLV(8, 1) COLV(8, 2)
 }
 
+#endif
+
 int main(int argc, char** argv) {
     Ctx c{};
     c.N = argc > 1 ? atoi(argv[1]) : 2048;
@@ -156,7 +256,13 @@ int main(int argc, char** argv) {
     fill_ktab<<<(c.N + 255) / 256, 256>>>(ktab, c.N, 1000.0f);
     CascadeDev cd{1000.0f, 40.0f, 0.7071f, 0.7071f, 2.0f, 0.1f, 1.0f, 0.0f};
     CK(cudaMemcpy(casc, &cd, sizeof(cd), cudaMemcpyHostToDevice));
-    c.fb = FrameBuffers{c.N, h0, ktab, casc, inter, disp, normal, jac};
+    float4 *hp, *nyq;
+    CK(cudaMalloc(&hp, nn / 2 * sizeof(float4)));
+    CK(cudaMalloc(&nyq, (size_t)(c.N / 2) * sizeof(float4)));
+    fill_h0<<<(unsigned)((nn / 2 + 255) / 256), 256>>>(hp, nn / 2, 777u);     // timing only: any finite coefficients do
+    fill_h0<<<(unsigned)((c.N / 2 + 255) / 256), 256>>>(nyq, c.N / 2, 778u);
+    c.fb = FrameBuffers{c.N, h0, hp, nyq, ktab, casc, inter, disp, normal, jac, argc > 4 ? atoi(argv[4]) : 1};
+    printf("discard_inter = %d\n", c.fb.discard_inter);
     for (int k = 0; k < c.nsets; ++k)
         for (int i = 0; i < c.count; ++i) { c.tab[k].cascade[i] = 0; c.tab[k].time[i] = 1.0f + i / 60.0f; c.tab[k].slot[i] = k * c.count + i; }
     for (auto& e : c.ev) CK(cudaEventCreate(&e));
