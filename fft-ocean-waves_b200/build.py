@@ -20,6 +20,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 # (source, extra flags). The init kernels keep the shader's unfused fp32 operation order.
 SOURCES = [
     ("ow_frame_kernels.cu", []),
+    ("ow_big_kernels.cu", []),
     ("ow_init_kernels.cu", ["-fmad=false"]),
     ("ow_api.cu", []),
     ("ow_slab.cu", []),

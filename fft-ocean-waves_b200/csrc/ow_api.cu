@@ -93,6 +93,7 @@ FrameBuffers buffers(const ow_ctx* c) {
     // frame is not bound by DRAM write-back — so it stays off; OW_DISCARD=1 turns it on for experiments.
     static const int discard = getenv("OW_DISCARD") ? 1 : 0;
     fb.discard_inter = discard;
+    fb.four_step = (c->flags & OW_FLAG_FOUR_STEP) ? 1 : 0;
     return fb;
 }
 
@@ -140,7 +141,9 @@ int ow_create(int32_t N, int32_t n_cascades, int32_t n_slots, const ow_params* c
               uint32_t flags, ow_ctx** out) {
     if (!out) return fail(nullptr, OW_ERR_INVALID, "ow_create: out is NULL");
     *out = nullptr;
-    if (!frame_supported(N)) return fail(nullptr, OW_ERR_INVALID, "ow_create: N must be 256, 512, 1024, 2048 or 4096");
+    if (!frame_supported(N)) return fail(nullptr, OW_ERR_INVALID, "ow_create: N must be a power of two in [256, 32768]");
+    if ((flags & OW_FLAG_FOUR_STEP) && !big_supported(N, true))
+        return fail(nullptr, OW_ERR_INVALID, "ow_create: OW_FLAG_FOUR_STEP is a test mode for N = 1024 or 2048");
     if (n_cascades < 1 || !cascades) return fail(nullptr, OW_ERR_INVALID, "ow_create: need >= 1 cascade");
     if (n_slots < n_cascades) return fail(nullptr, OW_ERR_INVALID, "ow_create: n_slots must be >= n_cascades");
     for (int i = 0; i < n_cascades; ++i)

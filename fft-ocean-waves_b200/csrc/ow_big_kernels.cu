@@ -1,0 +1,128 @@
+// ow_big_kernels.cu — launchers for grids whose lines do not fit one CTA's shared memory: N = A * B, B <= 4096
+// (N = 8192, 16384, 32768: BASELINE config C5 at its quoted size), plus the same code path forced onto small grids
+// (OW_FLAG_FOUR_STEP: N = 1024 as 4 x 256, N = 2048 as 4 x 512) so that the tests can compare it with the direct kernels.
+// Kernel bodies: "LINES LONGER THAN ONE CTA'S SHARED MEMORY" in ow_kernels.cuh.
+#include "ow_frame_kernels.cuh"
+
+namespace ow {
+
+namespace {
+
+template <int B, int A>
+struct Big {
+    static constexpr int N = A * B;
+    using C = Cfg<B>;
+    using R = typename C::Row;
+    using K = typename C::Col;
+    static constexpr int G = C::COL_G;
+    static constexpr int RY = 8, WARPS = 4, NMINB = 4;
+
+    static cudaError_t configure() {
+        cudaError_t e = cudaFuncSetAttribute(ow_bigrow_kernel<R, A, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<R, 1>());
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(ow_bigrow_kernel<R, A, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<R, 1>());
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(ow_bigrow_slab_kernel<R, A, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<R, 1>());
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(ow_bigrow_slab_kernel<R, A, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<R, 1>());
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(ow_bigcol_kernel<K, A, G, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ColLayout<K, G>::SMEM);
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(ow_bigcol_slab_kernel<K, A, G, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ColLayout<K, G>::SMEM);
+    }
+
+    static int frame(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_jac, bool fast, cudaStream_t st, cudaEvent_t* ev) {
+        if (ev) cudaEventRecord(ev[0], st);
+        const dim3 rgrid((N / 2) * A, count);
+        if (fast) ow_bigrow_kernel<R, A, 1, true><<<rgrid, R::T, row_smem<R, 1>(), st>>>(fb, tab);
+        else ow_bigrow_kernel<R, A, 1, false><<<rgrid, R::T, row_smem<R, 1>(), st>>>(fb, tab);
+        if (ev) cudaEventRecord(ev[1], st);
+        const float scale = 0.5f / ((float)N * (float)N);
+        ow_bigcol_kernel<K, A, G, 1><<<dim3(N / (2 * G) * A, 3, count), K::T * G, ColLayout<K, G>::SMEM, st>>>(fb, tab, scale);
+        if (ev) cudaEventRecord(ev[2], st);
+        const dim3 ngrid(N / 128, N / (WARPS * RY), count);
+        if (with_jac) ow_normal_kernel<N, true, RY, WARPS, NMINB><<<ngrid, dim3(32, WARPS), 0, st>>>(fb, tab);
+        else ow_normal_kernel<N, false, RY, WARPS, NMINB><<<ngrid, dim3(32, WARPS), 0, st>>>(fb, tab);
+        if (ev) cudaEventRecord(ev[3], st);
+        return cudaGetLastError() == cudaSuccess ? 3 : -1;
+    }
+
+    static bool slab_ok(int world) {
+        if (world < 1 || world > kMaxWorld || (N / 2) % world) return false;
+        const int XL = N / world, XH = XL + 2 * kHalo;
+        return XH % (2 * G) == 0 && XL % 128 == 0 && (XL & (XL - 1)) == 0;
+    }
+
+    static int slab_rows(const SlabGeom& g, const float4* h0_loc, const float4* hp_loc, const float4* nyq_loc, const float* ktab,
+                         float2* const sink_base[kSlabMaxWorld], float t, bool fast, cudaStream_t st) {
+        SlabRows<N> rows{h0_loc, hp_loc, nyq_loc, g.rank * g.PL, g.PL};
+        SlabSink<N> sink{};
+        for (int h = 0; h < g.world; ++h) sink.base[h] = sink_base[h];
+        sink.world = g.world; sink.p0 = g.rank * g.PL; sink.XL = g.XL; sink.XH = g.XH;
+        sink.xl_shift = 0;
+        while ((1 << sink.xl_shift) < g.XL) ++sink.xl_shift;
+        const dim3 grid(g.PL * A);
+        if (fast) ow_bigrow_slab_kernel<R, A, 1, true><<<grid, R::T, row_smem<R, 1>(), st>>>(rows, ktab, sink, t);
+        else ow_bigrow_slab_kernel<R, A, 1, false><<<grid, R::T, row_smem<R, 1>(), st>>>(rows, ktab, sink, t);
+        return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    }
+
+    static int slab_cols(const SlabGeom& g, const float2* recv, float* disp_loc, float4* normal_loc, float* jac_loc, float jac_scale,
+                         cudaStream_t st) {
+        const float scale = 0.5f / ((float)N * (float)N);
+        ow_bigcol_slab_kernel<K, A, G, 1><<<dim3(g.XH / (2 * G) * A, 3), K::T * G, ColLayout<K, G>::SMEM, st>>>(recv, disp_loc, g.XH, scale);
+        const dim3 ngrid(g.XL / 128, N / (WARPS * RY));
+        if (jac_loc) ow_normal_slab_kernel<N, true, RY, WARPS, NMINB><<<ngrid, dim3(32, WARPS), 0, st>>>(disp_loc, normal_loc, jac_loc, g.XL, g.XH, jac_scale);
+        else ow_normal_slab_kernel<N, false, RY, WARPS, NMINB><<<ngrid, dim3(32, WARPS), 0, st>>>(disp_loc, normal_loc, nullptr, g.XL, g.XH, 0.f);
+        return cudaGetLastError() == cudaSuccess ? 2 : -1;
+    }
+};
+
+// (N, forced) -> instantiation. Forced four-step exists for N = 1024 (4 x 256) and N = 2048 (4 x 512).
+#define OW_BIG_DISPATCH(N_, forced_, CALL)                                   \
+    do {                                                                     \
+        if (!(forced_)) {                                                    \
+            if ((N_) == 8192) return Big<4096, 2>::CALL;                     \
+            if ((N_) == 16384) return Big<4096, 4>::CALL;                    \
+            if ((N_) == 32768) return Big<4096, 8>::CALL;                    \
+        } else {                                                             \
+            if ((N_) == 1024) return Big<256, 4>::CALL;                      \
+            if ((N_) == 2048) return Big<512, 4>::CALL;                      \
+        }                                                                    \
+    } while (0)
+
+}  // namespace
+
+bool big_supported(int N, bool forced) {
+    return forced ? (N == 1024 || N == 2048) : (N == 8192 || N == 16384 || N == 32768);
+}
+
+cudaError_t configure_big(int N, bool forced) {
+    OW_BIG_DISPATCH(N, forced, configure());
+    return cudaErrorInvalidValue;
+}
+
+int launch_big_frame(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_jac, bool fast, cudaStream_t st, cudaEvent_t* ev,
+                     bool forced) {
+    OW_BIG_DISPATCH(fb.N, forced, frame(fb, tab, count, with_jac, fast, st, ev));
+    return -1;
+}
+
+bool big_slab_supported(int N, int world, bool forced) {
+    OW_BIG_DISPATCH(N, forced, slab_ok(world));
+    return false;
+}
+
+int launch_big_slab_rows(const SlabGeom& g, const float4* h0_loc, const float4* hp_loc, const float4* nyq_loc, const float* ktab,
+                         float2* const sink_base[kSlabMaxWorld], float t, bool fast, cudaStream_t st, bool forced) {
+    OW_BIG_DISPATCH(g.N, forced, slab_rows(g, h0_loc, hp_loc, nyq_loc, ktab, sink_base, t, fast, st));
+    return -1;
+}
+
+int launch_big_slab_cols(const SlabGeom& g, const float2* recv, float* disp_loc, float4* normal_loc, float* jac_loc, float jac_scale,
+                         cudaStream_t st, bool forced) {
+    OW_BIG_DISPATCH(g.N, forced, slab_cols(g, recv, disp_loc, normal_loc, jac_loc, jac_scale, st));
+    return -1;
+}
+
+}  // namespace ow

@@ -140,9 +140,14 @@ int launch_n(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_
     return cudaGetLastError() == cudaSuccess ? 3 : -1;
 }
 
-bool frame_supported(int N) { return N == 256 || N == 512 || N == 1024 || N == 2048 || N == 4096; }
+bool frame_supported(int N) { return N == 256 || N == 512 || N == 1024 || N == 2048 || N == 4096 || big_supported(N, false); }
 
 cudaError_t configure_frame_kernels(int N) {
+    if (big_supported(N, false)) return configure_big(N, false);
+    if (big_supported(N, true)) {
+        cudaError_t e = configure_big(N, true);
+        if (e != cudaSuccess) return e;
+    }
     switch (N) {
         case 256: return configure_n<256>();
         case 512: return configure_n<512>();
@@ -154,6 +159,7 @@ cudaError_t configure_frame_kernels(int N) {
 }
 
 bool slab_supported(int N, int world) {
+    if (big_supported(N, false)) return big_slab_supported(N, world, false);
     switch (N) {
         case 256: return slab_ok<256>(world);
         case 512: return slab_ok<512>(world);
@@ -166,6 +172,7 @@ bool slab_supported(int N, int world) {
 
 int launch_slab_rows(const SlabGeom& g, const float4* h0_loc, const float4* hp_loc, const float4* nyq_loc, const float* ktab,
                      float2* const sink_base[kSlabMaxWorld], float t, bool fast_phase, cudaStream_t st) {
+    if (big_supported(g.N, false)) return launch_big_slab_rows(g, h0_loc, hp_loc, nyq_loc, ktab, sink_base, t, fast_phase, st, false);
     switch (g.N) {
         case 256: return slab_rows_n<256>(g, h0_loc, hp_loc, nyq_loc, ktab, sink_base, t, fast_phase, st);
         case 512: return slab_rows_n<512>(g, h0_loc, hp_loc, nyq_loc, ktab, sink_base, t, fast_phase, st);
@@ -178,6 +185,7 @@ int launch_slab_rows(const SlabGeom& g, const float4* h0_loc, const float4* hp_l
 
 int launch_slab_cols(const SlabGeom& g, const float2* recv, float* disp_loc, float4* normal_loc, float* jac_loc, float jac_scale,
                      cudaStream_t st) {
+    if (big_supported(g.N, false)) return launch_big_slab_cols(g, recv, disp_loc, normal_loc, jac_loc, jac_scale, st, false);
     switch (g.N) {
         case 256: return slab_cols_n<256>(g, recv, disp_loc, normal_loc, jac_loc, jac_scale, st);
         case 512: return slab_cols_n<512>(g, recv, disp_loc, normal_loc, jac_loc, jac_scale, st);
@@ -189,6 +197,8 @@ int launch_slab_cols(const SlabGeom& g, const float2* recv, float* disp_loc, flo
 }
 
 int launch_frame(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_jac, bool fast_phase, cudaStream_t st, cudaEvent_t* ev) {
+    if (big_supported(fb.N, false)) return launch_big_frame(fb, tab, count, with_jac, fast_phase, st, ev, false);
+    if (fb.four_step && big_supported(fb.N, true)) return launch_big_frame(fb, tab, count, with_jac, fast_phase, st, ev, true);
     switch (fb.N) {
         case 256: return launch_n<256>(fb, tab, count, with_jac, fast_phase, st, ev);
         case 512: return launch_n<512>(fb, tab, count, with_jac, fast_phase, st, ev);

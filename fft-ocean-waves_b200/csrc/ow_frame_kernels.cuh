@@ -204,6 +204,85 @@ __global__ void __launch_bounds__(P::T* G, MINB) ow_col_slab_kernel(const float2
     col_phase2<P>(sm, base, ft, dst, scale, geom);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// N = A * B > 4096: one CTA per (row pair, sub-line ka) / (column tile, sub-line ka); see "LINES LONGER THAN ONE CTA'S
+// SHARED MEMORY" in ow_kernels.cuh. P is the sub-line plan (P::N = B).
+// ---------------------------------------------------------------------------------------------------
+template <class P, int A, int MINB, bool FAST>
+__global__ void __launch_bounds__(P::T, MINB) ow_bigrow_kernel(FrameBuffers fb, SlotTable tab) {
+    extern __shared__ __align__(16) float2 smem[];
+    constexpr int N = A * P::N;
+    const int ft = threadIdx.x;
+    const int p = blockIdx.x / A, ka = blockIdx.x % A;
+    const int e = blockIdx.y;
+    const int cascade = tab.cascade[e];
+    const SmemDirect sm{smem};
+    const FullRows<N> rows{fb.h0 + (size_t)cascade * N * N, fb.hp + (size_t)cascade * (N / 2) * N, fb.nyq + (size_t)cascade * (N / 2)};
+    bigrow_phase0<P, A, FAST>(sm, ft, p, ka, rows, fb.ktab + (size_t)cascade * N, tab.time[e]);
+    __syncthreads();
+    row_phase1<P>(sm, ft);
+    __syncthreads();
+    bigrow_phase2<P, A>(sm, ft, p, ka, FullSink<N>{fb.inter + (size_t)tab.slot[e] * 3 * (N / 2) * N});
+}
+
+template <class P, int A, int MINB, bool FAST>
+__global__ void __launch_bounds__(P::T, MINB) ow_bigrow_slab_kernel(SlabRows<A * P::N> rows, const float* __restrict__ ktab,
+                                                                    SlabSink<A * P::N> sink, float t) {
+    extern __shared__ __align__(16) float2 smem[];
+    const int ft = threadIdx.x;
+    const int p = rows.p0 + blockIdx.x / A, ka = blockIdx.x % A;
+    const SmemDirect sm{smem};
+    bigrow_phase0<P, A, FAST>(sm, ft, p, ka, rows, ktab, t);
+    __syncthreads();
+    row_phase1<P>(sm, ft);
+    __syncthreads();
+    bigrow_phase2<P, A>(sm, ft, p, ka, sink);
+}
+
+template <class P, int A, int G, int MINB>
+__global__ void __launch_bounds__(P::T* G, MINB) ow_bigcol_kernel(FrameBuffers fb, SlotTable tab, float scale) {
+    extern __shared__ __align__(16) float2 smem[];
+    constexpr int N = A * P::N;
+    using LY = ColLayout<P, G>;
+    const int job = threadIdx.x % G, ft = threadIdx.x / G;
+    const int tile = blockIdx.x / A, ka = blockIdx.x % A;
+    const int x = 2 * (tile * G + job);
+    const int f = blockIdx.y;
+    const int slot = tab.slot[blockIdx.z];
+    const SmemDirect sm{smem};
+    const int base = job * LY::SJ;
+    const float2* src = fb.inter + ((size_t)slot * 3 + f) * (N / 2) * N + x;
+    float* dst = fb.disp + ((size_t)slot * 3 + f) * N * N + x;
+    const FullColGeom<N> geom{};
+    bigcol_phase0<P, A>(sm, base, ft, ka, src, geom);
+    __syncthreads();
+    col_phase1<P>(sm, base, ft);
+    __syncthreads();
+    bigcol_phase2<P, A>(sm, base, ft, ka, dst, scale, geom);
+}
+
+template <class P, int A, int G, int MINB>
+__global__ void __launch_bounds__(P::T* G, MINB) ow_bigcol_slab_kernel(const float2* __restrict__ recv, float* __restrict__ disp, int XH,
+                                                                       float scale) {
+    extern __shared__ __align__(16) float2 smem[];
+    constexpr int N = A * P::N;
+    using LY = ColLayout<P, G>;
+    const int job = threadIdx.x % G, ft = threadIdx.x / G;
+    const int tile = blockIdx.x / A, ka = blockIdx.x % A;
+    const int x = 2 * (tile * G + job);
+    const int f = blockIdx.y;
+    const SmemDirect sm{smem};
+    const int base = job * LY::SJ;
+    const float2* src = recv + (size_t)f * XH + x;
+    float* dst = disp + (size_t)f * N * XH + x;
+    const SlabColGeom geom{(size_t)3 * XH, (size_t)XH};
+    bigcol_phase0<P, A>(sm, base, ft, ka, src, geom);
+    __syncthreads();
+    col_phase1<P>(sm, base, ft);
+    __syncthreads();
+    bigcol_phase2<P, A>(sm, base, ft, ka, dst, scale, geom);
+}
+
 constexpr int kNormalRows = 8;      // output rows per thread of the normal kernel's walk
 constexpr int kNormalWarps = 4;     // warps per CTA; each warp owns a 128-column x kNormalRows-row tile
 

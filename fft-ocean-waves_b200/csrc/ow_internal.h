@@ -31,9 +31,15 @@ struct FrameBuffers {
     float4* normal;        // [slot][N][N]
     float* jacobian;       // [slot][N][N] or nullptr
     int discard_inter;     // column kernel drops the intermediate's lines from L2 after reading them (no DRAM write-back)
+    int four_step;         // force the N = A*B line decomposition (ow_big_kernels.cu) on a grid the direct kernels could do
 };
 
-bool frame_supported(int N);
+bool frame_supported(int N);            // direct kernels (N <= 4096) or the N = A*B decomposition (8192 .. 32768)
+// N = A*B line decomposition (ow_big_kernels.cu). forced: the test-only mapping of N = 1024 / 2048 onto it.
+bool big_supported(int N, bool forced);
+cudaError_t configure_big(int N, bool forced);
+int launch_big_frame(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_jacobian, bool fast_phase, cudaStream_t st,
+                     cudaEvent_t* ev, bool forced);
 // Launch the three frame kernels for `count` table entries. Returns number of kernels launched (<0: error).
 // ev (optional): 4 events recorded before the row kernel and after each of the three kernels.
 // fast_phase: every |w*t| of this launch is below kFastPhaseLimit, so the SFU sin/cos path is accurate enough.
@@ -59,6 +65,12 @@ int launch_slab_rows(const SlabGeom& g, const float4* h0_loc, const float4* hp_l
 // interior columns -> normal_loc[N][XL], jac_loc[N][XL]. jac_scale = choppiness * N / (2 L).
 int launch_slab_cols(const SlabGeom& g, const float2* recv, float* disp_loc, float4* normal_loc, float* jac_loc, float jac_scale,
                      cudaStream_t st);
+
+bool big_slab_supported(int N, int world, bool forced);
+int launch_big_slab_rows(const SlabGeom& g, const float4* h0_loc, const float4* hp_loc, const float4* nyq_loc, const float* ktab,
+                         float2* const sink_base[kSlabMaxWorld], float t, bool fast_phase, cudaStream_t st, bool forced);
+int launch_big_slab_cols(const SlabGeom& g, const float2* recv, float* disp_loc, float4* normal_loc, float* jac_loc, float jac_scale,
+                         cudaStream_t st, bool forced);
 
 // Init-time kernels (ow_init_kernels.cu)
 cudaError_t launch_noise_seed(uint8_t* noise /* [4][N][N] */, int N, uint64_t seed, cudaStream_t st);

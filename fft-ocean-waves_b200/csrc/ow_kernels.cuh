@@ -473,6 +473,144 @@ OW_HD void col_phase2(const Smem& sm, int base, int ft, float* __restrict__ dst 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// LINES LONGER THAN ONE CTA'S SHARED MEMORY:  N = A * B with B = P::N <= 4096 and A in {2, 4, 8}  (N = 8192 .. 32768,
+// BASELINE config C5). Cooley-Tukey split n = a*B + m, k = ka + A*kb of the same unnormalised inverse DFT:
+//     X[ka + A*kb] = sum_m [ W_N^{m ka} * sum_a x[a*B + m] W_A^{a ka} ] W_B^{m kb},      W_n = e^{+2 pi i / n}
+// One CTA (row kernel: one thread group) owns sub-line ka of a line. Its stage-0 loader forms
+//     y_ka[m] = W_N^{m ka} * sum_a x[a*B + m] W_A^{a ka}
+// on the fly from the A source elements, the three in-CTA stages then transform the length-B sub-line exactly as for
+// N = B, and the stores scatter to k = ka + A*kb. Each of the A sub-line CTAs re-derives the radix-A sums (for rows:
+// re-evaluates the spectrum) instead of passing them through a scratch array in HBM; the A CTAs of one line run
+// back to back, so the source is read from DRAM once and from L2 afterwards. Written for a small register footprint
+// (rolled loops, butterfly inputs parked in local memory): these sizes are bound by their HBM footprint and the
+// NVLink transpose, not by this loader.
+// ---------------------------------------------------------------------------------------------------
+template <class P, int A, bool FAST, class Rows>
+OW_HD Sym3 big_row_element(const Rows& rows, const float* __restrict__ ktab, int p, int u, float ky, float t) {
+    constexpr int N = A * P::N;
+    if (p != 0) {
+        const FoldedPair fp = load_folded(rows.pair_row(p), ktab, u);
+        return spectrum_folded<FAST>(fp, ky, t, u == 0 ? rows.nyq_of(p) : nullptr);
+    }
+    // pair 0: rows 0 and N/2 are their own mirrors; Z = S(., 0) + i*S(., N/2) (see row_phase0_pair0)
+    const float4* row0 = rows.row(0);
+    const float4* rowh = rows.row(N / 2);
+    const Sym3 a = spectrum_sym<FAST>(load_pair<N>(row0, row0, ktab, u), u, OW_LDG(ktab), true, t);
+    const Sym3 q = spectrum_sym<FAST>(load_pair<N>(rowh, rowh, ktab, u), u, OW_LDG(ktab + N / 2), true, t);
+    Sym3 o;
+    o.y = make_float2(a.y.x - q.y.y, a.y.y + q.y.x);
+    o.x = make_float2(a.x.x - q.x.y, a.x.y + q.x.x);
+    o.z = make_float2(a.z.x - q.z.y, a.z.y + q.z.x);
+    return o;
+}
+
+template <class P, int A, bool FAST, class Smem, class Rows>
+__host__ __device__ __noinline__ void bigrow_phase0(const Smem& sm, int ft, int p, int ka, const Rows& rows, const float* __restrict__ ktab, float t) {
+    constexpr int B = P::N, N = A * B, R0 = P::R0;
+    float2 wa[A];
+    twiddle_powers<A>(unit_root(ka, A), wa);            // W_A^{a ka}
+    const float ky = OW_LDG(ktab + p);
+#pragma unroll 1
+    for (int c = 0; c < P::C0; ++c) {
+        const int b = ft + P::T * c;
+        if (b >= P::M) break;
+        float2 v[3][R0];
+#pragma unroll 1
+        for (int d0 = 0; d0 < R0; ++d0) {
+            const int m = d0 * P::M + b;
+            float2 ay = make_float2(0.f, 0.f), ax = ay, az = ay;
+#pragma unroll
+            for (int a = 0; a < A; ++a) {
+                const Sym3 s = big_row_element<P, A, FAST>(rows, ktab, p, a * B + m, ky, t);
+                ay = cadd(ay, cmul(s.y, wa[a])); ax = cadd(ax, cmul(s.x, wa[a])); az = cadd(az, cmul(s.z, wa[a]));
+            }
+            const float2 w = unit_root(m * ka, N);       // W_N^{m ka}
+            v[0][d0] = cmul(ay, w); v[1][d0] = cmul(ax, w); v[2][d0] = cmul(az, w);
+        }
+        float2 tw[R0];
+        twiddle_powers<R0>(unit_root(b, B), tw);
+#pragma unroll 1
+        for (int f = 0; f < 3; ++f) {
+            float2 w[R0];
+#pragma unroll
+            for (int d0 = 0; d0 < R0; ++d0) w[d0] = v[f][d0];
+            stage0_finish<P>(sm, f * P::LINE, b, w, tw);
+        }
+    }
+}
+
+template <class P, int A, class Smem, class Sink>
+OW_HD void bigrow_phase2(const Smem& sm, int ft, int p, int ka, const Sink& sink) {
+#pragma unroll 1
+    for (int c = 0; c < P::C2; ++c) {
+        const int bp = ft + P::T * c;
+        if (bp >= P::B2) break;
+#pragma unroll 1
+        for (int f = 0; f < 3; ++f) {
+            float2 v[P::R2];
+            stage2<P>(sm, f * P::LINE, bp, v);
+#pragma unroll
+            for (int k2 = 0; k2 < P::R2; ++k2) sink.put(f, p, ka + A * (bp + k2 * P::B2), v[k2]);
+        }
+    }
+}
+
+// Column source element Q_v of the Hermitian-packed intermediate (see the COLUMN KERNEL comment): v in [0, N).
+template <int N>
+OW_HD float2 col_source(const float2* __restrict__ src /* inter[c] + x */, size_t ss, int v) {
+    if (v == 0 || v == N / 2) {
+        const float4 r = OW_LDG(reinterpret_cast<const float4*>(src));
+        return v == 0 ? make_float2(r.x, r.z) : make_float2(r.y, r.w);
+    }
+    if (v < N / 2) return pack_fwd(OW_LDG(reinterpret_cast<const float4*>(src + (size_t)v * ss)));
+    return pack_cnj(OW_LDG(reinterpret_cast<const float4*>(src + (size_t)(N - v) * ss)));
+}
+
+template <class P, int A, class Smem, class Geom>
+__host__ __device__ __noinline__ void bigcol_phase0(const Smem& sm, int base, int ft, int ka, const float2* __restrict__ src, const Geom& geom) {
+    constexpr int B = P::N, N = A * B, R0 = P::R0;
+    const size_t ss = geom.src_stride();
+    float2 wa[A];
+    twiddle_powers<A>(unit_root(ka, A), wa);
+#pragma unroll 1
+    for (int b = ft; b < P::M; b += P::T) {
+        float2 v[R0];
+#pragma unroll 1
+        for (int d0 = 0; d0 < R0; ++d0) {
+            const int m = d0 * P::M + b;
+            float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int a = 0; a < A; ++a) acc = cadd(acc, cmul(col_source<N>(src, ss, a * B + m), wa[a]));
+            v[d0] = cmul(acc, unit_root(m * ka, N));
+        }
+        float2 tw[R0], w[R0];
+        twiddle_powers<R0>(unit_root(b, B), tw);
+#pragma unroll
+        for (int d0 = 0; d0 < R0; ++d0) w[d0] = v[d0];
+        stage0_finish<P>(sm, base, b, w, tw);
+    }
+}
+
+template <class P, int A, class Smem, class Geom>
+OW_HD void bigcol_phase2(const Smem& sm, int base, int ft, int ka, float* __restrict__ dst /* out[c] + x */, float scale, const Geom& geom) {
+    static_assert(A % 2 == 0, "the sign (-1)^y below uses y = ka + A*kb with A even");
+    const size_t ds = geom.dst_stride();
+    const float sg = (ka & 1) ? -scale : scale;            // y = ka + A*kb has the parity of ka; x is even
+#pragma unroll 1
+    for (int c = 0; c < P::C2; ++c) {
+        const int bp = ft + P::T * c;
+        if (bp >= P::B2) break;
+        float2 v[P::R2];
+        stage2<P>(sm, base, bp, v);
+#pragma unroll
+        for (int k2 = 0; k2 < P::R2; ++k2) {
+            const int y = ka + A * (bp + P::B2 * k2);
+            *reinterpret_cast<float2*>(dst + (size_t)y * ds) = make_float2(sg * v[k2].x, -sg * v[k2].y);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // NORMAL (+ JACOBIAN).  normal_map_cs.glsl:24-54: the eight texture() taps sit on texel corners, so with
 // LINEAR+REPEAT each tap is the mean of a 2x2 block ("box"); the stencil covers columns x-2..x+1 and rows
 // y-2..y+1 with wrap-around. One thread owns FOUR adjacent columns x0..x0+3 and walks down RY output rows with

@@ -48,6 +48,9 @@ typedef struct ow_params {
 #define OW_FLAG_EXACT_SINCOS 0x2u /* always use full-range sincosf for e^{iwt} (default: SFU sin/cos after an exact
                                     2*pi reduction whenever max|w*t| < 2e4, absolute error ~5e-7) */
 
+#define OW_FLAG_FOUR_STEP 0x4u   /* N = 1024 / 2048 only: run the N = A*B line decomposition that N > 4096 uses (A = 4), for
+                                    testing that code path against the direct kernels; slower, same results to round-off */
+
 typedef struct ow_ctx ow_ctx;
 
 /* Device pointers to one output set ("slot"); library-owned, valid until ow_destroy. Written by ow_step*.
@@ -70,7 +73,7 @@ typedef enum ow_image {
 
 /* ---- lifecycle: replaces create_textures() (src/main.cpp:1083-1145) for the sim resources ------------- */
 
-/* n_cascades independent patches of size N x N (N a power of two in [256, 4096]); n_slots >= n_cascades
+/* n_cascades independent patches of size N x N (N a power of two in [256, 32768]; N > 4096 uses the N = A*B line decomposition); n_slots >= n_cascades
  * output sets (extra slots let one cascade be evaluated at several times per launch, see ow_step_multi).
  * device = CUDA ordinal. */
 int ow_create(int32_t N, int32_t n_cascades, int32_t n_slots, const ow_params* cascades, int32_t device,

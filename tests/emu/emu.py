@@ -33,6 +33,7 @@ def lib():
         fp = C.POINTER(C.c_float)
         L.emu_frame.argtypes = [C.c_int, fp, fp, C.c_float, C.c_float, C.c_float, fp, fp, fp, fp, C.POINTER(C.c_long)]
         L.emu_dft.argtypes = [C.c_int, fp, fp]
+        L.emu_big_frame.argtypes = [C.c_int, C.c_int, fp, fp, C.c_float, C.c_float, C.c_float, fp, fp, fp]
         L.emu_slab_frame.argtypes = [C.c_int, C.c_int, fp, fp, C.c_float, C.c_float, C.c_float, fp, fp, fp]
         _lib = L
     return _lib
@@ -78,5 +79,17 @@ def slab_frame(N, world, h0k, h0minusk, L, t, choppiness=1.0):
     nm = np.empty((N, N, 4), np.float32)
     jac = np.empty((N, N), np.float32)
     rc = lib().emu_slab_frame(N, int(world), _p(a), _p(b), float(L), float(t), float(choppiness), _p(disp), _p(nm), _p(jac))
+    assert rc == 0, rc
+    return dict(dy=disp[0], dx=disp[1], dz=disp[2], normal=nm, jacobian=jac)
+
+
+def big_frame(N, A, h0k, h0minusk, L, t, choppiness=1.0):
+    """The N = A*B line decomposition used for N > 4096, emulated on a small grid (B = N/A = 256)."""
+    a = np.ascontiguousarray(h0k, np.float32)
+    b = np.ascontiguousarray(h0minusk, np.float32)
+    disp = np.empty((3, N, N), np.float32)
+    nm = np.empty((N, N, 4), np.float32)
+    jac = np.empty((N, N), np.float32)
+    rc = lib().emu_big_frame(N, int(A), _p(a), _p(b), float(L), float(t), float(choppiness), _p(disp), _p(nm), _p(jac))
     assert rc == 0, rc
     return dict(dy=disp[0], dx=disp[1], dz=disp[2], normal=nm, jacobian=jac)

@@ -239,6 +239,66 @@ extern "C" int emu_frame(int N, const float* h0k, const float* h0minusk, float L
     return -1;
 }
 
+// The N = A*B line decomposition (ow_big_kernels.cu) emulated for a small grid: sub-line plan Cfg<B>, A sub-lines per line.
+template <int B, int A>
+int emu_big_frame_n(const float* h0k, const float* h0minusk, float L, float t, float lambda, float* disp, float* normal, float* jac) {
+    constexpr int N = A * B;
+    using C = Cfg<B>;
+    using PR = typename C::Row;
+    using PK = typename C::Col;
+    constexpr int G = C::COL_G;
+    using LY = ColLayout<PK, G>;
+    std::vector<float4> h0((size_t)N * N), hp, nyq;
+    for (size_t i = 0; i < (size_t)N * N; ++i) h0[i] = make_float4(h0k[2 * i], h0k[2 * i + 1], h0minusk[2 * i], h0minusk[2 * i + 1]);
+    fold_full<N>(h0, hp, nyq);
+    std::vector<float> ktab(N);
+    const float pi = 3.1415926535897932384626433832795f;
+    for (int i = 0; i < N; ++i) ktab[i] = (2.0f * pi * ((float)i - (float)N / 2.0f)) / L;
+    std::vector<float2> inter((size_t)3 * (N / 2) * N);
+    const FullRows<N> rows{h0.data(), hp.data(), nyq.data()};
+    const FullSink<N> sink{inter.data()};
+    std::vector<int> dummy;
+    {
+        std::vector<float2> smem((size_t)3 * PR::LINE);
+        const SmemEmu sm{smem.data(), &dummy};
+        for (int p = 0; p < N / 2; ++p)
+            for (int ka = 0; ka < A; ++ka) {
+                for (int ft = 0; ft < PR::T; ++ft) { dummy.clear(); bigrow_phase0<PR, A, false>(sm, ft, p, ka, rows, ktab.data(), t); }
+                for (int ft = 0; ft < PR::T; ++ft) { dummy.clear(); row_phase1<PR>(sm, ft); }
+                for (int ft = 0; ft < PR::T; ++ft) { dummy.clear(); bigrow_phase2<PR, A>(sm, ft, p, ka, sink); }
+            }
+    }
+    {
+        std::vector<float2> smem((size_t)G * LY::SJ);
+        const SmemEmu sm{smem.data(), &dummy};
+        const float scale = 0.5f / ((float)N * (float)N);
+        const FullColGeom<N> geom{};
+        for (int f = 0; f < 3; ++f)
+            for (int tile = 0; tile < N / (2 * G); ++tile)
+                for (int ka = 0; ka < A; ++ka)
+                    for (int phase = 0; phase < 3; ++phase)
+                        for (int tid = 0; tid < PK::T * G; ++tid) {
+                            dummy.clear();
+                            const int job = tid % G, ft = tid / G, x = 2 * (tile * G + job), base = job * LY::SJ;
+                            const float2* src = inter.data() + (size_t)f * (N / 2) * N + x;
+                            float* dst = disp + (size_t)f * N * N + x;
+                            if (phase == 0) bigcol_phase0<PK, A>(sm, base, ft, ka, src, geom);
+                            if (phase == 1) col_phase1<PK>(sm, base, ft);
+                            if (phase == 2) bigcol_phase2<PK, A>(sm, base, ft, ka, dst, scale, geom);
+                        }
+    }
+    emu_normals<N>(disp, FullNrmGeom<N>{}, 0, N, reinterpret_cast<float4*>(normal), jac, N, lambda, L);
+    return 0;
+}
+
+extern "C" int emu_big_frame(int N, int A, const float* h0k, const float* h0minusk, float L, float t, float lambda, float* disp,
+                             float* normal, float* jac) {
+    if (N == 1024 && A == 4) return emu_big_frame_n<256, 4>(h0k, h0minusk, L, t, lambda, disp, normal, jac);
+    if (N == 512 && A == 2) return emu_big_frame_n<256, 2>(h0k, h0minusk, L, t, lambda, disp, normal, jac);
+    if (N == 2048 && A == 8) return emu_big_frame_n<256, 8>(h0k, h0minusk, L, t, lambda, disp, normal, jac);
+    return -1;
+}
+
 extern "C" int emu_slab_frame(int N, int world, const float* h0k, const float* h0minusk, float L, float t, float lambda,
                               float* disp, float* normal, float* jac) {
     switch (N) {

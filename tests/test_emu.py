@@ -80,3 +80,20 @@ def test_emulated_slab_frame_equals_full_frame(noise, N, world):
     slab = emu.slab_frame(N, world, a, b, 1000.0, 1.0, 1.0)
     for k in ("dy", "dx", "dz", "normal", "jacobian"):
         assert np.array_equal(full[k], slab[k]), k
+
+
+@pytest.mark.parametrize("N,A", [(512, 2), (1024, 4), (2048, 8)])
+def test_emulated_line_decomposition_matches_oracle_and_direct_kernels(noise, N, A):
+    """Grids above N=4096 split every line as N = A*B (Cooley-Tukey, sub-line B in one CTA). Same phase functions with
+    B = 256 on a grid the oracle and the direct kernels can also do: all three must agree (covers A = 2, 4, 8)."""
+    s = OracleSim(N, 1000.0, 40.0, (1.0, 1.0), 2.0, 0.1, noise, threads=8)
+    a, b = s.h0()
+    ref = s.frame(1.0, choppiness=1.0)
+    big = emu.big_frame(N, A, a, b, 1000.0, 1.0, 1.0)
+    direct = emu.frame(N, a, b, 1000.0, 1.0, 1.0)
+    for k in ("dy", "dx", "dz"):
+        peak = np.abs(ref[k]).max()
+        assert np.abs(big[k] - ref[k]).max() <= 5e-6 * peak, k
+        assert np.abs(big[k] - direct[k]).max() <= 5e-6 * peak, k
+    assert np.abs(big["normal"] - ref["normal"]).max() < 1e-4
+    assert np.abs(big["jacobian"] - ref["jacobian"]).max() < 1e-4
