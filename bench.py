@@ -46,10 +46,10 @@ WORKLOADS = {
     "c2": (512, 600, "C2: N=512 single patch, 600-frame sweep t=f/60, L=1000 wind 40 A=2 lambda=1, PNG noise, dy/dx/dz+normal", False),
     "c3": (2048, 64, "C3: N=2048 single patch + Jacobian, 64-frame sweep t=f/60, L=1000 wind 40 A=2, rng(2048) noise", True),
     "c4": (1024, 64, "C4: 64 cascades N=1024 (L=100*1.08^c, wind 10+0.5c, dir 2*pi*c/64), one frame each at t=1", False),
-    # C5 is quoted on N=32768; this round's in-CTA line FFT stops at N=4096, so the slab path is measured on the
-    # down-scaled grid SURVEY.md §8 d2 names for its parity check (identical code path; strong scaling over the ranks).
-    "c5": (4096, 32, "C5 (down-scaled to N=4096): ONE grid, slab-decomposed 2-D IFFT over the ranks, Philox(32768) noise, "
-                     "32-frame sweep t=f/60, dy/dx/dz+normal+Jacobian left column-slabbed", True),
+    # C5: ONE N=32768 grid, slab-decomposed over the ranks (strong scaling). --c5-n 4096 runs the down-scaled grid
+    # SURVEY.md §8 d2 names for the parity check (direct in-CTA lines instead of the N = A*B decomposition).
+    "c5": (32768, 4, "C5: ONE grid N=32768, slab-decomposed 2-D IFFT over the ranks, Philox(32768) noise, "
+                     "4-frame sweep t=f/60, dy/dx/dz+normal+Jacobian left column-slabbed", True),
 }
 
 
@@ -139,6 +139,9 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle.oracle import OracleSim, max_threads
+    if args.workload == "c5":
+        WORKLOADS["c5"] = (min(args.c5_n, 4096), 32, WORKLOADS["c5"][2].replace("N=32768", f"N={min(args.c5_n, 4096)} (CPU arm: down-scaled, the "
+                           "oracle's reference textures need 116 GB at N=32768)"), True)
     w = workload_setup(args.workload)
     N, cores = w["N"], max_threads()
     p = w["cascades"][0]
@@ -206,6 +209,9 @@ def run_slab(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     N, frames, desc, jac = WORKLOADS["c5"]
+    if args.c5_n != N:
+        N, frames = args.c5_n, (32 if args.c5_n <= 4096 else 4)
+        desc = desc.replace("N=32768", f"N={N} (down-scaled)").replace("4-frame", f"{frames}-frame")
     p = fow.OceanParams(L=1000.0, wind_speed=40.0, wind_dir=(1.0, 1.0), amplitude=2.0, suppression=0.1, choppiness=1.0)
     times = [float(np.float32(f / 60.0)) for f in range(frames)]
     sim = fow.SlabOcean(N=N, params=p, device=local, jacobian=jac, transport=args.transport)
@@ -336,7 +342,7 @@ def run_slab(args):
                                  f"({(16 + 12 + 12 + 20) * N * N / world / 1e6:.0f} MB per GPU) exceeds L2 at world <= 4",
                            "parallelism": f"slab{world}: row pairs -> transpose (peer stores / all-to-all over NVLink) -> column slabs"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(3 * frames * args.steps), "roofline": roofline}
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and N <= 4096:      # the CPU oracle's reference textures need 108 B/texel: 116 GB at N=32768
             w = dict(N=N, frames=frames, jacobian=True, cascades=[p], noise=[_philox_noise(32768, N)], times=times)
             line["cpu_baseline"] = cpu_baseline(w)
     sim.close()
@@ -560,6 +566,7 @@ def main():
     ap.add_argument("--group", type=int, default=0, help="slots per launch group (0 = library default)")
     ap.add_argument("--streams", type=int, default=0, help="internal streams the launch groups are spread over (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--c5-n", type=int, default=32768, help="c5 only: grid size (32768 = BASELINE config C5; 4096 = its down-scaled parity grid)")
     ap.add_argument("--transport", choices=["auto", "peer", "alltoall"], default="auto", help="c5 only: how the transpose crosses GPUs")
     ap.add_argument("--profile", action="store_true",
                     help="profiler mode (ncu): run warm-up + timed sweeps only and exit without printing a bench line")

@@ -34,6 +34,7 @@ struct ow_ctx {
     float4* d_normal = nullptr;
     float* d_jac = nullptr;
     float* d_tmp = nullptr;       // 2 * N*N*2 floats staging for h0 split/merge
+    float2* d_scratch = nullptr;  // N = A*B line decomposition only (N > 4096 or OW_FLAG_FOUR_STEP): one frame of radix-A sums
     cudaStream_t stream = nullptr;
     // Launch groups of one ow_step_multi call are independent frames: they are spread round-robin over these
     // auxiliary streams (fork/join around the caller's stream) so one group's tail overlaps the next group's head.
@@ -94,6 +95,7 @@ FrameBuffers buffers(const ow_ctx* c) {
     static const int discard = getenv("OW_DISCARD") ? 1 : 0;
     fb.discard_inter = discard;
     fb.four_step = (c->flags & OW_FLAG_FOUR_STEP) ? 1 : 0;
+    fb.scratch = c->d_scratch;
     return fb;
 }
 
@@ -102,6 +104,7 @@ FrameBuffers buffers(const ow_ctx* c) {
 // Then the slots are split evenly (32 -> 11+11+10, not 15+15+2) into at least n_streams groups, so that the
 // independent groups can overlap on the auxiliary streams.
 int pick_group(const ow_ctx* c, int count) {
+    if (c->d_scratch) return 1;       // the line decomposition's scratch holds one frame
     int gmax;
     if (c->group_size > 0) {
         gmax = c->group_size;
@@ -125,7 +128,7 @@ void release(ow_ctx* c) {
     cudaSetDevice(c->device);
     if (c->gl_registered) for (auto& r : c->gl_res) if (r) cudaGraphicsUnregisterResource(r);
     cudaFree(c->d_noise); cudaFree(c->d_h0); cudaFree(c->d_hp); cudaFree(c->d_nyq); cudaFree(c->d_ktab); cudaFree(c->d_casc); cudaFree(c->d_inter);
-    cudaFree(c->d_disp); cudaFree(c->d_normal); cudaFree(c->d_jac); cudaFree(c->d_tmp);
+    cudaFree(c->d_disp); cudaFree(c->d_normal); cudaFree(c->d_jac); cudaFree(c->d_tmp); cudaFree(c->d_scratch);
     if (c->stream) cudaStreamDestroy(c->stream);
     for (auto& s : c->aux) if (s) cudaStreamDestroy(s);
     for (auto& e : c->ev_join) if (e) cudaEventDestroy(e);
@@ -182,6 +185,7 @@ int ow_create(int32_t N, int32_t n_cascades, int32_t n_slots, const ow_params* c
     OW_TRY(cudaMalloc(&c->d_normal, nn * n_slots * sizeof(float4)));
     if (flags & OW_FLAG_JACOBIAN) OW_TRY(cudaMalloc(&c->d_jac, nn * n_slots * sizeof(float)));
     OW_TRY(cudaMalloc(&c->d_tmp, nn * 4 * sizeof(float)));
+    if (big_supported(N, false) || (flags & OW_FLAG_FOUR_STEP)) OW_TRY(cudaMalloc(&c->d_scratch, nn / 2 * 3 * sizeof(float2)));
     OW_TRY(configure_frame_kernels(N));
 #undef OW_TRY
     *out = c;
@@ -315,7 +319,7 @@ static int step_impl(ow_ctx* c, int32_t count, const int32_t* cascade_of_slot, c
         for (auto& e : ev) OW_CUDA(c, cudaEventCreate(&e));
     }
     const int ngroups = (count + group - 1) / group;
-    const int nfan = (kernel_ms || ngroups < 2 || c->n_streams < 2) ? 0 : (ngroups < c->n_streams ? ngroups : c->n_streams);
+    const int nfan = (kernel_ms || ngroups < 2 || c->n_streams < 2 || c->d_scratch) ? 0 : (ngroups < c->n_streams ? ngroups : c->n_streams);
     if (nfan) {
         OW_CUDA(c, cudaEventRecord(c->ev_fork, st));
         for (int i = 0; i < nfan; ++i) OW_CUDA(c, cudaStreamWaitEvent(c->aux[i], c->ev_fork, 0));

@@ -18,33 +18,49 @@ struct Big {
     static constexpr int RY = 8, WARPS = 4, NMINB = 4;
 
     static cudaError_t configure() {
-        cudaError_t e = cudaFuncSetAttribute(ow_bigrow_kernel<R, A, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<R, 1>());
+        cudaError_t e = cudaFuncSetAttribute(ow_bigrow_lines_kernel<R, A, 1, FullSink<N>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<R, 1>());
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(ow_bigrow_kernel<R, A, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<R, 1>());
+        e = cudaFuncSetAttribute(ow_bigrow_lines_kernel<R, A, 1, SlabSink<N>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<R, 1>());
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(ow_bigrow_slab_kernel<R, A, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<R, 1>());
+        e = cudaFuncSetAttribute(ow_bigcol_lines_kernel<K, A, G, 1, FullColGeom<N>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ColLayout<K, G>::SMEM);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(ow_bigrow_slab_kernel<R, A, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<R, 1>());
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(ow_bigcol_kernel<K, A, G, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ColLayout<K, G>::SMEM);
-        if (e != cudaSuccess) return e;
-        return cudaFuncSetAttribute(ow_bigcol_slab_kernel<K, A, G, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ColLayout<K, G>::SMEM);
+        return cudaFuncSetAttribute(ow_bigcol_lines_kernel<K, A, G, 1, SlabColGeom>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ColLayout<K, G>::SMEM);
     }
 
-    static int frame(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_jac, bool fast, cudaStream_t st, cudaEvent_t* ev) {
-        if (ev) cudaEventRecord(ev[0], st);
-        const dim3 rgrid((N / 2) * A, count);
-        if (fast) ow_bigrow_kernel<R, A, 1, true><<<rgrid, R::T, row_smem<R, 1>(), st>>>(fb, tab);
-        else ow_bigrow_kernel<R, A, 1, false><<<rgrid, R::T, row_smem<R, 1>(), st>>>(fb, tab);
-        if (ev) cudaEventRecord(ev[1], st);
+    template <class Rows, class Sink>
+    static void rows_pass(const Rows& rows, const float* ktab, int p_first, int npairs_rows, float t, bool fast, float2* scratch, const Sink& sink,
+                          cudaStream_t st) {
+        const dim3 pgrid((B + 255) / 256, npairs_rows);
+        if (fast) ow_bigrow_prep_kernel<B, A, true, Rows><<<pgrid, 256, 0, st>>>(rows, ktab, p_first, t, scratch);
+        else ow_bigrow_prep_kernel<B, A, false, Rows><<<pgrid, 256, 0, st>>>(rows, ktab, p_first, t, scratch);
+        ow_bigrow_lines_kernel<R, A, 1, Sink><<<npairs_rows * A, R::T, row_smem<R, 1>(), st>>>(scratch, p_first, sink);
+    }
+
+    template <class Geom>
+    static void cols_pass(const float2* src, size_t ss, size_t src_chan, int npairs, float2* scratch, float* dst, size_t dst_chan, const Geom& geom,
+                          cudaStream_t st) {
         const float scale = 0.5f / ((float)N * (float)N);
-        ow_bigcol_kernel<K, A, G, 1><<<dim3(N / (2 * G) * A, 3, count), K::T * G, ColLayout<K, G>::SMEM, st>>>(fb, tab, scale);
+        ow_bigcol_prep_kernel<B, A><<<dim3((npairs + 31) / 32, B / 8, 3), dim3(32, 8), 0, st>>>(src, ss, src_chan, npairs, scratch);
+        ow_bigcol_lines_kernel<K, A, G, 1, Geom><<<dim3(npairs / G * A, 3), K::T * G, ColLayout<K, G>::SMEM, st>>>(scratch, npairs, dst, dst_chan, scale, geom);
+    }
+
+    // One slot entry per call (the scratch holds one frame).
+    static int frame(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_jac, bool fast, cudaStream_t st, cudaEvent_t* ev) {
+        if (count != 1 || !fb.scratch) return -1;
+        const int cascade = tab.cascade[0], slot = tab.slot[0];
+        const size_t nn = (size_t)N * N;
+        if (ev) cudaEventRecord(ev[0], st);
+        const FullRows<N> rows{fb.h0 + (size_t)cascade * nn, fb.hp + (size_t)cascade * (nn / 2), fb.nyq + (size_t)cascade * (N / 2)};
+        float2* inter = fb.inter + (size_t)slot * 3 * (nn / 2);
+        rows_pass(rows, fb.ktab + (size_t)cascade * N, 0, N / 2, tab.time[0], fast, fb.scratch, FullSink<N>{inter}, st);
+        if (ev) cudaEventRecord(ev[1], st);
+        cols_pass(inter, (size_t)N, nn / 2, N / 2, fb.scratch, fb.disp + (size_t)slot * 3 * nn, nn, FullColGeom<N>{}, st);
         if (ev) cudaEventRecord(ev[2], st);
-        const dim3 ngrid(N / 128, N / (WARPS * RY), count);
+        const dim3 ngrid(N / 128, N / (WARPS * RY), 1);
         if (with_jac) ow_normal_kernel<N, true, RY, WARPS, NMINB><<<ngrid, dim3(32, WARPS), 0, st>>>(fb, tab);
         else ow_normal_kernel<N, false, RY, WARPS, NMINB><<<ngrid, dim3(32, WARPS), 0, st>>>(fb, tab);
         if (ev) cudaEventRecord(ev[3], st);
-        return cudaGetLastError() == cudaSuccess ? 3 : -1;
+        return cudaGetLastError() == cudaSuccess ? 5 : -1;
     }
 
     static bool slab_ok(int world) {
@@ -54,27 +70,24 @@ struct Big {
     }
 
     static int slab_rows(const SlabGeom& g, const float4* h0_loc, const float4* hp_loc, const float4* nyq_loc, const float* ktab,
-                         float2* const sink_base[kSlabMaxWorld], float t, bool fast, cudaStream_t st) {
+                         float2* const sink_base[kSlabMaxWorld], float t, bool fast, float2* scratch, cudaStream_t st) {
         SlabRows<N> rows{h0_loc, hp_loc, nyq_loc, g.rank * g.PL, g.PL};
         SlabSink<N> sink{};
         for (int h = 0; h < g.world; ++h) sink.base[h] = sink_base[h];
         sink.world = g.world; sink.p0 = g.rank * g.PL; sink.XL = g.XL; sink.XH = g.XH;
         sink.xl_shift = 0;
         while ((1 << sink.xl_shift) < g.XL) ++sink.xl_shift;
-        const dim3 grid(g.PL * A);
-        if (fast) ow_bigrow_slab_kernel<R, A, 1, true><<<grid, R::T, row_smem<R, 1>(), st>>>(rows, ktab, sink, t);
-        else ow_bigrow_slab_kernel<R, A, 1, false><<<grid, R::T, row_smem<R, 1>(), st>>>(rows, ktab, sink, t);
-        return cudaGetLastError() == cudaSuccess ? 1 : -1;
+        rows_pass(rows, ktab, g.rank * g.PL, g.PL, t, fast, scratch, sink, st);
+        return cudaGetLastError() == cudaSuccess ? 2 : -1;
     }
 
     static int slab_cols(const SlabGeom& g, const float2* recv, float* disp_loc, float4* normal_loc, float* jac_loc, float jac_scale,
-                         cudaStream_t st) {
-        const float scale = 0.5f / ((float)N * (float)N);
-        ow_bigcol_slab_kernel<K, A, G, 1><<<dim3(g.XH / (2 * G) * A, 3), K::T * G, ColLayout<K, G>::SMEM, st>>>(recv, disp_loc, g.XH, scale);
+                         float2* scratch, cudaStream_t st) {
+        cols_pass(recv, (size_t)3 * g.XH, (size_t)g.XH, g.XH / 2, scratch, disp_loc, (size_t)N * g.XH, SlabColGeom{(size_t)3 * g.XH, (size_t)g.XH}, st);
         const dim3 ngrid(g.XL / 128, N / (WARPS * RY));
         if (jac_loc) ow_normal_slab_kernel<N, true, RY, WARPS, NMINB><<<ngrid, dim3(32, WARPS), 0, st>>>(disp_loc, normal_loc, jac_loc, g.XL, g.XH, jac_scale);
         else ow_normal_slab_kernel<N, false, RY, WARPS, NMINB><<<ngrid, dim3(32, WARPS), 0, st>>>(disp_loc, normal_loc, nullptr, g.XL, g.XH, 0.f);
-        return cudaGetLastError() == cudaSuccess ? 2 : -1;
+        return cudaGetLastError() == cudaSuccess ? 3 : -1;
     }
 };
 
@@ -114,14 +127,14 @@ bool big_slab_supported(int N, int world, bool forced) {
 }
 
 int launch_big_slab_rows(const SlabGeom& g, const float4* h0_loc, const float4* hp_loc, const float4* nyq_loc, const float* ktab,
-                         float2* const sink_base[kSlabMaxWorld], float t, bool fast, cudaStream_t st, bool forced) {
-    OW_BIG_DISPATCH(g.N, forced, slab_rows(g, h0_loc, hp_loc, nyq_loc, ktab, sink_base, t, fast, st));
+                         float2* const sink_base[kSlabMaxWorld], float t, bool fast, float2* scratch, cudaStream_t st, bool forced) {
+    OW_BIG_DISPATCH(g.N, forced, slab_rows(g, h0_loc, hp_loc, nyq_loc, ktab, sink_base, t, fast, scratch, st));
     return -1;
 }
 
 int launch_big_slab_cols(const SlabGeom& g, const float2* recv, float* disp_loc, float4* normal_loc, float* jac_loc, float jac_scale,
-                         cudaStream_t st, bool forced) {
-    OW_BIG_DISPATCH(g.N, forced, slab_cols(g, recv, disp_loc, normal_loc, jac_loc, jac_scale, st));
+                         float2* scratch, cudaStream_t st, bool forced) {
+    OW_BIG_DISPATCH(g.N, forced, slab_cols(g, recv, disp_loc, normal_loc, jac_loc, jac_scale, scratch, st));
     return -1;
 }
 

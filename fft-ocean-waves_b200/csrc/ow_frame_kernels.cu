@@ -171,8 +171,8 @@ bool slab_supported(int N, int world) {
 }
 
 int launch_slab_rows(const SlabGeom& g, const float4* h0_loc, const float4* hp_loc, const float4* nyq_loc, const float* ktab,
-                     float2* const sink_base[kSlabMaxWorld], float t, bool fast_phase, cudaStream_t st) {
-    if (big_supported(g.N, false)) return launch_big_slab_rows(g, h0_loc, hp_loc, nyq_loc, ktab, sink_base, t, fast_phase, st, false);
+                     float2* const sink_base[kSlabMaxWorld], float t, bool fast_phase, float2* scratch, cudaStream_t st) {
+    if (big_supported(g.N, false)) return launch_big_slab_rows(g, h0_loc, hp_loc, nyq_loc, ktab, sink_base, t, fast_phase, scratch, st, false);
     switch (g.N) {
         case 256: return slab_rows_n<256>(g, h0_loc, hp_loc, nyq_loc, ktab, sink_base, t, fast_phase, st);
         case 512: return slab_rows_n<512>(g, h0_loc, hp_loc, nyq_loc, ktab, sink_base, t, fast_phase, st);
@@ -183,9 +183,15 @@ int launch_slab_rows(const SlabGeom& g, const float4* h0_loc, const float4* hp_l
     return -1;
 }
 
+size_t slab_scratch_elems(const SlabGeom& g) {
+    if (!big_supported(g.N, false)) return 0;
+    const size_t rows = (size_t)g.PL * 3 * g.N, cols = (size_t)3 * g.N * (g.XH / 2);
+    return rows > cols ? rows : cols;
+}
+
 int launch_slab_cols(const SlabGeom& g, const float2* recv, float* disp_loc, float4* normal_loc, float* jac_loc, float jac_scale,
-                     cudaStream_t st) {
-    if (big_supported(g.N, false)) return launch_big_slab_cols(g, recv, disp_loc, normal_loc, jac_loc, jac_scale, st, false);
+                     float2* scratch, cudaStream_t st) {
+    if (big_supported(g.N, false)) return launch_big_slab_cols(g, recv, disp_loc, normal_loc, jac_loc, jac_scale, scratch, st, false);
     switch (g.N) {
         case 256: return slab_cols_n<256>(g, recv, disp_loc, normal_loc, jac_loc, jac_scale, st);
         case 512: return slab_cols_n<512>(g, recv, disp_loc, normal_loc, jac_loc, jac_scale, st);

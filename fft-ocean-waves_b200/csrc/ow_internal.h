@@ -31,6 +31,7 @@ struct FrameBuffers {
     float4* normal;        // [slot][N][N]
     float* jacobian;       // [slot][N][N] or nullptr
     int discard_inter;     // column kernel drops the intermediate's lines from L2 after reading them (no DRAM write-back)
+    float2* scratch;       // N = A*B decomposition only: one frame of radix-A sums, 12 B/texel (ow_big_kernels.cu)
     int four_step;         // force the N = A*B line decomposition (ow_big_kernels.cu) on a grid the direct kernels could do
 };
 
@@ -60,17 +61,19 @@ struct SlabGeom {
 bool slab_supported(int N, int world);
 // Row kernel for this rank's pairs; block h of the result goes to sink_base[h] ([PL][3][XH] float2 each).
 int launch_slab_rows(const SlabGeom& g, const float4* h0_loc, const float4* hp_loc, const float4* nyq_loc, const float* ktab,
-                     float2* const sink_base[kSlabMaxWorld], float t, bool fast_phase, cudaStream_t st);
+                     float2* const sink_base[kSlabMaxWorld], float t, bool fast_phase, float2* scratch, cudaStream_t st);
 // Column kernel on recv[N/2][3][XH] -> disp_loc[3][N][XH], then normals (+ Jacobian when jac != nullptr) for the XL
 // interior columns -> normal_loc[N][XL], jac_loc[N][XL]. jac_scale = choppiness * N / (2 L).
 int launch_slab_cols(const SlabGeom& g, const float2* recv, float* disp_loc, float4* normal_loc, float* jac_loc, float jac_scale,
-                     cudaStream_t st);
+                     float2* scratch, cudaStream_t st);
 
 bool big_slab_supported(int N, int world, bool forced);
 int launch_big_slab_rows(const SlabGeom& g, const float4* h0_loc, const float4* hp_loc, const float4* nyq_loc, const float* ktab,
-                         float2* const sink_base[kSlabMaxWorld], float t, bool fast_phase, cudaStream_t st, bool forced);
+                         float2* const sink_base[kSlabMaxWorld], float t, bool fast_phase, float2* scratch, cudaStream_t st, bool forced);
 int launch_big_slab_cols(const SlabGeom& g, const float2* recv, float* disp_loc, float4* normal_loc, float* jac_loc, float jac_scale,
-                         cudaStream_t st, bool forced);
+                         float2* scratch, cudaStream_t st, bool forced);
+// float2 elements of scratch a slab rank needs for the N = A*B decomposition (0 when the direct kernels apply).
+size_t slab_scratch_elems(const SlabGeom& g);
 
 // Init-time kernels (ow_init_kernels.cu)
 cudaError_t launch_noise_seed(uint8_t* noise /* [4][N][N] */, int N, uint64_t seed, cudaStream_t st);

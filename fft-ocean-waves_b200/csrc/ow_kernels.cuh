@@ -475,19 +475,17 @@ OW_HD void col_phase2(const Smem& sm, int base, int ft, float* __restrict__ dst 
 // ---------------------------------------------------------------------------------------------------
 // LINES LONGER THAN ONE CTA'S SHARED MEMORY:  N = A * B with B = P::N <= 4096 and A in {2, 4, 8}  (N = 8192 .. 32768,
 // BASELINE config C5). Cooley-Tukey split n = a*B + m, k = ka + A*kb of the same unnormalised inverse DFT:
-//     X[ka + A*kb] = sum_m [ W_N^{m ka} * sum_a x[a*B + m] W_A^{a ka} ] W_B^{m kb},      W_n = e^{+2 pi i / n}
-// One CTA (row kernel: one thread group) owns sub-line ka of a line. Its stage-0 loader forms
-//     y_ka[m] = W_N^{m ka} * sum_a x[a*B + m] W_A^{a ka}
-// on the fly from the A source elements, the three in-CTA stages then transform the length-B sub-line exactly as for
-// N = B, and the stores scatter to k = ka + A*kb. Each of the A sub-line CTAs re-derives the radix-A sums (for rows:
-// re-evaluates the spectrum) instead of passing them through a scratch array in HBM; the A CTAs of one line run
-// back to back, so the source is read from DRAM once and from L2 afterwards. Written for a small register footprint
-// (rolled loops, butterfly inputs parked in local memory): these sizes are bound by their HBM footprint and the
-// NVLink transpose, not by this loader.
+//     X[ka + A*kb] = sum_m y_ka[m] W_B^{m kb},    y_ka[m] = W_N^{m ka} * sum_a x[a*B + m] W_A^{a ka},    W_n = e^{+2 pi i / n}
+// Two kernels per direction ("four-step" FFT with the transposes folded into the index maps):
+//   prep   one thread per m: the A source elements x[a*B + m] (rows: the spectrum at A texels; columns: the Hermitian-
+//          unpacked intermediate at A rows), a radix-A DFT in registers, the twiddles W_N^{m ka}, and A coalesced stores
+//          into a scratch array laid out [ka][m] — 12 B/texel written once and read once;
+//   lines  one CTA (group) per sub-line ka: plain loads from the scratch, the usual three in-CTA stages on the length-B
+//          sub-line, stores scattered to k = ka + A*kb (rows: through the same sinks, so the slab transpose still
+//          happens in the store; columns: output row y = ka + A*kb, inversion sign/scale as the epilogue).
 // ---------------------------------------------------------------------------------------------------
-template <class P, int A, bool FAST, class Rows>
+template <int N, bool FAST, class Rows>
 OW_HD Sym3 big_row_element(const Rows& rows, const float* __restrict__ ktab, int p, int u, float ky, float t) {
-    constexpr int N = A * P::N;
     if (p != 0) {
         const FoldedPair fp = load_folded(rows.pair_row(p), ktab, u);
         return spectrum_folded<FAST>(fp, ky, t, u == 0 ? rows.nyq_of(p) : nullptr);
@@ -504,37 +502,45 @@ OW_HD Sym3 big_row_element(const Rows& rows, const float* __restrict__ ktab, int
     return o;
 }
 
-template <class P, int A, bool FAST, class Smem, class Rows>
-__host__ __device__ __noinline__ void bigrow_phase0(const Smem& sm, int ft, int p, int ka, const Rows& rows, const float* __restrict__ ktab, float t) {
-    constexpr int B = P::N, N = A * B, R0 = P::R0;
-    float2 wa[A];
-    twiddle_powers<A>(unit_root(ka, A), wa);            // W_A^{a ka}
+// Row prep for (pair p, m): y[c][ka][m] for the three channels. scratch row layout: [c][ka][m], c stride = A*B = N.
+template <int B, int A, bool FAST, class Rows>
+OW_HD void bigrow_prep(const Rows& rows, const float* __restrict__ ktab, int p, int m, float t, float2* __restrict__ yrow /* scratch row of pair p: [3][A][B] */) {
+    constexpr int N = A * B;
     const float ky = OW_LDG(ktab + p);
+    float2 vy[A], vx[A], vz[A];
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        const Sym3 s = big_row_element<N, FAST>(rows, ktab, p, a * B + m, ky, t);
+        vy[a] = s.y; vx[a] = s.x; vz[a] = s.z;
+    }
+    Dft<A>::run(vy); Dft<A>::run(vx); Dft<A>::run(vz);
+    float2 tw[A];
+    twiddle_powers<A>(unit_root(m, N), tw);                       // W_N^{m ka}
+#pragma unroll
+    for (int ka = 0; ka < A; ++ka) {
+        yrow[(size_t)(0 * A + ka) * B + m] = ka ? cmul(vy[ka], tw[ka]) : vy[0];
+        yrow[(size_t)(1 * A + ka) * B + m] = ka ? cmul(vx[ka], tw[ka]) : vx[0];
+        yrow[(size_t)(2 * A + ka) * B + m] = ka ? cmul(vz[ka], tw[ka]) : vz[0];
+    }
+}
+
+// Row lines, stage 0: plain loads of sub-line ka of the three channels from the scratch row.
+template <class P, int A, class Smem>
+OW_HD void bigrow_phase0(const Smem& sm, int ft, int ka, const float2* __restrict__ yrow) {
+    constexpr int B = P::N, R0 = P::R0;
 #pragma unroll 1
     for (int c = 0; c < P::C0; ++c) {
         const int b = ft + P::T * c;
         if (b >= P::M) break;
-        float2 v[3][R0];
-#pragma unroll 1
-        for (int d0 = 0; d0 < R0; ++d0) {
-            const int m = d0 * P::M + b;
-            float2 ay = make_float2(0.f, 0.f), ax = ay, az = ay;
-#pragma unroll
-            for (int a = 0; a < A; ++a) {
-                const Sym3 s = big_row_element<P, A, FAST>(rows, ktab, p, a * B + m, ky, t);
-                ay = cadd(ay, cmul(s.y, wa[a])); ax = cadd(ax, cmul(s.x, wa[a])); az = cadd(az, cmul(s.z, wa[a]));
-            }
-            const float2 w = unit_root(m * ka, N);       // W_N^{m ka}
-            v[0][d0] = cmul(ay, w); v[1][d0] = cmul(ax, w); v[2][d0] = cmul(az, w);
-        }
         float2 tw[R0];
         twiddle_powers<R0>(unit_root(b, B), tw);
 #pragma unroll 1
         for (int f = 0; f < 3; ++f) {
-            float2 w[R0];
+            const float2* src = yrow + (size_t)(f * A + ka) * B + b;
+            float2 v[R0];
 #pragma unroll
-            for (int d0 = 0; d0 < R0; ++d0) w[d0] = v[f][d0];
-            stage0_finish<P>(sm, f * P::LINE, b, w, tw);
+            for (int d0 = 0; d0 < R0; ++d0) v[d0] = OW_LDG(src + d0 * P::M);
+            stage0_finish<P>(sm, f * P::LINE, b, v, tw);
         }
     }
 }
@@ -566,28 +572,31 @@ OW_HD float2 col_source(const float2* __restrict__ src /* inter[c] + x */, size_
     return pack_cnj(OW_LDG(reinterpret_cast<const float4*>(src + (size_t)(N - v) * ss)));
 }
 
-template <class P, int A, class Smem, class Geom>
-__host__ __device__ __noinline__ void bigcol_phase0(const Smem& sm, int base, int ft, int ka, const float2* __restrict__ src, const Geom& geom) {
-    constexpr int B = P::N, N = A * B, R0 = P::R0;
-    const size_t ss = geom.src_stride();
-    float2 wa[A];
-    twiddle_powers<A>(unit_root(ka, A), wa);
+// Column prep for (column pair at src, m): z[ka][m][pair] with zs = elements between consecutive m (pairs per row).
+template <int B, int A>
+OW_HD void bigcol_prep(const float2* __restrict__ src /* inter[c] + x */, size_t ss, int m, float2* __restrict__ z /* scratch[c] + pair */, size_t zs) {
+    constexpr int N = A * B;
+    float2 v[A];
+#pragma unroll
+    for (int a = 0; a < A; ++a) v[a] = col_source<N>(src, ss, a * B + m);
+    Dft<A>::run(v);
+    float2 tw[A];
+    twiddle_powers<A>(unit_root(m, N), tw);
+#pragma unroll
+    for (int ka = 0; ka < A; ++ka) z[((size_t)ka * B + m) * zs] = ka ? cmul(v[ka], tw[ka]) : v[0];
+}
+
+// Column lines, stage 0: plain loads of sub-line ka for this job's column pair (zsub = scratch[c][ka] + pair).
+template <class P, class Smem>
+OW_HD void bigcol_phase0(const Smem& sm, int base, int ft, const float2* __restrict__ zsub, size_t zs) {
+    constexpr int B = P::N, R0 = P::R0;
 #pragma unroll 1
     for (int b = ft; b < P::M; b += P::T) {
-        float2 v[R0];
-#pragma unroll 1
-        for (int d0 = 0; d0 < R0; ++d0) {
-            const int m = d0 * P::M + b;
-            float2 acc = make_float2(0.f, 0.f);
+        float2 v[R0], tw[R0];
 #pragma unroll
-            for (int a = 0; a < A; ++a) acc = cadd(acc, cmul(col_source<N>(src, ss, a * B + m), wa[a]));
-            v[d0] = cmul(acc, unit_root(m * ka, N));
-        }
-        float2 tw[R0], w[R0];
+        for (int d0 = 0; d0 < R0; ++d0) v[d0] = OW_LDG(zsub + (size_t)(d0 * P::M + b) * zs);
         twiddle_powers<R0>(unit_root(b, B), tw);
-#pragma unroll
-        for (int d0 = 0; d0 < R0; ++d0) w[d0] = v[d0];
-        stage0_finish<P>(sm, base, b, w, tw);
+        stage0_finish<P>(sm, base, b, v, tw);
     }
 }
 

@@ -39,6 +39,7 @@ struct ow_slab {
     float* d_disp = nullptr;      // [3][N][XH]
     float4* d_normal = nullptr;   // [N][XL]
     float* d_jac = nullptr;       // [N][XL]
+    float2* d_scratch = nullptr;  // N > 4096 only: radix-A sums of the line decomposition
     float2* peer_recv[kSlabMaxWorld] = {};   // peer mappings of every rank's d_recv (own entry = d_recv)
     bool peers_open = false;
     bool spectrum_ready = false;
@@ -71,7 +72,7 @@ void srelease(ow_slab* s) {
         for (int h = 0; h < s->g.world; ++h)
             if (h != s->g.rank && s->peer_recv[h]) cudaIpcCloseMemHandle(s->peer_recv[h]);
     cudaFree(s->d_h0); cudaFree(s->d_hp); cudaFree(s->d_nyq); cudaFree(s->d_ktab); cudaFree(s->d_send); cudaFree(s->d_recv); cudaFree(s->d_disp);
-    cudaFree(s->d_normal); cudaFree(s->d_jac);
+    cudaFree(s->d_normal); cudaFree(s->d_jac); cudaFree(s->d_scratch);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -87,7 +88,7 @@ int ow_slab_create(int32_t N, int32_t world, int32_t rank, const ow_params* p, i
     *out = nullptr;
     if (!p) return sfail(nullptr, OW_ERR_INVALID, "ow_slab_create: params is NULL");
     if (!frame_supported(N) || !slab_supported(N, world))
-        return sfail(nullptr, OW_ERR_INVALID, "ow_slab_create: unsupported (N, world): N in {256..4096}, world in {1,2,4,8} with N/world >= 128");
+        return sfail(nullptr, OW_ERR_INVALID, "ow_slab_create: unsupported (N, world): N a power of two in [256, 32768], world in {1,2,4,8} with N/world >= 128");
     if (rank < 0 || rank >= world) return sfail(nullptr, OW_ERR_INVALID, "ow_slab_create: rank out of range");
     if (!(p->L > 0.0f) || !(p->wind_speed > 0.0f) || (p->wind_dir[0] == 0.0f && p->wind_dir[1] == 0.0f))
         return sfail(nullptr, OW_ERR_INVALID, "ow_slab_create: invalid parameters");
@@ -123,6 +124,7 @@ int ow_slab_create(int32_t N, int32_t world, int32_t rank, const ow_params* p, i
     OWS_TRY(cudaMalloc(&s->d_disp, (size_t)3 * N * g.XH * sizeof(float)));
     OWS_TRY(cudaMalloc(&s->d_normal, (size_t)N * g.XL * sizeof(float4)));
     if (flags & OW_FLAG_JACOBIAN) OWS_TRY(cudaMalloc(&s->d_jac, (size_t)N * g.XL * sizeof(float)));
+    if (slab_scratch_elems(g)) OWS_TRY(cudaMalloc(&s->d_scratch, slab_scratch_elems(g) * sizeof(float2)));
     OWS_TRY(configure_frame_kernels(N));
 #undef OWS_TRY
     s->peer_recv[rank] = s->d_recv;
@@ -209,7 +211,7 @@ int ow_slab_rows(ow_slab* s, float t, int32_t transport, void* stream) {
     bool fast = (s->flags & OW_FLAG_EXACT_SINCOS) == 0;
     const float kmax = 1.41421356f * 3.14159265f * (float)g.N / s->params.L;
     if (!(sqrtf(9.81f * kmax) * fabsf(t) < kFastPhaseLimit)) fast = false;
-    if (launch_slab_rows(g, s->d_h0, s->d_hp, s->d_nyq, s->d_ktab, base, t, fast, spick(s, stream)) < 0) return scuda(s, cudaGetLastError(), "launch_slab_rows");
+    if (launch_slab_rows(g, s->d_h0, s->d_hp, s->d_nyq, s->d_ktab, base, t, fast, s->d_scratch, spick(s, stream)) < 0) return scuda(s, cudaGetLastError(), "launch_slab_rows");
     return OW_OK;
 }
 
@@ -219,7 +221,7 @@ int ow_slab_cols(ow_slab* s, void* stream) {
     OWS_CUDA(s, cudaSetDevice(s->device));
     const SlabGeom& g = s->g;
     const float js = s->casc.choppiness * ((float)g.N / (2.0f * s->casc.L));
-    if (launch_slab_cols(g, s->d_recv, s->d_disp, s->d_normal, s->d_jac, js, spick(s, stream)) < 0)
+    if (launch_slab_cols(g, s->d_recv, s->d_disp, s->d_normal, s->d_jac, js, s->d_scratch, spick(s, stream)) < 0)
         return scuda(s, cudaGetLastError(), "launch_slab_cols");
     return OW_OK;
 }

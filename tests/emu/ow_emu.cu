@@ -254,20 +254,29 @@ int emu_big_frame_n(const float* h0k, const float* h0minusk, float L, float t, f
     std::vector<float> ktab(N);
     const float pi = 3.1415926535897932384626433832795f;
     for (int i = 0; i < N; ++i) ktab[i] = (2.0f * pi * ((float)i - (float)N / 2.0f)) / L;
-    std::vector<float2> inter((size_t)3 * (N / 2) * N);
+    std::vector<float2> inter((size_t)3 * (N / 2) * N), scratch((size_t)3 * (N / 2) * N);
     const FullRows<N> rows{h0.data(), hp.data(), nyq.data()};
     const FullSink<N> sink{inter.data()};
     std::vector<int> dummy;
+    // rows: prep kernel (one thread per (pair, m)), then one group per (pair, sub-line)
+    for (int p = 0; p < N / 2; ++p)
+        for (int m = 0; m < B; ++m) bigrow_prep<B, A, false>(rows, ktab.data(), p, m, t, scratch.data() + (size_t)p * 3 * N);
     {
         std::vector<float2> smem((size_t)3 * PR::LINE);
         const SmemEmu sm{smem.data(), &dummy};
         for (int p = 0; p < N / 2; ++p)
             for (int ka = 0; ka < A; ++ka) {
-                for (int ft = 0; ft < PR::T; ++ft) { dummy.clear(); bigrow_phase0<PR, A, false>(sm, ft, p, ka, rows, ktab.data(), t); }
+                for (int ft = 0; ft < PR::T; ++ft) { dummy.clear(); bigrow_phase0<PR, A>(sm, ft, ka, scratch.data() + (size_t)p * 3 * N); }
                 for (int ft = 0; ft < PR::T; ++ft) { dummy.clear(); row_phase1<PR>(sm, ft); }
                 for (int ft = 0; ft < PR::T; ++ft) { dummy.clear(); bigrow_phase2<PR, A>(sm, ft, p, ka, sink); }
             }
     }
+    // columns: prep kernel (one thread per (channel, pair, m)), then one CTA per (channel, tile, sub-line)
+    const int npairs = N / 2;
+    for (int c = 0; c < 3; ++c)
+        for (int pair = 0; pair < npairs; ++pair)
+            for (int m = 0; m < B; ++m)
+                bigcol_prep<B, A>(inter.data() + (size_t)c * (N / 2) * N + 2 * pair, (size_t)N, m, scratch.data() + (size_t)c * N * npairs + pair, (size_t)npairs);
     {
         std::vector<float2> smem((size_t)G * LY::SJ);
         const SmemEmu sm{smem.data(), &dummy};
@@ -279,10 +288,10 @@ int emu_big_frame_n(const float* h0k, const float* h0minusk, float L, float t, f
                     for (int phase = 0; phase < 3; ++phase)
                         for (int tid = 0; tid < PK::T * G; ++tid) {
                             dummy.clear();
-                            const int job = tid % G, ft = tid / G, x = 2 * (tile * G + job), base = job * LY::SJ;
-                            const float2* src = inter.data() + (size_t)f * (N / 2) * N + x;
-                            float* dst = disp + (size_t)f * N * N + x;
-                            if (phase == 0) bigcol_phase0<PK, A>(sm, base, ft, ka, src, geom);
+                            const int job = tid % G, ft = tid / G, pair = tile * G + job, base = job * LY::SJ;
+                            const float2* zsub = scratch.data() + (size_t)f * N * npairs + (size_t)ka * B * npairs + pair;
+                            float* dst = disp + (size_t)f * N * N + 2 * pair;
+                            if (phase == 0) bigcol_phase0<PK>(sm, base, ft, zsub, (size_t)npairs);
                             if (phase == 1) col_phase1<PK>(sm, base, ft);
                             if (phase == 2) bigcol_phase2<PK, A>(sm, base, ft, ka, dst, scale, geom);
                         }

@@ -35,7 +35,7 @@ def test_seeded_noise_is_philox_and_matches_the_oracle():
         assert np.abs(got[k] - ref[k]).max() <= 1e-4 * np.abs(ref[k]).max()
 
 
-@pytest.mark.parametrize("N", [256, 1024, 4096])
+@pytest.mark.parametrize("N", [256, 1024, 4096, 8192])
 @pytest.mark.parametrize("transport", ["peer", "alltoall"])
 def test_single_rank_slab_equals_single_gpu_path(N, transport):
     """world = 1: the slab kernels (permuted h0 rows, transposing sink with wrap-around halo columns, strided column
@@ -72,7 +72,7 @@ def test_slab_api_errors():
         assert lib.ow_slab_rows(sim.backend._h, 0.0, 7, None) == 1    # unknown transport -> OW_ERR_INVALID
 
 
-@pytest.mark.parametrize("N", [1024, 4096])
+@pytest.mark.parametrize("N", [1024, 4096, 8192])
 def test_multi_rank_slab_over_nvlink(N):
     """2 (or 4/8 when present) ranks under torchrun: peer-store and all-to-all transports vs the single-GPU path."""
     import torch

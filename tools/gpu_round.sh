@@ -9,7 +9,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > $
 tail -3 $O/pytest_$TAG.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke_$TAG.log 2>&1; tail -2 $O/smoke_$TAG.log
 for w in c2 c3 c4 c5; do
-  timeout 600 python bench.py --workload $w > $O/b_$w.json 2> $O/b_$w.err; echo "bench $w exit $?"
+  timeout 900 python bench.py --workload $w > $O/b_$w.json 2> $O/b_$w.err; echo "bench $w exit $?"
 done
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $O/b_ref.json 2> $O/b_ref.err
 python tools/summ.py c2 c3 c4 c5
