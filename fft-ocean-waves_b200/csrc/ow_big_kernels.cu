@@ -18,9 +18,13 @@ struct Big {
     static constexpr int RY = 8, WARPS = 4, NMINB = 4;
 
     static cudaError_t configure() {
-        cudaError_t e = cudaFuncSetAttribute(ow_bigrow_lines_kernel<R, A, 1, FullSink<N>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<R, 1>());
+        cudaError_t e = cudaFuncSetAttribute(ow_bigrow_lines_kernel<R, A, 1, false, FullRows<N>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<R, 1>());
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(ow_bigrow_lines_kernel<R, A, 1, SlabSink<N>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<R, 1>());
+        e = cudaFuncSetAttribute(ow_bigrow_lines_kernel<R, A, 1, true, FullRows<N>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<R, 1>());
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(ow_bigrow_lines_kernel<R, A, 1, false, SlabRows<N>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<R, 1>());
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(ow_bigrow_lines_kernel<R, A, 1, true, SlabRows<N>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<R, 1>());
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(ow_bigcol_lines_kernel<K, A, G, 1, FullColGeom<N>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ColLayout<K, G>::SMEM);
         if (e != cudaSuccess) return e;
@@ -30,18 +34,17 @@ struct Big {
     template <class Rows, class Sink>
     static void rows_pass(const Rows& rows, const float* ktab, int p_first, int npairs_rows, float t, bool fast, float2* scratch, const Sink& sink,
                           cudaStream_t st) {
-        const dim3 pgrid((B + 255) / 256, npairs_rows);
-        if (fast) ow_bigrow_prep_kernel<B, A, true, Rows><<<pgrid, 256, 0, st>>>(rows, ktab, p_first, t, scratch);
-        else ow_bigrow_prep_kernel<B, A, false, Rows><<<pgrid, 256, 0, st>>>(rows, ktab, p_first, t, scratch);
-        ow_bigrow_lines_kernel<R, A, 1, Sink><<<npairs_rows * A, R::T, row_smem<R, 1>(), st>>>(scratch, p_first, sink);
+        if (fast) ow_bigrow_lines_kernel<R, A, 1, true, Rows><<<npairs_rows * A, R::T, row_smem<R, 1>(), st>>>(rows, ktab, p_first, t, scratch);
+        else ow_bigrow_lines_kernel<R, A, 1, false, Rows><<<npairs_rows * A, R::T, row_smem<R, 1>(), st>>>(rows, ktab, p_first, t, scratch);
+        ow_bigrow_post_kernel<B, A, Sink><<<dim3((B + 255) / 256, npairs_rows, 3), 256, 0, st>>>(scratch, p_first, sink);
     }
 
     template <class Geom>
-    static void cols_pass(const float2* src, size_t ss, size_t src_chan, int npairs, float2* scratch, float* dst, size_t dst_chan, const Geom& geom,
+    static void cols_pass(const float2* src, size_t src_chan, int npairs, float2* scratch, float* dst, size_t dst_chan, const Geom& geom,
                           cudaStream_t st) {
         const float scale = 0.5f / ((float)N * (float)N);
-        ow_bigcol_prep_kernel<B, A><<<dim3((npairs + 31) / 32, B / 8, 3), dim3(32, 8), 0, st>>>(src, ss, src_chan, npairs, scratch);
-        ow_bigcol_lines_kernel<K, A, G, 1, Geom><<<dim3(npairs / G * A, 3), K::T * G, ColLayout<K, G>::SMEM, st>>>(scratch, npairs, dst, dst_chan, scale, geom);
+        ow_bigcol_lines_kernel<K, A, G, 1, Geom><<<dim3(npairs / G * A, 3), K::T * G, ColLayout<K, G>::SMEM, st>>>(src, src_chan, npairs, scratch, geom);
+        ow_bigcol_post_kernel<B, A><<<dim3((npairs + 31) / 32, B / 8, 3), dim3(32, 8), 0, st>>>(scratch, npairs, dst, dst_chan, geom.dst_stride(), scale);
     }
 
     // One slot entry per call (the scratch holds one frame).
@@ -54,7 +57,7 @@ struct Big {
         float2* inter = fb.inter + (size_t)slot * 3 * (nn / 2);
         rows_pass(rows, fb.ktab + (size_t)cascade * N, 0, N / 2, tab.time[0], fast, fb.scratch, FullSink<N>{inter}, st);
         if (ev) cudaEventRecord(ev[1], st);
-        cols_pass(inter, (size_t)N, nn / 2, N / 2, fb.scratch, fb.disp + (size_t)slot * 3 * nn, nn, FullColGeom<N>{}, st);
+        cols_pass(inter, nn / 2, N / 2, fb.scratch, fb.disp + (size_t)slot * 3 * nn, nn, FullColGeom<N>{}, st);
         if (ev) cudaEventRecord(ev[2], st);
         const dim3 ngrid(N / 128, N / (WARPS * RY), 1);
         if (with_jac) ow_normal_kernel<N, true, RY, WARPS, NMINB><<<ngrid, dim3(32, WARPS), 0, st>>>(fb, tab);
@@ -83,7 +86,7 @@ struct Big {
 
     static int slab_cols(const SlabGeom& g, const float2* recv, float* disp_loc, float4* normal_loc, float* jac_loc, float jac_scale,
                          float2* scratch, cudaStream_t st) {
-        cols_pass(recv, (size_t)3 * g.XH, (size_t)g.XH, g.XH / 2, scratch, disp_loc, (size_t)N * g.XH, SlabColGeom{(size_t)3 * g.XH, (size_t)g.XH}, st);
+        cols_pass(recv, (size_t)g.XH, g.XH / 2, scratch, disp_loc, (size_t)N * g.XH, SlabColGeom{(size_t)3 * g.XH, (size_t)g.XH}, st);
         const dim3 ngrid(g.XL / 128, N / (WARPS * RY));
         if (jac_loc) ow_normal_slab_kernel<N, true, RY, WARPS, NMINB><<<ngrid, dim3(32, WARPS), 0, st>>>(disp_loc, normal_loc, jac_loc, g.XL, g.XH, jac_scale);
         else ow_normal_slab_kernel<N, false, RY, WARPS, NMINB><<<ngrid, dim3(32, WARPS), 0, st>>>(disp_loc, normal_loc, nullptr, g.XL, g.XH, 0.f);

@@ -205,63 +205,62 @@ __global__ void __launch_bounds__(P::T* G, MINB) ow_col_slab_kernel(const float2
 }
 
 // ---------------------------------------------------------------------------------------------------
-// N = A * B > 4096 (see "LINES LONGER THAN ONE CTA'S SHARED MEMORY" in ow_kernels.cuh): a prep kernel (radix-A sums and
-// twiddles into a scratch array) and a lines kernel (one CTA per sub-line) per direction. P is the sub-line plan
-// (P::N = B). Rows is FullRows<N> or SlabRows<N>, Sink FullSink<N> or SlabSink<N>.
+// N = A * B > 4096 (see "LINES LONGER THAN ONE CTA'S SHARED MEMORY" in ow_kernels.cuh): a lines kernel (one CTA per sub-line
+// of decimated input) and a post kernel (twiddles + radix-A + coalesced final stores) per direction. P is the sub-line
+// plan (P::N = B). Rows is FullRows<N> or SlabRows<N>, Sink FullSink<N> or SlabSink<N>.
 //   row scratch   [pair][3][A][B]      (pair index local to the launch: p - p_first)
 //   col scratch   [3][A][B][npairs]    (npairs = column pairs of the launch: N/2, or XH/2 for a slab)
 // ---------------------------------------------------------------------------------------------------
-template <int B, int A, bool FAST, class Rows>
-__global__ void __launch_bounds__(256) ow_bigrow_prep_kernel(Rows rows, const float* __restrict__ ktab, int p_first, float t,
-                                                             float2* __restrict__ scratch) {
-    constexpr int N = A * B;
-    const int m = blockIdx.x * 256 + threadIdx.x, pl = blockIdx.y;
-    if (m < B) bigrow_prep<B, A, FAST>(rows, ktab, p_first + pl, m, t, scratch + (size_t)pl * 3 * N);
-}
-
-template <class P, int A, int MINB, class Sink>
-__global__ void __launch_bounds__(P::T, MINB) ow_bigrow_lines_kernel(const float2* __restrict__ scratch, int p_first, Sink sink) {
+template <class P, int A, int MINB, bool FAST, class Rows>
+__global__ void __launch_bounds__(P::T, MINB) ow_bigrow_lines_kernel(Rows rows, const float* __restrict__ ktab, int p_first, float t,
+                                                                     float2* __restrict__ scratch) {
     extern __shared__ __align__(16) float2 smem[];
     constexpr int N = A * P::N;
     const int ft = threadIdx.x;
-    const int pl = blockIdx.x / A, ka = blockIdx.x % A;
+    const int pl = blockIdx.x / A, a = blockIdx.x % A;
     const SmemDirect sm{smem};
-    bigrow_phase0<P, A>(sm, ft, ka, scratch + (size_t)pl * 3 * N);
+    bigrow_phase0<P, A, FAST>(sm, ft, p_first + pl, a, rows, ktab, t);
     __syncthreads();
     row_phase1<P>(sm, ft);
     __syncthreads();
-    bigrow_phase2<P, A>(sm, ft, p_first + pl, ka, sink);
+    bigrow_phase2<P, A>(sm, ft, a, scratch + (size_t)pl * 3 * N);
 }
 
-// src: channel-0 base of the Hermitian-packed intermediate; channel c at src + c*src_chan, pair rows ss elements apart.
-template <int B, int A>
-__global__ void __launch_bounds__(256) ow_bigcol_prep_kernel(const float2* __restrict__ src, size_t ss, size_t src_chan, int npairs,
-                                                             float2* __restrict__ scratch) {
+template <int B, int A, class Sink>
+__global__ void __launch_bounds__(256) ow_bigrow_post_kernel(const float2* __restrict__ scratch, int p_first, Sink sink) {
     constexpr int N = A * B;
-    const int pair = blockIdx.x * 32 + threadIdx.x, m = blockIdx.y * 8 + threadIdx.y, c = blockIdx.z;
-    if (pair < npairs && m < B)
-        bigcol_prep<B, A>(src + (size_t)c * src_chan + 2 * pair, ss, m, scratch + (size_t)c * N * npairs + pair, (size_t)npairs);
+    const int kb = blockIdx.x * 256 + threadIdx.x, pl = blockIdx.y, c = blockIdx.z;
+    if (kb < B) bigrow_post<B, A>(scratch + (size_t)pl * 3 * N, c, p_first + pl, kb, sink);
 }
 
-// dst: channel-0 base of the displacement planes; channel c at dst + c*dst_chan.
+// src: channel-0 base of the Hermitian-packed intermediate; channel c at src + c*src_chan.
 template <class P, int A, int G, int MINB, class Geom>
-__global__ void __launch_bounds__(P::T* G, MINB) ow_bigcol_lines_kernel(const float2* __restrict__ scratch, int npairs, float* __restrict__ dst,
-                                                                        size_t dst_chan, float scale, Geom geom) {
+__global__ void __launch_bounds__(P::T* G, MINB) ow_bigcol_lines_kernel(const float2* __restrict__ src, size_t src_chan, int npairs,
+                                                                        float2* __restrict__ scratch, Geom geom) {
     extern __shared__ __align__(16) float2 smem[];
     constexpr int N = A * P::N;
     using LY = ColLayout<P, G>;
     const int job = threadIdx.x % G, ft = threadIdx.x / G;
-    const int tile = blockIdx.x / A, ka = blockIdx.x % A;
+    const int tile = blockIdx.x / A, a = blockIdx.x % A;
     const int pair = tile * G + job;
     const int f = blockIdx.y;
     const SmemDirect sm{smem};
     const int base = job * LY::SJ;
-    const float2* zsub = scratch + (size_t)f * N * npairs + (size_t)ka * P::N * npairs + pair;
-    bigcol_phase0<P>(sm, base, ft, zsub, (size_t)npairs);
+    bigcol_phase0<P, A>(sm, base, ft, a, src + (size_t)f * src_chan + 2 * pair, geom);
     __syncthreads();
     col_phase1<P>(sm, base, ft);
     __syncthreads();
-    bigcol_phase2<P, A>(sm, base, ft, ka, dst + (size_t)f * dst_chan + 2 * pair, scale, geom);
+    bigcol_phase2<P>(sm, base, ft, scratch + (size_t)f * N * npairs + (size_t)a * P::N * npairs + pair, (size_t)npairs);
+}
+
+// dst: channel-0 base of the displacement planes; channel c at dst + c*dst_chan, rows ds floats apart.
+template <int B, int A>
+__global__ void __launch_bounds__(256) ow_bigcol_post_kernel(const float2* __restrict__ scratch, int npairs, float* __restrict__ dst, size_t dst_chan,
+                                                             size_t ds, float scale) {
+    constexpr int N = A * B;
+    const int pair = blockIdx.x * 32 + threadIdx.x, kb = blockIdx.y * 8 + threadIdx.y, c = blockIdx.z;
+    if (pair < npairs && kb < B)
+        bigcol_post<B, A>(scratch + (size_t)c * N * npairs + pair, (size_t)npairs, kb, dst + (size_t)c * dst_chan + 2 * pair, ds, scale);
 }
 
 constexpr int kNormalRows = 8;      // output rows per thread of the normal kernel's walk

@@ -474,79 +474,61 @@ OW_HD void col_phase2(const Smem& sm, int base, int ft, float* __restrict__ dst 
 
 // ---------------------------------------------------------------------------------------------------
 // LINES LONGER THAN ONE CTA'S SHARED MEMORY:  N = A * B with B = P::N <= 4096 and A in {2, 4, 8}  (N = 8192 .. 32768,
-// BASELINE config C5). Cooley-Tukey split n = a*B + m, k = ka + A*kb of the same unnormalised inverse DFT:
-//     X[ka + A*kb] = sum_m y_ka[m] W_B^{m kb},    y_ka[m] = W_N^{m ka} * sum_a x[a*B + m] W_A^{a ka},    W_n = e^{+2 pi i / n}
+// BASELINE config C5). Cooley-Tukey split n = A*m + a, k = kb + B*ka of the same unnormalised inverse DFT:
+//     X[kb + B*ka] = sum_a W_A^{a ka} * ( W_N^{a kb} * z_a[kb] ),     z_a[kb] = sum_m x[A*m + a] W_B^{m kb},     W_n = e^{+2 pi i / n}
 // Two kernels per direction ("four-step" FFT with the transposes folded into the index maps):
-//   prep   one thread per m: the A source elements x[a*B + m] (rows: the spectrum at A texels; columns: the Hermitian-
-//          unpacked intermediate at A rows), a radix-A DFT in registers, the twiddles W_N^{m ka}, and A coalesced stores
-//          into a scratch array laid out [ka][m] — 12 B/texel written once and read once;
-//   lines  one CTA (group) per sub-line ka: plain loads from the scratch, the usual three in-CTA stages on the length-B
-//          sub-line, stores scattered to k = ka + A*kb (rows: through the same sinks, so the slab transpose still
-//          happens in the store; columns: output row y = ka + A*kb, inversion sign/scale as the epilogue).
+//   lines  one CTA (row kernel: one thread group) per sub-line a: the stage-0 loader gathers the decimated input x[A*m + a]
+//          (rows: the spectrum evaluated at those texels; columns: the Hermitian-unpacked intermediate at those rows), the usual
+//          three in-CTA stages transform the length-B sub-line, and z_a goes to a scratch array [a][kb] — 12 B/texel written once
+//          and read once;
+//   post   one thread per kb: the A values z_a[kb], the twiddles W_N^{a kb}, a radix-A DFT in registers, and A stores to
+//          k = kb + B*ka — for each ka a run that is CONTIGUOUS in kb across the warp, so the final stores (rows: through the same
+//          sinks as the direct kernel, i.e. the slab transpose over NVLink; columns: output rows with the inversion sign/scale)
+//          are as coalesced as the direct kernels'.
 // ---------------------------------------------------------------------------------------------------
-template <int N, bool FAST, class Rows>
-OW_HD Sym3 big_row_element(const Rows& rows, const float* __restrict__ ktab, int p, int u, float ky, float t) {
-    if (p != 0) {
-        const FoldedPair fp = load_folded(rows.pair_row(p), ktab, u);
-        return spectrum_folded<FAST>(fp, ky, t, u == 0 ? rows.nyq_of(p) : nullptr);
-    }
-    // pair 0: rows 0 and N/2 are their own mirrors; Z = S(., 0) + i*S(., N/2) (see row_phase0_pair0)
-    const float4* row0 = rows.row(0);
-    const float4* rowh = rows.row(N / 2);
-    const Sym3 a = spectrum_sym<FAST>(load_pair<N>(row0, row0, ktab, u), u, OW_LDG(ktab), true, t);
-    const Sym3 q = spectrum_sym<FAST>(load_pair<N>(rowh, rowh, ktab, u), u, OW_LDG(ktab + N / 2), true, t);
-    Sym3 o;
-    o.y = make_float2(a.y.x - q.y.y, a.y.y + q.y.x);
-    o.x = make_float2(a.x.x - q.x.y, a.x.y + q.x.x);
-    o.z = make_float2(a.z.x - q.z.y, a.z.y + q.z.x);
-    return o;
-}
-
-// Row prep for (pair p, m): y[c][ka][m] for the three channels. scratch row layout: [c][ka][m], c stride = A*B = N.
-template <int B, int A, bool FAST, class Rows>
-OW_HD void bigrow_prep(const Rows& rows, const float* __restrict__ ktab, int p, int m, float t, float2* __restrict__ yrow /* scratch row of pair p: [3][A][B] */) {
-    constexpr int N = A * B;
+// Row lines, stage 0: spectrum at the decimated texels u = A*m + a of pair p (folded path; pair 0: the literal two-row path).
+template <class P, int A, bool FAST, class Smem, class Rows>
+__host__ __device__ __noinline__ void bigrow_phase0(const Smem& sm, int ft, int p, int a, const Rows& rows, const float* __restrict__ ktab, float t) {
+    constexpr int B = P::N, N = A * B, R0 = P::R0;
     const float ky = OW_LDG(ktab + p);
-    float2 vy[A], vx[A], vz[A];
-#pragma unroll
-    for (int a = 0; a < A; ++a) {
-        const Sym3 s = big_row_element<N, FAST>(rows, ktab, p, a * B + m, ky, t);
-        vy[a] = s.y; vx[a] = s.x; vz[a] = s.z;
-    }
-    Dft<A>::run(vy); Dft<A>::run(vx); Dft<A>::run(vz);
-    float2 tw[A];
-    twiddle_powers<A>(unit_root(m, N), tw);                       // W_N^{m ka}
-#pragma unroll
-    for (int ka = 0; ka < A; ++ka) {
-        yrow[(size_t)(0 * A + ka) * B + m] = ka ? cmul(vy[ka], tw[ka]) : vy[0];
-        yrow[(size_t)(1 * A + ka) * B + m] = ka ? cmul(vx[ka], tw[ka]) : vx[0];
-        yrow[(size_t)(2 * A + ka) * B + m] = ka ? cmul(vz[ka], tw[ka]) : vz[0];
-    }
-}
-
-// Row lines, stage 0: plain loads of sub-line ka of the three channels from the scratch row.
-template <class P, int A, class Smem>
-OW_HD void bigrow_phase0(const Smem& sm, int ft, int ka, const float2* __restrict__ yrow) {
-    constexpr int B = P::N, R0 = P::R0;
 #pragma unroll 1
     for (int c = 0; c < P::C0; ++c) {
         const int b = ft + P::T * c;
         if (b >= P::M) break;
+        float2 v[3][R0];
+#pragma unroll 1
+        for (int d0 = 0; d0 < R0; ++d0) {
+            const int u = A * (d0 * P::M + b) + a;
+            Sym3 s;
+            if (p != 0) {
+                s = spectrum_folded<FAST>(load_folded(rows.pair_row(p), ktab, u), ky, t, u == 0 ? rows.nyq_of(p) : nullptr);
+            } else {   // rows 0 and N/2 are their own mirrors; Z = S(., 0) + i*S(., N/2) (see row_phase0_pair0)
+                const float4* row0 = rows.row(0);
+                const float4* rowh = rows.row(N / 2);
+                const Sym3 x0 = spectrum_sym<FAST>(load_pair<N>(row0, row0, ktab, u), u, OW_LDG(ktab), true, t);
+                const Sym3 xh = spectrum_sym<FAST>(load_pair<N>(rowh, rowh, ktab, u), u, OW_LDG(ktab + N / 2), true, t);
+                s.y = make_float2(x0.y.x - xh.y.y, x0.y.y + xh.y.x);
+                s.x = make_float2(x0.x.x - xh.x.y, x0.x.y + xh.x.x);
+                s.z = make_float2(x0.z.x - xh.z.y, x0.z.y + xh.z.x);
+            }
+            v[0][d0] = s.y; v[1][d0] = s.x; v[2][d0] = s.z;
+        }
         float2 tw[R0];
         twiddle_powers<R0>(unit_root(b, B), tw);
 #pragma unroll 1
         for (int f = 0; f < 3; ++f) {
-            const float2* src = yrow + (size_t)(f * A + ka) * B + b;
-            float2 v[R0];
+            float2 w[R0];
 #pragma unroll
-            for (int d0 = 0; d0 < R0; ++d0) v[d0] = OW_LDG(src + d0 * P::M);
-            stage0_finish<P>(sm, f * P::LINE, b, v, tw);
+            for (int d0 = 0; d0 < R0; ++d0) w[d0] = v[f][d0];
+            stage0_finish<P>(sm, f * P::LINE, b, w, tw);
         }
     }
 }
 
-template <class P, int A, class Smem, class Sink>
-OW_HD void bigrow_phase2(const Smem& sm, int ft, int p, int ka, const Sink& sink) {
+// Row lines, stage 2: z_a[kb] of the three channels -> scratch row of pair p, layout [c][a][kb].
+template <class P, int A, class Smem>
+OW_HD void bigrow_phase2(const Smem& sm, int ft, int a, float2* __restrict__ zrow) {
+    constexpr int B = P::N;
 #pragma unroll 1
     for (int c = 0; c < P::C2; ++c) {
         const int bp = ft + P::T * c;
@@ -555,10 +537,27 @@ OW_HD void bigrow_phase2(const Smem& sm, int ft, int p, int ka, const Sink& sink
         for (int f = 0; f < 3; ++f) {
             float2 v[P::R2];
             stage2<P>(sm, f * P::LINE, bp, v);
+            float2* dst = zrow + (size_t)(f * A + a) * B + bp;
 #pragma unroll
-            for (int k2 = 0; k2 < P::R2; ++k2) sink.put(f, p, ka + A * (bp + k2 * P::B2), v[k2]);
+            for (int k2 = 0; k2 < P::R2; ++k2) dst[k2 * P::B2] = v[k2];
         }
     }
+}
+
+// Row post for (pair p, channel c, kb): X[kb + B*ka] for all ka, through the sink.
+template <int B, int A, class Sink>
+OW_HD void bigrow_post(const float2* __restrict__ zrow /* scratch row of pair p: [3][A][B] */, int c, int p, int kb, const Sink& sink) {
+    constexpr int N = A * B;
+    float2 v[A], tw[A];
+    twiddle_powers<A>(unit_root(kb, N), tw);                      // W_N^{a kb}
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        const float2 z = OW_LDG(zrow + (size_t)(c * A + a) * B + kb);
+        v[a] = a ? cmul(z, tw[a]) : z;
+    }
+    Dft<A>::run(v);
+#pragma unroll
+    for (int ka = 0; ka < A; ++ka) sink.put(c, p, kb + B * ka, v[ka]);
 }
 
 // Column source element Q_v of the Hermitian-packed intermediate (see the COLUMN KERNEL comment): v in [0, N).
@@ -572,39 +571,24 @@ OW_HD float2 col_source(const float2* __restrict__ src /* inter[c] + x */, size_
     return pack_cnj(OW_LDG(reinterpret_cast<const float4*>(src + (size_t)(N - v) * ss)));
 }
 
-// Column prep for (column pair at src, m): z[ka][m][pair] with zs = elements between consecutive m (pairs per row).
-template <int B, int A>
-OW_HD void bigcol_prep(const float2* __restrict__ src /* inter[c] + x */, size_t ss, int m, float2* __restrict__ z /* scratch[c] + pair */, size_t zs) {
-    constexpr int N = A * B;
-    float2 v[A];
-#pragma unroll
-    for (int a = 0; a < A; ++a) v[a] = col_source<N>(src, ss, a * B + m);
-    Dft<A>::run(v);
-    float2 tw[A];
-    twiddle_powers<A>(unit_root(m, N), tw);
-#pragma unroll
-    for (int ka = 0; ka < A; ++ka) z[((size_t)ka * B + m) * zs] = ka ? cmul(v[ka], tw[ka]) : v[0];
-}
-
-// Column lines, stage 0: plain loads of sub-line ka for this job's column pair (zsub = scratch[c][ka] + pair).
-template <class P, class Smem>
-OW_HD void bigcol_phase0(const Smem& sm, int base, int ft, const float2* __restrict__ zsub, size_t zs) {
-    constexpr int B = P::N, R0 = P::R0;
+// Column lines, stage 0: the decimated source rows v = A*m + a of this job's column pair.
+template <class P, int A, class Smem, class Geom>
+OW_HD void bigcol_phase0(const Smem& sm, int base, int ft, int a, const float2* __restrict__ src /* inter[c] + x */, const Geom& geom) {
+    constexpr int B = P::N, N = A * B, R0 = P::R0;
+    const size_t ss = geom.src_stride();
 #pragma unroll 1
     for (int b = ft; b < P::M; b += P::T) {
         float2 v[R0], tw[R0];
 #pragma unroll
-        for (int d0 = 0; d0 < R0; ++d0) v[d0] = OW_LDG(zsub + (size_t)(d0 * P::M + b) * zs);
+        for (int d0 = 0; d0 < R0; ++d0) v[d0] = col_source<N>(src, ss, A * (d0 * P::M + b) + a);
         twiddle_powers<R0>(unit_root(b, B), tw);
         stage0_finish<P>(sm, base, b, v, tw);
     }
 }
 
-template <class P, int A, class Smem, class Geom>
-OW_HD void bigcol_phase2(const Smem& sm, int base, int ft, int ka, float* __restrict__ dst /* out[c] + x */, float scale, const Geom& geom) {
-    static_assert(A % 2 == 0, "the sign (-1)^y below uses y = ka + A*kb with A even");
-    const size_t ds = geom.dst_stride();
-    const float sg = (ka & 1) ? -scale : scale;            // y = ka + A*kb has the parity of ka; x is even
+// Column lines, stage 2: z_a[kb] of this job's column pair -> scratch [a][kb][pair] (zsub = scratch[c][a] + pair).
+template <class P, class Smem>
+OW_HD void bigcol_phase2(const Smem& sm, int base, int ft, float2* __restrict__ zsub, size_t zs) {
 #pragma unroll 1
     for (int c = 0; c < P::C2; ++c) {
         const int bp = ft + P::T * c;
@@ -612,11 +596,27 @@ OW_HD void bigcol_phase2(const Smem& sm, int base, int ft, int ka, float* __rest
         float2 v[P::R2];
         stage2<P>(sm, base, bp, v);
 #pragma unroll
-        for (int k2 = 0; k2 < P::R2; ++k2) {
-            const int y = ka + A * (bp + P::B2 * k2);
-            *reinterpret_cast<float2*>(dst + (size_t)y * ds) = make_float2(sg * v[k2].x, -sg * v[k2].y);
-        }
+        for (int k2 = 0; k2 < P::R2; ++k2) zsub[(size_t)(bp + P::B2 * k2) * zs] = v[k2];
     }
+}
+
+// Column post for (column pair, kb): output rows y = kb + B*ka with the inversion sign/scale (inversion_cs.glsl:29-36).
+template <int B, int A>
+OW_HD void bigcol_post(const float2* __restrict__ z /* scratch[c] + pair */, size_t zs, int kb, float* __restrict__ dst /* out[c] + x */, size_t ds,
+                       float scale) {
+    constexpr int N = A * B;
+    float2 v[A], tw[A];
+    twiddle_powers<A>(unit_root(kb, N), tw);
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        const float2 q = OW_LDG(z + ((size_t)a * B + kb) * zs);
+        v[a] = a ? cmul(q, tw[a]) : q;
+    }
+    Dft<A>::run(v);
+    const float sg = (kb & 1) ? -scale : scale;            // y = kb + B*ka has the parity of kb (B is even); x is even
+#pragma unroll
+    for (int ka = 0; ka < A; ++ka)
+        *reinterpret_cast<float2*>(dst + (size_t)(kb + B * ka) * ds) = make_float2(sg * v[ka].x, -sg * v[ka].y);
 }
 
 // ---------------------------------------------------------------------------------------------------

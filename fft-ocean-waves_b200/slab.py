@@ -208,10 +208,6 @@ class SlabOcean:
     # ---- init (reference init(): tilde_h0_k, src/main.cpp:218) ----------------------------------------------------
     def init(self, seed: int = 32768):
         self.backend.init_spectrum(seed)
-        if self.transport == "auto" and self.world > 1 and self.N > 4096:
-            # the N = A*B line decomposition stores with stride A (x = ka + A*kb): fine into local L2, but over NVLink every
-            # 8-byte store travels alone (measured at N=32768 on 2 GPUs: peer stores 20 fps, all-to-all 38 fps)
-            self.transport = "alltoall"
         if self.transport in ("auto", "peer") and self.world > 1:
             try:
                 self._open_peers()

@@ -258,44 +258,43 @@ int emu_big_frame_n(const float* h0k, const float* h0minusk, float L, float t, f
     const FullRows<N> rows{h0.data(), hp.data(), nyq.data()};
     const FullSink<N> sink{inter.data()};
     std::vector<int> dummy;
-    // rows: prep kernel (one thread per (pair, m)), then one group per (pair, sub-line)
-    for (int p = 0; p < N / 2; ++p)
-        for (int m = 0; m < B; ++m) bigrow_prep<B, A, false>(rows, ktab.data(), p, m, t, scratch.data() + (size_t)p * 3 * N);
+    // rows: one group per (pair, sub-line a) -> scratch, then the post kernel (one thread per (pair, channel, kb))
     {
         std::vector<float2> smem((size_t)3 * PR::LINE);
         const SmemEmu sm{smem.data(), &dummy};
         for (int p = 0; p < N / 2; ++p)
-            for (int ka = 0; ka < A; ++ka) {
-                for (int ft = 0; ft < PR::T; ++ft) { dummy.clear(); bigrow_phase0<PR, A>(sm, ft, ka, scratch.data() + (size_t)p * 3 * N); }
+            for (int a = 0; a < A; ++a) {
+                for (int ft = 0; ft < PR::T; ++ft) { dummy.clear(); bigrow_phase0<PR, A, false>(sm, ft, p, a, rows, ktab.data(), t); }
                 for (int ft = 0; ft < PR::T; ++ft) { dummy.clear(); row_phase1<PR>(sm, ft); }
-                for (int ft = 0; ft < PR::T; ++ft) { dummy.clear(); bigrow_phase2<PR, A>(sm, ft, p, ka, sink); }
+                for (int ft = 0; ft < PR::T; ++ft) { dummy.clear(); bigrow_phase2<PR, A>(sm, ft, a, scratch.data() + (size_t)p * 3 * N); }
             }
     }
-    // columns: prep kernel (one thread per (channel, pair, m)), then one CTA per (channel, tile, sub-line)
+    for (int p = 0; p < N / 2; ++p)
+        for (int c = 0; c < 3; ++c)
+            for (int kb = 0; kb < B; ++kb) bigrow_post<B, A>(scratch.data() + (size_t)p * 3 * N, c, p, kb, sink);
+    // columns: one CTA per (channel, tile, sub-line a) -> scratch, then the post kernel (one thread per (channel, pair, kb))
     const int npairs = N / 2;
-    for (int c = 0; c < 3; ++c)
-        for (int pair = 0; pair < npairs; ++pair)
-            for (int m = 0; m < B; ++m)
-                bigcol_prep<B, A>(inter.data() + (size_t)c * (N / 2) * N + 2 * pair, (size_t)N, m, scratch.data() + (size_t)c * N * npairs + pair, (size_t)npairs);
+    const float scale = 0.5f / ((float)N * (float)N);
     {
         std::vector<float2> smem((size_t)G * LY::SJ);
         const SmemEmu sm{smem.data(), &dummy};
-        const float scale = 0.5f / ((float)N * (float)N);
         const FullColGeom<N> geom{};
         for (int f = 0; f < 3; ++f)
             for (int tile = 0; tile < N / (2 * G); ++tile)
-                for (int ka = 0; ka < A; ++ka)
+                for (int a = 0; a < A; ++a)
                     for (int phase = 0; phase < 3; ++phase)
                         for (int tid = 0; tid < PK::T * G; ++tid) {
                             dummy.clear();
                             const int job = tid % G, ft = tid / G, pair = tile * G + job, base = job * LY::SJ;
-                            const float2* zsub = scratch.data() + (size_t)f * N * npairs + (size_t)ka * B * npairs + pair;
-                            float* dst = disp + (size_t)f * N * N + 2 * pair;
-                            if (phase == 0) bigcol_phase0<PK>(sm, base, ft, zsub, (size_t)npairs);
+                            if (phase == 0) bigcol_phase0<PK, A>(sm, base, ft, a, inter.data() + (size_t)f * (N / 2) * N + 2 * pair, geom);
                             if (phase == 1) col_phase1<PK>(sm, base, ft);
-                            if (phase == 2) bigcol_phase2<PK, A>(sm, base, ft, ka, dst, scale, geom);
+                            if (phase == 2) bigcol_phase2<PK>(sm, base, ft, scratch.data() + (size_t)f * N * npairs + (size_t)a * B * npairs + pair, (size_t)npairs);
                         }
     }
+    for (int c = 0; c < 3; ++c)
+        for (int pair = 0; pair < npairs; ++pair)
+            for (int kb = 0; kb < B; ++kb)
+                bigcol_post<B, A>(scratch.data() + (size_t)c * N * npairs + pair, (size_t)npairs, kb, disp + (size_t)c * N * N + 2 * pair, (size_t)N, scale);
     emu_normals<N>(disp, FullNrmGeom<N>{}, 0, N, reinterpret_cast<float4*>(normal), jac, N, lambda, L);
     return 0;
 }
