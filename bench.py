@@ -377,16 +377,17 @@ def run_ours(args):
     N, frames = w["N"], w["frames"]
     # C4 (BASELINE.json configs[3]): the 64 cascades are SHARDED, a contiguous block of 64/world per GPU,
     # no data-path collective -> strong scaling (total work fixed). Every other workload replicates per GPU (weak).
-    sharded = args.workload == "c4" and world > 1
+    sharded = args.workload == "c4" and (world > 1 or args.c4_shard_of > 1)
     if sharded:
-        if 64 % world:
+        parts = world if world > 1 else args.c4_shard_of       # --c4-shard-of P: time ONE GPU's share of a P-GPU run (tuning aid)
+        if 64 % parts:
             raise SystemExit("bench.py: c4 shards 64 cascades; --gpus must divide 64")
-        per = 64 // world
+        per = 64 // parts
         lo = rank * per
         w["cascades"], w["noise"] = w["cascades"][lo:lo + per], w["noise"][lo:lo + per]
         w["cascade_of"], w["times"] = list(range(per)), w["times"][lo:lo + per]
         frames = w["frames"] = per
-    job_frames = 64 if sharded else world * frames            # frames the WHOLE job produces per step
+    job_frames = (64 if world > 1 else frames) if sharded else world * frames            # frames the WHOLE job produces per step
     slots = min(args.slots or (128 if N <= 512 else 32), frames) if args.workload != "c4" else frames
     sim = fow.FFTOceanWaves(N=N, cascades=w["cascades"], n_slots=max(slots, len(w["cascades"])), device=local, jacobian=w["jacobian"])
     for i, nz in enumerate(w["noise"]):
@@ -566,6 +567,7 @@ def main():
     ap.add_argument("--group", type=int, default=0, help="slots per launch group (0 = library default)")
     ap.add_argument("--streams", type=int, default=0, help="internal streams the launch groups are spread over (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--c4-shard-of", type=int, default=1, help="c4 on one GPU only: run the 64/P cascades one rank of a P-GPU job would get")
     ap.add_argument("--c5-n", type=int, default=32768, help="c5 only: grid size (32768 = BASELINE config C5; 4096 = its down-scaled parity grid)")
     ap.add_argument("--transport", choices=["auto", "peer", "alltoall"], default="auto", help="c5 only: how the transpose crosses GPUs")
     ap.add_argument("--profile", action="store_true",
