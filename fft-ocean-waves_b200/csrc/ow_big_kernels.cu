@@ -4,6 +4,11 @@
 // Kernel bodies: "LINES LONGER THAN ONE CTA'S SHARED MEMORY" in ow_kernels.cuh.
 #include "ow_frame_kernels.cuh"
 
+// Sub-line length of the production instantiations (N = 8192, 16384, 32768 -> A = N / OW_BIG_B).
+#ifndef OW_BIG_B
+#define OW_BIG_B 2048
+#endif
+
 namespace ow {
 
 namespace {
@@ -15,27 +20,28 @@ struct Big {
     using R = typename C::Row;
     using K = typename C::Col;
     static constexpr int G = C::COL_G;
+    static constexpr int RMB = C::ROW_MINB, KMB = C::COL_MINB;
     static constexpr int RY = 8, WARPS = 4, NMINB = 4;
 
     static cudaError_t configure() {
-        cudaError_t e = cudaFuncSetAttribute(ow_bigrow_lines_kernel<R, A, 1, false, FullRows<N>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<R, 1>());
+        cudaError_t e = cudaFuncSetAttribute(ow_bigrow_lines_kernel<R, A, RMB, false, FullRows<N>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<R, 1>());
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(ow_bigrow_lines_kernel<R, A, 1, true, FullRows<N>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<R, 1>());
+        e = cudaFuncSetAttribute(ow_bigrow_lines_kernel<R, A, RMB, true, FullRows<N>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<R, 1>());
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(ow_bigrow_lines_kernel<R, A, 1, false, SlabRows<N>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<R, 1>());
+        e = cudaFuncSetAttribute(ow_bigrow_lines_kernel<R, A, RMB, false, SlabRows<N>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<R, 1>());
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(ow_bigrow_lines_kernel<R, A, 1, true, SlabRows<N>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<R, 1>());
+        e = cudaFuncSetAttribute(ow_bigrow_lines_kernel<R, A, RMB, true, SlabRows<N>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<R, 1>());
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(ow_bigcol_lines_kernel<K, A, G, 1, FullColGeom<N>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ColLayout<K, G>::SMEM);
+        e = cudaFuncSetAttribute(ow_bigcol_lines_kernel<K, A, G, KMB, FullColGeom<N>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ColLayout<K, G>::SMEM);
         if (e != cudaSuccess) return e;
-        return cudaFuncSetAttribute(ow_bigcol_lines_kernel<K, A, G, 1, SlabColGeom>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ColLayout<K, G>::SMEM);
+        return cudaFuncSetAttribute(ow_bigcol_lines_kernel<K, A, G, KMB, SlabColGeom>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ColLayout<K, G>::SMEM);
     }
 
     template <class Rows, class Sink>
     static void rows_pass(const Rows& rows, const float* ktab, int p_first, int npairs_rows, float t, bool fast, float2* scratch, const Sink& sink,
                           cudaStream_t st) {
-        if (fast) ow_bigrow_lines_kernel<R, A, 1, true, Rows><<<npairs_rows * A, R::T, row_smem<R, 1>(), st>>>(rows, ktab, p_first, t, scratch);
-        else ow_bigrow_lines_kernel<R, A, 1, false, Rows><<<npairs_rows * A, R::T, row_smem<R, 1>(), st>>>(rows, ktab, p_first, t, scratch);
+        if (fast) ow_bigrow_lines_kernel<R, A, RMB, true, Rows><<<npairs_rows * A, R::T, row_smem<R, 1>(), st>>>(rows, ktab, p_first, t, scratch);
+        else ow_bigrow_lines_kernel<R, A, RMB, false, Rows><<<npairs_rows * A, R::T, row_smem<R, 1>(), st>>>(rows, ktab, p_first, t, scratch);
         ow_bigrow_post_kernel<B, A, Sink><<<dim3((B + 255) / 256, npairs_rows, 3), 256, 0, st>>>(scratch, p_first, sink);
     }
 
@@ -43,7 +49,7 @@ struct Big {
     static void cols_pass(const float2* src, size_t src_chan, int npairs, float2* scratch, float* dst, size_t dst_chan, const Geom& geom,
                           cudaStream_t st) {
         const float scale = 0.5f / ((float)N * (float)N);
-        ow_bigcol_lines_kernel<K, A, G, 1, Geom><<<dim3(npairs / G * A, 3), K::T * G, ColLayout<K, G>::SMEM, st>>>(src, src_chan, npairs, scratch, geom);
+        ow_bigcol_lines_kernel<K, A, G, KMB, Geom><<<dim3(npairs / G * A, 3), K::T * G, ColLayout<K, G>::SMEM, st>>>(src, src_chan, npairs, scratch, geom);
         ow_bigcol_post_kernel<B, A><<<dim3((npairs + 31) / 32, B / 8, 3), dim3(32, 8), 0, st>>>(scratch, npairs, dst, dst_chan, geom.dst_stride(), scale);
     }
 
@@ -98,9 +104,9 @@ struct Big {
 #define OW_BIG_DISPATCH(N_, forced_, CALL)                                   \
     do {                                                                     \
         if (!(forced_)) {                                                    \
-            if ((N_) == 8192) return Big<4096, 2>::CALL;                     \
-            if ((N_) == 16384) return Big<4096, 4>::CALL;                    \
-            if ((N_) == 32768) return Big<4096, 8>::CALL;                    \
+            if ((N_) == 8192) return Big<OW_BIG_B, 8192 / OW_BIG_B>::CALL;   \
+            if ((N_) == 16384) return Big<OW_BIG_B, 16384 / OW_BIG_B>::CALL; \
+            if ((N_) == 32768) return Big<OW_BIG_B, 32768 / OW_BIG_B>::CALL; \
         } else {                                                             \
             if ((N_) == 1024) return Big<256, 4>::CALL;                      \
             if ((N_) == 2048) return Big<512, 4>::CALL;                      \

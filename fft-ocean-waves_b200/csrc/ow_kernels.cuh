@@ -473,7 +473,7 @@ OW_HD void col_phase2(const Smem& sm, int base, int ft, float* __restrict__ dst 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// LINES LONGER THAN ONE CTA'S SHARED MEMORY:  N = A * B with B = P::N <= 4096 and A in {2, 4, 8}  (N = 8192 .. 32768,
+// LINES LONGER THAN ONE CTA'S SHARED MEMORY:  N = A * B with B = P::N <= 4096 and A in {2, 4, 8, 16}  (N = 8192 .. 32768,
 // BASELINE config C5). Cooley-Tukey split n = A*m + a, k = kb + B*ka of the same unnormalised inverse DFT:
 //     X[kb + B*ka] = sum_a W_A^{a ka} * ( W_N^{a kb} * z_a[kb] ),     z_a[kb] = sum_m x[A*m + a] W_B^{m kb},     W_n = e^{+2 pi i / n}
 // Two kernels per direction ("four-step" FFT with the transposes folded into the index maps):
