@@ -285,7 +285,9 @@ def run_slab(args):
     clocks = sampler.stop() if rank == 0 else None
     peak, peak_src = measured_peak()
     texels_rank = float(N) * N / world
-    kb = {"ow_row_slab_kernel": 16 + 12, "ow_col_slab_kernel+ow_normal_slab_kernel": 12 + 12 + 4 + 8 + 16 + 4}
+    # compulsory bytes per texel of the two phases (folded spectrum 8 -> intermediate 12; intermediate 12 -> dy,dx,dz 12, then
+    # dy,dx,dz 12 -> normal 16 + J 4); above N=4096 the line decomposition's scratch adds 24 B/texel per direction, not counted
+    kb = {"ow_row_slab_kernel": 8 + 12, "ow_col_slab_kernel+ow_normal_slab_kernel": 12 + 12 + 4 + 8 + 16 + 4}
     per_kernel = []
     for i, k in enumerate(kb):
         gbs = kb[k] * texels_rank * frames / (kms[i] * 1e-3) / 1e9
