@@ -47,7 +47,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJDIR, exist_ok=True)
     nvcc = _nvcc()
     hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
-    objs = []
+    objs, jobs = [], []
     for src, extra in SOURCES:
         s = os.path.join(CSRC, src)
         o = os.path.join(OBJDIR, src.replace(".cu", ".o"))
@@ -57,7 +57,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
                 print(" ".join(cmd))
-            subprocess.check_call(cmd)
+            jobs.append(cmd)
+    procs = [subprocess.Popen(cmd) for cmd in jobs]          # the translation units are independent: compile them side by side
+    for cmd, pr in zip(jobs, procs):
+        if pr.wait() != 0:
+            raise subprocess.CalledProcessError(pr.returncode, cmd)
     if force or _stale(LIB, objs):
         cmd = [nvcc, *ARCH, "-shared", "-cudart", "static", "-o", LIB, *objs]
         if verbose:

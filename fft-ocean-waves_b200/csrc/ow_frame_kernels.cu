@@ -12,7 +12,6 @@ template <int N>
 int g_row_pipe_ctas_per_sm[2] = {0, 0};
 static int g_sm_count = 148;
 static int g_row_classic = -1;   // OW_ROW_KERNEL=classic|pipe overrides the per-N choice Cfg<N>::ROW_PIPE (A/B runs, tools)
-static int g_skip = 0;           // OW_SKIP=[r][c][n]: development switch, leaves kernels out to study their overlap (results invalid)
 
 template <int N>
 cudaError_t configure_n() {
@@ -37,8 +36,6 @@ cudaError_t configure_n() {
         if (g_row_classic < 0) {
             const char* v = getenv("OW_ROW_KERNEL");
             g_row_classic = (v && v[0] == 'c') ? 1 : (v && v[0] == 'p') ? 0 : 2;
-            const char* k = getenv("OW_SKIP");
-            for (; k && *k; ++k) g_skip |= (*k == 'r') ? 1 : (*k == 'c') ? 2 : (*k == 'n') ? 4 : 0;
         }
     }
     cudaError_t e = cudaFuncSetAttribute(ow_row_kernel<typename C::Row, C::ROW_PAIRS, C::ROW_MINB, false>,
@@ -110,8 +107,7 @@ int launch_n(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_
     using R = typename C::Row;
     using K = typename C::Col;
     if (ev) cudaEventRecord(ev[0], st);
-    if (g_skip & 1) {
-    } else if (g_row_classic == 1 || (g_row_classic == 2 && !C::ROW_PIPE)) {
+    if (g_row_classic == 1 || (g_row_classic == 2 && !C::ROW_PIPE)) {
         const dim3 rgrid(N / 2 / C::ROW_PAIRS, count);
         if (fast_phase)
             ow_row_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true><<<rgrid, R::T * C::ROW_PAIRS, row_smem<R, C::ROW_PAIRS>(), st>>>(fb, tab);
@@ -128,13 +124,11 @@ int launch_n(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_
     }
     if (ev) cudaEventRecord(ev[1], st);
     const float scale = 0.5f / ((float)N * (float)N);   // 1/2 from the Hermitian split, 1/N^2 from inversion_cs.glsl:36
-    if (!(g_skip & 2))
     ow_col_kernel<K, C::COL_G, C::COL_MINB>
         <<<dim3(N / (2 * C::COL_G), 3, count), K::T * C::COL_G, ColLayout<K, C::COL_G>::SMEM, st>>>(fb, tab, scale);
     if (ev) cudaEventRecord(ev[2], st);
     const dim3 ngrid(N / 128, N / (C::NRM_WARPS * C::NRM_RY), count);
-    if (g_skip & 4) {
-    } else if (with_jac) ow_normal_kernel<N, true, C::NRM_RY, C::NRM_WARPS, C::NRM_MINB><<<ngrid, dim3(32, C::NRM_WARPS), 0, st>>>(fb, tab);
+    if (with_jac) ow_normal_kernel<N, true, C::NRM_RY, C::NRM_WARPS, C::NRM_MINB><<<ngrid, dim3(32, C::NRM_WARPS), 0, st>>>(fb, tab);
     else ow_normal_kernel<N, false, C::NRM_RY, C::NRM_WARPS, C::NRM_MINB><<<ngrid, dim3(32, C::NRM_WARPS), 0, st>>>(fb, tab);
     if (ev) cudaEventRecord(ev[3], st);
     return cudaGetLastError() == cudaSuccess ? 3 : -1;
