@@ -486,11 +486,14 @@ OW_HD void col_phase2(const Smem& sm, int base, int ft, float* __restrict__ dst 
 //          sinks as the direct kernel, i.e. the slab transpose over NVLink; columns: output rows with the inversion sign/scale)
 //          are as coalesced as the direct kernels'.
 // ---------------------------------------------------------------------------------------------------
-// Row lines, stage 0: spectrum at the decimated texels u = A*m + a of pair p (folded path; pair 0: the literal two-row path).
+// Row lines, stage 0, pair 0 only: rows 0 and N/2 are their own mirrors; Z = S(., 0) + i*S(., N/2) at the decimated texels
+// u = A*m + a. One pair in N/2: small register footprint, not speed (see row_phase0_pair0).
 template <class P, int A, bool FAST, class Smem, class Rows>
-__host__ __device__ __noinline__ void bigrow_phase0(const Smem& sm, int ft, int p, int a, const Rows& rows, const float* __restrict__ ktab, float t) {
+__host__ __device__ __noinline__ void bigrow_phase0_pair0(const Smem& sm, int ft, int a, const Rows& rows, const float* __restrict__ ktab, float t) {
     constexpr int B = P::N, N = A * B, R0 = P::R0;
-    const float ky = OW_LDG(ktab + p);
+    const float4* row0 = rows.row(0);
+    const float4* rowh = rows.row(N / 2);
+    const float ky0 = OW_LDG(ktab), kyh = OW_LDG(ktab + N / 2);
 #pragma unroll 1
     for (int c = 0; c < P::C0; ++c) {
         const int b = ft + P::T * c;
@@ -499,19 +502,11 @@ __host__ __device__ __noinline__ void bigrow_phase0(const Smem& sm, int ft, int 
 #pragma unroll 1
         for (int d0 = 0; d0 < R0; ++d0) {
             const int u = A * (d0 * P::M + b) + a;
-            Sym3 s;
-            if (p != 0) {
-                s = spectrum_folded<FAST>(load_folded(rows.pair_row(p), ktab, u), ky, t, u == 0 ? rows.nyq_of(p) : nullptr);
-            } else {   // rows 0 and N/2 are their own mirrors; Z = S(., 0) + i*S(., N/2) (see row_phase0_pair0)
-                const float4* row0 = rows.row(0);
-                const float4* rowh = rows.row(N / 2);
-                const Sym3 x0 = spectrum_sym<FAST>(load_pair<N>(row0, row0, ktab, u), u, OW_LDG(ktab), true, t);
-                const Sym3 xh = spectrum_sym<FAST>(load_pair<N>(rowh, rowh, ktab, u), u, OW_LDG(ktab + N / 2), true, t);
-                s.y = make_float2(x0.y.x - xh.y.y, x0.y.y + xh.y.x);
-                s.x = make_float2(x0.x.x - xh.x.y, x0.x.y + xh.x.x);
-                s.z = make_float2(x0.z.x - xh.z.y, x0.z.y + xh.z.x);
-            }
-            v[0][d0] = s.y; v[1][d0] = s.x; v[2][d0] = s.z;
+            const Sym3 x0 = spectrum_sym<FAST>(load_pair<N>(row0, row0, ktab, u), u, ky0, true, t);
+            const Sym3 xh = spectrum_sym<FAST>(load_pair<N>(rowh, rowh, ktab, u), u, kyh, true, t);
+            v[0][d0] = make_float2(x0.y.x - xh.y.y, x0.y.y + xh.y.x);
+            v[1][d0] = make_float2(x0.x.x - xh.x.y, x0.x.y + xh.x.x);
+            v[2][d0] = make_float2(x0.z.x - xh.z.y, x0.z.y + xh.z.x);
         }
         float2 tw[R0];
         twiddle_powers<R0>(unit_root(b, B), tw);
@@ -522,6 +517,38 @@ __host__ __device__ __noinline__ void bigrow_phase0(const Smem& sm, int ft, int 
             for (int d0 = 0; d0 < R0; ++d0) w[d0] = v[f][d0];
             stage0_finish<P>(sm, f * P::LINE, b, w, tw);
         }
+    }
+}
+
+// Row lines, stage 0: spectrum at the decimated texels u = A*m + a of pair p — row_phase0 with a strided texel index
+// (all loads of a butterfly in flight before the first use).
+template <class P, int A, bool FAST, class Smem, class Rows>
+OW_HD void bigrow_phase0(const Smem& sm, int ft, int p, int a, const Rows& rows, const float* __restrict__ ktab, float t) {
+    constexpr int B = P::N, R0 = P::R0;
+    if (p == 0) {
+        bigrow_phase0_pair0<P, A, FAST>(sm, ft, a, rows, ktab, t);
+        return;
+    }
+    const float ky = OW_LDG(ktab + p);
+    const float4* prow = rows.pair_row(p);
+#pragma unroll 1
+    for (int c = 0; c < P::C0; ++c) {
+        const int b = ft + P::T * c;
+        if (b >= P::M) break;
+        float2 vy[R0], vx[R0], vz[R0];
+        FoldedPair fp[R0];
+#pragma unroll
+        for (int d0 = 0; d0 < R0; ++d0) fp[d0] = load_folded(prow, ktab, A * (d0 * P::M + b) + a);
+#pragma unroll
+        for (int d0 = 0; d0 < R0; ++d0) {
+            const Sym3 s = spectrum_folded<FAST>(fp[d0], ky, t, (d0 == 0 && b == 0 && a == 0) ? rows.nyq_of(p) : nullptr);
+            vy[d0] = s.y; vx[d0] = s.x; vz[d0] = s.z;
+        }
+        float2 tw[R0];
+        twiddle_powers<R0>(unit_root(b, B), tw);
+        stage0_finish<P>(sm, 0 * P::LINE, b, vy, tw);
+        stage0_finish<P>(sm, 1 * P::LINE, b, vx, tw);
+        stage0_finish<P>(sm, 2 * P::LINE, b, vz, tw);
     }
 }
 
@@ -560,17 +587,6 @@ OW_HD void bigrow_post(const float2* __restrict__ zrow /* scratch row of pair p:
     for (int ka = 0; ka < A; ++ka) sink.put(c, p, kb + B * ka, v[ka]);
 }
 
-// Column source element Q_v of the Hermitian-packed intermediate (see the COLUMN KERNEL comment): v in [0, N).
-template <int N>
-OW_HD float2 col_source(const float2* __restrict__ src /* inter[c] + x */, size_t ss, int v) {
-    if (v == 0 || v == N / 2) {
-        const float4 r = OW_LDG(reinterpret_cast<const float4*>(src));
-        return v == 0 ? make_float2(r.x, r.z) : make_float2(r.y, r.w);
-    }
-    if (v < N / 2) return pack_fwd(OW_LDG(reinterpret_cast<const float4*>(src + (size_t)v * ss)));
-    return pack_cnj(OW_LDG(reinterpret_cast<const float4*>(src + (size_t)(N - v) * ss)));
-}
-
 // Column lines, stage 0: the decimated source rows v = A*m + a of this job's column pair.
 template <class P, int A, class Smem, class Geom>
 OW_HD void bigcol_phase0(const Smem& sm, int base, int ft, int a, const float2* __restrict__ src /* inter[c] + x */, const Geom& geom) {
@@ -579,8 +595,19 @@ OW_HD void bigcol_phase0(const Smem& sm, int base, int ft, int a, const float2* 
 #pragma unroll 1
     for (int b = ft; b < P::M; b += P::T) {
         float2 v[R0], tw[R0];
+        float4 r[R0];
+        // all R0 row loads first (row of v: v itself below N/2, N - v above, row 0 for the two packed real rows), then the unpacking
 #pragma unroll
-        for (int d0 = 0; d0 < R0; ++d0) v[d0] = col_source<N>(src, ss, A * (d0 * P::M + b) + a);
+        for (int d0 = 0; d0 < R0; ++d0) {
+            const int vv = A * (d0 * P::M + b) + a;
+            const int row = (vv < N / 2 ? vv : N - vv) & (N / 2 - 1);
+            r[d0] = OW_LDG(reinterpret_cast<const float4*>(src + (size_t)row * ss));
+        }
+#pragma unroll
+        for (int d0 = 0; d0 < R0; ++d0) {
+            const int vv = A * (d0 * P::M + b) + a;
+            v[d0] = vv == 0 ? make_float2(r[d0].x, r[d0].z) : vv == N / 2 ? make_float2(r[d0].y, r[d0].w) : vv < N / 2 ? pack_fwd(r[d0]) : pack_cnj(r[d0]);
+        }
         twiddle_powers<R0>(unit_root(b, B), tw);
         stage0_finish<P>(sm, base, b, v, tw);
     }
