@@ -59,6 +59,34 @@ def test_single_rank_slab_equals_single_gpu_path(N, transport):
                 assert np.abs(got - ref[k]).max() <= 1e-6 * max(1.0, 0.0) * max(np.abs(ref[k]).max(), 1e-30) + (2e-6 if k in ("normal", "jacobian") else 0.0), (k, t)
 
 
+def test_c5_full_size_slab_equals_single_gpu_path():
+    """BASELINE config C5 at its quoted size, N = 32768, on one rank: the slab kernels (line decomposition A = 16, transposing
+    sink, halo columns, column slab stencils) against ow_step on the same Philox seed. One image at a time: a context is ~90 GB."""
+    import psutil
+    import torch
+    N, seed, t = 32768, 32768, 1.0
+    if psutil.virtual_memory().available < 40e9 or torch.cuda.mem_get_info()[0] < 120e9:
+        pytest.skip("not enough host or device memory for N = 32768")
+    ref = {}
+    with fow.FFTOceanWaves(N=N, cascades=[P], jacobian=True) as one:
+        one.set_noise_seed(seed)
+        one.tilde_h0_k()
+        one.update(t)
+        one.sync()
+        for k in ("dy", "dz", "jacobian"):
+            ref[k] = one.download(k)
+    with fow.SlabOcean(N=N, params=P, jacobian=True) as sim:
+        sim.init(seed)
+        sim.update(t)
+        sim.sync()
+        for k in ("dy", "dz", "jacobian"):
+            got = sim.download(k)
+            tol = 1e-6 * float(np.abs(ref[k]).max()) + (2e-6 if k == "jacobian" else 0.0)
+            assert np.abs(got - ref[k]).max() <= tol, k
+            del got
+    assert float(np.abs(ref["dy"]).max()) > 0 and np.isfinite(ref["jacobian"]).all()
+
+
 def test_slab_api_errors():
     lib = fow.load_library()
     with pytest.raises(fow.OceanWavesError):
