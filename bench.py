@@ -406,13 +406,14 @@ def run_ours(args):
     sp = stream.cuda_stream
     assert sp != 0
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
-    launches = [0]
+    launches, groups = [0], [0]
 
     def sweep():
         for base in range(0, frames, slots):
             n = min(slots, frames - base)
             sim.update_multi(w["cascade_of"][base:base + n], w["times"][base:base + n], stream=sp)
             launches[0] += sim.last_launch_count()
+            groups[0] += sim.last_group_count()
 
     def barrier():
         torch.cuda.synchronize()
@@ -427,7 +428,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    launches[0] = 0
+    launches[0] = groups[0] = 0
     evs = []
     t_wall = time.perf_counter()
     for _ in range(args.steps):
@@ -460,28 +461,35 @@ def run_ours(args):
             kms += np.array(sim.update_multi_timed(w["cascade_of"][base:base + n], w["times"][base:base + n], stream=sp))
     clocks = sampler.stop() if rank == 0 else None
     kms /= prof_sweeps                                      # ms per sweep per kernel
-    groups_per_sweep = timed_launches / 3 / args.steps
+    groups_per_sweep = groups[0] / args.steps
+    fused = not w["jacobian"] and kms[2] == 0.0          # normal map produced by the column kernel's epilogue (no separate kernel)
     peak, peak_src = measured_peak()
     texels = float(N) * N
     kb = dict(KERNEL_BYTES_PER_TEXEL)
     if w["jacobian"]:
         kb["ow_normal_kernel"] += 8 + 4                     # + read dx,dz, write J
+    if fused:
+        kb["ow_col_kernel"] += 16                           # ow_col_fused_kernel also writes the normal map (and never re-reads dy)
     per_kernel = []
     for i, k in enumerate(KERNELS):
-        gbs = kb[k] * texels * frames / (kms[i] * 1e-3) / 1e9
+        if kms[i] == 0.0:
+            continue
+        if fused and k == "ow_col_kernel":
+            k = "ow_col_fused_kernel"
+        gbs = kb.get(k, kb["ow_col_kernel"]) * texels * frames / (kms[i] * 1e-3) / 1e9
         per_kernel.append({"kernel": k, "ms_per_launch": kms[i] / groups_per_sweep, "share": kms[i] / kms.sum(),
-                           "bytes_per_texel": kb[k], "achieved_gbs": gbs, "frac": gbs / peak})
-    dom = int(np.argmax(kms))
+                           "bytes_per_texel": kb.get(k, kb["ow_col_kernel"]), "achieved_gbs": gbs, "frac": gbs / peak})
+    dom = int(np.argmax([pk["share"] for pk in per_kernel]))
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{args.workload}:{KERNELS[dom]}")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{args.workload}:{per_kernel[dom]['kernel']}")
     except Exception:
         pass
     alg = ALG_BYTES_PER_TEXEL + (4 if w["jacobian"] else 0)
     frame_gbs = alg * texels * value / world / 1e9
-    roofline = {"bound": "hbm", "kernel": KERNELS[dom], "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": per_kernel[dom]["kernel"], "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": per_kernel[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
-                "bytes_per_launch": kb[KERNELS[dom]] * texels * frames / groups_per_sweep,
+                "bytes_per_launch": per_kernel[dom]["bytes_per_texel"] * texels * frames / groups_per_sweep,
                 "kernels": per_kernel,
                 "frame": {"algorithmic_bytes_per_texel": alg, "achieved": frame_gbs, "frac": frame_gbs / peak,
                           "note": "whole frame on SURVEY.md's 44 B/texel (48 with Jacobian), per GPU; the 3-kernel design moves 64 B/texel (8+12, 12+12, 4+16) of which 36 are compulsory since the h0 fold"}}

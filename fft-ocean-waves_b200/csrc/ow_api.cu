@@ -44,7 +44,7 @@ struct ow_ctx {
     int n_streams = 3;
     bool spectrum_ready = false;
     int group_size = 0;
-    int last_launches = 0;
+    int last_launches = 0, last_groups = 0;
     std::string err;
     // GL interop
     cudaGraphicsResource* gl_res[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -356,6 +356,7 @@ static int step_impl(ow_ctx* c, int32_t count, const int32_t* cascade_of_slot, c
     }
     if (kernel_ms) for (auto& e : ev) cudaEventDestroy(e);
     c->last_launches = launches;
+    c->last_groups = ngroups;
     return OW_OK;
 }
 
@@ -463,6 +464,7 @@ int ow_set_streams(ow_ctx* c, int32_t n) {
 }
 
 int ow_last_launch_count(const ow_ctx* c) { return c ? c->last_launches : 0; }
+int ow_last_group_count(const ow_ctx* c) { return c ? c->last_groups : 0; }
 
 // ---- CUDA-GL interop -------------------------------------------------------------------------------
 // The image has no GL headers, so the three cudart entry points are declared here with GL's own scalar

@@ -10,6 +10,8 @@ namespace ow {
 // ROW_PIPE selects the persistent software-pipelined row kernel (ow_row_pipe_kernel) instead of one CTA per ROW_PAIRS
 // row pairs; chosen per N from whole-frame throughput in multi-stream sweeps (tools/tune/tune.cu -DTUNE_SWEEP), where a
 // variant that wins in isolation does not always win (profiles/r01d_tune_sweep_*.txt).
+// COL_FUSE: frames without the Jacobian run ow_col_fused_kernel (normal map as the epilogue of the dy column tiles) and no
+// separate normal kernel; needs COL_G == 8.
 // Normal kernel: NRM_RY output rows per thread walk, NRM_WARPS warps per CTA, NRM_MINB resident CTAs per SM.
 // Column plans interleave G jobs in the lane index, need S0 odd and a job stride == 16/G (mod 16).
 // ---------------------------------------------------------------------------------------------------
@@ -23,6 +25,7 @@ struct Cfg<256> {
     static constexpr bool ROW_PIPE = false;
     using Col = Plan<256, 4, 4, 16, 32, 0, 1>;
     static constexpr int COL_G = 8, COL_MINB = 2;
+    static constexpr bool COL_FUSE = true;
     static constexpr int NRM_RY = 8, NRM_WARPS = 4, NRM_MINB = 4;
 };
 template <>
@@ -32,6 +35,7 @@ struct Cfg<512> {
     static constexpr bool ROW_PIPE = false;
     using Col = Plan<512, 8, 4, 16, 32, 0, 1>;
     static constexpr int COL_G = 8, COL_MINB = 2;
+    static constexpr bool COL_FUSE = true;
     static constexpr int NRM_RY = 8, NRM_WARPS = 4, NRM_MINB = 4;
 };
 template <>
@@ -41,6 +45,7 @@ struct Cfg<1024> {
     static constexpr bool ROW_PIPE = true;
     using Col = Plan<1024, 8, 8, 16, 64, 0, 1>;
     static constexpr int COL_G = 8, COL_MINB = 2;
+    static constexpr bool COL_FUSE = true;
     static constexpr int NRM_RY = 8, NRM_WARPS = 4, NRM_MINB = 4;
 };
 template <>
@@ -50,6 +55,7 @@ struct Cfg<2048> {
     static constexpr bool ROW_PIPE = false;
     using Col = Plan<2048, 8, 16, 16, 64, 0, 1>;
     static constexpr int COL_G = 8, COL_MINB = 1;
+    static constexpr bool COL_FUSE = true;
     static constexpr int NRM_RY = 8, NRM_WARPS = 4, NRM_MINB = 4;
 };
 template <>
@@ -59,6 +65,7 @@ struct Cfg<4096> {
     static constexpr bool ROW_PIPE = false;
     using Col = Plan<4096, 16, 16, 16, 128, 0, 1>;
     static constexpr int COL_G = 4, COL_MINB = 1;
+    static constexpr bool COL_FUSE = false;
     static constexpr int NRM_RY = 8, NRM_WARPS = 4, NRM_MINB = 4;
 };
 

@@ -181,6 +181,48 @@ __global__ void __launch_bounds__(P::T* G, MINB) ow_col_kernel(FrameBuffers fb, 
     col_phase2<P>(sm, base, ft, dst, scale, geom);
 }
 
+// Column kernel with the normal map fused into the dy tiles (see "COLUMN KERNEL WITH THE NORMAL MAP AS ITS EPILOGUE").
+// grid.x = ndy dy tiles (6 output pairs + 2 halo pairs each) followed by 2 * N/16 ordinary tiles for dx and dz; grid.y = slot entries.
+template <class P, int G, int MINB, int RY>
+__global__ void __launch_bounds__(P::T* G, MINB) ow_col_fused_kernel(FrameBuffers fb, SlotTable tab, float scale, int ndy) {
+    static_assert(G == 8, "dy tiles are 6 output pairs + 2 halo pairs");
+    extern __shared__ __align__(16) float2 smem[];
+    constexpr int N = P::N, HP = N / 2;
+    using LY = ColLayout<P, G>;
+    const int job = threadIdx.x % G, ft = threadIdx.x / G;
+    const int slot = tab.slot[blockIdx.y];
+    const SmemDirect sm{smem};
+    const int base = job * LY::SJ;
+    const FullColGeom<N> geom{};
+    const bool dy_tile = (int)blockIdx.x < ndy;
+    int f, pair;
+    bool store = true;
+    if (dy_tile) {
+        f = 0;
+        pair = (6 * (int)blockIdx.x - 1 + job) & (HP - 1);
+        store = job >= 1 && job <= 6 && 6 * (int)blockIdx.x + job - 1 < HP;
+    } else {
+        const int r = (int)blockIdx.x - ndy;
+        f = 1 + r / (HP / G);
+        pair = (r % (HP / G)) * G + job;
+    }
+    const int x = 2 * pair;
+    const float2* src = fb.inter + ((size_t)slot * 3 + f) * HP * N + x;
+    float* dst = fb.disp + ((size_t)slot * 3 + f) * N * N + x;
+#pragma unroll 1
+    for (int j = ft; j < P::M / 2; j += P::T) col_phase0<P>(sm, base, j, src, geom);
+    __syncthreads();
+    col_phase1<P>(sm, base, ft);
+    __syncthreads();
+    if (!dy_tile) {
+        col_phase2<P>(sm, base, ft, dst, scale, geom);
+        return;
+    }
+    col_phase2_keep<P>(sm, base, ft, dst, scale, geom, store);
+    __syncthreads();
+    col_normals_phase<P, RY>(sm, threadIdx.x, P::T * G, LY::SJ, 12 * (int)blockIdx.x, fb.normal + (size_t)slot * N * N);
+}
+
 // Slab variant: the column slab's receive buffer [p][c][XH] (row stride 3*XH) -> disp_loc[c][y][XH].
 template <class P, int G, int MINB>
 __global__ void __launch_bounds__(P::T* G, MINB) ow_col_slab_kernel(const float2* __restrict__ recv, float* __restrict__ disp, int XH,

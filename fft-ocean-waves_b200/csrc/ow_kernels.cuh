@@ -712,8 +712,25 @@ OW_HD NormalRowIn normal_row_load(const float* __restrict__ disp, const Geom& ge
     return in;
 }
 
+// Row source of the walk: where the seven heights (and, for the Jacobian, Dx/Dz) of h row rr come from.
+template <int N, bool JAC, class Geom>
+struct GlobalRowSrc {           // the displacement planes in global memory (the stand-alone normal kernel)
+    const float* disp;
+    Geom geom;
+    int x0;
+    OW_HD NormalRowIn load(int rr, bool want_xz, bool want_dd) const { return normal_row_load<N, JAC>(disp, geom, x0, rr, want_xz, want_dd); }
+};
+
+template <int N, int RY, bool JAC, class Src, class Emit>
+OW_HD void normal_quad_walk_src(const Src& src, int y0, float s, const Emit& emit);
+
 template <int N, int RY, bool JAC, class Geom, class Emit>
 OW_HD void normal_quad_walk(const float* __restrict__ disp /* dy,dx,dz planes */, const Geom& geom, int x0, int y0, float s, const Emit& emit) {
+    normal_quad_walk_src<N, RY, JAC>(GlobalRowSrc<N, JAC, Geom>{disp, geom, x0}, y0, s, emit);
+}
+
+template <int N, int RY, bool JAC, class Src, class Emit>
+OW_HD void normal_quad_walk_src(const Src& src, int y0, float s, const Emit& emit) {
     constexpr int MSK = N - 1;
     float hs_prev[6], sx_m1[4], sx_0[4], dxb_m1[4], dxb_0[4];
     float xc_m1[4], xc_0[4], zc_m1[4], zc_0[4], ddx_0[4], ddz_0[4];
@@ -724,11 +741,11 @@ OW_HD void normal_quad_walk(const float* __restrict__ disp /* dy,dx,dz planes */
     }
 #pragma unroll
     for (int c = 0; c < 6; ++c) hs_prev[c] = 0.f;
-    NormalRowIn nxt = normal_row_load<N, JAC>(disp, geom, x0, (y0 - 2) & MSK, false, false);
+    NormalRowIn nxt = src.load((y0 - 2) & MSK, false, false);
 #pragma unroll
     for (int i = -2; i <= RY; ++i) {              // h row r = y0 + i ; emits output row r - 1 once i >= 1
         const NormalRowIn in = nxt;
-        if (i < RY) nxt = normal_row_load<N, JAC>(disp, geom, x0, (y0 + i + 1) & MSK, i + 1 >= -1, i + 1 >= 0 && i + 1 < RY);
+        if (i < RY) nxt = src.load((y0 + i + 1) & MSK, i + 1 >= -1, i + 1 >= 0 && i + 1 < RY);
         const float4 m = in.m;
         const float hs[6] = {in.l.x + in.l.y, in.l.y + m.x, m.x + m.y, m.y + m.z, m.z + m.w, m.w + in.e};
         float sx[4] = {0.f, 0.f, 0.f, 0.f}, dxb[4] = {0.f, 0.f, 0.f, 0.f};
@@ -768,6 +785,85 @@ OW_HD void normal_quad_walk(const float* __restrict__ disp /* dy,dx,dz planes */
             sx_m1[j] = sx_0[j]; sx_0[j] = sx[j]; dxb_m1[j] = dxb_0[j]; dxb_0[j] = dxb[j];
             xc_m1[j] = xc_0[j]; xc_0[j] = xc[j]; zc_m1[j] = zc_0[j]; zc_0[j] = zc[j]; ddx_0[j] = ddx[j]; ddz_0[j] = ddz[j];
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// COLUMN KERNEL WITH THE NORMAL MAP AS ITS EPILOGUE (no Jacobian; tiles of G = 8 column pairs).
+// A dy tile carries one halo pair either side: jobs 0..7 = pairs 6t-1 .. 6t+6 (mod N/2), of which jobs 1..6 are the tile's
+// OUTPUT pairs (columns 12t .. 12t+11). After stage 2 every job's final heights are written back IN PLACE into its line
+// (row y = k0 + R0 k1 + R0 R1 k2 at addr(k0,k1,k2); .x = even column, .y = odd column), the tile syncs, and the same
+// sliding-window stencil as the stand-alone normal kernel runs out of shared memory: one thread per (column quad, RY rows),
+// lanes spread over the unit-stride digit k2 so that every LDS.64 phase is conflict-free. The heights never make the
+// round trip through L2/HBM, and the normal map's HBM writes overlap the FFT work of the other resident tiles.
+// Cost: 8 transformed pairs per 6 output pairs on the dy channel (+11 % column FFT work overall).
+// ---------------------------------------------------------------------------------------------------
+template <class P, class Smem, class Geom>
+OW_HD void col_phase2_keep(const Smem& sm, int base, int ft, float* __restrict__ dst /* out[c] + x */, float scale, const Geom& geom, bool store) {
+    const size_t ds = geom.dst_stride();
+#pragma unroll 1
+    for (int c = 0; c < P::C2; ++c) {
+        const int bp = ft + P::T * c;
+        if (bp >= P::B2) break;
+        const int k0 = bp % P::R0, k1 = bp / P::R0;
+        float2 v[P::R2];
+        stage2<P>(sm, base, bp, v);
+        const float sg = (bp & 1) ? -scale : scale;
+#pragma unroll
+        for (int k2 = 0; k2 < P::R2; ++k2) {
+            const float2 h = make_float2(sg * v[k2].x, -sg * v[k2].y);
+            if (store) *reinterpret_cast<float2*>(dst + (size_t)(bp + P::B2 * k2) * ds) = h;
+            sm.st(base + P::addr(k0, k1, k2), h);
+        }
+    }
+}
+
+template <class P, class Smem>
+struct SmemRowSrc {             // final heights of four adjacent jobs (pairs q-1, q, q+1, q+2 of a column quad) in the tile's lines
+    Smem sm;
+    int base0, SJ;              // line base of the leftmost job; float2 elements between jobs
+    OW_HD NormalRowIn load(int rr, bool, bool) const {
+        const int a = base0 + P::addr(rr % P::R0, (rr / P::R0) % P::R1, rr / (P::R0 * P::R1));
+        const float2 q0 = sm.ld(a), q1 = sm.ld(a + SJ), q2 = sm.ld(a + 2 * SJ), q3 = sm.ld(a + 3 * SJ);
+        NormalRowIn in;
+        in.l = q0; in.m = make_float4(q1.x, q1.y, q2.x, q2.y); in.e = q3.x;
+        in.a = in.b = make_float4(0.f, 0.f, 0.f, 0.f);
+        in.al = in.ar = in.bl = in.br = 0.f;
+        return in;
+    }
+};
+
+template <bool STREAM>
+struct EmitQuad {               // four adjacent normals of one row straight to global memory
+    float4* normal;             // slot base, [N][N]
+    size_t ostride;
+    int xout;
+    OW_HD void operator()(int y, const float4 (&n)[4], float4) const {
+        float4* d = normal + (size_t)y * ostride + xout;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#ifdef __CUDA_ARCH__
+            if (STREAM) { __stcs(d + j, n[j]); continue; }
+#endif
+            d[j] = n[j];
+        }
+    }
+};
+
+// Normal-map epilogue of one dy tile: items = (column quad j < 3) x (row chunk of RY rows); item -> (k2 fastest, then the chunk's
+// position w inside a block of R0*R1 rows, then j), so the 16 lanes of an LDS.64 phase differ only in the unit-stride digit.
+template <class P, int RY, class Smem>
+OW_HD void col_normals_phase(const Smem& sm, int tid, int nthreads, int SJ, int x_first /* first output column of the tile */,
+                             float4* __restrict__ normal /* slot base */) {
+    constexpr int N = P::N, LOW = P::R0 * P::R1, WPER = LOW / RY, NITEMS = 3 * P::R2 * WPER;
+    static_assert(LOW % RY == 0, "row chunks must tile a block of R0*R1 rows");
+#pragma unroll 1
+    for (int item = tid; item < NITEMS; item += nthreads) {
+        const int k2 = item % P::R2, w = (item / P::R2) % WPER, j = item / (P::R2 * WPER);
+        const int x0 = x_first + 4 * j;
+        if (x0 >= N) continue;                                  // wrapped duplicate pairs of the last tile
+        const SmemRowSrc<P, Smem> src{sm, 2 * j * SJ, SJ};
+        normal_quad_walk_src<N, RY, false>(src, LOW * k2 + RY * w, 0.f, EmitQuad<true>{normal, (size_t)N, x0});
     }
 }
 

@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = [
     "ow_create", "ow_destroy", "ow_last_error", "ow_set_params", "ow_set_noise", "ow_init_spectrum", "ow_set_h0",
     "ow_step", "ow_step_multi", "ow_step_multi_timed", "ow_sync", "ow_get_outputs", "ow_download", "ow_download_frame_async",
     "ow_frame_bytes", "ow_set_group_size", "ow_set_streams", "ow_last_launch_count", "ow_gl_register", "ow_gl_step", "ow_gl_unregister",
-    "ow_set_noise_seed",
+    "ow_set_noise_seed", "ow_last_group_count",
     "ow_slab_create", "ow_slab_destroy", "ow_slab_last_error", "ow_slab_get_info", "ow_slab_init_spectrum_seeded", "ow_slab_ipc_handle",
     "ow_slab_open_peers", "ow_slab_rows", "ow_slab_cols", "ow_slab_local_exchange", "ow_slab_sync", "ow_slab_download",
 ]
@@ -119,6 +119,7 @@ def load_library():
     L.ow_set_group_size.argtypes = [vp, i32]
     L.ow_set_streams.argtypes = [vp, i32]
     L.ow_last_launch_count.argtypes = [vp]
+    L.ow_last_group_count.argtypes = [vp]
     L.ow_gl_register.argtypes = [vp, u32, u32, u32, u32]
     L.ow_gl_step.argtypes = [vp, f32]
     L.ow_gl_unregister.argtypes = [vp]
@@ -250,6 +251,9 @@ class FFTOceanWaves:
 
     def last_launch_count(self) -> int:
         return int(self._lib.ow_last_launch_count(self._h))
+
+    def last_group_count(self) -> int:
+        return int(self._lib.ow_last_group_count(self._h))
 
     # ---- outputs -----------------------------------------------------------------------------------
     def outputs(self, slot: int = 0) -> _Outputs:

@@ -132,8 +132,10 @@ int ow_set_group_size(ow_ctx* ctx, int32_t slots_per_group);
  * joined back into the caller's stream), so one group's tail overlaps the next group's head. 1 = strictly serial.
  * Default 3; n in [1, 4]. Results do not depend on it. */
 int ow_set_streams(ow_ctx* ctx, int32_t n);
-/* Number of kernels the last ow_step/ow_step_multi launched (for launch accounting in bench.py). */
+/* Number of kernels the last ow_step/ow_step_multi launched (for launch accounting in bench.py), and the number of launch
+ * groups they formed (a group = the row, column[, normal] kernels of the slots that share launches). */
 int ow_last_launch_count(const ow_ctx* ctx);
+int ow_last_group_count(const ow_ctx* ctx);
 
 /* ---- CUDA-GL interop: replaces the renderer's texture binds (src/main.cpp:477-487) ------------------- */
 

@@ -33,6 +33,7 @@ def lib():
         fp = C.POINTER(C.c_float)
         L.emu_frame.argtypes = [C.c_int, fp, fp, C.c_float, C.c_float, C.c_float, fp, fp, fp, fp, C.POINTER(C.c_long)]
         L.emu_dft.argtypes = [C.c_int, fp, fp]
+        L.emu_frame_fused.argtypes = [C.c_int, fp, fp, C.c_float, C.c_float, fp, fp, C.POINTER(C.c_long)]
         L.emu_big_frame.argtypes = [C.c_int, C.c_int, fp, fp, C.c_float, C.c_float, C.c_float, fp, fp, fp]
         L.emu_slab_frame.argtypes = [C.c_int, C.c_int, fp, fp, C.c_float, C.c_float, C.c_float, fp, fp, fp]
         _lib = L
@@ -93,3 +94,17 @@ def big_frame(N, A, h0k, h0minusk, L, t, choppiness=1.0):
     rc = lib().emu_big_frame(N, int(A), _p(a), _p(b), float(L), float(t), float(choppiness), _p(disp), _p(nm), _p(jac))
     assert rc == 0, rc
     return dict(dy=disp[0], dx=disp[1], dz=disp[2], normal=nm, jacobian=jac)
+
+
+def frame_fused(N, h0k, h0minusk, L, t):
+    """The frame without the Jacobian as the product runs it: normal map fused into the dy column tiles (ow_col_fused_kernel)."""
+    a = np.ascontiguousarray(h0k, np.float32)
+    b = np.ascontiguousarray(h0minusk, np.float32)
+    disp = np.empty((3, N, N), np.float32)
+    nm = np.full((N, N, 4), np.nan, np.float32)
+    stats = np.zeros(14, np.int64)
+    rc = lib().emu_frame_fused(N, _p(a), _p(b), float(L), float(t), _p(disp), _p(nm), stats.ctypes.data_as(C.POINTER(C.c_long)))
+    assert rc == 0, rc
+    out = dict(dy=disp[0], dx=disp[1], dz=disp[2], normal=nm)
+    out["conflicts"] = {n: (int(stats[2 * i]), int(stats[2 * i + 1])) for i, n in enumerate(PHASES + ["col_normals"])}
+    return out

@@ -162,6 +162,64 @@ int emu_frame_n(const float* h0k, const float* h0minusk, float L, float t, float
     return 0;
 }
 
+// ow_col_fused_kernel thread by thread: dy tiles of 6 output + 2 halo pairs with the normal map as their epilogue, ordinary
+// tiles for dx and dz. st.req/wf[3..5] = the three FFT phases of the dy tiles, stats6 = the stencil phase out of shared memory.
+template <int N>
+void emu_cols_fused(const float2* inter, float* disp, float4* normal, Stats& st, long* stats6) {
+    using C = Cfg<N>;
+    using P = typename C::Col;
+    constexpr int G = C::COL_G, NT = P::T * G, HP = N / 2, RY = C::NRM_RY;
+    using LY = ColLayout<P, G>;
+    std::vector<float2> smem((size_t)G * LY::SJ);
+    const float scale = 0.5f / ((float)N * (float)N);
+    const FullColGeom<N> geom{};
+    Recorder rec;
+    const int ndy = (HP + 5) / 6, nblk = ndy + 2 * (HP / G);
+    for (int blk = 0; blk < nblk; ++blk) {
+        const bool dy_tile = blk < ndy;
+        for (int phase = 0; phase < 4; ++phase) {
+            if (phase == 3 && !dy_tile) break;
+            rec.begin(NT);
+            for (int tid = 0; tid < NT; ++tid) {
+                const int job = tid % G, ft = tid / G, base = job * LY::SJ;
+                int f, pair;
+                bool store = true;
+                if (dy_tile) { f = 0; pair = (6 * blk - 1 + job) & (HP - 1); store = job >= 1 && job <= 6 && 6 * blk + job - 1 < HP; }
+                else { const int r = blk - ndy; f = 1 + r / (HP / G); pair = (r % (HP / G)) * G + job; }
+                const SmemEmu sm{smem.data(), &rec.seq[tid]};
+                const float2* src = inter + (size_t)f * HP * N + 2 * pair;
+                float* dst = disp + (size_t)f * N * N + 2 * pair;
+                if (phase == 0) for (int j = ft; j < P::M / 2; j += P::T) col_phase0<P>(sm, base, j, src, geom);
+                if (phase == 1) col_phase1<P>(sm, base, ft);
+                if (phase == 2) { if (dy_tile) col_phase2_keep<P>(sm, base, ft, dst, scale, geom, store); else col_phase2<P>(sm, base, ft, dst, scale, geom); }
+                if (phase == 3) col_normals_phase<P, RY>(sm, tid, NT, LY::SJ, 12 * blk, normal);
+            }
+            if (blk < 2) {
+                rec.requests = rec.wavefronts = 0; rec.end();
+                if (phase < 3) { st.req[3 + phase] += rec.requests; st.wf[3 + phase] += rec.wavefronts; }
+                else { stats6[0] += rec.requests; stats6[1] += rec.wavefronts; }
+            }
+        }
+    }
+}
+
+template <int N>
+int emu_frame_fused_n(const float* h0k, const float* h0minusk, float L, float t, float* disp, float* normal, long* stats) {
+    std::vector<float4> h0((size_t)N * N), hp, nyq;
+    for (size_t i = 0; i < (size_t)N * N; ++i) h0[i] = make_float4(h0k[2 * i], h0k[2 * i + 1], h0minusk[2 * i], h0minusk[2 * i + 1]);
+    fold_full<N>(h0, hp, nyq);
+    std::vector<float> ktab(N);
+    const float pi = 3.1415926535897932384626433832795f;
+    for (int i = 0; i < N; ++i) ktab[i] = (2.0f * pi * ((float)i - (float)N / 2.0f)) / L;
+    std::vector<float2> inter((size_t)3 * (N / 2) * N);
+    Stats st;
+    long s6[2] = {0, 0};
+    emu_rows<N>(FullRows<N>{h0.data(), hp.data(), nyq.data()}, ktab.data(), t, FullSink<N>{inter.data()}, 0, N / 2, st);
+    emu_cols_fused<N>(inter.data(), disp, reinterpret_cast<float4*>(normal), st, s6);
+    if (stats) { for (int i = 0; i < 6; ++i) { stats[2 * i] = st.req[i]; stats[2 * i + 1] = st.wf[i]; } stats[12] = s6[0]; stats[13] = s6[1]; }
+    return 0;
+}
+
 // The slab-decomposed frame with `world` emulated ranks run one after the other: every rank's row
 // kernel stores through SlabSink straight into the owners' receive buffers (what the peer-store mode does over
 // NVLink), then every rank runs the column + normal kernels on its padded column slab. Outputs are re-assembled into
@@ -297,6 +355,16 @@ int emu_big_frame_n(const float* h0k, const float* h0minusk, float L, float t, f
                 bigcol_post<B, A>(scratch.data() + (size_t)c * N * npairs + pair, (size_t)npairs, kb, disp + (size_t)c * N * N + 2 * pair, (size_t)N, scale);
     emu_normals<N>(disp, FullNrmGeom<N>{}, 0, N, reinterpret_cast<float4*>(normal), jac, N, lambda, L);
     return 0;
+}
+
+extern "C" int emu_frame_fused(int N, const float* h0k, const float* h0minusk, float L, float t, float* disp, float* normal, long* stats) {
+    switch (N) {
+        case 256: return emu_frame_fused_n<256>(h0k, h0minusk, L, t, disp, normal, stats);
+        case 512: return emu_frame_fused_n<512>(h0k, h0minusk, L, t, disp, normal, stats);
+        case 1024: return emu_frame_fused_n<1024>(h0k, h0minusk, L, t, disp, normal, stats);
+        case 2048: return emu_frame_fused_n<2048>(h0k, h0minusk, L, t, disp, normal, stats);
+    }
+    return -1;
 }
 
 extern "C" int emu_big_frame(int N, int A, const float* h0k, const float* h0minusk, float L, float t, float lambda, float* disp,

@@ -97,3 +97,19 @@ def test_emulated_line_decomposition_matches_oracle_and_direct_kernels(noise, N,
         assert np.abs(big[k] - direct[k]).max() <= 5e-6 * peak, k
     assert np.abs(big["normal"] - ref["normal"]).max() < 1e-4
     assert np.abs(big["jacobian"] - ref["jacobian"]).max() < 1e-4
+
+
+@pytest.mark.parametrize("N", [256, 512, 1024])
+def test_emulated_fused_column_normal_kernel_equals_separate_kernels(noise, N):
+    """Frames without the Jacobian run the normal map as the epilogue of the dy column tiles (6 output pairs + 2 halo pairs per
+    tile, heights kept in the tile's shared-memory lines). Same stencil code, same inputs: the result must be bit-identical to
+    the column kernel + stand-alone normal kernel, every texel written exactly once, and the stencil's LDS phases conflict-free."""
+    s = OracleSim(N, 1000.0, 40.0, (1.0, 1.0), 2.0, 0.1, noise, threads=4)
+    a, b = s.h0()
+    sep = emu.frame(N, a, b, 1000.0, 1.0, 1.0)
+    fused = emu.frame_fused(N, a, b, 1000.0, 1.0)
+    assert not np.isnan(fused["normal"]).any()
+    for k in ("dy", "dx", "dz", "normal"):
+        assert np.array_equal(fused[k], sep[k]), k
+    for phase, (req, wf) in fused["conflicts"].items():
+        assert req > 0 and wf == req, f"{phase}: {wf} wavefronts for {req} requests (bank conflicts)"

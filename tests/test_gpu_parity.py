@@ -223,7 +223,8 @@ def test_multi_slot_time_sweep_equals_single_steps(noise):
         sim.set_group_size(1)            # different launch grouping, same numbers
         sim.update_multi([0] * len(times), times)
         sim.sync()
-        assert sim.last_launch_count() == 3 * len(times)
+        assert sim.last_group_count() == len(times)
+        assert sim.last_launch_count() == 2 * len(times)      # row + column kernel with the normal map as its epilogue (no Jacobian)
         for i in range(len(times)):
             assert np.array_equal(sim.download("dy", i), singles[i])
 
@@ -272,3 +273,22 @@ def test_set_params_requires_reinit(noise):
         d80 = sim.frame(1.0)["dy"]
     ref = OracleSim(256, 1000.0, 80.0, (1.0, 1.0), 2.0, 0.1, noise, threads=8).frame(1.0)["dy"]
     assert np.abs(d80 - ref).max() <= REL_TOL * np.abs(ref).max() and not np.allclose(d40, d80)
+
+
+@pytest.mark.parametrize("N", [256, 512, 1024, 2048])
+def test_fused_normal_epilogue_equals_separate_normal_kernel(noise, N):
+    """Without the Jacobian the normal map comes out of the column kernel's dy tiles (ow_col_fused_kernel); with it, out of the
+    stand-alone normal kernel. Same stencil on the same heights: identical displacement and normal images, every texel written."""
+    with fow.FFTOceanWaves(N=N, cascades=[params()], jacobian=True) as sim:
+        sim.init(noise)
+        sep = sim.frame(2.0)
+        assert sim.last_launch_count() == 3
+    with fow.FFTOceanWaves(N=N, cascades=[params()]) as sim:
+        sim.init(noise)
+        lib = fow.load_library()
+        sim.update(0.0)                      # fill the normal buffer with another frame first: stale texels would show
+        fused = sim.frame(2.0)
+        assert sim.last_launch_count() == 2
+    for k in ("dy", "dx", "dz", "normal"):
+        assert np.array_equal(fused[k], sep[k]), k
+    check_frame(fused, oracle_for(N, noise).frame(2.0), f"fused N={N} ")
