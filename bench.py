@@ -391,7 +391,8 @@ def run_ours(args):
         frames = w["frames"] = per
     job_frames = (64 if world > 1 else frames) if sharded else world * frames            # frames the WHOLE job produces per step
     slots = min(args.slots or (128 if N <= 512 else 32), frames) if args.workload != "c4" else frames
-    sim = fow.FFTOceanWaves(N=N, cascades=w["cascades"], n_slots=max(slots, len(w["cascades"])), device=local, jacobian=w["jacobian"])
+    sim = fow.FFTOceanWaves(N=N, cascades=w["cascades"], n_slots=max(slots, len(w["cascades"])), device=local, jacobian=w["jacobian"],
+                            fused_normals=args.fused_normals)
     for i, nz in enumerate(w["noise"]):
         sim.set_noise(nz, cascade=i)
     sim.tilde_h0_k()
@@ -577,6 +578,7 @@ def main():
     ap.add_argument("--group", type=int, default=0, help="slots per launch group (0 = library default)")
     ap.add_argument("--streams", type=int, default=0, help="internal streams the launch groups are spread over (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--fused-normals", action="store_true", help="experimental OW_FLAG_FUSED_NORMALS (normal map as the column kernel's epilogue)")
     ap.add_argument("--c4-shard-of", type=int, default=1, help="c4 on one GPU only: run the 64/P cascades one rank of a P-GPU job would get")
     ap.add_argument("--c5-n", type=int, default=32768, help="c5 only: grid size (32768 = BASELINE config C5; 4096 = its down-scaled parity grid)")
     ap.add_argument("--transport", choices=["auto", "peer", "alltoall"], default="auto", help="c5 only: how the transpose crosses GPUs")

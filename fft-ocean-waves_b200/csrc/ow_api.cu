@@ -96,6 +96,7 @@ FrameBuffers buffers(const ow_ctx* c) {
     fb.discard_inter = discard;
     fb.four_step = (c->flags & OW_FLAG_FOUR_STEP) ? 1 : 0;
     fb.scratch = c->d_scratch;
+    fb.fuse_normals = (c->flags & OW_FLAG_FUSED_NORMALS) && !(c->flags & OW_FLAG_JACOBIAN) && c->N <= 2048 ? 1 : 0;
     return fb;
 }
 

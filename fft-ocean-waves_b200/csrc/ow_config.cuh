@@ -10,8 +10,8 @@ namespace ow {
 // ROW_PIPE selects the persistent software-pipelined row kernel (ow_row_pipe_kernel) instead of one CTA per ROW_PAIRS
 // row pairs; chosen per N from whole-frame throughput in multi-stream sweeps (tools/tune/tune.cu -DTUNE_SWEEP), where a
 // variant that wins in isolation does not always win (profiles/r01d_tune_sweep_*.txt).
-// COL_FUSE: frames without the Jacobian run ow_col_fused_kernel (normal map as the epilogue of the dy column tiles) and no
-// separate normal kernel; needs COL_G == 8.
+// COL_FUSE: ow_col_fused_kernel (normal map as the epilogue of the dy column tiles) is available for this N (needs COL_G == 8);
+// used only when the context asks for it (OW_FLAG_FUSED_NORMALS): on B200 it is slower than the two separate kernels.
 // Normal kernel: NRM_RY output rows per thread walk, NRM_WARPS warps per CTA, NRM_MINB resident CTAs per SM.
 // Column plans interleave G jobs in the lane index, need S0 odd and a job stride == 16/G (mod 16).
 // ---------------------------------------------------------------------------------------------------

@@ -11,7 +11,6 @@ namespace ow {
 template <int N>
 int g_row_pipe_ctas_per_sm[2] = {0, 0};
 static int g_sm_count = 148;
-static int g_col_fuse = -1;      // OW_COL_FUSE=0 keeps the separate normal kernel even where Cfg<N>::COL_FUSE is set (A/B runs)
 static int g_row_classic = -1;   // OW_ROW_KERNEL=classic|pipe overrides the per-N choice Cfg<N>::ROW_PIPE (A/B runs, tools)
 
 template <int N>
@@ -37,8 +36,6 @@ cudaError_t configure_n() {
         if (g_row_classic < 0) {
             const char* v = getenv("OW_ROW_KERNEL");
             g_row_classic = (v && v[0] == 'c') ? 1 : (v && v[0] == 'p') ? 0 : 2;
-            const char* cf = getenv("OW_COL_FUSE");
-            g_col_fuse = (cf && cf[0] == '0') ? 0 : 1;
         }
     }
     cudaError_t e = cudaFuncSetAttribute(ow_row_kernel<typename C::Row, C::ROW_PAIRS, C::ROW_MINB, false>,
@@ -133,7 +130,7 @@ int launch_n(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_
     if (ev) cudaEventRecord(ev[1], st);
     const float scale = 0.5f / ((float)N * (float)N);   // 1/2 from the Hermitian split, 1/N^2 from inversion_cs.glsl:36
     if constexpr (C::COL_FUSE) {
-        if (!with_jac && g_col_fuse != 0) {
+        if (!with_jac && fb.fuse_normals) {
             // normal map fused into the dy tiles: 6 output pairs per dy tile, ordinary 8-pair tiles for dx and dz
             const int ndy = (N / 2 + 5) / 6;
             ow_col_fused_kernel<K, C::COL_G, C::COL_MINB, C::NRM_RY>

@@ -32,6 +32,7 @@ struct FrameBuffers {
     float* jacobian;       // [slot][N][N] or nullptr
     int discard_inter;     // column kernel drops the intermediate's lines from L2 after reading them (no DRAM write-back)
     float2* scratch;       // N = A*B decomposition only: one frame of radix-A sums, 12 B/texel (ow_big_kernels.cu)
+    int fuse_normals;      // OW_FLAG_FUSED_NORMALS: normal map as the epilogue of the dy column tiles (ow_col_fused_kernel)
     int four_step;         // force the N = A*B line decomposition (ow_big_kernels.cu) on a grid the direct kernels could do
 };
 

@@ -833,37 +833,61 @@ struct SmemRowSrc {             // final heights of four adjacent jobs (pairs q-
     }
 };
 
-template <bool STREAM>
-struct EmitQuad {               // four adjacent normals of one row straight to global memory
+// Emit of the fused epilogue. The four lanes of a group (c = lane % 4) hold the normals of the SAME column quad on four
+// different rows (y_c = y + (r - c) * row_step for the lane r). A 4x4 transpose through two xor-shuffle steps turns
+// "lane c: four columns of row y_c" into "lane c: column c of rows y_0..y_3", so that every store instruction covers whole
+// rows: 64 contiguous bytes per group, 192 per half-warp (the three quads of a tile are neighbours in the lane index)
+// instead of 32 scattered 16-byte pieces per warp. On the host (emulator) the plain per-thread stores give the same image.
+struct EmitQuad {
     float4* normal;             // slot base, [N][N]
     size_t ostride;
-    int xout;
+    int xout;                   // first column of the quad
+    int c;                      // lane % 4
+    int row_step;               // rows between the lanes of a group
     OW_HD void operator()(int y, const float4 (&n)[4], float4) const {
-        float4* d = normal + (size_t)y * ostride + xout;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
 #ifdef __CUDA_ARCH__
-            if (STREAM) { __stcs(d + j, n[j]); continue; }
-#endif
-            d[j] = n[j];
+        float4 a[4] = {n[0], n[1], n[2], n[3]};
+        const unsigned mask = 0xFu << ((threadIdx.x & 31) & ~3);
+#pragma unroll
+        for (int bit = 0; bit < 2; ++bit) {
+            const bool up = (c >> bit) & 1;
+#pragma unroll
+            for (int lo = 0; lo < 4; ++lo) {
+                if ((lo >> bit) & 1) continue;
+                const int hi = lo | (1 << bit);
+                const float4 send = up ? a[lo] : a[hi];
+                float4 recv;
+                recv.x = __shfl_xor_sync(mask, send.x, 1 << bit); recv.y = __shfl_xor_sync(mask, send.y, 1 << bit);
+                recv.z = __shfl_xor_sync(mask, send.z, 1 << bit); recv.w = __shfl_xor_sync(mask, send.w, 1 << bit);
+                if (up) a[lo] = recv; else a[hi] = recv;
+            }
         }
+        // a[r] = column c of the row held by lane r of the group
+#pragma unroll
+        for (int r = 0; r < 4; ++r) __stcs(normal + (size_t)(y + (r - c) * row_step) * ostride + xout + c, a[r]);
+#else
+        float4* d = normal + (size_t)y * ostride + xout;
+        for (int j = 0; j < 4; ++j) d[j] = n[j];
+#endif
     }
 };
 
-// Normal-map epilogue of one dy tile: items = (column quad j < 3) x (row chunk of RY rows); item -> (k2 fastest, then the chunk's
-// position w inside a block of R0*R1 rows, then j), so the 16 lanes of an LDS.64 phase differ only in the unit-stride digit.
+// Normal-map epilogue of one dy tile. Lane layout inside a half-warp: c = lane % 4 -> low bits of the unit-stride digit k2,
+// j = (lane / 4) % 4 -> column quad (3 quads per tile; j == 3 idles). The 16 LDS.64 of a phase then hit 16 different bank pairs
+// (jobs are SJ = 2 (mod 16) apart: bank pair = const + c + 4j), and the stores of the 12 active lanes are 192 contiguous bytes.
 template <class P, int RY, class Smem>
 OW_HD void col_normals_phase(const Smem& sm, int tid, int nthreads, int SJ, int x_first /* first output column of the tile */,
                              float4* __restrict__ normal /* slot base */) {
-    constexpr int N = P::N, LOW = P::R0 * P::R1, WPER = LOW / RY, NITEMS = 3 * P::R2 * WPER;
-    static_assert(LOW % RY == 0, "row chunks must tile a block of R0*R1 rows");
+    constexpr int N = P::N, LOW = P::R0 * P::R1, WPER = LOW / RY, NITEMS = 4 * P::R2 * WPER;
+    static_assert(LOW % RY == 0 && P::R2 % 4 == 0, "row chunks must tile a block of R0*R1 rows; k2 is split 4 x R2/4");
 #pragma unroll 1
     for (int item = tid; item < NITEMS; item += nthreads) {
-        const int k2 = item % P::R2, w = (item / P::R2) % WPER, j = item / (P::R2 * WPER);
+        const int c = item % 4, j = (item / 4) % 4, h = item / 16;
+        const int k2 = c + 4 * (h % (P::R2 / 4)), w = h / (P::R2 / 4);
         const int x0 = x_first + 4 * j;
-        if (x0 >= N) continue;                                  // wrapped duplicate pairs of the last tile
+        if (j == 3 || x0 >= N) continue;                        // idle quad slot / wrapped duplicate pairs of the last tile
         const SmemRowSrc<P, Smem> src{sm, 2 * j * SJ, SJ};
-        normal_quad_walk_src<N, RY, false>(src, LOW * k2 + RY * w, 0.f, EmitQuad<true>{normal, (size_t)N, x0});
+        normal_quad_walk_src<N, RY, false>(src, LOW * k2 + RY * w, 0.f, EmitQuad{normal, (size_t)N, x0, c, LOW});
     }
 }
 

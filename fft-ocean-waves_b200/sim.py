@@ -38,6 +38,7 @@ EXPORTED_SYMBOLS = [
 OW_FLAG_JACOBIAN = 0x1
 OW_FLAG_EXACT_SINCOS = 0x2
 OW_FLAG_FOUR_STEP = 0x4
+OW_FLAG_FUSED_NORMALS = 0x8
 IMAGES = {"dy": 0, "dx": 1, "dz": 2, "normal": 3, "jacobian": 4, "h0k": 5, "h0minusk": 6}
 
 
@@ -151,7 +152,8 @@ class FFTOceanWaves:
     """One context = `len(cascades)` independent N x N patches on one GPU (see module docstring)."""
 
     def __init__(self, N: int = 256, cascades: Optional[Sequence[OceanParams]] = None, n_slots: Optional[int] = None,
-                 device: int = 0, jacobian: bool = False, exact_sincos: bool = False, four_step: bool = False):
+                 device: int = 0, jacobian: bool = False, exact_sincos: bool = False, four_step: bool = False,
+                 fused_normals: bool = False):
         self._lib = load_library()
         self._h = C.c_void_p()
         self.N = int(N)
@@ -161,7 +163,7 @@ class FFTOceanWaves:
         arr = (_Params * len(self.cascades))(*[c.to_c() for c in self.cascades])
         rc = self._lib.ow_create(self.N, len(self.cascades), self.n_slots, arr, int(device),
                                  (OW_FLAG_JACOBIAN if jacobian else 0) | (OW_FLAG_EXACT_SINCOS if exact_sincos else 0)
-                                 | (OW_FLAG_FOUR_STEP if four_step else 0),
+                                 | (OW_FLAG_FOUR_STEP if four_step else 0) | (OW_FLAG_FUSED_NORMALS if fused_normals else 0),
                                  C.byref(self._h))
         if rc != 0:
             msg = self._lib.ow_last_error(None)

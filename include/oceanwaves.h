@@ -51,6 +51,9 @@ typedef struct ow_params {
 #define OW_FLAG_FOUR_STEP 0x4u   /* N = 1024 / 2048 only: run the N = A*B line decomposition that N > 4096 uses (A = 4), for
                                     testing that code path against the direct kernels; slower, same results to round-off */
 
+#define OW_FLAG_FUSED_NORMALS 0x8u /* experimental (N <= 2048, no Jacobian): produce the normal map as the epilogue of the dy column
+                                      tiles instead of a separate kernel. Identical images; measured SLOWER on B200, so off by default */
+
 typedef struct ow_ctx ow_ctx;
 
 /* Device pointers to one output set ("slot"); library-owned, valid until ow_destroy. Written by ow_step*.

@@ -224,7 +224,7 @@ def test_multi_slot_time_sweep_equals_single_steps(noise):
         sim.update_multi([0] * len(times), times)
         sim.sync()
         assert sim.last_group_count() == len(times)
-        assert sim.last_launch_count() == 2 * len(times)      # row + column kernel with the normal map as its epilogue (no Jacobian)
+        assert sim.last_launch_count() == 3 * len(times)
         for i in range(len(times)):
             assert np.array_equal(sim.download("dy", i), singles[i])
 
@@ -277,13 +277,13 @@ def test_set_params_requires_reinit(noise):
 
 @pytest.mark.parametrize("N", [256, 512, 1024, 2048])
 def test_fused_normal_epilogue_equals_separate_normal_kernel(noise, N):
-    """Without the Jacobian the normal map comes out of the column kernel's dy tiles (ow_col_fused_kernel); with it, out of the
-    stand-alone normal kernel. Same stencil on the same heights: identical displacement and normal images, every texel written."""
-    with fow.FFTOceanWaves(N=N, cascades=[params()], jacobian=True) as sim:
+    """OW_FLAG_FUSED_NORMALS (experimental): the normal map out of the column kernel's dy tiles (ow_col_fused_kernel) instead of
+    the stand-alone normal kernel. Same stencil on the same heights: identical displacement and normal images, every texel written."""
+    with fow.FFTOceanWaves(N=N, cascades=[params()]) as sim:
         sim.init(noise)
         sep = sim.frame(2.0)
         assert sim.last_launch_count() == 3
-    with fow.FFTOceanWaves(N=N, cascades=[params()]) as sim:
+    with fow.FFTOceanWaves(N=N, cascades=[params()], fused_normals=True) as sim:
         sim.init(noise)
         lib = fow.load_library()
         sim.update(0.0)                      # fill the normal buffer with another frame first: stale texels would show
