@@ -164,7 +164,8 @@ void sweep(Ctx& c) {
         using R2x = Plan<N, R::R0, R::R1, R::R2, 2 * R::T, R::S1 - R::R2, R::S0 - R::R1 * R::S1>;
 #define RC2(PAIRS, MB) rep("row only: classic 2xT PAIRS=" #PAIRS " minb=" #MB, row_variant<R2x, PAIRS, MB>(), none, none);
 #define RP2(PAIRS, MB) rep("row only: pipe 2xT PAIRS=" #PAIRS " minb=" #MB, row_pipe_variant<R2x, PAIRS, MB>(), none, none);
-        RC2(1, 2) RC2(1, 3) RC2(1, 4) RC2(2, 2) RC2(2, 3) RP2(1, 2) RP2(1, 3) RP2(2, 2)
+        RC2(1, 2) RC2(1, 3) RC2(1, 4) RC2(2, 2) RC2(2, 3)
+        if constexpr (R::M % (2 * R::T) == 0) { RP2(1, 2) RP2(1, 3) RP2(2, 2) }      // the pipelined kernel needs whole stage-0 batches
         if (N <= 1024) { RC2(4, 1) RC2(4, 2) RC2(1, 8) RC2(2, 4) }
         using K2x = Plan<N, K::R0, K::R1, K::R2, 2 * K::T, K::S1 - K::R2, K::S0 - K::R1 * K::S1>;
         rep("all: classic 2xT P1 minb3 row, default col, normal", row_variant<R2x, 1, 3>(), col0, nrm1);
