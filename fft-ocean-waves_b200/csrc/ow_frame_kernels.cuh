@@ -8,6 +8,14 @@
 
 namespace ow {
 
+// Barrier between the phases of one line group. A row-pair group of 32 threads is exactly one warp (N <= 512): its lines are
+// private to the warp, so a warp barrier orders the shared-memory traffic and the CTA's other groups are not held up.
+template <int T>
+__device__ __forceinline__ void group_sync() {
+    if (T == 32) __syncwarp();
+    else __syncthreads();
+}
+
 // Per-CTA timeline for tools/tune (never defined in the library build): thread 0 stamps clock64 + globaltimer + smid at
 // the phase boundaries into g_ow_trace[cta][8].
 #ifdef OW_TRACE
@@ -44,11 +52,11 @@ __global__ void __launch_bounds__(P::T* PAIRS, MINB) ow_row_kernel(FrameBuffers 
     OW_STAMP(blockIdx.x, 0); OW_STAMP(blockIdx.x, 1);
     row_phase0<P, FAST>(sm, ft, p, rows, ktab, t);
     OW_STAMP(blockIdx.x, 2);
-    __syncthreads();
+    group_sync<P::T>();
     OW_STAMP(blockIdx.x, 3);
     row_phase1<P>(sm, ft);
     OW_STAMP(blockIdx.x, 4);
-    __syncthreads();
+    group_sync<P::T>();
     OW_STAMP(blockIdx.x, 5);
     row_phase2<P>(sm, ft, p, FullSink<N>{inter});
     OW_STAMP(blockIdx.x, 6);
