@@ -30,13 +30,8 @@ struct Cfg<256> {
 };
 template <>
 struct Cfg<512> {
-#ifdef OW_EXP_ROW512_2XT
-    using Row = Plan<512, 8, 4, 16, 64, 1, 14>;
-    static constexpr int ROW_PAIRS = 2, ROW_MINB = 4;
-#else
     using Row = Plan<512, 8, 4, 16, 32, 1, 14>;
     static constexpr int ROW_PAIRS = 4, ROW_MINB = 3;
-#endif
     static constexpr bool ROW_PIPE = false;
     using Col = Plan<512, 8, 4, 16, 32, 0, 1>;
     static constexpr int COL_G = 8, COL_MINB = 2;

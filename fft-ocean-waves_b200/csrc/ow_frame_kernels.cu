@@ -40,10 +40,10 @@ cudaError_t configure_n() {
     }
     cudaError_t e = cudaFuncSetAttribute(ow_row_kernel<typename C::Row, C::ROW_PAIRS, C::ROW_MINB, false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)row_smem<typename C::Row, C::ROW_PAIRS>());
+                                         (int)(row_smem<typename C::Row, C::ROW_PAIRS>()));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(ow_row_kernel<typename C::Row, C::ROW_PAIRS, C::ROW_MINB, true>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<typename C::Row, C::ROW_PAIRS>());
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(row_smem<typename C::Row, C::ROW_PAIRS>()));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(ow_col_kernel<typename C::Col, C::COL_G, C::COL_MINB>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ColLayout<typename C::Col, C::COL_G>::SMEM);

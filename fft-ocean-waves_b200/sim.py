@@ -82,7 +82,8 @@ class OceanParams:
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "lib", "liboceanwaves.so")
+    """In-tree library; OCEANWAVES_LIB points at another build of it (A/B runs of kernel variants)."""
+    return os.environ.get("OCEANWAVES_LIB") or os.path.join(_HERE, "lib", "liboceanwaves.so")
 
 
 _lib = None
