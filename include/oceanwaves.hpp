@@ -61,6 +61,8 @@ public:
     bool tilde_h0_k(const uint8_t* const noise[4], int w = 256, int h = 256) {
         return ok(ow_set_noise(ctx_, -1, noise, w, h)) && ok(ow_init_spectrum(ctx_));
     }
+    // Same, with device-generated Philox noise instead of the PNGs (grids with no noise image to ship: config C5).
+    bool tilde_h0_k_seeded(uint64_t seed) { return ok(ow_set_noise_seed(ctx_, -1, seed)) && ok(ow_init_spectrum(ctx_)); }
     // The reference never re-runs tilde_h0_k() after a GUI edit; this makes the re-generation explicit.
     bool set_params(const Params& p) {
         const ow_params c = to_c(p);

@@ -144,3 +144,38 @@ def philox_noise(seed: int, N: int) -> np.ndarray:
     ctr[..., 1] = np.arange(N, dtype=np.uint32)[:, None]
     out = philox4x32_10(ctr, (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF))
     return np.ascontiguousarray(np.moveaxis(out & np.uint32(0xFF), -1, 0).astype(np.uint8))
+
+
+def fold_pairs(h0k, h0minusk):
+    """fp64 restatement of the init-time fold (csrc/ow_kernels.cuh: fold_pair / fold_pair_nyq; ow_init_kernels.cu: ow_fold_kernel).
+    A = (h0k, h0minusk) at texel (u, v), B = the same at the mirror texel ((N-u) mod N, (N-v) mod N). Returns f[N][N][4] with
+    S_y = H + conj(H_mirror) = (f0 c + f1 s, f2 s + f3 c), and g[N][N][4] with D = H - conj(H_mirror) = (g0 c + g1 s, g2 s + g3 c),
+    c = cos(wt), s = sin(wt). The kernels keep f for rows 1..N/2-1 and g for their column 0 only."""
+    N = h0k.shape[0]
+    idx = (-np.arange(N)) % N
+    Ax, Ay, Az, Aw = h0k.real, h0k.imag, h0minusk.real, h0minusk.imag
+    Bk, Bm = h0k[idx][:, idx], h0minusk[idx][:, idx]
+    Bx, By, Bz, Bw = Bk.real, Bk.imag, Bm.real, Bm.imag
+    f = np.stack([Ax + Az + Bx + Bz, Aw + Bw - Ay - By, Ax - Az - Bx + Bz, Ay + Aw - By - Bw], -1)
+    g = np.stack([Ax + Az - Bx - Bz, Aw - Ay - Bw + By, Ax - Az + Bx - Bz, Ay + Aw + By + Bw], -1)
+    return f, g
+
+
+def hermitian_parts_from_fold(f, g, N, L, t):
+    """S_y, S_x, S_z (the spectra whose plain inverse DFT is TWICE the real displacement) from the folded coefficients,
+    the way the row kernel evaluates them: S_x = -i kx/|k| S_y and S_z = -i ky/|k| S_y, except S_x on the Nyquist column
+    (u = 0: the shader's k is not negated by mirroring there) which uses D, and likewise S_z on the Nyquist row (v = 0)."""
+    kx, ky = wave_vectors(N, L)
+    km = np.maximum(np.sqrt(kx ** 2 + ky ** 2), 1e-5)
+    km32 = np.maximum(np.sqrt((kx.astype(np.float32) ** 2 + ky.astype(np.float32) ** 2).astype(np.float32)),
+                      np.float32(1e-5)).astype(np.float32)
+    w32 = np.sqrt((np.float32(G) * km32).astype(np.float32)).astype(np.float32)
+    ph = (w32 * np.float32(t)).astype(np.float32).astype(np.float64)
+    c, s = np.cos(ph), np.sin(ph)
+    Sy = (f[..., 0] * c + f[..., 1] * s) + 1j * (f[..., 2] * s + f[..., 3] * c)
+    D = (g[..., 0] * c + g[..., 1] * s) + 1j * (g[..., 2] * s + g[..., 3] * c)
+    Sx = -1j * (kx / km) * Sy
+    Sz = -1j * (ky / km) * Sy
+    Sx[:, 0] = (-1j * (kx / km) * D)[:, 0]
+    Sz[0, :] = (-1j * (ky / km) * D)[0, :]
+    return Sy, Sx, Sz
