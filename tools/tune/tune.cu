@@ -171,6 +171,8 @@ void sweep(Ctx& c) {
         if (N <= 1024) {
             rep("all: classic 2xT P2 minb2 row, default col, normal", row_variant<R2x, 2, 2>(), col0, nrm1);
             rep("all: classic 2xT P2 minb4 row, default col, normal", row_variant<R2x, 2, 4>(), col0, nrm1);
+            rep("all: classic cfg row, G4 minb2 col, normal", rowc, col_variant<K, 4, 2>(), nrm1);
+            rep("all: classic cfg row, G4 minb4 col, normal", rowc, col_variant<K, 4, 4>(), nrm1);
             rep("all: classic cfg row, G8 minb3 col, normal", rowc, col_variant<K, 8, 3>(), nrm1);
             rep("all: classic cfg row, G8 minb4 col, normal", rowc, col_variant<K, 8, 4>(), nrm1);
             rep("all: classic 2xT P2 minb4 row, G8 minb3 col, normal", row_variant<R2x, 2, 4>(), col_variant<K, 8, 3>(), nrm1);
