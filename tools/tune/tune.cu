@@ -168,6 +168,12 @@ void sweep(Ctx& c) {
         if constexpr (R::M % (2 * R::T) == 0) { RP2(1, 2) RP2(1, 3) RP2(2, 2) }      // the pipelined kernel needs whole stage-0 batches
         if (N <= 1024) { RC2(4, 1) RC2(4, 2) RC2(1, 8) RC2(2, 4) }
         using K2x = Plan<N, K::R0, K::R1, K::R2, 2 * K::T, K::S1 - K::R2, K::S0 - K::R1 * K::S1>;
+        if (N == 2048) {
+            rep("all+J: classic cfg row, default col, normal+J", rowc, col0, nrm0);
+            rep("all+J: classic cfg row, G4 minb1 col, normal+J", rowc, col_variant<K, 4, 1>(), nrm0);
+            rep("all+J: classic cfg row, G4 minb2 col, normal+J", rowc, col_variant<K, 4, 2>(), nrm0);
+            rep("all+J: classic cfg row, G4 minb3 col, normal+J", rowc, col_variant<K, 4, 3>(), nrm0);
+        }
         if (N <= 1024) {
             rep("all: classic 2xT P2 minb2 row, default col, normal", row_variant<R2x, 2, 2>(), col0, nrm1);
             rep("all: classic 2xT P2 minb4 row, default col, normal", row_variant<R2x, 2, 4>(), col0, nrm1);
