@@ -1,8 +1,9 @@
 """ctypes front-end of the CPU ORACLE (oracle/ow_oracle.cpp) — test infrastructure, NOT the product.
 
 Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) may import this.
-"PARITY UNPINNED": the reference has no golden vectors for this path; see the header of
-ow_oracle.cpp for what the oracle is pinned to instead.
+PARITY PIN: the reference has no golden vectors for this path, but its six compute shaders compile for the
+CPU (oracle/_ref: their GLSL text through oracle/glsl_emu.hpp, dispatched in the reference's order), and this oracle reproduces
+them — tests/test_ref_pin.py; see the header of ow_oracle.cpp.
 """
 from __future__ import annotations
 

@@ -9,11 +9,15 @@
 // Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) may
 // load this file's library. The product path (fft-ocean-waves_b200/csrc) never does.
 //
-// PARITY STATUS: "parity unpinned". The reference ships no tests, golden vectors or KATs for
-// this path and cannot be built or run here (it is GLSL on an OpenGL 4.5
-// driver; no GL/EGL/llvmpipe in the image). The pins this oracle is held to are (a) an
-// independent fp64 numpy formulation (oracle/numpy_ref.py), (b) analytic known-answer tests
-// derived from the shaders alone, (c) the survey-time spot values.
+// PARITY STATUS: pinned against the reference's own shaders. The reference ships no tests, golden vectors or KATs for
+// this path and its executable needs an OpenGL 4.5 driver (none in the image), but its six compute
+// shaders compile for the CPU: oracle/make_ref.py reads their GLSL text from the reference tree and builds oracle/_ref/
+// (glsl_emu.hpp = the GLSL types/built-ins, ref_driver.cpp = the dispatch order of src/main.cpp). This restatement reproduces
+// that build to the last bit for the butterfly/index table and the DC texel, to 1 ulp on the initial spectrum and to 1e-7 of
+// peak on whole frames (tests/test_ref_pin.py). What stays a restatement is the host dispatch loop (src/main.cpp cannot be
+// compiled without GL) and the precision of GL built-ins, which the GL spec leaves to the driver. Further pins: (a) an
+// independent fp64 numpy formulation (oracle/numpy_ref.py), (b) analytic known-answer tests derived from the shaders alone,
+// (c) the survey-time spot values.
 //
 // Build: see oracle/Makefile  (g++ -O2 -ffp-contract=off -fopenmp -shared -fPIC).
 // GL built-ins are restated as IEEE fp32 libm calls; pow(x,2.0) is x*x; clamp() is

@@ -1,7 +1,7 @@
 """Regenerates tests/golden/*.npz from the CPU oracle (oracle/ow_oracle.cpp).
 
-The reference has no golden vectors for this path and cannot run here (GLSL on OpenGL), so these fixtures
-pin the ORACLE's output ("parity unpinned" w.r.t. the reference itself). Each file holds a
+The reference has no golden vectors for this path and its executable cannot run here (OpenGL), so these fixtures
+are generated from the ORACLE, which tests/test_ref_pin.py pins to the reference's own shaders compiled for the CPU. Each file holds a
 strided sample of every output image plus whole-image statistics, for BASELINE.md configs C1 and C2.
 
     python tests/golden/make_golden.py
