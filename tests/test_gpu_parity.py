@@ -292,3 +292,20 @@ def test_fused_normal_epilogue_equals_separate_normal_kernel(noise, N):
     for k in ("dy", "dx", "dz", "normal"):
         assert np.array_equal(fused[k], sep[k]), k
     check_frame(fused, oracle_for(N, noise).frame(2.0), f"fused N={N} ")
+
+
+@pytest.mark.parametrize("N,t", [(256, 1.0), (512, 9.98), (1024, 2.0)])
+def test_cuda_path_vs_the_reference_shaders_themselves(noise, N, t):
+    """The CUDA path against oracle/_ref — the reference's OWN compute shaders (GLSL text compiled for the CPU, dispatched in the
+    reference's order) — without the hand-written oracle in between. Same tolerance as everywhere: 1e-4 of peak, plus the RMS bound."""
+    from oracle import ref as refmod
+    if not refmod.available():
+        pytest.skip("oracle/_ref not available (needs the reference tree at build time or the prebuilt library)")
+    ref = refmod.RefSim(N, 1000, 40.0, (1.0, 1.0), 2.0, 0.1, noise, threads=8).frame(np.float32(t))
+    with fow.FFTOceanWaves(N=N, cascades=[params()]) as sim:
+        sim.init(noise)
+        a = sim.download("h0k")
+        got = sim.frame(float(np.float32(t)))
+    ra, _ = refmod.RefSim(N, 1000, 40.0, (1.0, 1.0), 2.0, 0.1, noise).h0()
+    assert np.abs(a - ra).max() <= 2e-6 * np.abs(ra).max()
+    check_frame(got, ref, f"vs reference shaders N={N} ")
