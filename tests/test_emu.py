@@ -113,3 +113,18 @@ def test_emulated_fused_column_normal_kernel_equals_separate_kernels(noise, N):
         assert np.array_equal(fused[k], sep[k]), k
     for phase, (req, wf) in fused["conflicts"].items():
         assert req > 0 and wf == req, f"{phase}: {wf} wavefronts for {req} requests (bank conflicts)"
+
+
+def test_emulated_frame_matches_the_reference_shaders(noise):
+    """The kernels' phase functions (emulated on the CPU) against oracle/_ref, the reference's own shaders compiled for the CPU."""
+    from oracle import ref as refmod
+    if not refmod.available():
+        pytest.skip("oracle/_ref not available")
+    N, t = 256, 1.0
+    rs = refmod.RefSim(N, 1000, 40.0, (1.0, 1.0), 2.0, 0.1, noise)
+    a, b = rs.h0()
+    ref = rs.frame(t)
+    got = emu.frame(N, a, b, 1000.0, t, 1.0)
+    for k in ("dy", "dx", "dz"):
+        assert np.abs(got[k] - ref[k]).max() <= 5e-6 * np.abs(ref[k]).max(), k
+    assert np.abs(got["normal"] - ref["normal"]).max() < 1e-4
