@@ -62,3 +62,22 @@ def test_reference_shaders_with_other_parameters(noise):
     r, o = ref.frame(2.5), orc.frame(2.5)
     for k in ("dy", "dx", "dz"):
         assert np.abs(o[k] - r[k]).max() <= 2e-6 * np.abs(r[k]).max(), k
+
+
+@pytest.mark.parametrize("name", ["c1_n256.npz", "c2_n512.npz"])
+def test_committed_golden_fixtures_agree_with_the_reference_shaders(noise, name):
+    """tests/golden/*.npz were generated from the oracle; here they are held against the reference's own shaders, so the fixtures the
+    GPU parity tests use are pinned to the reference too (they travel to the GPU box; the reference tree does not)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name))
+    N, st = int(g["N"]), int(g["stride"])
+    ref = R.RefSim(N, 1000, 40.0, (1.0, 1.0), 2.0, 0.1, noise)
+    ra, _ = ref.h0()
+    assert np.abs(ra[::st, ::st] - g["h0k"]).max() <= 2.5e-7 * np.abs(ra).max()
+    for i, t in enumerate(g["times"]):
+        r = ref.frame(np.float32(t))
+        for k in ("dy", "dx", "dz"):
+            peak = g[f"{k}_{i}_stats"][0]
+            assert np.abs(r[k][::st, ::st] - g[f"{k}_{i}"]).max() <= 2e-6 * peak, (k, i)
+            assert np.abs(r[k]).max() == pytest.approx(peak, rel=1e-5)
+        assert np.abs(r["normal"][::st, ::st] - g[f"normal_{i}"]).max() <= 2e-6
