@@ -1,20 +1,25 @@
 #!/usr/bin/env python
 """bench.py — frames/sec of the per-frame Tessendorf hot path (spectrum + 3x IFFT + inversion + normals).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload default|c2|c3|c4|c5]
 
-Default workload = BASELINE.json configs[1] ("C2"): N=512 single patch, L=1000 m, wind 40 m/s, A=2, the
+The JSON line's `value` is BASELINE.json configs[1] ("C2"): N=512 single patch, L=1000 m, wind 40 m/s, A=2, the
 reference's PNG noise, a 600-frame time sweep t_f = f/60. One STEP = one full 600-frame sweep; every frame writes
 its complete dy/dx/dz/normal set to HBM. `value` = frames/s with inputs resident in HBM (CUDA events on the launching
 stream); `e2e` = the same sweep through the C ABI with HOST buffers (noise upload + h0 init + every frame's outputs
 copied back to pinned host memory inside the timed region).
 
---impl reference times the CPU oracle (oracle/ow_oracle.cpp, the scalar C++ restatement of the reference's GLSL
-dispatch chain; the reference itself needs an OpenGL driver and cannot run here) on all host threads, on a
-bounded sample of the same workload.
+The default run (`--workload default`) ALSO measures the configurations the north star's targets are quoted on and puts
+them in the same line under `configs`, each with its own CUDA-event timing, roofline and clock sample:
+    configs.c3   N=2048 + Jacobian (the >= 0.70-of-HBM target); one replica per GPU
+    configs.c4   64 cascades N=1024, SHARDED across the ranks under torchrun (the >= 7x-at-8-GPUs target)
+    configs.c5   ONE N=32768 grid, slab-decomposed over the ranks (transpose over NVLink), checked against the single-GPU
+                 path on a down-scaled grid of the same code before it is timed
+`--workload c2|c3|c4|c5` runs one of them alone as the headline (development, profiling).
 
-Under torchrun (--gpus N > 1) every rank runs the same sweep on its own GPU (independent patches, no data-path
-collective; weak scaling); timing = max over ranks.
+--impl reference times the reference's own compute shaders compiled for the CPU (oracle/_ref; the oracle port where that
+library is absent) on ALL host cores of the box — also under torchrun, where rank 0 alone runs it — on a fixed sample of
+the same workload.
 """
 from __future__ import annotations
 
@@ -33,7 +38,8 @@ import numpy as np  # noqa: E402
 
 METRIC = "ocean frames/sec (spectrum+IFFT+normals)"
 UNIT = "frames/s"
-ALG_BYTES_PER_TEXEL = 44            # read h0k+h0minusk 16 B, write dy,dx,dz 12 B + normal 16 B
+ALG_BYTES_PER_TEXEL = 44            # read h0k+h0minusk 16 B, write dy,dx,dz 12 B + normal 16 B (+4 Jacobian)
+OWN_BYTES_PER_TEXEL = 36            # what THIS implementation must move: the folded spectrum is 8 B/texel, not 16
 KERNEL_BYTES_PER_TEXEL = {          # compulsory bytes of each kernel of the 3-kernel frame
     "ow_row_kernel": 8 + 12,        # read the folded initial spectrum (16 B per texel PAIR) -> write Hermitian half-spectra (12)
     "ow_col_kernel": 12 + 12,       # read intermediate (12) -> write dy,dx,dz (12)
@@ -51,20 +57,33 @@ WORKLOADS = {
     "c5": (32768, 4, "C5: ONE grid N=32768, slab-decomposed 2-D IFFT over the ranks, Philox(32768) noise, "
                      "4-frame sweep t=f/60, dy/dx/dz+normal+Jacobian left column-slabbed", True),
 }
+# Fixed CPU-arm samples (the same at every --gpus N, so the driver's ratios compare like with like)
+REFERENCE_SAMPLE = {"c2": 128, "c3": 4, "c4": 4, "c5": 8}
 
 
-def workload_setup(name):
+def host_cores() -> int:
+    """Cores this process may run on. NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def workload_setup(name, only=None):
+    """only = (lo, hi): build just that block of C4's cascades (a rank's shard)."""
     import fft_ocean_waves_b200 as fow
     N, frames, desc, jac = WORKLOADS[name]
     if name == "c4":
-        casc = []
-        for c in range(64):
+        lo, hi = only if only else (0, 64)
+        casc, noise = [], []
+        for c in range(lo, hi):
             ang = 2 * np.pi * c / 64
             casc.append(fow.OceanParams(L=float(100.0 * 1.08 ** c), wind_speed=float(10 + 0.5 * c),
                                         wind_dir=(float(np.cos(ang)), float(np.sin(ang))), amplitude=2.0, suppression=0.1, choppiness=1.0))
-        noise = [np.random.default_rng(1024 + c).integers(0, 256, (4, N, N), dtype=np.uint8) for c in range(64)]
-        cascade_of = list(range(64))
-        times = [1.0] * 64
+            noise.append(np.random.default_rng(1024 + c).integers(0, 256, (4, N, N), dtype=np.uint8))
+        cascade_of = list(range(hi - lo))
+        times = [1.0] * (hi - lo)
+        frames = hi - lo
     else:
         casc = [fow.OceanParams(L=1000.0, wind_speed=40.0, wind_dir=(1.0, 1.0), amplitude=2.0, suppression=0.1, choppiness=1.0)]
         if name == "c5":
@@ -73,7 +92,7 @@ def workload_setup(name):
             noise = [fow.default_noise() if name == "c2" else np.random.default_rng(2048).integers(0, 256, (4, N, N), dtype=np.uint8)]
         cascade_of = [0] * frames
         times = [float(np.float32(f / 60.0)) for f in range(frames)]
-    return dict(N=N, frames=frames, desc=desc, jacobian=jac, cascades=casc, noise=noise, cascade_of=cascade_of, times=times)
+    return dict(name=name, N=N, frames=frames, desc=desc, jacobian=jac, cascades=casc, noise=noise, cascade_of=cascade_of, times=times)
 
 
 def measured_peak():
@@ -100,6 +119,7 @@ class ClockSampler:
             self.thread.start()
         except Exception:
             self.proc = None
+        return self
 
     def _read(self):
         for ln in self.proc.stdout:
@@ -133,44 +153,52 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": float(max(power))}
 
 
+# ======================================================================================================================
+# CPU arm
+# ======================================================================================================================
 def run_reference(args):
-    """CPU arm: the oracle (scalar C++ restatement of the reference's GLSL chain) on all host threads."""
+    """CPU arm: the reference's own shaders compiled for the CPU (oracle/_ref), else the oracle port, on all host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle.oracle import OracleSim, max_threads
+    from oracle.oracle import OracleSim
     from oracle import ref as refmod
-    if args.workload == "c5":
+    name = "c2" if args.workload == "default" else args.workload
+    if name == "c5":
         WORKLOADS["c5"] = (min(args.c5_n, 4096), 32, WORKLOADS["c5"][2].replace("N=32768", f"N={min(args.c5_n, 4096)} (CPU arm: down-scaled, the "
                            "oracle's reference textures need 116 GB at N=32768)"), True)
-    w = workload_setup(args.workload)
-    N, cores = w["N"], max_threads()
+    w = workload_setup(name, only=(0, REFERENCE_SAMPLE["c4"]) if name == "c4" else None)
+    N, cores = w["N"], host_cores()
     p = w["cascades"][0]
     # oracle/_ref = the reference's own compute shaders compiled for the CPU (oracle/make_ref.py): the reference arm proper. It needs
     # the reference's integer patch size and has no Jacobian (neither has the reference); otherwise the oracle port stands in.
-    use_ref = refmod.available() and float(p.L) == int(p.L)
+    use_ref = refmod.available() and all(float(q.L) == int(q.L) for q in w["cascades"])
+    sims = []
+    for i, q in enumerate(w["cascades"]):
+        if use_ref:
+            sims.append(refmod.RefSim(N, int(q.L), q.wind_speed, q.wind_dir, q.amplitude, q.suppression, w["noise"][i], threads=cores))
+        else:
+            sims.append(OracleSim(N, q.L, q.wind_speed, q.wind_dir, q.amplitude, q.suppression, w["noise"][i], threads=cores))
     if use_ref:
-        rs = refmod.RefSim(N, int(p.L), p.wind_speed, p.wind_dir, p.amplitude, p.suppression, w["noise"][0], threads=cores)
-
-        class _Sim:
-            def frame(self, t, choppiness=None):
-                return rs.frame(t)
-        sim, kind = _Sim(), "reference"
+        kind = "reference"
         what = ("oracle/_ref: the reference's own GLSL compute shaders (tilde_h0_t, butterfly x 2 log2 N x 3, inversion x 3, normal_map) compiled "
                 "as C++ and dispatched in the reference's order on the host cores (OpenMP over rows); no Jacobian, as in the reference")
     else:
-        sim, kind = OracleSim(N, p.L, p.wind_speed, p.wind_dir, p.amplitude, p.suppression, w["noise"][0], threads=cores), "port"
-        what = "CPU oracle = scalar C++ restatement of the reference's GLSL dispatch chain (oracle/_ref not available here)"
+        kind = "port"
+        what = "CPU oracle = scalar C++ restatement of the reference's GLSL dispatch chain (oracle/_ref not available or not applicable here)"
     lam = 1.0 if (w["jacobian"] and not use_ref) else None
-    sim.frame(w["times"][0], choppiness=lam)                  # first call pays thread start-up and page faults
-    t0 = time.perf_counter()
-    sim.frame(w["times"][1 % len(w["times"])], choppiness=lam)
-    one = time.perf_counter() - t0
-    budget = 120.0 / max(1, args.steps + args.warmup)          # whole run within a few minutes
-    sample = int(max(1, min(w["frames"], min(budget, 8.0) / max(one, 1e-6))))
+
+    def one(f):
+        s = sims[w["cascade_of"][f % len(w["cascade_of"])] % len(sims)]
+        t = w["times"][f % len(w["times"])]
+        return s.frame(t) if use_ref else s.frame(t, choppiness=lam)
+
+    sample = min(REFERENCE_SAMPLE[name], w["frames"])
+    one(0)                                                     # first call pays thread start-up and page faults
+
     def step():
         for f in range(sample):
-            sim.frame(w["times"][f % len(w["times"])], choppiness=lam)
+            one(f)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -178,19 +206,20 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     fps = sample * args.steps / dt
-    desc = f"first {sample} frames of the {w['frames']}-frame sweep per step"
+    desc = f"first {sample} frames of the workload's {WORKLOADS[name][1]} per step (fixed sample, the same at every --gpus)"
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["desc"], "N": N, "frames_per_step": sample, "sample": desc,
-                       "what": what},
+            "config": {"workload": w["desc"], "N": N, "frames_per_step": sample, "sample": desc, "what": what,
+                       "threads": cores, "OMP_NUM_THREADS_env": os.environ.get("OMP_NUM_THREADS")},
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     if use_ref:
         # for transparency: the hand-written restatement (oracle/ow_oracle.cpp) is faster than the reference's shader text compiled through
         # the GLSL emulation layer; its throughput on the same frames, same cores, is reported beside the reference arm's
-        port = OracleSim(N, p.L, p.wind_speed, p.wind_dir, p.amplitude, p.suppression, w["noise"][0], threads=cores)
+        q = w["cascades"][0]
+        port = OracleSim(N, q.L, q.wind_speed, q.wind_dir, q.amplitude, q.suppression, w["noise"][0], threads=cores)
         port.frame(w["times"][0])
         n, t0 = 0, time.perf_counter()
         while time.perf_counter() - t0 < 2.0 or n < 3:
@@ -202,8 +231,8 @@ def run_reference(args):
 
 
 def cpu_baseline(w, seconds=10.0):
-    from oracle.oracle import OracleSim, max_threads
-    cores = max_threads()
+    from oracle.oracle import OracleSim
+    cores = host_cores()
     p = w["cascades"][0]
     sim = OracleSim(w["N"], p.L, p.wind_speed, p.wind_dir, p.amplitude, p.suppression, w["noise"][0], threads=cores)
     lam = 1.0 if w["jacobian"] else None
@@ -216,169 +245,7 @@ def cpu_baseline(w, seconds=10.0):
         if (dt > seconds and n >= 3) or n >= w["frames"]:
             break
     return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"first {n} frames of the sweep ({dt:.1f} s), oracle/ow_oracle.cpp with OpenMP over rows"}
-
-
-def run_slab(args):
-    """--workload c5: one grid over all ranks (strong scaling). A step = one 32-frame sweep of SlabOcean.update."""
-    import torch
-    import fft_ocean_waves_b200 as fow
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    N, frames, desc, jac = WORKLOADS["c5"]
-    if args.c5_n != N:
-        N, frames = args.c5_n, (32 if args.c5_n <= 4096 else 4)
-        desc = desc.replace("N=32768", f"N={N} (down-scaled)").replace("4-frame", f"{frames}-frame")
-    p = fow.OceanParams(L=1000.0, wind_speed=40.0, wind_dir=(1.0, 1.0), amplitude=2.0, suppression=0.1, choppiness=1.0)
-    times = [float(np.float32(f / 60.0)) for f in range(frames)]
-    sim = fow.SlabOcean(N=N, params=p, device=local, jacobian=jac, transport=args.transport)
-    sim.init(32768)
-    stream = torch.cuda.Stream()
-    torch.cuda.set_stream(stream)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def sweep():
-        for t in times:
-            sim.update(t)
-
-    for _ in range(args.warmup):
-        flush.zero_()
-        sweep()
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    evs = []
-    for _ in range(args.steps):
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
-        sweep()
-        b.record(stream)
-        evs.append((a, b))
-    barrier()
-    total_ms = sum(a.elapsed_time(b) for a, b in evs)
-    if dist is not None:
-        tt = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        total_ms = float(tt.item())
-    value = frames * args.steps / (total_ms * 1e-3)
-    if args.profile:
-        sim.close()
-        return
-    # per-phase durations: events around ow_slab_rows (1 kernel) and ow_slab_cols (column + normal kernels)
-    b_ = sim.backend
-    st = b_.current_stream()
-    kms = np.zeros(2)
-    for t in times:
-        if sim.transport == "peer":
-            sim._barrier()
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        e[0].record(stream)
-        b_.rows(t, 1 if sim.transport == "peer" else 0, st)
-        e[1].record(stream)
-        if sim.transport == "peer":
-            sim._barrier()
-        elif world == 1:
-            b_.local_exchange(st)
-        else:
-            send, recv = b_.exchange_tensors()
-            dist.all_to_all_single(recv, send)
-        e[2].record(stream)
-        b_.cols(st)
-        e[3].record(stream)
-        torch.cuda.synchronize()
-        kms += np.array([e[0].elapsed_time(e[1]), e[2].elapsed_time(e[3])])
-    if dist is not None:
-        tt = torch.tensor(kms, device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        kms = tt.cpu().numpy()
-    clocks = sampler.stop() if rank == 0 else None
-    peak, peak_src = measured_peak()
-    texels_rank = float(N) * N / world
-    # compulsory bytes per texel of the two phases (folded spectrum 8 -> intermediate 12; intermediate 12 -> dy,dx,dz 12, then
-    # dy,dx,dz 12 -> normal 16 + J 4); above N=4096 the line decomposition's scratch adds 24 B/texel per direction, not counted
-    kb = {"ow_row_slab_kernel": 8 + 12, "ow_col_slab_kernel+ow_normal_slab_kernel": 12 + 12 + 4 + 8 + 16 + 4}
-    per_kernel = []
-    for i, k in enumerate(kb):
-        gbs = kb[k] * texels_rank * frames / (kms[i] * 1e-3) / 1e9
-        per_kernel.append({"kernel": k, "ms_per_launch": kms[i] / frames, "share": kms[i] / kms.sum(), "bytes_per_texel": kb[k],
-                           "achieved_gbs": gbs, "frac": gbs / peak})
-    dom = int(np.argmax(kms))
-    frame_gbs = 48 * texels_rank * value / 1e9
-    xbytes = sim.exchange_bytes_per_frame()
-    roofline = {"bound": "hbm", "kernel": per_kernel[dom]["kernel"], "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": per_kernel[dom]["frac"], "traffic": None, "peak_source": peak_src,
-                "bytes_per_launch": per_kernel[dom]["bytes_per_texel"] * texels_rank, "kernels": per_kernel,
-                "frame": {"algorithmic_bytes_per_texel": 48, "achieved": frame_gbs, "frac": frame_gbs / peak,
-                          "note": "per GPU: 48 B/texel x N^2/world texels x frames/s"},
-                "nvlink": {"bytes_per_frame_per_gpu_per_direction": xbytes, "achieved_gbs": xbytes * value / 1e9, "peak_gbs": 770.0,
-                           "frac": xbytes * value / 1e9 / 770.0,
-                           "note": "12 B/texel Hermitian-packed intermediate x (world-1)/world of this rank's texels (+ halo columns); "
-                                   "peak = measured peer copy 770 GB/s per direction (B200_PROFILING.md)"}}
-    # ---- end to end: seed in, every frame's column slab copied to pinned host memory ---------------------------------
-    outs = b_.output_tensors()
-    host = {k: torch.empty(v.shape, dtype=torch.float32, pin_memory=True) for k, v in outs.items()}
-    fbytes = sum(h.numel() * 4 for h in host.values())
-
-    def e2e_step():
-        sim.init(32768)
-        for t in times:
-            sim.update(t)
-            for k, v in outs.items():
-                host[k].copy_(v, non_blocking=True)
-        torch.cuda.synchronize()
-        return float(host["dy"][0, 0])
-
-    e2e_step()
-    barrier()
-    e2e_steps = max(1, min(args.steps, 3))
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_t = time.perf_counter() - t0
-    if dist is not None:
-        tt = torch.tensor([e2e_t], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_t = float(tt.item())
-    e2e = {"value": frames * e2e_steps / e2e_t, "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": int(frames * fbytes * world),
-           "steps": e2e_steps, "what": "ow_slab_init_spectrum_seeded (8-byte seed) + SlabOcean.update + every rank's column slab "
-                                       "(dy,dx,dz,normal,J) copied to pinned host memory every frame"}
-    line = None
-    if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
-                "config": {"workload": desc, "N": N, "frames_per_step": frames, "transport": sim.transport,
-                           "l2": "flushed between timed steps (256 MiB memset outside the event pair); a frame's working set "
-                                 f"({(16 + 12 + 12 + 20) * N * N / world / 1e6:.0f} MB per GPU) exceeds L2 at world <= 4",
-                           "parallelism": f"slab{world}: row pairs -> transpose (peer stores / all-to-all over NVLink) -> column slabs"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(3 * frames * args.steps), "roofline": roofline}
-        if world == 1 and not args.no_cpu and N <= 4096:      # the CPU oracle's reference textures need 108 B/texel: 116 GB at N=32768
-            w = dict(N=N, frames=frames, jacobian=True, cascades=[p], noise=[_philox_noise(32768, N)], times=times)
-            line["cpu_baseline"] = cpu_baseline(w)
-    sim.close()
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
-    if line is not None:
-        print(json.dumps(line), flush=True)
+            "sample": f"first {n} frames of the sweep ({dt:.1f} s), oracle/ow_oracle.cpp with OpenMP over rows on {cores} threads"}
 
 
 def _philox_noise(seed, N):
@@ -386,38 +253,90 @@ def _philox_noise(seed, N):
     return philox_noise(seed, N)
 
 
-def run_ours(args):
-    import torch
+# ======================================================================================================================
+# GPU arm plumbing
+# ======================================================================================================================
+class Env:
+    """One process per GPU: torch for streams/events/pinned memory, torch.distributed (NCCL) for the barrier and the slab exchange."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
+        # A dedicated non-default stream: its handle is what the C ABI launches on, and the torch events are recorded
+        # on the same stream (handle 0 would mean "the context's own stream" to ow_step*).
+        self.stream = torch.cuda.Stream()
+        torch.cuda.set_stream(self.stream)
+        self.sp = self.stream.cuda_stream
+        assert self.sp != 0
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, values):
+        if self.dist is None:
+            return [float(v) for v in values]
+        tt = self.torch.tensor(list(values), device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(tt, op=self.dist.ReduceOp.MAX)
+        return [float(v) for v in tt.cpu().numpy()]
+
+    def event(self):
+        return self.torch.cuda.Event(enable_timing=True)
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def traffic_per_launch(name, kernel, frames_per_launch):
+    """dram bytes per launch of `kernel` = this round's ncu capture (bytes per FRAME, profiles/traffic.json) x frames per launch."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        per_frame = t["per_frame"].get(f"{name}:{kernel}")
+        return None if per_frame is None else float(per_frame) * frames_per_launch
+    except Exception:
+        return None
+
+
+# ======================================================================================================================
+# Independent patches / cascades (C2, C3, C4)
+# ======================================================================================================================
+def measure_patch(env, args, name, steps, warmup, full):
+    """One JSON-able record for workload `name`. full=True adds e2e, the single-frame (drop-in) numbers, the cuFFT comparison
+    and the CPU baseline (rank 0, world 1)."""
     import fft_ocean_waves_b200 as fow
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    w = workload_setup(args.workload)
-    N, frames = w["N"], w["frames"]
+    torch = env.torch
+    world, rank = env.world, env.rank
     # C4 (BASELINE.json configs[3], SURVEY.md §8 e1): the 64 cascades are SHARDED, a contiguous block of 64/world per GPU,
     # no data-path collective -> strong scaling (total work fixed). Every other workload replicates per GPU (weak).
-    sharded = args.workload == "c4" and (world > 1 or args.c4_shard_of > 1)
+    sharded = name == "c4" and (world > 1 or args.c4_shard_of > 1)
+    only = None
     if sharded:
         parts = world if world > 1 else args.c4_shard_of       # --c4-shard-of P: time ONE GPU's share of a P-GPU run (tuning aid)
         if 64 % parts:
             raise SystemExit("bench.py: c4 shards 64 cascades; --gpus must divide 64")
         per = 64 // parts
-        lo = rank * per
-        w["cascades"], w["noise"] = w["cascades"][lo:lo + per], w["noise"][lo:lo + per]
-        w["cascade_of"], w["times"] = list(range(per)), w["times"][lo:lo + per]
-        frames = w["frames"] = per
+        only = (rank * per, rank * per + per)
+    w = workload_setup(name, only=only)
+    N, frames = w["N"], w["frames"]
     job_frames = (64 if world > 1 else frames) if sharded else world * frames            # frames the WHOLE job produces per step
-    slots = min(args.slots or (128 if N <= 512 else 32), frames) if args.workload != "c4" else frames
-    sim = fow.FFTOceanWaves(N=N, cascades=w["cascades"], n_slots=max(slots, len(w["cascades"])), device=local, jacobian=w["jacobian"],
+    slots = min(args.slots or (128 if N <= 512 else 32), frames) if name != "c4" else frames
+    sim = fow.FFTOceanWaves(N=N, cascades=w["cascades"], n_slots=max(slots, len(w["cascades"])), device=env.local, jacobian=w["jacobian"],
                             fused_normals=args.fused_normals)
     for i, nz in enumerate(w["noise"]):
         sim.set_noise(nz, cascade=i)
@@ -426,13 +345,11 @@ def run_ours(args):
         sim.set_group_size(args.group)
     if args.streams:
         sim.set_streams(args.streams)
-    # A dedicated non-default stream: its handle is what the C ABI launches on, and the torch events below are
-    # recorded on the same stream (handle 0 would mean "the context's own stream" to ow_step*).
-    stream = torch.cuda.Stream()
-    torch.cuda.set_stream(stream)
-    sp = stream.cuda_stream
-    assert sp != 0
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    if args.row_kernel:
+        sim.set_row_kernel(args.row_kernel)
+    if args.discard:
+        sim.set_discard_intermediate(True)
+    sp, stream = env.sp, env.stream
     launches, groups = [0], [0]
 
     def sweep():
@@ -442,84 +359,95 @@ def run_ours(args):
             launches[0] += sim.last_launch_count()
             groups[0] += sim.last_group_count()
 
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        flush.zero_()
+    for _ in range(warmup):
+        env.flush.zero_()
         sweep()
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    env.barrier()
+    sampler = ClockSampler(env.local).start() if rank == 0 else None
     launches[0] = groups[0] = 0
     evs = []
     t_wall = time.perf_counter()
-    for _ in range(args.steps):
-        flush.zero_()                      # L2 flush between timed iterations (outside the event pair)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(steps):
+        env.flush.zero_()                      # L2 flush between timed iterations (outside the event pair)
+        a, b = env.event(), env.event()
         a.record(stream)
         sweep()
         b.record(stream)
         evs.append((a, b))
-    barrier()
+    env.barrier()
     t_wall = time.perf_counter() - t_wall
     total_ms = sum(a.elapsed_time(b) for a, b in evs)
     timed_launches = launches[0]
-    if dist is not None:
-        tt = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        total_ms = float(tt.item())
-    value = job_frames * args.steps / (total_ms * 1e-3)
+    total_ms = env.max_over_ranks([total_ms])[0]
+    value = job_frames * steps / (total_ms * 1e-3)
 
     if args.profile:
         sim.close()
-        return
+        return None
     # ---- per-kernel durations (CUDA events around each kernel, same stream, same workload) -> roofline ----
     kms = np.zeros(3)
     prof_sweeps = 2
     for _ in range(prof_sweeps):
-        flush.zero_()
+        env.flush.zero_()
         for base in range(0, frames, slots):
             n = min(slots, frames - base)
             kms += np.array(sim.update_multi_timed(w["cascade_of"][base:base + n], w["times"][base:base + n], stream=sp))
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if sampler else None
     kms /= prof_sweeps                                      # ms per sweep per kernel
-    groups_per_sweep = groups[0] / args.steps
-    fused = not w["jacobian"] and kms[2] == 0.0          # normal map produced by the column kernel's epilogue (no separate kernel)
+    groups_per_sweep = groups[0] / steps
+    fused = kms[2] == 0.0                                   # normal map (+ Jacobian) produced by the column kernel's epilogue (no separate kernel)
     peak, peak_src = measured_peak()
     texels = float(N) * N
     kb = dict(KERNEL_BYTES_PER_TEXEL)
     if w["jacobian"]:
         kb["ow_normal_kernel"] += 8 + 4                     # + read dx,dz, write J
     if fused:
-        kb["ow_col_kernel"] += 16                           # ow_col_fused_kernel also writes the normal map (and never re-reads dy)
+        kb["ow_col_kernel"] += 16 + (4 if w["jacobian"] else 0)   # the fused column kernel also writes the normal map (+ J) and never re-reads dy
     per_kernel = []
     for i, k in enumerate(KERNELS):
         if kms[i] == 0.0:
             continue
+        bpt = kb[k]
         if fused and k == "ow_col_kernel":
             k = "ow_col_fused_kernel"
-        gbs = kb.get(k, kb["ow_col_kernel"]) * texels * frames / (kms[i] * 1e-3) / 1e9
+        gbs = bpt * texels * frames / (kms[i] * 1e-3) / 1e9
         per_kernel.append({"kernel": k, "ms_per_launch": kms[i] / groups_per_sweep, "share": kms[i] / kms.sum(),
-                           "bytes_per_texel": kb.get(k, kb["ow_col_kernel"]), "achieved_gbs": gbs, "frac": gbs / peak})
+                           "bytes_per_texel": bpt, "achieved_gbs": gbs, "frac": gbs / peak})
     dom = int(np.argmax([pk["share"] for pk in per_kernel]))
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{args.workload}:{per_kernel[dom]['kernel']}")
-    except Exception:
-        pass
+    frames_per_launch = frames / groups_per_sweep
     alg = ALG_BYTES_PER_TEXEL + (4 if w["jacobian"] else 0)
+    own = OWN_BYTES_PER_TEXEL + (4 if w["jacobian"] else 0)
     frame_gbs = alg * texels * value / world / 1e9
+    own_gbs = own * texels * value / world / 1e9
     roofline = {"bound": "hbm", "kernel": per_kernel[dom]["kernel"], "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": per_kernel[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
-                "bytes_per_launch": per_kernel[dom]["bytes_per_texel"] * texels * frames / groups_per_sweep,
+                "frac": per_kernel[dom]["frac"], "traffic": traffic_per_launch(name, per_kernel[dom]["kernel"], frames_per_launch),
+                "peak_source": peak_src,
+                "bytes_per_launch": per_kernel[dom]["bytes_per_texel"] * texels * frames_per_launch,
                 "kernels": per_kernel,
                 "frame": {"algorithmic_bytes_per_texel": alg, "achieved": frame_gbs, "frac": frame_gbs / peak,
-                          "note": "whole frame on SURVEY.md's 44 B/texel (48 with Jacobian), per GPU; the 3-kernel design moves 64 B/texel (8+12, 12+12, 4+16) of which 36 are compulsory since the h0 fold"}}
+                          "own_compulsory_bytes_per_texel": own, "own_achieved": own_gbs, "own_frac": own_gbs / peak,
+                          "note": "whole frame per GPU. frac: on SURVEY.md §8 d4's 44 B/texel (48 with Jacobian), the figure the target is quoted on; "
+                                  "own_frac: on the bytes THIS implementation must move (36 / 40: the folded spectrum is 8 B/texel). The separate-kernel "
+                                  "frame moves 64 (76) B/texel through L2"}}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["desc"], "N": N, "frames_per_step": job_frames if sharded else frames, "slots_per_launch": slots,
+                       "launch_groups_per_step": groups_per_sweep,
+                       "l2": "flushed between timed steps (256 MiB memset outside the event pair); within a step the outputs "
+                             f"({frames * sim.frame_bytes() / 1e9:.2f} GB) stream through L2, the folded spectrum ({8 * texels * len(w['cascades']) / 1e6:.1f} MB) is re-read every frame",
+                       "parallelism": (f"64 cascades sharded {frames} per GPU over {world} GPUs, no communication" if sharded
+                                       else f"{world} x independent patch per GPU, no communication"),
+                       "wall_s_timed_region": t_wall},
+            "clocks": clocks, "gpu_launches": int(timed_launches), "roofline": roofline}
+
+    # ---- the drop-in call itself: ONE frame per ow_step (what FFTOceanWaves::update() does, src/main.cpp:240-244) ---------------
+    if name != "c4":
+        line["config"]["single_frame"] = single_frame_numbers(env, sim, w)
+        line["config"]["single_slot_sequential_fps"] = line["config"]["single_frame"]["graph"]["back_to_back_fps"]
+    if not full:
+        sim.close()
+        return line
 
     # ---- end to end through the C ABI with HOST buffers --------------------------------------------------
     fbytes = sim.frame_bytes()
@@ -540,56 +468,378 @@ def run_ours(args):
         return float(host[:4].view(torch.float32)[0])          # host-side read of the result
 
     e2e_step()
-    barrier()
-    e2e_steps = max(1, min(args.steps, 3))
+    env.barrier()
+    e2e_steps = max(1, min(steps, 3))
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
-    barrier()
-    e2e_t = time.perf_counter() - t0
-    if dist is not None:
-        tt = torch.tensor([e2e_t], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_t = float(tt.item())
-    e2e = {"value": job_frames * e2e_steps / e2e_t, "unit": UNIT,
-           "h2d_bytes_per_step": int(sum(nz.numel() for nz in pinned_noise)), "d2h_bytes_per_step": int(frames * fbytes),
-           "steps": e2e_steps,
-           "what": "ow_set_noise + ow_init_spectrum + ow_step_multi + ow_download_frame_async of every frame into pinned host memory"}
-
-    # ---- latency-style number: one frame per call, single output slot (what an interactive renderer does) ----
-    seq_fps = None
-    if args.workload != "c4":
-        nseq = min(frames, 200)
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
-        for f in range(nseq):
-            sim.update_multi([0], [w["times"][f]], stream=sp)
-        b.record(stream)
-        torch.cuda.synchronize()
-        seq_fps = nseq / (a.elapsed_time(b) * 1e-3)
-
-    line = None
-    if rank == 0:
-        cpu = cpu_baseline(w) if world == 1 and not args.no_cpu else None
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
-                "config": {"workload": w["desc"], "N": N, "frames_per_step": job_frames if sharded else frames, "slots_per_launch": slots,
-                           "launch_groups_per_step": groups_per_sweep,
-                           "l2": "flushed between timed steps (256 MiB memset outside the event pair); within a step the outputs "
-                                 f"({frames * fbytes / 1e9:.2f} GB) stream through L2, h0 ({16 * texels * len(w['cascades']) / 1e6:.1f} MB) is re-read every frame as in the reference",
-                           "parallelism": (f"64 cascades sharded {frames} per GPU over {world} GPUs, no communication" if sharded
-                                           else f"{world} x independent patch per GPU, no communication"),
-                           "single_slot_sequential_fps": seq_fps, "wall_s_timed_region": t_wall},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(timed_launches), "roofline": roofline}
-        if cpu is not None:
-            line["cpu_baseline"] = cpu
+    env.barrier()
+    e2e_t = env.max_over_ranks([time.perf_counter() - t0])[0]
+    line["e2e"] = {"value": job_frames * e2e_steps / e2e_t, "unit": UNIT,
+                   "h2d_bytes_per_step": int(sum(nz.numel() for nz in pinned_noise)), "d2h_bytes_per_step": int(frames * fbytes),
+                   "steps": e2e_steps,
+                   "what": "ow_set_noise + ow_init_spectrum + ow_step_multi + ow_download_frame_async of every frame into pinned host memory "
+                           "(the reference's texture formats: 28 B/texel, +4 with the Jacobian)"}
+    del host
+    cmp_rec = None
+    if rank == 0 and not args.no_compare and name != "c4":
+        try:
+            cmp_rec = compare_cufft(env, sim, w)
+        except Exception as e:  # noqa: BLE001 - a comparison point must never take the bench line down
+            cmp_rec = {"cufft": {"unavailable": f"{type(e).__name__}: {e}"}}
     sim.close()
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
-    if line is not None:
+    # ---- the same end-to-end sweep with the packed output set: 12 B/texel over PCIe instead of 28 ----
+    if name != "c4":
+        line["e2e_packed_f16"] = e2e_packed(env, fow, w, args, slots, pinned_noise, job_frames, steps)
+    if cmp_rec is not None:
+        line["comparison"] = cmp_rec
+    if rank == 0 and world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(w)
+    return line
+
+
+def single_frame_numbers(env, sim, w):
+    """ow_step(t), one frame per call into slot 0 — the call that replaces the reference's update() chain. With the CUDA
+    graph (default) and with plain launches: frames/s back to back (no host sync between frames: throughput of the call path) and
+    the latency of one synchronous frame (ow_step + ow_sync, host clock)."""
+    torch = env.torch
+    out = {}
+    nseq = min(len(w["times"]), 200)
+    for label, on in (("graph", True), ("launches", False)):
+        sim.set_graph(on)
+        for f in range(10):
+            sim.update(w["times"][f % len(w["times"])], stream=env.sp)
+        torch.cuda.synchronize()
+        a, b = env.event(), env.event()
+        a.record(env.stream)
+        for f in range(nseq):
+            sim.update(w["times"][f], stream=env.sp)
+        b.record(env.stream)
+        torch.cuda.synchronize()
+        fps = nseq / (a.elapsed_time(b) * 1e-3)
+        lat = []
+        for f in range(50):
+            t0 = time.perf_counter()
+            sim.update(w["times"][f % len(w["times"])], stream=env.sp)
+            sim.sync(stream=env.sp)
+            lat.append(time.perf_counter() - t0)
+        out[label] = {"back_to_back_fps": fps, "sync_latency_us_median": float(np.median(lat) * 1e6), "frames": nseq}
+    sim.set_graph(True)
+    out["what"] = "sim.update(t) = ow_step: slot 0 <- cascade 0 at time t, one call per frame (the reference's update(), src/main.cpp:240-244)"
+    return out
+
+
+def e2e_packed(env, fow, w, args, slots, pinned_noise, job_frames, steps):
+    """End to end with OW_FLAG_PACKED_F16: RGBA16F (dx,dy,dz,J) + RG16_SNORM normal.xz copied back instead of the reference formats."""
+    torch = env.torch
+    N, frames = w["N"], w["frames"]
+    sim = fow.FFTOceanWaves(N=N, cascades=w["cascades"], n_slots=max(slots, len(w["cascades"])), device=env.local, jacobian=w["jacobian"], packed="f16")
+    pbytes = sim.packed_bytes()
+    host = torch.empty(slots * pbytes, dtype=torch.uint8, pin_memory=True)
+    hp = host.data_ptr()
+
+    def step():
+        for i, nz in enumerate(pinned_noise):
+            sim.set_noise(nz.numpy(), cascade=i)
+        sim.tilde_h0_k()
+        for base in range(0, frames, slots):
+            n = min(slots, frames - base)
+            sim.update_multi(w["cascade_of"][base:base + n], w["times"][base:base + n], stream=env.sp)
+            for s in range(n):
+                sim.download_packed_async(s, hp + s * pbytes, pbytes, stream=env.sp)
+        sim.sync(stream=env.sp)
+        return float(host[:2].view(torch.float16)[0])
+
+    step()
+    env.barrier()
+    n = max(1, min(steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        step()
+    env.barrier()
+    dt = env.max_over_ranks([time.perf_counter() - t0])[0]
+    sim.close()
+    return {"value": job_frames * n / dt, "unit": UNIT, "h2d_bytes_per_step": int(sum(nz.numel() for nz in pinned_noise)),
+            "d2h_bytes_per_step": int(frames * pbytes), "steps": n,
+            "what": "same sweep, context created with OW_FLAG_PACKED_F16: ow_download_packed_async of every frame (12 B/texel: RGBA16F dx,dy,dz,J + "
+                    "RG16_SNORM normal.xz; decode in INTEGRATION.md; tolerance 1e-3 of peak, tests/test_gpu_packed.py)"}
+
+
+def compare_cufft(env, sim, w):
+    """Comparison point only (never the product): the same frame through cuFFT (torch.fft.ifft2 = batched 2-D C2C inverse) on the
+    identical spectra, plus torch element-wise ops for the inversion and the normal map. Also reports how far the cuFFT result is
+    from this library's output (an independent check of the hand-written FFT)."""
+    torch = env.torch
+    N = w["N"]
+    p = w["cascades"][0]
+    dev = "cuda"
+    h0k = torch.from_numpy(sim.download("h0k", 0)).to(dev)
+    h0m = torch.from_numpy(sim.download("h0minusk", 0)).to(dev)
+    h0k = torch.complex(h0k[..., 0], h0k[..., 1])
+    h0m = torch.complex(h0m[..., 0], h0m[..., 1])
+    idx = torch.arange(N, device=dev, dtype=torch.float32) - N / 2.0
+    k1 = (2.0 * np.float32(np.pi) * idx) / np.float32(p.L)             # tilde_h0_t_cs.glsl:72-73
+    kx, ky = k1[None, :].expand(N, N), k1[:, None].expand(N, N)
+    km = torch.sqrt(kx * kx + ky * ky).clamp_min(1e-5)                  # :74-79
+    wdisp = torch.sqrt(9.81 * km)
+
+    def spectra(t):
+        ph = wdisp * np.float32(t)
+        e = torch.complex(torch.cos(ph), torch.sin(ph))
+        h = h0k * e + h0m * torch.conj(e)                                  # :96-110 (conjugate() is a no-op in the shader: h0minusk is NOT conjugated)
+        mi = torch.complex(torch.zeros_like(km), -torch.ones_like(km))
+        return torch.stack([h, mi * (kx / km) * h, mi * (ky / km) * h])   # dy, dx, dz  (:113-126)
+
+    def ifft_frame(H):
+        D = torch.fft.ifft2(torch.fft.ifftshift(H, dim=(-2, -1)))         # = butterfly passes + inversion_cs.glsl (SURVEY.md §0)
+        return D.real.contiguous()
+
+    def normals(h):                                                       # normal_map_cs.glsl:24-54; LINEAR/REPEAT corner taps = 2x2 box means
+        box = 0.25 * (h + torch.roll(h, 1, 0) + torch.roll(h, 1, 1) + torch.roll(h, (1, 1), (0, 1)))
+        z = lambda dx, dy: torch.roll(box, (-dy, -dx), (0, 1))
+        nz = z(-1, -1) + 2 * z(0, -1) + z(1, -1) - z(-1, 1) - 2 * z(0, 1) - z(1, 1)
+        nx = z(-1, -1) + 2 * z(-1, 0) + z(-1, 1) - z(1, -1) - 2 * z(1, 0) - z(1, 1)
+        r = torch.rsqrt(nx * nx + 1.0 + nz * nz)
+        return torch.stack([nx * r, r, nz * r], dim=-1)
+
+    t = w["times"][min(1, len(w["times"]) - 1)]
+    H = spectra(t)
+    D = ifft_frame(H)
+    ours = sim.frame(t)
+    err = {k: float(np.abs(D[i].cpu().numpy() - ours[k]).max() / np.abs(ours[k]).max()) for i, k in enumerate(("dy", "dx", "dz"))}
+    nrm = normals(D[0])
+    err["normal_abs"] = float(np.abs(nrm.cpu().numpy() - ours["normal"][..., :3]).max())
+    Hs = torch.fft.ifftshift(H, dim=(-2, -1)).contiguous()
+    reps = 50 if N <= 1024 else 20
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = env.event(), env.event()
+        a.record(env.stream)
+        for _ in range(reps):
+            fn()
+        b.record(env.stream)
+        torch.cuda.synchronize()
+        return reps / (a.elapsed_time(b) * 1e-3)
+
+    fft_only = timed(lambda: torch.fft.ifft2(Hs))
+    pipeline = timed(lambda: normals(torch.fft.ifft2(Hs).real[0]))
+    full = timed(lambda: normals(ifft_frame(spectra(t))[0]))
+    return {"cufft": {"ifft2_only_fps": fft_only, "ifft2_plus_normals_fps": pipeline, "spectrum_ifft2_normals_fps": full, "unit": UNIT,
+                      "max_rel_diff_vs_ours": err,
+                      "what": "torch.fft.ifft2 (cuFFT batched 2-D C2C inverse, 3 x NxN complex64) on the identical spectra; +normals = .real + the "
+                              "normal map in torch element-wise ops; spectrum_... also evaluates h(k,t) in torch ops. Comparison point only; back to "
+                              "back on one stream, spectra resident in HBM (and in L2 for small N)"}}
+
+
+# ======================================================================================================================
+# One grid over all ranks (C5)
+# ======================================================================================================================
+def slab_parity_check(env, fow, N, transport):
+    """Before timing: the slab path on all ranks against the single-GPU path, one frame, on a grid the single-GPU context fits
+    beside the slab (same code: line decomposition when N > 4096, the transpose, the halo columns)."""
+    p = fow.OceanParams(L=1000.0, wind_speed=40.0, wind_dir=(1.0, 1.0), amplitude=2.0, suppression=0.1, choppiness=1.0)
+    t = 1.0
+    slab = fow.SlabOcean(N=N, params=p, device=env.local, jacobian=True, transport=transport)
+    slab.init(32768)
+    slab.update(t)
+    slab.sync()
+    got = {k: slab.gather(k) for k in ("dy", "dx", "dz", "jacobian")}
+    slab.close()
+    res = None
+    if env.rank == 0:
+        with fow.FFTOceanWaves(N=N, cascades=[p], jacobian=True, device=env.local) as one:
+            one.set_noise_seed(32768)
+            one.tilde_h0_k()
+            ref = one.frame(t)
+        res = {"N": N, "world": env.world}
+        for k in ("dy", "dx", "dz"):
+            res[k + "_max_rel"] = float(np.abs(got[k] - ref[k]).max() / np.abs(ref[k]).max())
+        res["jacobian_max_abs"] = float(np.abs(got["jacobian"] - ref["jacobian"]).max())
+        res["ok"] = bool(max(res["dy_max_rel"], res["dx_max_rel"], res["dz_max_rel"]) <= 1e-4 and res["jacobian_max_abs"] <= 1e-3)
+    env.barrier()
+    return res
+
+
+def measure_slab(env, args, n_grid, steps, warmup, full):
+    """One grid over all ranks (strong scaling). A step = one sweep of SlabOcean.update."""
+    import fft_ocean_waves_b200 as fow
+    torch = env.torch
+    world, rank, dist = env.world, env.rank, env.dist
+    N, frames, desc, jac = WORKLOADS["c5"]
+    if n_grid != N:
+        N, frames = n_grid, (32 if n_grid <= 4096 else 4)
+        desc = desc.replace("N=32768", f"N={N} (down-scaled)").replace("4-frame", f"{frames}-frame")
+    parity = None
+    if not args.profile and not args.no_slab_check:
+        parity = slab_parity_check(env, fow, min(N, 8192), args.transport)
+        if rank == 0 and not parity["ok"]:
+            raise SystemExit(f"bench.py: slab path disagrees with the single-GPU path: {parity}")
+    p = fow.OceanParams(L=1000.0, wind_speed=40.0, wind_dir=(1.0, 1.0), amplitude=2.0, suppression=0.1, choppiness=1.0)
+    times = [float(np.float32(f / 60.0)) for f in range(frames)]
+    sim = fow.SlabOcean(N=N, params=p, device=env.local, jacobian=jac, transport=args.transport)
+    sim.init(32768)
+    stream = env.stream
+
+    def sweep():
+        for t in times:
+            sim.update(t)
+
+    for _ in range(warmup):
+        env.flush.zero_()
+        sweep()
+    env.barrier()
+    sampler = ClockSampler(env.local).start() if rank == 0 else None
+    evs = []
+    for _ in range(steps):
+        env.flush.zero_()
+        a, b = env.event(), env.event()
+        a.record(stream)
+        sweep()
+        b.record(stream)
+        evs.append((a, b))
+    env.barrier()
+    total_ms = env.max_over_ranks([sum(a.elapsed_time(b) for a, b in evs)])[0]
+    value = frames * steps / (total_ms * 1e-3)
+    if args.profile:
+        sim.close()
+        return None
+    # per-phase durations: events around ow_slab_rows (1 kernel) and ow_slab_cols (column + normal kernels)
+    b_ = sim.backend
+    st = b_.current_stream()
+    kms = np.zeros(3)
+    for t in times:
+        if sim.transport == "peer":
+            sim._barrier()
+        e = [env.event() for _ in range(4)]
+        e[0].record(stream)
+        b_.rows(t, 1 if sim.transport == "peer" else 0, st)
+        e[1].record(stream)
+        if sim.transport == "peer":
+            sim._barrier()
+        elif world == 1:
+            b_.local_exchange(st)
+        else:
+            send, recv = b_.exchange_tensors()
+            dist.all_to_all_single(recv, send)
+        e[2].record(stream)
+        b_.cols(st)
+        e[3].record(stream)
+        torch.cuda.synchronize()
+        kms += np.array([e[0].elapsed_time(e[1]), e[2].elapsed_time(e[3]), e[1].elapsed_time(e[2])])
+    kms = np.array(env.max_over_ranks(kms))
+    clocks = sampler.stop() if sampler else None
+    peak, peak_src = measured_peak()
+    texels_rank = float(N) * N / world
+    # compulsory bytes per texel of the two phases (folded spectrum 8 -> intermediate 12; intermediate 12 -> dy,dx,dz 12, then
+    # dy,dx,dz 12 -> normal 16 + J 4); above N=4096 the line decomposition's scratch adds 24 B/texel per direction, not counted
+    kb = {"ow_row_slab_kernel": 8 + 12, "ow_col_slab_kernel+ow_normal_slab_kernel": 12 + 12 + 4 + 8 + 16 + 4}
+    per_kernel = []
+    for i, k in enumerate(kb):
+        gbs = kb[k] * texels_rank * frames / (kms[i] * 1e-3) / 1e9
+        per_kernel.append({"kernel": k, "ms_per_launch": kms[i] / frames, "share": kms[i] / kms[:2].sum(), "bytes_per_texel": kb[k],
+                           "achieved_gbs": gbs, "frac": gbs / peak})
+    dom = int(np.argmax(kms[:2]))
+    frame_gbs = 48 * texels_rank * value / 1e9
+    xbytes = sim.exchange_bytes_per_frame()
+    # NVLink: with peer stores the exchange happens INSIDE the row phase, so its bandwidth is bytes / row-phase time
+    row_s = kms[0] * 1e-3 / frames
+    nv_during = xbytes / row_s / 1e9 if sim.transport == "peer" and world > 1 else (xbytes / (kms[2] * 1e-3 / frames) / 1e9 if world > 1 and kms[2] > 0 else 0.0)
+    roofline = {"bound": "hbm", "kernel": per_kernel[dom]["kernel"], "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": per_kernel[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "bytes_per_launch": per_kernel[dom]["bytes_per_texel"] * texels_rank, "kernels": per_kernel,
+                "frame": {"algorithmic_bytes_per_texel": 48, "achieved": frame_gbs, "frac": frame_gbs / peak,
+                          "note": "per GPU: 48 B/texel x N^2/world texels x frames/s"},
+                "nvlink": {"bytes_per_frame_per_gpu_per_direction": xbytes, "achieved_gbs_over_frame": xbytes * value / 1e9,
+                           "achieved_gbs_during_exchange": nv_during, "peak_gbs": 770.0, "frac": nv_during / 770.0,
+                           "exchange_ms_per_frame": (kms[0] if sim.transport == "peer" else kms[2]) / frames,
+                           "note": "12 B/texel Hermitian-packed intermediate x (world-1)/world of this rank's texels (+ halo columns); "
+                                   "frac = bytes / (time of the phase that moves them: the row kernel for peer stores, the all-to-all otherwise) against the "
+                                   "measured peer copy 770 GB/s per direction (B200_PROFILING.md)"}}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "N": N, "frames_per_step": frames, "transport": sim.transport,
+                       "l2": "flushed between timed steps (256 MiB memset outside the event pair); a frame's working set "
+                             f"({(16 + 12 + 12 + 20) * N * N / world / 1e6:.0f} MB per GPU) exceeds L2 at world <= 4",
+                       "parallelism": f"slab{world}: row pairs -> transpose (peer stores / all-to-all over NVLink) -> column slabs",
+                       "slab_vs_single_gpu_check": parity},
+            "clocks": clocks, "gpu_launches": int(sim.launches_per_frame() * frames * steps), "roofline": roofline}
+    if full:
+        # ---- end to end: seed in, every frame's column slab copied to pinned host memory ---------------------------------
+        outs = b_.output_tensors()
+        host = {k: torch.empty(v.shape, dtype=torch.float32, pin_memory=True) for k, v in outs.items()}
+        fbytes = sum(h.numel() * 4 for h in host.values())
+
+        def e2e_step():
+            sim.init(32768)
+            for t in times:
+                sim.update(t)
+                for k, v in outs.items():
+                    host[k].copy_(v, non_blocking=True)
+            torch.cuda.synchronize()
+            return float(host["dy"][0, 0])
+
+        e2e_step()
+        env.barrier()
+        e2e_steps = max(1, min(steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        env.barrier()
+        e2e_t = env.max_over_ranks([time.perf_counter() - t0])[0]
+        line["e2e"] = {"value": frames * e2e_steps / e2e_t, "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": int(frames * fbytes * world),
+                       "steps": e2e_steps, "what": "ow_slab_init_spectrum_seeded (8-byte seed) + SlabOcean.update + every rank's column slab "
+                                                   "(dy,dx,dz,normal,J) copied to pinned host memory every frame"}
+        if rank == 0 and world == 1 and not args.no_cpu and N <= 4096:      # the CPU oracle's reference textures need 108 B/texel: 116 GB at N=32768
+            w = dict(N=N, frames=frames, jacobian=True, cascades=[p], noise=[_philox_noise(32768, N)], times=times)
+            line["cpu_baseline"] = cpu_baseline(w)
+    sim.close()
+    return line
+
+
+def sub_record(line):
+    """What a configs.* entry keeps of a full record."""
+    if line is None:
+        return None
+    keep = ("value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "config", "clocks", "gpu_launches", "roofline", "e2e")
+    return {k: line[k] for k in keep if k in line}
+
+
+def run_ours(args):
+    env = Env()
+    name = args.workload
+    line = None
+    if name == "default":
+        line = measure_patch(env, args, "c2", args.steps, args.warmup, full=True)
+        if not args.profile:
+            sub_steps = max(1, min(args.steps, 3))
+            configs = {}
+            for cname in ("c3", "c4"):
+                try:
+                    configs[cname] = sub_record(measure_patch(env, args, cname, sub_steps, 3, full=False))
+                except Exception as e:  # noqa: BLE001 - a sub-record must not take the headline down; the failure is recorded instead
+                    configs[cname] = {"error": f"{type(e).__name__}: {e}"}
+                    if env.world > 1:
+                        raise
+            try:
+                configs["c5"] = sub_record(measure_slab(env, args, args.c5_n, sub_steps, 3, full=False))
+            except Exception as e:  # noqa: BLE001
+                configs["c5"] = {"error": f"{type(e).__name__}: {e}"}
+                if env.world > 1:
+                    raise
+            if line is not None:
+                line["configs"] = configs
+                line["config"]["workload_note"] = ("value/e2e/roofline = C2 (BASELINE.json configs[1]); configs.c3/c4/c5 = the target configurations "
+                                                   "measured in the same run (c4 sharded and c5 slab-decomposed over the ranks under torchrun)")
+    elif name == "c5":
+        line = measure_slab(env, args, args.c5_n, args.steps, args.warmup, full=True)
+    else:
+        line = measure_patch(env, args, name, args.steps, args.warmup, full=True)
+    env.close()
+    if line is not None and env.rank == 0:
         print(json.dumps(line), flush=True)
 
 
@@ -599,11 +849,15 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
+    ap.add_argument("--workload", choices=["default"] + sorted(WORKLOADS), default="default")
     ap.add_argument("--slots", type=int, default=0, help="frames evaluated per ow_step_multi call (0 = 128 for c2, 32 for c3, 64 for c4)")
     ap.add_argument("--group", type=int, default=0, help="slots per launch group (0 = library default)")
     ap.add_argument("--streams", type=int, default=0, help="internal streams the launch groups are spread over (0 = library default)")
+    ap.add_argument("--row-kernel", type=int, default=0, help="ow_set_row_kernel mode (0 = per-N default, 1 = classic, 2 = persistent pipelined)")
+    ap.add_argument("--discard", action="store_true", help="ow_set_discard_intermediate(1)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-compare", action="store_true", help="skip the cuFFT comparison leg")
+    ap.add_argument("--no-slab-check", action="store_true", help="c5: skip the slab-vs-single-GPU agreement check before timing")
     ap.add_argument("--fused-normals", action="store_true", help="experimental OW_FLAG_FUSED_NORMALS (normal map as the column kernel's epilogue)")
     ap.add_argument("--c4-shard-of", type=int, default=1, help="c4 on one GPU only: run the 64/P cascades one rank of a P-GPU job would get")
     ap.add_argument("--c5-n", type=int, default=32768, help="c5 only: grid size (32768 = BASELINE config C5; 4096 = its down-scaled parity grid)")
@@ -615,8 +869,6 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload == "c5":
-        run_slab(args)
     else:
         run_ours(args)
 

@@ -22,6 +22,7 @@ SOURCES = [
     ("ow_frame_kernels.cu", []),
     ("ow_big_kernels.cu", []),
     ("ow_init_kernels.cu", ["-fmad=false"]),
+    ("ow_pack_kernels.cu", []),
     ("ow_api.cu", []),
     ("ow_slab.cu", []),
 ]

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <new>
 #include <string>
 #include <vector>
@@ -42,12 +43,25 @@ struct ow_ctx {
     cudaStream_t aux[kMaxAux] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[kMaxAux] = {nullptr, nullptr, nullptr, nullptr};
     int n_streams = 3;
-    bool spectrum_ready = false;
+    std::vector<char> h0_ready;   // per cascade: h0/hp/nyq/ktab hold the spectrum of the CURRENT parameters
+    bool casc_uploaded = false;   // d_casc matches params
     int group_size = 0;
     int last_launches = 0, last_groups = 0;
     std::string err;
+    KernelConfig kcfg;            // per-context (device) launch facts: SM count, persistent-kernel occupancy
+    int row_mode = 0;             // ow_set_row_kernel
+    int discard_inter = 0;        // ow_set_discard_intermediate
+    // ow_step (slot i <- cascade i at ONE time t) as a CUDA graph: [exact sincos, fast sincos]; rebuilt when a tuning knob changes
+    bool graph_enabled = true;
+    std::unique_ptr<GraphPlan> plan[2];
+    std::vector<int32_t> ident;   // 0..n_cascades-1 (ow_step's slot map; no per-call allocation)
+    std::vector<float> tbuf;
+    // packed outputs (OW_FLAG_PACKED_F32 / _F16)
+    char* d_packed = nullptr;
+    PackedBuffers pk{};
     // GL interop
     cudaGraphicsResource* gl_res[4] = {nullptr, nullptr, nullptr, nullptr};
+    int gl_count = 0;             // 4 = dy,dx,dz,normal; 2 = packed displacement + normal_xz
     bool gl_registered = false;
 };
 
@@ -90,15 +104,30 @@ FrameBuffers buffers(const ow_ctx* c) {
     FrameBuffers fb{};
     fb.N = c->N; fb.h0 = c->d_h0; fb.hp = c->d_hp; fb.nyq = c->d_nyq; fb.ktab = c->d_ktab; fb.casc = c->d_casc; fb.inter = c->d_inter;
     fb.disp = c->d_disp; fb.normal = c->d_normal; fb.jacobian = c->d_jac;
-    // Measured on B200 (profiles/r01d_discard_ab.txt): dropping the consumed intermediate from L2 changes nothing — the
-    // frame is not bound by DRAM write-back — so it stays off; OW_DISCARD=1 turns it on for experiments.
-    static const int discard = getenv("OW_DISCARD") ? 1 : 0;
-    fb.discard_inter = discard;
+    // Measured on B200 (profiles/r01d_discard_ab.txt): dropping the consumed intermediate from L2 changed nothing in the
+    // multi-stream sweep, so it is off unless ow_set_discard_intermediate turns it on.
+    fb.discard_inter = c->discard_inter;
     fb.four_step = (c->flags & OW_FLAG_FOUR_STEP) ? 1 : 0;
     fb.scratch = c->d_scratch;
     fb.fuse_normals = (c->flags & OW_FLAG_FUSED_NORMALS) && !(c->flags & OW_FLAG_JACOBIAN) && c->N <= 2048 ? 1 : 0;
+    fb.row_mode = c->row_mode;
+    fb.sm_count = c->kcfg.sm_count;
+    fb.row_pipe_ctas[0] = c->kcfg.row_pipe_ctas[0]; fb.row_pipe_ctas[1] = c->kcfg.row_pipe_ctas[1];
     return fb;
 }
+
+void drop_plans(ow_ctx* c) { c->plan[0].reset(); c->plan[1].reset(); }
+
+bool all_ready(const ow_ctx* c) {
+    for (char r : c->h0_ready) if (!r) return false;
+    return true;
+}
+
+// Destroys the timing events of ow_step_multi_timed on every exit path.
+struct EventGuard {
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    ~EventGuard() { for (auto& e : ev) if (e) cudaEventDestroy(e); }
+};
 
 // Slots per launch group. Upper bound: a group's 12 B/texel intermediate should not exceed ~100 MB (measured on
 // B200: launch count and tail efficiency matter more than keeping the intermediate strictly inside the 126 MB L2).
@@ -128,8 +157,10 @@ void release(ow_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->gl_registered) for (auto& r : c->gl_res) if (r) cudaGraphicsUnregisterResource(r);
+    c->gl_registered = false;
     cudaFree(c->d_noise); cudaFree(c->d_h0); cudaFree(c->d_hp); cudaFree(c->d_nyq); cudaFree(c->d_ktab); cudaFree(c->d_casc); cudaFree(c->d_inter);
-    cudaFree(c->d_disp); cudaFree(c->d_normal); cudaFree(c->d_jac); cudaFree(c->d_tmp); cudaFree(c->d_scratch);
+    drop_plans(c);
+    cudaFree(c->d_disp); cudaFree(c->d_normal); cudaFree(c->d_jac); cudaFree(c->d_tmp); cudaFree(c->d_scratch); cudaFree(c->d_packed);
     if (c->stream) cudaStreamDestroy(c->stream);
     for (auto& s : c->aux) if (s) cudaStreamDestroy(s);
     for (auto& e : c->ev_join) if (e) cudaEventDestroy(e);
@@ -148,6 +179,8 @@ int ow_create(int32_t N, int32_t n_cascades, int32_t n_slots, const ow_params* c
     if (!frame_supported(N)) return fail(nullptr, OW_ERR_INVALID, "ow_create: N must be a power of two in [256, 32768]");
     if ((flags & OW_FLAG_FOUR_STEP) && !big_supported(N, true))
         return fail(nullptr, OW_ERR_INVALID, "ow_create: OW_FLAG_FOUR_STEP is a test mode for N = 1024 or 2048");
+    if ((flags & OW_FLAG_PACKED_F32) && (flags & OW_FLAG_PACKED_F16))
+        return fail(nullptr, OW_ERR_INVALID, "ow_create: OW_FLAG_PACKED_F32 and OW_FLAG_PACKED_F16 are mutually exclusive");
     if (n_cascades < 1 || !cascades) return fail(nullptr, OW_ERR_INVALID, "ow_create: need >= 1 cascade");
     if (n_slots < n_cascades) return fail(nullptr, OW_ERR_INVALID, "ow_create: n_slots must be >= n_cascades");
     for (int i = 0; i < n_cascades; ++i)
@@ -161,6 +194,11 @@ int ow_create(int32_t N, int32_t n_cascades, int32_t n_slots, const ow_params* c
     c->N = N; c->n_cascades = n_cascades; c->n_slots = n_slots; c->device = device; c->flags = flags;
     c->params.assign(cascades, cascades + n_cascades);
     c->noise_set.assign(n_cascades, 0);
+    c->h0_ready.assign(n_cascades, 0);
+    c->ident.resize(n_cascades);
+    for (int i = 0; i < n_cascades; ++i) c->ident[i] = i;
+    c->tbuf.assign(n_cascades, 0.0f);
+    c->casc_host.resize(n_cascades);
     const size_t nn = (size_t)N * N;
 #define OW_TRY(call)                                                                 \
     do {                                                                             \
@@ -187,7 +225,14 @@ int ow_create(int32_t N, int32_t n_cascades, int32_t n_slots, const ow_params* c
     if (flags & OW_FLAG_JACOBIAN) OW_TRY(cudaMalloc(&c->d_jac, nn * n_slots * sizeof(float)));
     OW_TRY(cudaMalloc(&c->d_tmp, nn * 4 * sizeof(float)));
     if (big_supported(N, false) || (flags & OW_FLAG_FOUR_STEP)) OW_TRY(cudaMalloc(&c->d_scratch, nn / 2 * 3 * sizeof(float2)));
-    OW_TRY(configure_frame_kernels(N));
+    if (flags & (OW_FLAG_PACKED_F32 | OW_FLAG_PACKED_F16)) {
+        c->pk.half = (flags & OW_FLAG_PACKED_F16) ? 1 : 0;
+        c->pk.normal_offset = nn * (c->pk.half ? 8 : 16);
+        c->pk.slot_bytes = c->pk.normal_offset + nn * 4;
+        OW_TRY(cudaMalloc(&c->d_packed, c->pk.slot_bytes * n_slots));
+        c->pk.base = c->d_packed;
+    }
+    OW_TRY(configure_frame_kernels(N, &c->kcfg));
 #undef OW_TRY
     *out = c;
     return OW_OK;
@@ -202,7 +247,8 @@ int ow_set_params(ow_ctx* c, int32_t cascade, const ow_params* p) {
     if (cascade < 0 || cascade >= c->n_cascades) return fail(c, OW_ERR_INVALID, "ow_set_params: cascade out of range");
     if (!valid_params(*p)) return fail(c, OW_ERR_INVALID, "ow_set_params: invalid parameters");
     c->params[cascade] = *p;
-    c->spectrum_ready = false;
+    c->h0_ready[cascade] = 0;          // only this cascade needs a new ow_init_spectrum / ow_set_h0
+    c->casc_uploaded = false;
     return OW_OK;
 }
 
@@ -217,6 +263,7 @@ int ow_set_noise(ow_ctx* c, int32_t cascade, const uint8_t* const planes[4], int
         OW_CUDA(c, cudaStreamSynchronize(c->stream));
         cudaFree(c->d_noise); c->d_noise = nullptr;
         std::fill(c->noise_set.begin(), c->noise_set.end(), 0);
+        std::fill(c->h0_ready.begin(), c->h0_ready.end(), 0);
     }
     if (!c->d_noise) {
         OW_CUDA(c, cudaMalloc(&c->d_noise, plane * 4 * c->n_cascades));
@@ -227,9 +274,9 @@ int ow_set_noise(ow_ctx* c, int32_t cascade, const uint8_t* const planes[4], int
         for (int j = 0; j < 4; ++j)
             OW_CUDA(c, cudaMemcpyAsync(c->d_noise + ((size_t)i * 4 + j) * plane, planes[j], plane, cudaMemcpyHostToDevice, c->stream));
         c->noise_set[i] = 1;
+        c->h0_ready[i] = 0;
     }
     OW_CUDA(c, cudaStreamSynchronize(c->stream));   // host planes may be freed by the caller on return
-    c->spectrum_ready = false;
     return OW_OK;
 }
 
@@ -243,6 +290,7 @@ int ow_set_noise_seed(ow_ctx* c, int32_t cascade, uint64_t seed) {
         OW_CUDA(c, cudaStreamSynchronize(c->stream));
         cudaFree(c->d_noise); c->d_noise = nullptr;
         std::fill(c->noise_set.begin(), c->noise_set.end(), 0);
+        std::fill(c->h0_ready.begin(), c->h0_ready.end(), 0);
     }
     if (!c->d_noise) {
         OW_CUDA(c, cudaMalloc(&c->d_noise, plane * 4 * c->n_cascades));
@@ -252,30 +300,42 @@ int ow_set_noise_seed(ow_ctx* c, int32_t cascade, uint64_t seed) {
     for (int i = lo; i < hi; ++i) {
         OW_CUDA(c, launch_noise_seed(c->d_noise + (size_t)i * 4 * plane, N, seed, c->stream));
         c->noise_set[i] = 1;
+        c->h0_ready[i] = 0;
     }
     OW_CUDA(c, cudaStreamSynchronize(c->stream));
-    c->spectrum_ready = false;
     return OW_OK;
 }
 
-int ow_init_spectrum(ow_ctx* c) {
-    if (!c) return OW_ERR_INVALID;
-    for (int i = 0; i < c->n_cascades; ++i)
-        if (!c->noise_set[i]) return fail(c, OW_ERR_STATE, "ow_init_spectrum: ow_set_noise has not been called for every cascade");
+// tilde_h0_k_cs.glsl for the cascades in [lo, hi) + the constants every cascade's kernels read.
+static int init_range(ow_ctx* c, int lo, int hi, const char* who) {
+    for (int i = lo; i < hi; ++i)
+        if (!c->noise_set[i]) return fail(c, OW_ERR_STATE, std::string(who) + ": ow_set_noise has not been called for every cascade involved");
     OW_CUDA(c, cudaSetDevice(c->device));
-    c->casc_host.resize(c->n_cascades);
     const size_t nn = (size_t)c->N * c->N, plane = (size_t)c->noise_w * c->noise_h;
-    for (int i = 0; i < c->n_cascades; ++i) {
+    for (int i = lo; i < hi; ++i) {
         c->casc_host[i] = to_dev(c->params[i]);
         OW_CUDA(c, launch_ktab(c->d_ktab + (size_t)i * c->N, c->N, c->params[i].L, c->stream));
         OW_CUDA(c, launch_h0(c->d_h0 + (size_t)i * nn, c->d_noise + (size_t)i * 4 * plane, c->noise_w, c->noise_h, c->N,
                              c->casc_host[i], c->stream));
         OW_CUDA(c, launch_fold(c->d_h0 + (size_t)i * nn, c->d_hp + (size_t)i * (nn / 2), c->d_nyq + (size_t)i * (c->N / 2), c->N, c->stream));
     }
+    for (int i = 0; i < c->n_cascades; ++i) c->casc_host[i] = to_dev(c->params[i]);
     OW_CUDA(c, cudaMemcpyAsync(c->d_casc, c->casc_host.data(), c->n_cascades * sizeof(CascadeDev), cudaMemcpyHostToDevice, c->stream));
     OW_CUDA(c, cudaStreamSynchronize(c->stream));   // the reference ends tilde_h0_k() with glFinish (main.cpp:582)
-    c->spectrum_ready = true;
+    c->casc_uploaded = true;
+    for (int i = lo; i < hi; ++i) c->h0_ready[i] = 1;
     return OW_OK;
+}
+
+int ow_init_spectrum(ow_ctx* c) {
+    if (!c) return OW_ERR_INVALID;
+    return init_range(c, 0, c->n_cascades, "ow_init_spectrum");
+}
+
+int ow_init_spectrum_cascade(ow_ctx* c, int32_t cascade) {
+    if (!c) return OW_ERR_INVALID;
+    if (cascade < 0 || cascade >= c->n_cascades) return fail(c, OW_ERR_INVALID, "ow_init_spectrum_cascade: cascade out of range");
+    return init_range(c, cascade, cascade + 1, "ow_init_spectrum_cascade");
 }
 
 int ow_set_h0(ow_ctx* c, int32_t cascade, const float* h0k, const float* h0minusk) {
@@ -287,37 +347,48 @@ int ow_set_h0(ow_ctx* c, int32_t cascade, const float* h0k, const float* h0minus
     OW_CUDA(c, cudaMemcpyAsync(c->d_tmp + nn * 2, h0minusk, nn * 2 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     OW_CUDA(c, launch_merge_h0(c->d_h0 + (size_t)cascade * nn, c->d_tmp, c->d_tmp + nn * 2, (int)nn, c->stream));
     OW_CUDA(c, launch_fold(c->d_h0 + (size_t)cascade * nn, c->d_hp + (size_t)cascade * (nn / 2), c->d_nyq + (size_t)cascade * (c->N / 2), c->N, c->stream));
-    if (!c->spectrum_ready) {
-        // k table and cascade constants are needed even when h0 is supplied directly
-        c->casc_host.resize(c->n_cascades);
-        for (int i = 0; i < c->n_cascades; ++i) {
-            c->casc_host[i] = to_dev(c->params[i]);
-            OW_CUDA(c, launch_ktab(c->d_ktab + (size_t)i * c->N, c->N, c->params[i].L, c->stream));
-        }
-        OW_CUDA(c, cudaMemcpyAsync(c->d_casc, c->casc_host.data(), c->n_cascades * sizeof(CascadeDev), cudaMemcpyHostToDevice, c->stream));
-    }
+    // this cascade's k table and the cascade constants follow the CURRENT parameters (h0 itself is the caller's)
+    OW_CUDA(c, launch_ktab(c->d_ktab + (size_t)cascade * c->N, c->N, c->params[cascade].L, c->stream));
+    for (int i = 0; i < c->n_cascades; ++i) c->casc_host[i] = to_dev(c->params[i]);
+    OW_CUDA(c, cudaMemcpyAsync(c->d_casc, c->casc_host.data(), c->n_cascades * sizeof(CascadeDev), cudaMemcpyHostToDevice, c->stream));
     OW_CUDA(c, cudaStreamSynchronize(c->stream));
-    c->spectrum_ready = true;
+    c->casc_uploaded = true;
+    c->h0_ready[cascade] = 1;         // ONLY this cascade: the others keep their own state
     return OW_OK;
+}
+
+// Fast sincos is allowed when every |w*t| of the entries stays below kFastPhaseLimit: w_max = sqrt(g*|k|max), |k|max = sqrt(2)*pi*N/L.
+static bool fast_phase_ok(const ow_ctx* c, int cascade, float t) {
+    const float kmax = 1.41421356f * 3.14159265f * (float)c->N / c->params[cascade].L;
+    return sqrtf(9.81f * kmax) * fabsf(t) < kFastPhaseLimit;
+}
+
+static int launch_failed(ow_ctx* c, const char* what) {
+    const cudaError_t e = take_launch_error();
+    if (e != cudaSuccess) return cuda_fail(c, e, what);
+    return fail(c, OW_ERR_STATE, std::string(what) + ": this launch shape is not supported by the context (e.g. several slots per group with the N = A*B line decomposition)");
 }
 
 static int step_impl(ow_ctx* c, int32_t count, const int32_t* cascade_of_slot, const float* time_of_slot, void* stream,
                      float* kernel_ms) {
     if (!c || !cascade_of_slot || !time_of_slot) return OW_ERR_INVALID;
-    if (!c->spectrum_ready) return fail(c, OW_ERR_STATE, "ow_step: call ow_init_spectrum (or ow_set_h0) first");
     if (count < 1 || count > c->n_slots) return fail(c, OW_ERR_INVALID, "ow_step_multi: count out of range");
-    for (int i = 0; i < count; ++i)
+    for (int i = 0; i < count; ++i) {
         if (cascade_of_slot[i] < 0 || cascade_of_slot[i] >= c->n_cascades)
             return fail(c, OW_ERR_INVALID, "ow_step_multi: cascade index out of range");
+        if (!c->h0_ready[cascade_of_slot[i]])
+            return fail(c, OW_ERR_STATE, "ow_step: a referenced cascade has no current spectrum: call ow_init_spectrum (or ow_set_h0) after "
+                                         "ow_create / ow_set_params / ow_set_noise");
+    }
     OW_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = pick(c, stream);
     const FrameBuffers fb = buffers(c);
     const int group = pick_group(c, count);
     int launches = 0;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    EventGuard guard;
     if (kernel_ms) {
         kernel_ms[0] = kernel_ms[1] = kernel_ms[2] = 0.0f;
-        for (auto& e : ev) OW_CUDA(c, cudaEventCreate(&e));
+        for (auto& e : guard.ev) OW_CUDA(c, cudaEventCreate(&e));
     }
     const int ngroups = (count + group - 1) / group;
     const int nfan = (kernel_ms || ngroups < 2 || c->n_streams < 2 || c->d_scratch) ? 0 : (ngroups < c->n_streams ? ngroups : c->n_streams);
@@ -328,25 +399,28 @@ static int step_impl(ow_ctx* c, int32_t count, const int32_t* cascade_of_slot, c
     int gi = 0;
     for (int base = 0; base < count; base += group, ++gi) {
         const int n = count - base < group ? count - base : group;
-        cudaStream_t gst = nfan ? c->aux[gi % nfan] : st;
+        Launcher L(nfan ? c->aux[gi % nfan] : st);
         SlotTable tab{};
         bool fast = (c->flags & OW_FLAG_EXACT_SINCOS) == 0;
         for (int i = 0; i < n; ++i) {
             tab.cascade[i] = cascade_of_slot[base + i];
             tab.time[i] = time_of_slot[base + i];
             tab.slot[i] = base + i;
-            // largest phase of this cascade: w_max = sqrt(g*|k|max), |k|max = sqrt(2)*pi*N/L
-            const float kmax = 1.41421356f * 3.14159265f * (float)c->N / c->params[tab.cascade[i]].L;
-            if (!(sqrtf(9.81f * kmax) * fabsf(tab.time[i]) < kFastPhaseLimit)) fast = false;
+            if (!fast_phase_ok(c, tab.cascade[i], tab.time[i])) fast = false;
         }
-        const int k = launch_frame(fb, tab, n, (c->flags & OW_FLAG_JACOBIAN) != 0, fast, gst, kernel_ms ? ev : nullptr);
-        if (k < 0) return cuda_fail(c, cudaGetLastError(), "launch_frame");
+        int k = launch_frame(fb, tab, n, (c->flags & OW_FLAG_JACOBIAN) != 0, fast, L, kernel_ms ? guard.ev : nullptr);
+        if (k < 0) return launch_failed(c, "launch_frame");
         launches += k;
+        if (c->d_packed) {
+            k = launch_pack(fb, tab, n, c->pk, L);
+            if (k < 0) return launch_failed(c, "launch_pack");
+            launches += k;
+        }
         if (kernel_ms) {
-            OW_CUDA(c, cudaEventSynchronize(ev[3]));
+            OW_CUDA(c, cudaEventSynchronize(guard.ev[3]));
             for (int i = 0; i < 3; ++i) {
                 float ms = 0.0f;
-                OW_CUDA(c, cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+                OW_CUDA(c, cudaEventElapsedTime(&ms, guard.ev[i], guard.ev[i + 1]));
                 kernel_ms[i] += ms;
             }
         }
@@ -355,7 +429,6 @@ static int step_impl(ow_ctx* c, int32_t count, const int32_t* cascade_of_slot, c
         OW_CUDA(c, cudaEventRecord(c->ev_join[i], c->aux[i]));
         OW_CUDA(c, cudaStreamWaitEvent(st, c->ev_join[i], 0));
     }
-    if (kernel_ms) for (auto& e : ev) cudaEventDestroy(e);
     c->last_launches = launches;
     c->last_groups = ngroups;
     return OW_OK;
@@ -371,12 +444,84 @@ int ow_step_multi_timed(ow_ctx* c, int32_t count, const int32_t* cascade_of_slot
     return step_impl(c, count, cascade_of_slot, time_of_slot, stream, kernel_ms);
 }
 
+// The frame of ow_step as a CUDA graph: one chain of kernel nodes per launch group (groups stay independent, as on the
+// auxiliary streams). Built once per (context, sincos variant); per frame only the time inside the row kernels' slot
+// tables changes, patched with cudaGraphExecKernelNodeSetParams. This is the reference's update() (src/main.cpp:240-244)
+// - 53 dispatches there - as ONE submission.
+static int build_plan(ow_ctx* c, bool fast, std::unique_ptr<GraphPlan>* out) {
+    auto plan = std::make_unique<GraphPlan>();
+    OW_CUDA(c, cudaGraphCreate(&plan->graph, 0));
+    const FrameBuffers fb = buffers(c);
+    const int count = c->n_cascades, group = pick_group(c, count);
+    for (int base = 0; base < count; base += group) {
+        const int n = count - base < group ? count - base : group;
+        SlotTable tab{};
+        for (int i = 0; i < n; ++i) { tab.cascade[i] = base + i; tab.time[i] = 0.0f; tab.slot[i] = base + i; }
+        Launcher L(plan.get());
+        int k = launch_frame(fb, tab, n, (c->flags & OW_FLAG_JACOBIAN) != 0, fast, L, nullptr);
+        if (k < 0) return launch_failed(c, "launch_frame (graph)");
+        plan->launches += k;
+        if (c->d_packed) {
+            k = launch_pack(fb, tab, n, c->pk, L);
+            if (k < 0) return launch_failed(c, "launch_pack (graph)");
+            plan->launches += k;
+        }
+        ++plan->groups;
+    }
+    OW_CUDA(c, cudaGraphInstantiate(&plan->exec, plan->graph, 0));
+    *out = std::move(plan);
+    return OW_OK;
+}
+
 int ow_step(ow_ctx* c, float t, void* stream) {
     if (!c) return OW_ERR_INVALID;
-    std::vector<int32_t> cs(c->n_cascades);
-    std::vector<float> ts(c->n_cascades, t);
-    for (int i = 0; i < c->n_cascades; ++i) cs[i] = i;
-    return ow_step_multi(c, c->n_cascades, cs.data(), ts.data(), stream);
+    const FrameBuffers fb = buffers(c);
+    if (!c->graph_enabled || !frame_graphable(fb)) {
+        std::fill(c->tbuf.begin(), c->tbuf.end(), t);
+        return step_impl(c, c->n_cascades, c->ident.data(), c->tbuf.data(), stream, nullptr);
+    }
+    if (!all_ready(c))
+        return fail(c, OW_ERR_STATE, "ow_step: a cascade has no current spectrum: call ow_init_spectrum (or ow_set_h0) after ow_create / "
+                                     "ow_set_params / ow_set_noise");
+    OW_CUDA(c, cudaSetDevice(c->device));
+    bool fast = (c->flags & OW_FLAG_EXACT_SINCOS) == 0;
+    for (int i = 0; i < c->n_cascades && fast; ++i) fast = fast_phase_ok(c, i, t);
+    std::unique_ptr<GraphPlan>& plan = c->plan[fast ? 1 : 0];
+    if (!plan) {
+        const int rc = build_plan(c, fast, &plan);
+        if (rc != OW_OK) return rc;
+    }
+    for (GraphNodeRec& n : plan->nodes) {
+        if (!n.tab) continue;
+        for (int i = 0; i < kMaxGroup; ++i) n.tab->time[i] = t;
+        OW_CUDA(c, cudaGraphExecKernelNodeSetParams(plan->exec, n.node, &n.params));
+    }
+    OW_CUDA(c, cudaGraphLaunch(plan->exec, pick(c, stream)));
+    c->last_launches = plan->launches;
+    c->last_groups = plan->groups;
+    return OW_OK;
+}
+
+int ow_set_graph(ow_ctx* c, int32_t enabled) {
+    if (!c) return OW_ERR_INVALID;
+    c->graph_enabled = enabled != 0;
+    if (!c->graph_enabled) drop_plans(c);
+    return OW_OK;
+}
+
+int ow_set_row_kernel(ow_ctx* c, int32_t mode) {
+    if (!c) return OW_ERR_INVALID;
+    if (mode < 0 || mode > 2) return fail(c, OW_ERR_INVALID, "ow_set_row_kernel: mode must be 0 (per-N default), 1 (one CTA per row-pair group) or 2 (persistent pipelined)");
+    c->row_mode = mode;
+    drop_plans(c);
+    return OW_OK;
+}
+
+int ow_set_discard_intermediate(ow_ctx* c, int32_t on) {
+    if (!c) return OW_ERR_INVALID;
+    c->discard_inter = on ? 1 : 0;
+    drop_plans(c);
+    return OW_OK;
 }
 
 int ow_sync(ow_ctx* c, void* stream) {
@@ -452,15 +597,40 @@ int ow_download_frame_async(ow_ctx* c, int32_t slot, void* host, size_t bytes, v
     return OW_OK;
 }
 
+int ow_get_packed(ow_ctx* c, int32_t slot, ow_packed* out) {
+    if (!c || !out) return OW_ERR_INVALID;
+    if (!c->d_packed) return fail(c, OW_ERR_STATE, "ow_get_packed: context created without OW_FLAG_PACKED_F32 / OW_FLAG_PACKED_F16");
+    if (slot < 0 || slot >= c->n_slots) return fail(c, OW_ERR_INVALID, "ow_get_packed: slot out of range");
+    out->N = c->N;
+    out->displacement_texel_bytes = c->pk.half ? 8 : 16;
+    out->displacement = c->d_packed + (size_t)slot * c->pk.slot_bytes;
+    out->normal_xz = c->d_packed + (size_t)slot * c->pk.slot_bytes + c->pk.normal_offset;
+    return OW_OK;
+}
+
+size_t ow_packed_bytes(const ow_ctx* c) { return (c && c->d_packed) ? c->pk.slot_bytes : 0; }
+
+int ow_download_packed_async(ow_ctx* c, int32_t slot, void* host, size_t bytes, void* stream) {
+    if (!c || !host) return OW_ERR_INVALID;
+    if (!c->d_packed) return fail(c, OW_ERR_STATE, "ow_download_packed_async: context created without OW_FLAG_PACKED_F32 / OW_FLAG_PACKED_F16");
+    if (slot < 0 || slot >= c->n_slots) return fail(c, OW_ERR_INVALID, "ow_download_packed_async: slot out of range");
+    if (bytes != c->pk.slot_bytes) return fail(c, OW_ERR_INVALID, "ow_download_packed_async: size mismatch");
+    OW_CUDA(c, cudaSetDevice(c->device));
+    OW_CUDA(c, cudaMemcpyAsync(host, c->d_packed + (size_t)slot * c->pk.slot_bytes, bytes, cudaMemcpyDeviceToHost, pick(c, stream)));
+    return OW_OK;
+}
+
 int ow_set_group_size(ow_ctx* c, int32_t g) {
     if (!c || g < 0) return OW_ERR_INVALID;
     c->group_size = g;
+    drop_plans(c);
     return OW_OK;
 }
 
 int ow_set_streams(ow_ctx* c, int32_t n) {
     if (!c || n < 1 || n > ow_ctx::kMaxAux) return c ? fail(c, OW_ERR_INVALID, "ow_set_streams: n must be in [1, 4]") : OW_ERR_INVALID;
     c->n_streams = n;
+    drop_plans(c);
     return OW_OK;
 }
 
@@ -475,12 +645,10 @@ typedef unsigned int ow_GLenum;
 extern cudaError_t cudaGraphicsGLRegisterImage(struct cudaGraphicsResource** resource, ow_GLuint image, ow_GLenum target, unsigned int flags);
 #define OW_GL_TEXTURE_2D 0x0DE1
 
-int ow_gl_register(ow_ctx* c, uint32_t tex_dy, uint32_t tex_dx, uint32_t tex_dz, uint32_t tex_normal) {
-    if (!c) return OW_ERR_INVALID;
+static int gl_register_n(ow_ctx* c, const uint32_t* tex, int n) {
     if (c->gl_registered) ow_gl_unregister(c);
     cudaSetDevice(c->device);
-    const uint32_t tex[4] = {tex_dy, tex_dx, tex_dz, tex_normal};
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < n; ++i) {
         cudaError_t e = cudaGraphicsGLRegisterImage(&c->gl_res[i], tex[i], OW_GL_TEXTURE_2D, cudaGraphicsRegisterFlagsWriteDiscard);
         if (e != cudaSuccess) {
             for (int j = 0; j < i; ++j) { cudaGraphicsUnregisterResource(c->gl_res[j]); c->gl_res[j] = nullptr; }
@@ -490,8 +658,22 @@ int ow_gl_register(ow_ctx* c, uint32_t tex_dy, uint32_t tex_dx, uint32_t tex_dz,
                                              " (is the caller's GL context current on this thread?)");
         }
     }
+    c->gl_count = n;
     c->gl_registered = true;
     return OW_OK;
+}
+
+int ow_gl_register(ow_ctx* c, uint32_t tex_dy, uint32_t tex_dx, uint32_t tex_dz, uint32_t tex_normal) {
+    if (!c) return OW_ERR_INVALID;
+    const uint32_t tex[4] = {tex_dy, tex_dx, tex_dz, tex_normal};
+    return gl_register_n(c, tex, 4);
+}
+
+int ow_gl_register_packed(ow_ctx* c, uint32_t tex_displacement, uint32_t tex_normal_xz) {
+    if (!c) return OW_ERR_INVALID;
+    if (!c->d_packed) return fail(c, OW_ERR_STATE, "ow_gl_register_packed: context created without OW_FLAG_PACKED_F32 / OW_FLAG_PACKED_F16");
+    const uint32_t tex[2] = {tex_displacement, tex_normal_xz};
+    return gl_register_n(c, tex, 2);
 }
 
 int ow_gl_unregister(ow_ctx* c) {
@@ -500,6 +682,7 @@ int ow_gl_unregister(ow_ctx* c) {
         cudaSetDevice(c->device);
         for (auto& r : c->gl_res) { if (r) cudaGraphicsUnregisterResource(r); r = nullptr; }
         c->gl_registered = false;
+        c->gl_count = 0;
     }
     return OW_OK;
 }
@@ -509,16 +692,24 @@ int ow_gl_step(ow_ctx* c, float t) {
     if (!c->gl_registered) return fail(c, OW_ERR_NO_GL, "ow_gl_step: ow_gl_register has not succeeded");
     int r = ow_step(c, t, nullptr);
     if (r != OW_OK) return r;
-    OW_CUDA(c, cudaGraphicsMapResources(4, c->gl_res, c->stream));
+    OW_CUDA(c, cudaGraphicsMapResources(c->gl_count, c->gl_res, c->stream));
     const size_t nn = (size_t)c->N * c->N;
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < c->gl_count; ++i) {
         cudaArray_t arr = nullptr;
         OW_CUDA(c, cudaGraphicsSubResourceGetMappedArray(&arr, c->gl_res[i], 0, 0));
-        const void* src = i < 3 ? (const void*)(c->d_disp + (size_t)i * nn) : (const void*)c->d_normal;
-        const size_t pitch = (size_t)c->N * (i < 3 ? sizeof(float) : sizeof(float4));
+        const void* src;
+        size_t texel;
+        if (c->gl_count == 2) {       // packed set of slot 0: displacement (RGBA32F / RGBA16F), normal_xz (RG16_SNORM)
+            src = i == 0 ? (const void*)c->d_packed : (const void*)(c->d_packed + c->pk.normal_offset);
+            texel = i == 0 ? (c->pk.half ? 8 : 16) : 4;
+        } else {
+            src = i < 3 ? (const void*)(c->d_disp + (size_t)i * nn) : (const void*)c->d_normal;
+            texel = i < 3 ? sizeof(float) : sizeof(float4);
+        }
+        const size_t pitch = (size_t)c->N * texel;
         OW_CUDA(c, cudaMemcpy2DToArrayAsync(arr, 0, 0, src, pitch, pitch, c->N, cudaMemcpyDeviceToDevice, c->stream));
     }
-    OW_CUDA(c, cudaGraphicsUnmapResources(4, c->gl_res, c->stream));   // unmap orders the copies before GL's next use
+    OW_CUDA(c, cudaGraphicsUnmapResources(c->gl_count, c->gl_res, c->stream));   // unmap orders the copies before GL's next use
     return OW_OK;
 }
 

@@ -69,7 +69,7 @@ struct Big {
         if (with_jac) ow_normal_kernel<N, true, RY, WARPS, NMINB><<<ngrid, dim3(32, WARPS), 0, st>>>(fb, tab);
         else ow_normal_kernel<N, false, RY, WARPS, NMINB><<<ngrid, dim3(32, WARPS), 0, st>>>(fb, tab);
         if (ev) cudaEventRecord(ev[3], st);
-        return cudaGetLastError() == cudaSuccess ? 5 : -1;
+        return launches_ok() ? 5 : -1;
     }
 
     static bool slab_ok(int world) {
@@ -87,7 +87,7 @@ struct Big {
         sink.xl_shift = 0;
         while ((1 << sink.xl_shift) < g.XL) ++sink.xl_shift;
         rows_pass(rows, ktab, g.rank * g.PL, g.PL, t, fast, scratch, sink, st);
-        return cudaGetLastError() == cudaSuccess ? 2 : -1;
+        return launches_ok() ? 2 : -1;
     }
 
     static int slab_cols(const SlabGeom& g, const float2* recv, float* disp_loc, float4* normal_loc, float* jac_loc, float jac_scale,
@@ -96,7 +96,7 @@ struct Big {
         const dim3 ngrid(g.XL / 128, N / (WARPS * RY));
         if (jac_loc) ow_normal_slab_kernel<N, true, RY, WARPS, NMINB><<<ngrid, dim3(32, WARPS), 0, st>>>(disp_loc, normal_loc, jac_loc, g.XL, g.XH, jac_scale);
         else ow_normal_slab_kernel<N, false, RY, WARPS, NMINB><<<ngrid, dim3(32, WARPS), 0, st>>>(disp_loc, normal_loc, nullptr, g.XL, g.XH, 0.f);
-        return cudaGetLastError() == cudaSuccess ? 3 : -1;
+        return launches_ok() ? 3 : -1;
     }
 };
 
@@ -119,7 +119,7 @@ bool big_supported(int N, bool forced) {
     return forced ? (N == 1024 || N == 2048) : (N == 8192 || N == 16384 || N == 32768);
 }
 
-cudaError_t configure_big(int N, bool forced) {
+cudaError_t configure_big(int N, bool forced, KernelConfig*) {
     OW_BIG_DISPATCH(N, forced, configure());
     return cudaErrorInvalidValue;
 }

@@ -1,66 +1,50 @@
 // ow_frame_kernels.cu — __global__ wrappers and launchers of the per-frame kernels (sm_100a).
 // Kernel bodies live in ow_kernels.cuh (shared with the CPU emulator used by the tests).
-#include <cstdlib>
-
 #include "ow_frame_kernels.cuh"
 
 namespace ow {
 
 // ---------------------------------------------------------------------------------------------------
-// CTAs of the persistent row kernel that fit one SM (queried once per N and variant).
-template <int N>
-int g_row_pipe_ctas_per_sm[2] = {0, 0};
-static int g_sm_count = 148;
-static int g_row_classic = -1;   // OW_ROW_KERNEL=classic|pipe overrides the per-N choice Cfg<N>::ROW_PIPE (A/B runs, tools)
+static thread_local cudaError_t t_launch_error = cudaSuccess;
+void stash_launch_error(cudaError_t e) { t_launch_error = e; }
+cudaError_t take_launch_error() {
+    const cudaError_t e = t_launch_error;
+    t_launch_error = cudaSuccess;
+    return e;
+}
+
+template <class K>
+static cudaError_t opt_in_smem(K kernel, size_t bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
 
 template <int N>
-cudaError_t configure_n() {
+cudaError_t configure_n(KernelConfig* cfg) {
     using C = Cfg<N>;
-    {
-        using R = typename C::Row;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-        cudaError_t e0 = cudaFuncSetAttribute(ow_row_pipe_kernel<R, C::ROW_PAIRS, C::ROW_MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)row_smem<R, C::ROW_PAIRS>());
-        if (e0 != cudaSuccess) return e0;
-        e0 = cudaFuncSetAttribute(ow_row_pipe_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)row_smem<R, C::ROW_PAIRS>());
-        if (e0 != cudaSuccess) return e0;
-        e0 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_row_pipe_ctas_per_sm<N>[0], ow_row_pipe_kernel<R, C::ROW_PAIRS, C::ROW_MINB, false>,
-                                                           R::T * C::ROW_PAIRS, row_smem<R, C::ROW_PAIRS>());
-        if (e0 != cudaSuccess) return e0;
-        e0 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_row_pipe_ctas_per_sm<N>[1], ow_row_pipe_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true>,
-                                                           R::T * C::ROW_PAIRS, row_smem<R, C::ROW_PAIRS>());
-        if (e0 != cudaSuccess) return e0;
-        if (g_row_classic < 0) {
-            const char* v = getenv("OW_ROW_KERNEL");
-            g_row_classic = (v && v[0] == 'c') ? 1 : (v && v[0] == 'p') ? 0 : 2;
-        }
-    }
-    cudaError_t e = cudaFuncSetAttribute(ow_row_kernel<typename C::Row, C::ROW_PAIRS, C::ROW_MINB, false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(row_smem<typename C::Row, C::ROW_PAIRS>()));
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(ow_row_kernel<typename C::Row, C::ROW_PAIRS, C::ROW_MINB, true>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(row_smem<typename C::Row, C::ROW_PAIRS>()));
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(ow_col_kernel<typename C::Col, C::COL_G, C::COL_MINB>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ColLayout<typename C::Col, C::COL_G>::SMEM);
-    if (e != cudaSuccess) return e;
+    using R = typename C::Row;
+    using K = typename C::Col;
+    constexpr size_t rs = row_smem<R, C::ROW_PAIRS>(), cs = ColLayout<K, C::COL_G>::SMEM;
+    cudaError_t e;
+    if ((e = opt_in_smem(ow_row_pipe_kernel<R, C::ROW_PAIRS, C::ROW_MINB, false>, rs)) != cudaSuccess) return e;
+    if ((e = opt_in_smem(ow_row_pipe_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true>, rs)) != cudaSuccess) return e;
+    if ((e = opt_in_smem(ow_row_kernel<R, C::ROW_PAIRS, C::ROW_MINB, false>, rs)) != cudaSuccess) return e;
+    if ((e = opt_in_smem(ow_row_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true>, rs)) != cudaSuccess) return e;
+    if ((e = opt_in_smem(ow_row_slab_kernel<R, C::ROW_PAIRS, C::ROW_MINB, false>, rs)) != cudaSuccess) return e;
+    if ((e = opt_in_smem(ow_row_slab_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true>, rs)) != cudaSuccess) return e;
+    if ((e = opt_in_smem(ow_col_kernel<K, C::COL_G, C::COL_MINB>, cs)) != cudaSuccess) return e;
+    if ((e = opt_in_smem(ow_col_slab_kernel<K, C::COL_G, C::COL_MINB>, cs)) != cudaSuccess) return e;
     if constexpr (C::COL_FUSE) {
-        e = cudaFuncSetAttribute(ow_col_fused_kernel<typename C::Col, C::COL_G, C::COL_MINB, C::NRM_RY>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ColLayout<typename C::Col, C::COL_G>::SMEM);
-        if (e != cudaSuccess) return e;
+        if ((e = opt_in_smem(ow_col_fused_kernel<K, C::COL_G, C::COL_MINB, C::NRM_RY>, cs)) != cudaSuccess) return e;
     }
-    e = cudaFuncSetAttribute(ow_row_slab_kernel<typename C::Row, C::ROW_PAIRS, C::ROW_MINB, false>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<typename C::Row, C::ROW_PAIRS>());
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(ow_row_slab_kernel<typename C::Row, C::ROW_PAIRS, C::ROW_MINB, true>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem<typename C::Row, C::ROW_PAIRS>());
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(ow_col_slab_kernel<typename C::Col, C::COL_G, C::COL_MINB>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ColLayout<typename C::Col, C::COL_G>::SMEM);
+    // resident CTAs per SM of the persistent row kernel ON THIS DEVICE (the grid of ow_row_pipe_kernel)
+    for (int fast = 0; fast < 2; ++fast) {
+        int n = 0;
+        e = fast ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ow_row_pipe_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true>, R::T * C::ROW_PAIRS, rs)
+                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ow_row_pipe_kernel<R, C::ROW_PAIRS, C::ROW_MINB, false>, R::T * C::ROW_PAIRS, rs);
+        if (e != cudaSuccess) return e;
+        cfg->row_pipe_ctas[fast] = n > 0 ? n : 1;
+    }
+    return cudaSuccess;
 }
 
 template <int N>
@@ -87,7 +71,7 @@ int slab_rows_n(const SlabGeom& g, const float4* h0_loc, const float4* hp_loc, c
         ow_row_slab_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true><<<grid, R::T * C::ROW_PAIRS, row_smem<R, C::ROW_PAIRS>(), st>>>(rows, ktab, sink, t);
     else
         ow_row_slab_kernel<R, C::ROW_PAIRS, C::ROW_MINB, false><<<grid, R::T * C::ROW_PAIRS, row_smem<R, C::ROW_PAIRS>(), st>>>(rows, ktab, sink, t);
-    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    return launches_ok() ? 1 : -1;
 }
 
 template <int N>
@@ -103,66 +87,66 @@ int slab_cols_n(const SlabGeom& g, const float2* recv, float* disp_loc, float4* 
         ow_normal_slab_kernel<N, true, C::NRM_RY, C::NRM_WARPS, C::NRM_MINB><<<ngrid, dim3(32, C::NRM_WARPS), 0, st>>>(disp_loc, normal_loc, jac_loc, g.XL, g.XH, jac_scale);
     else
         ow_normal_slab_kernel<N, false, C::NRM_RY, C::NRM_WARPS, C::NRM_MINB><<<ngrid, dim3(32, C::NRM_WARPS), 0, st>>>(disp_loc, normal_loc, nullptr, g.XL, g.XH, 0.f);
-    return cudaGetLastError() == cudaSuccess ? 2 : -1;
+    return launches_ok() ? 2 : -1;
 }
 
 template <int N>
-int launch_n(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_jac, bool fast_phase, cudaStream_t st, cudaEvent_t* ev) {
+int launch_n(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_jac, bool fast_phase, Launcher& L, cudaEvent_t* ev) {
     using C = Cfg<N>;
     using R = typename C::Row;
     using K = typename C::Col;
-    if (ev) cudaEventRecord(ev[0], st);
-    if (g_row_classic == 1 || (g_row_classic == 2 && !C::ROW_PIPE)) {
+    constexpr size_t rs = row_smem<R, C::ROW_PAIRS>(), cs = ColLayout<K, C::COL_G>::SMEM;
+    if (ev) cudaEventRecord(ev[0], L.st);
+    L.reads_time = true;
+    if (fb.row_mode == 1 || (fb.row_mode == 0 && !C::ROW_PIPE)) {
         const dim3 rgrid(N / 2 / C::ROW_PAIRS, count);
-        if (fast_phase)
-            ow_row_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true><<<rgrid, R::T * C::ROW_PAIRS, row_smem<R, C::ROW_PAIRS>(), st>>>(fb, tab);
-        else
-            ow_row_kernel<R, C::ROW_PAIRS, C::ROW_MINB, false><<<rgrid, R::T * C::ROW_PAIRS, row_smem<R, C::ROW_PAIRS>(), st>>>(fb, tab);
+        if (fast_phase) L(ow_row_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true>, rgrid, R::T * C::ROW_PAIRS, rs, fb, tab);
+        else L(ow_row_kernel<R, C::ROW_PAIRS, C::ROW_MINB, false>, rgrid, R::T * C::ROW_PAIRS, rs, fb, tab);
     } else {
         const int n_cta_items = count * (N / 2 / C::ROW_PAIRS);
-        const int resident = g_sm_count * (g_row_pipe_ctas_per_sm<N>[fast_phase ? 1 : 0] > 0 ? g_row_pipe_ctas_per_sm<N>[fast_phase ? 1 : 0] : 1);
+        const int resident = fb.sm_count * fb.row_pipe_ctas[fast_phase ? 1 : 0];
         const int grid = n_cta_items < resident ? n_cta_items : resident;
-        if (fast_phase)
-            ow_row_pipe_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true><<<grid, R::T * C::ROW_PAIRS, row_smem<R, C::ROW_PAIRS>(), st>>>(fb, tab, n_cta_items);
-        else
-            ow_row_pipe_kernel<R, C::ROW_PAIRS, C::ROW_MINB, false><<<grid, R::T * C::ROW_PAIRS, row_smem<R, C::ROW_PAIRS>(), st>>>(fb, tab, n_cta_items);
+        if (fast_phase) L(ow_row_pipe_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true>, grid, R::T * C::ROW_PAIRS, rs, fb, tab, n_cta_items);
+        else L(ow_row_pipe_kernel<R, C::ROW_PAIRS, C::ROW_MINB, false>, grid, R::T * C::ROW_PAIRS, rs, fb, tab, n_cta_items);
     }
-    if (ev) cudaEventRecord(ev[1], st);
+    if (ev) cudaEventRecord(ev[1], L.st);
     const float scale = 0.5f / ((float)N * (float)N);   // 1/2 from the Hermitian split, 1/N^2 from inversion_cs.glsl:36
     if constexpr (C::COL_FUSE) {
         if (!with_jac && fb.fuse_normals) {
             // normal map fused into the dy tiles: 6 output pairs per dy tile, ordinary 8-pair tiles for dx and dz
             const int ndy = (N / 2 + 5) / 6;
-            ow_col_fused_kernel<K, C::COL_G, C::COL_MINB, C::NRM_RY>
-                <<<dim3(ndy + 2 * (N / (2 * C::COL_G)), count), K::T * C::COL_G, ColLayout<K, C::COL_G>::SMEM, st>>>(fb, tab, scale, ndy);
-            if (ev) { cudaEventRecord(ev[2], st); cudaEventRecord(ev[3], st); }
-            return cudaGetLastError() == cudaSuccess ? 2 : -1;
+            L(ow_col_fused_kernel<K, C::COL_G, C::COL_MINB, C::NRM_RY>, dim3(ndy + 2 * (N / (2 * C::COL_G)), count), K::T * C::COL_G, cs, fb, tab, scale, ndy);
+            if (ev) { cudaEventRecord(ev[2], L.st); cudaEventRecord(ev[3], L.st); }
+            return launches_ok() && L.err == cudaSuccess ? 2 : -1;
         }
     }
-    ow_col_kernel<K, C::COL_G, C::COL_MINB>
-        <<<dim3(N / (2 * C::COL_G), 3, count), K::T * C::COL_G, ColLayout<K, C::COL_G>::SMEM, st>>>(fb, tab, scale);
-    if (ev) cudaEventRecord(ev[2], st);
+    L(ow_col_kernel<K, C::COL_G, C::COL_MINB>, dim3(N / (2 * C::COL_G), 3, count), K::T * C::COL_G, cs, fb, tab, scale);
+    if (ev) cudaEventRecord(ev[2], L.st);
     const dim3 ngrid(N / 128, N / (C::NRM_WARPS * C::NRM_RY), count);
-    if (with_jac) ow_normal_kernel<N, true, C::NRM_RY, C::NRM_WARPS, C::NRM_MINB><<<ngrid, dim3(32, C::NRM_WARPS), 0, st>>>(fb, tab);
-    else ow_normal_kernel<N, false, C::NRM_RY, C::NRM_WARPS, C::NRM_MINB><<<ngrid, dim3(32, C::NRM_WARPS), 0, st>>>(fb, tab);
-    if (ev) cudaEventRecord(ev[3], st);
-    return cudaGetLastError() == cudaSuccess ? 3 : -1;
+    if (with_jac) L(ow_normal_kernel<N, true, C::NRM_RY, C::NRM_WARPS, C::NRM_MINB>, ngrid, dim3(32, C::NRM_WARPS), 0, fb, tab);
+    else L(ow_normal_kernel<N, false, C::NRM_RY, C::NRM_WARPS, C::NRM_MINB>, ngrid, dim3(32, C::NRM_WARPS), 0, fb, tab);
+    if (ev) cudaEventRecord(ev[3], L.st);
+    if (L.err != cudaSuccess) stash_launch_error(L.err);
+    return launches_ok() && L.err == cudaSuccess ? 3 : -1;
 }
 
 bool frame_supported(int N) { return N == 256 || N == 512 || N == 1024 || N == 2048 || N == 4096 || big_supported(N, false); }
 
-cudaError_t configure_frame_kernels(int N) {
-    if (big_supported(N, false)) return configure_big(N, false);
+cudaError_t configure_frame_kernels(int N, KernelConfig* cfg) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&cfg->sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    if (big_supported(N, false)) return configure_big(N, false, cfg);
     if (big_supported(N, true)) {
-        cudaError_t e = configure_big(N, true);
-        if (e != cudaSuccess) return e;
+        if ((e = configure_big(N, true, cfg)) != cudaSuccess) return e;
     }
     switch (N) {
-        case 256: return configure_n<256>();
-        case 512: return configure_n<512>();
-        case 1024: return configure_n<1024>();
-        case 2048: return configure_n<2048>();
-        case 4096: return configure_n<4096>();
+        case 256: return configure_n<256>(cfg);
+        case 512: return configure_n<512>(cfg);
+        case 1024: return configure_n<1024>(cfg);
+        case 2048: return configure_n<2048>(cfg);
+        case 4096: return configure_n<4096>(cfg);
     }
     return cudaErrorInvalidValue;
 }
@@ -211,15 +195,19 @@ int launch_slab_cols(const SlabGeom& g, const float2* recv, float* disp_loc, flo
     return -1;
 }
 
-int launch_frame(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_jac, bool fast_phase, cudaStream_t st, cudaEvent_t* ev) {
-    if (big_supported(fb.N, false)) return launch_big_frame(fb, tab, count, with_jac, fast_phase, st, ev, false);
-    if (fb.four_step && big_supported(fb.N, true)) return launch_big_frame(fb, tab, count, with_jac, fast_phase, st, ev, true);
+bool frame_graphable(const FrameBuffers& fb) { return !big_supported(fb.N, false) && !(fb.four_step && big_supported(fb.N, true)); }
+
+int launch_frame(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_jac, bool fast_phase, Launcher& L, cudaEvent_t* ev) {
+    if (!frame_graphable(fb)) {
+        if (L.plan) return -1;                  // the line decomposition launches on a stream only
+        return launch_big_frame(fb, tab, count, with_jac, fast_phase, L.st, ev, !big_supported(fb.N, false));
+    }
     switch (fb.N) {
-        case 256: return launch_n<256>(fb, tab, count, with_jac, fast_phase, st, ev);
-        case 512: return launch_n<512>(fb, tab, count, with_jac, fast_phase, st, ev);
-        case 1024: return launch_n<1024>(fb, tab, count, with_jac, fast_phase, st, ev);
-        case 2048: return launch_n<2048>(fb, tab, count, with_jac, fast_phase, st, ev);
-        case 4096: return launch_n<4096>(fb, tab, count, with_jac, fast_phase, st, ev);
+        case 256: return launch_n<256>(fb, tab, count, with_jac, fast_phase, L, ev);
+        case 512: return launch_n<512>(fb, tab, count, with_jac, fast_phase, L, ev);
+        case 1024: return launch_n<1024>(fb, tab, count, with_jac, fast_phase, L, ev);
+        case 2048: return launch_n<2048>(fb, tab, count, with_jac, fast_phase, L, ev);
+        case 4096: return launch_n<4096>(fb, tab, count, with_jac, fast_phase, L, ev);
     }
     return -1;
 }

@@ -3,6 +3,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <memory>
+#include <tuple>
+#include <type_traits>
+#include <vector>
+
 namespace ow {
 
 // Per-cascade constants as the kernels want them (wind direction already normalised).
@@ -34,21 +39,115 @@ struct FrameBuffers {
     float2* scratch;       // N = A*B decomposition only: one frame of radix-A sums, 12 B/texel (ow_big_kernels.cu)
     int fuse_normals;      // OW_FLAG_FUSED_NORMALS: normal map as the epilogue of the dy column tiles (ow_col_fused_kernel)
     int four_step;         // force the N = A*B line decomposition (ow_big_kernels.cu) on a grid the direct kernels could do
+    int row_mode;          // 0 = the per-N choice Cfg<N>::ROW_PIPE, 1 = one CTA per ROW_PAIRS row pairs, 2 = persistent pipelined kernel (ow_set_row_kernel)
+    int sm_count;          // of the context's device (grid size of the persistent kernels)
+    int row_pipe_ctas[2];  // resident CTAs per SM of the persistent row kernel on that device: [exact sincos, fast sincos]
+};
+
+// What configure_frame_kernels found out about the device the calling context lives on (kept per context: no process-global state).
+struct KernelConfig {
+    int sm_count = 148;
+    int row_pipe_ctas[2] = {1, 1};
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Where a launcher's kernels go: straight onto a stream, or into a CUDA graph under construction (the single-frame path
+// of ow_step: the three kernels of a frame become one cudaGraphLaunch, and only the time inside the row kernel's slot table
+// is patched per frame). In graph mode consecutive launches form a dependency chain; begin_chain() starts a new,
+// independent chain (one per launch group, so groups still overlap the way they do on the auxiliary streams).
+// ---------------------------------------------------------------------------------------------------
+struct GraphNodeRec {
+    cudaGraphNode_t node = nullptr;
+    cudaKernelNodeParams params{};
+    std::shared_ptr<void> blob;        // owns the argument tuple
+    std::vector<void*> ptrs;           // params.kernelParams
+    SlotTable* tab = nullptr;          // the SlotTable argument inside the blob (kernels that read the frame time), else nullptr
+};
+
+struct GraphPlan {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    std::vector<GraphNodeRec> nodes;
+    int launches = 0, groups = 0;
+    ~GraphPlan() {
+        if (exec) cudaGraphExecDestroy(exec);
+        if (graph) cudaGraphDestroy(graph);
+    }
+};
+
+struct Launcher {
+    cudaStream_t st = nullptr;
+    GraphPlan* plan = nullptr;         // non-null: append kernel nodes instead of launching
+    cudaGraphNode_t prev = nullptr;
+    cudaError_t err = cudaSuccess;
+    bool reads_time = false;           // set before launching a kernel that reads SlotTable::time: its node is patched per frame
+
+    explicit Launcher(cudaStream_t s) : st(s) {}
+    explicit Launcher(GraphPlan* p) : plan(p) {}
+    void begin_chain() { prev = nullptr; }
+
+    template <class... KArgs, class... Args>
+    void operator()(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+        static_assert(sizeof...(KArgs) == sizeof...(Args), "argument count");
+        const bool timed = reads_time;
+        reads_time = false;
+        if (!plan) {
+            kernel<<<grid, block, smem, st>>>(static_cast<KArgs>(args)...);
+            return;
+        }
+        using Tup = std::tuple<std::decay_t<KArgs>...>;
+        auto blob = std::make_shared<Tup>(static_cast<KArgs>(args)...);
+        GraphNodeRec rec;
+        rec.blob = blob;
+        std::apply([&](auto&... a) {
+            (rec.ptrs.push_back(static_cast<void*>(&a)), ...);
+            ((rec.tab = pick_tab(&a, rec.tab)), ...);
+        }, *blob);
+        if (!timed) rec.tab = nullptr;
+        rec.params.func = reinterpret_cast<void*>(kernel);
+        rec.params.gridDim = grid;
+        rec.params.blockDim = block;
+        rec.params.sharedMemBytes = (unsigned)smem;
+        rec.params.kernelParams = rec.ptrs.data();
+        rec.params.extra = nullptr;
+        const cudaError_t e = cudaGraphAddKernelNode(&rec.node, plan->graph, prev ? &prev : nullptr, prev ? 1 : 0, &rec.params);
+        if (e != cudaSuccess && err == cudaSuccess) err = e;
+        prev = rec.node;
+        plan->nodes.push_back(std::move(rec));
+        plan->nodes.back().params.kernelParams = plan->nodes.back().ptrs.data();
+    }
+
+private:
+    static SlotTable* pick_tab(SlotTable* a, SlotTable* cur) { return cur ? cur : a; }
+    template <class T>
+    static SlotTable* pick_tab(T*, SlotTable* cur) { return cur; }
 };
 
 bool frame_supported(int N);            // direct kernels (N <= 4096) or the N = A*B decomposition (8192 .. 32768)
 // N = A*B line decomposition (ow_big_kernels.cu). forced: the test-only mapping of N = 1024 / 2048 onto it.
 bool big_supported(int N, bool forced);
-cudaError_t configure_big(int N, bool forced);
+cudaError_t configure_big(int N, bool forced, KernelConfig* cfg);
 int launch_big_frame(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_jacobian, bool fast_phase, cudaStream_t st,
                      cudaEvent_t* ev, bool forced);
 // Launch the three frame kernels for `count` table entries. Returns number of kernels launched (<0: error).
 // ev (optional): 4 events recorded before the row kernel and after each of the three kernels.
 // fast_phase: every |w*t| of this launch is below kFastPhaseLimit, so the SFU sin/cos path is accurate enough.
 int launch_frame(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_jacobian, bool fast_phase,
-                 cudaStream_t st, cudaEvent_t* ev = nullptr);
+                 Launcher& L, cudaEvent_t* ev = nullptr);
 constexpr float kFastPhaseLimit = 2.0e4f;
-cudaError_t configure_frame_kernels(int N);   // opt-in shared memory sizes; call once per device
+bool frame_graphable(const FrameBuffers& fb);   // launch_frame can build graph nodes for this context (direct kernels, N <= 4096)
+cudaError_t configure_frame_kernels(int N, KernelConfig* cfg);   // opt-in shared memory sizes + occupancy queries; call once per context
+// The launchers below return a launch count (< 0: error) and have then already consumed the CUDA error; it is kept here
+// (per thread) so the API layer can report what actually went wrong. cudaSuccess when the failure was not a CUDA error.
+cudaError_t take_launch_error();
+void stash_launch_error(cudaError_t e);
+// cudaGetLastError() wrapper for the launchers: true when the launches since the last check went through.
+inline bool launches_ok() {
+    const cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) return true;
+    stash_launch_error(e);
+    return false;
+}
 
 // ---- slab decomposition of one grid over `world` GPUs (layouts: SlabRows/SlabSink in ow_kernels.cuh) ----
 constexpr int kSlabHalo = 8;       // == ow::kHalo
@@ -75,6 +174,14 @@ int launch_big_slab_cols(const SlabGeom& g, const float2* recv, float* disp_loc,
                          float2* scratch, cudaStream_t st, bool forced);
 // float2 elements of scratch a slab rank needs for the N = A*B decomposition (0 when the direct kernels apply).
 size_t slab_scratch_elems(const SlabGeom& g);
+
+// ---- packed output formats (ow_pack_kernels.cu) ----
+struct PackedBuffers {
+    char* base;            // [slot][slot_bytes]: displacement image first, normal_xz image at normal_offset
+    size_t slot_bytes, normal_offset;
+    int half;              // displacement texels are RGBA16F (8 B) instead of RGBA32F (16 B)
+};
+int launch_pack(const FrameBuffers& fb, const SlotTable& tab, int count, const PackedBuffers& pk, Launcher& L);
 
 // Init-time kernels (ow_init_kernels.cu)
 cudaError_t launch_noise_seed(uint8_t* noise /* [4][N][N] */, int N, uint64_t seed, cudaStream_t st);

@@ -125,7 +125,8 @@ int ow_slab_create(int32_t N, int32_t world, int32_t rank, const ow_params* p, i
     OWS_TRY(cudaMalloc(&s->d_normal, (size_t)N * g.XL * sizeof(float4)));
     if (flags & OW_FLAG_JACOBIAN) OWS_TRY(cudaMalloc(&s->d_jac, (size_t)N * g.XL * sizeof(float)));
     if (slab_scratch_elems(g)) OWS_TRY(cudaMalloc(&s->d_scratch, slab_scratch_elems(g) * sizeof(float2)));
-    OWS_TRY(configure_frame_kernels(N));
+    KernelConfig kcfg;
+    OWS_TRY(configure_frame_kernels(N, &kcfg));
 #undef OWS_TRY
     s->peer_recv[rank] = s->d_recv;
     *out = s;

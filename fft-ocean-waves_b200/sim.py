@@ -30,7 +30,8 @@ EXPORTED_SYMBOLS = [
     "ow_create", "ow_destroy", "ow_last_error", "ow_set_params", "ow_set_noise", "ow_init_spectrum", "ow_set_h0",
     "ow_step", "ow_step_multi", "ow_step_multi_timed", "ow_sync", "ow_get_outputs", "ow_download", "ow_download_frame_async",
     "ow_frame_bytes", "ow_set_group_size", "ow_set_streams", "ow_last_launch_count", "ow_gl_register", "ow_gl_step", "ow_gl_unregister",
-    "ow_set_noise_seed", "ow_last_group_count",
+    "ow_set_noise_seed", "ow_last_group_count", "ow_init_spectrum_cascade", "ow_set_graph", "ow_get_packed", "ow_packed_bytes",
+    "ow_download_packed_async", "ow_set_row_kernel", "ow_set_discard_intermediate", "ow_gl_register_packed",
     "ow_slab_create", "ow_slab_destroy", "ow_slab_last_error", "ow_slab_get_info", "ow_slab_init_spectrum_seeded", "ow_slab_ipc_handle",
     "ow_slab_open_peers", "ow_slab_rows", "ow_slab_cols", "ow_slab_local_exchange", "ow_slab_sync", "ow_slab_download",
 ]
@@ -39,6 +40,8 @@ OW_FLAG_JACOBIAN = 0x1
 OW_FLAG_EXACT_SINCOS = 0x2
 OW_FLAG_FOUR_STEP = 0x4
 OW_FLAG_FUSED_NORMALS = 0x8
+OW_FLAG_PACKED_F32 = 0x10
+OW_FLAG_PACKED_F16 = 0x20
 IMAGES = {"dy": 0, "dx": 1, "dz": 2, "normal": 3, "jacobian": 4, "h0k": 5, "h0minusk": 6}
 
 
@@ -54,6 +57,10 @@ class _Params(C.Structure):
 class _Outputs(C.Structure):
     _fields_ = [("N", C.c_int32), ("dy", C.c_void_p), ("dx", C.c_void_p), ("dz", C.c_void_p), ("normal", C.c_void_p),
                 ("jacobian", C.c_void_p)]
+
+
+class _Packed(C.Structure):
+    _fields_ = [("N", C.c_int32), ("displacement_texel_bytes", C.c_int32), ("displacement", C.c_void_p), ("normal_xz", C.c_void_p)]
 
 
 class _SlabInfo(C.Structure):
@@ -126,6 +133,15 @@ def load_library():
     L.ow_gl_step.argtypes = [vp, f32]
     L.ow_gl_unregister.argtypes = [vp]
     L.ow_set_noise_seed.argtypes = [vp, i32, C.c_uint64]
+    L.ow_init_spectrum_cascade.argtypes = [vp, i32]
+    L.ow_set_graph.argtypes = [vp, i32]
+    L.ow_get_packed.argtypes = [vp, i32, C.POINTER(_Packed)]
+    L.ow_packed_bytes.argtypes = [vp]
+    L.ow_packed_bytes.restype = C.c_size_t
+    L.ow_download_packed_async.argtypes = [vp, i32, vp, C.c_size_t, vp]
+    L.ow_set_row_kernel.argtypes = [vp, i32]
+    L.ow_set_discard_intermediate.argtypes = [vp, i32]
+    L.ow_gl_register_packed.argtypes = [vp, u32, u32]
     L.ow_slab_create.argtypes = [i32, i32, i32, C.POINTER(_Params), i32, u32, C.POINTER(vp)]
     L.ow_slab_destroy.argtypes = [vp]
     L.ow_slab_destroy.restype = None
@@ -154,17 +170,21 @@ class FFTOceanWaves:
 
     def __init__(self, N: int = 256, cascades: Optional[Sequence[OceanParams]] = None, n_slots: Optional[int] = None,
                  device: int = 0, jacobian: bool = False, exact_sincos: bool = False, four_step: bool = False,
-                 fused_normals: bool = False):
+                 fused_normals: bool = False, packed: Optional[str] = None):
         self._lib = load_library()
         self._h = C.c_void_p()
         self.N = int(N)
         self.cascades = list(cascades) if cascades is not None else [OceanParams()]
         self.n_slots = int(n_slots) if n_slots is not None else len(self.cascades)
         self.jacobian = bool(jacobian)
+        if packed not in (None, "f32", "f16"):
+            raise ValueError("packed must be None, 'f32' or 'f16'")
+        self.packed = packed
         arr = (_Params * len(self.cascades))(*[c.to_c() for c in self.cascades])
         rc = self._lib.ow_create(self.N, len(self.cascades), self.n_slots, arr, int(device),
                                  (OW_FLAG_JACOBIAN if jacobian else 0) | (OW_FLAG_EXACT_SINCOS if exact_sincos else 0)
-                                 | (OW_FLAG_FOUR_STEP if four_step else 0) | (OW_FLAG_FUSED_NORMALS if fused_normals else 0),
+                                 | (OW_FLAG_FOUR_STEP if four_step else 0) | (OW_FLAG_FUSED_NORMALS if fused_normals else 0)
+                                 | {None: 0, "f32": OW_FLAG_PACKED_F32, "f16": OW_FLAG_PACKED_F16}[packed],
                                  C.byref(self._h))
         if rc != 0:
             msg = self._lib.ow_last_error(None)
@@ -219,6 +239,10 @@ class FFTOceanWaves:
         self._check(self._lib.ow_set_params(self._h, int(cascade), C.byref(c)), "ow_set_params")
         self.cascades[cascade] = p
 
+    def tilde_h0_k_cascade(self, cascade: int):
+        """Re-generate ONE cascade's initial spectrum (after set_params on it)."""
+        self._check(self._lib.ow_init_spectrum_cascade(self._h, int(cascade)), "ow_init_spectrum_cascade")
+
     def set_h0(self, h0k: np.ndarray, h0minusk: np.ndarray, cascade: int = 0):
         a = np.ascontiguousarray(h0k, np.float32).reshape(self.N, self.N, 2)
         b = np.ascontiguousarray(h0minusk, np.float32).reshape(self.N, self.N, 2)
@@ -252,6 +276,15 @@ class FFTOceanWaves:
     def set_streams(self, n: int):
         self._check(self._lib.ow_set_streams(self._h, int(n)), "ow_set_streams")
 
+    def set_graph(self, enabled: bool):
+        self._check(self._lib.ow_set_graph(self._h, int(bool(enabled))), "ow_set_graph")
+
+    def set_row_kernel(self, mode: int):
+        self._check(self._lib.ow_set_row_kernel(self._h, int(mode)), "ow_set_row_kernel")
+
+    def set_discard_intermediate(self, on: bool):
+        self._check(self._lib.ow_set_discard_intermediate(self._h, int(bool(on))), "ow_set_discard_intermediate")
+
     def last_launch_count(self) -> int:
         return int(self._lib.ow_last_launch_count(self._h))
 
@@ -279,6 +312,35 @@ class FFTOceanWaves:
     def download_frame_async(self, slot: int, host_ptr: int, nbytes: int, stream: int = 0):
         self._check(self._lib.ow_download_frame_async(self._h, int(slot), C.c_void_p(host_ptr), nbytes,
                                                       C.c_void_p(stream or None)), "ow_download_frame_async")
+
+    # ---- packed output set (OW_FLAG_PACKED_*) ---------------------------------------
+    def packed_bytes(self) -> int:
+        return int(self._lib.ow_packed_bytes(self._h))
+
+    def download_packed_async(self, slot: int, host_ptr: int, nbytes: int, stream: int = 0):
+        self._check(self._lib.ow_download_packed_async(self._h, int(slot), C.c_void_p(host_ptr), nbytes,
+                                                       C.c_void_p(stream or None)), "ow_download_packed_async")
+
+    def download_packed(self, slot: int = 0, stream: int = 0) -> dict:
+        """Raw packed images of `slot`: 'displacement' (N,N,4) float32 or float16 = (dx,dy,dz,J); 'normal_xz' (N,N,2) int16 (SNORM)."""
+        nb = self.packed_bytes()
+        buf = np.empty(nb, np.uint8)
+        self.download_packed_async(slot, buf.ctypes.data, nb, stream)
+        self.sync(stream)
+        n = self.N
+        tb = 8 if self.packed == "f16" else 16
+        disp = buf[:n * n * tb].view(np.float16 if self.packed == "f16" else np.float32).reshape(n, n, 4)
+        nxz = buf[n * n * tb:].view(np.int16).reshape(n, n, 2)
+        return {"displacement": disp, "normal_xz": nxz}
+
+    @staticmethod
+    def decode_packed(pk: dict) -> dict:
+        """What the consumer's shader does with the packed set: dx,dy,dz,J and the unit normal."""
+        d = pk["displacement"].astype(np.float32)
+        xz = np.maximum(pk["normal_xz"].astype(np.float32) / 32767.0, -1.0)
+        ny = np.sqrt(np.maximum(0.0, 1.0 - xz[..., 0] ** 2 - xz[..., 1] ** 2))
+        normal = np.stack([xz[..., 0], ny, xz[..., 1], np.ones_like(ny)], axis=-1)
+        return {"dx": d[..., 0], "dy": d[..., 1], "dz": d[..., 2], "jacobian": d[..., 3], "normal": normal}
 
     def frame(self, t: float, slot: int = 0) -> dict:
         """Convenience for tests: update(t) then download every image of `slot`."""

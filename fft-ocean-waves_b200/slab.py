@@ -208,14 +208,23 @@ class SlabOcean:
     # ---- init (reference init(): tilde_h0_k, src/main.cpp:218) ----------------------------------------------------
     def init(self, seed: int = 32768):
         self.backend.init_spectrum(seed)
-        if self.transport in ("auto", "peer") and self.world > 1:
+        if self.transport in ("auto", "peer") and self.world > 1 and not self._peers_ready:
+            # Every rank must end up on the SAME transport: a rank whose peer mapping failed cannot fall back on its own
+            # while the others keep storing into peer buffers (mixed barriers and all-to-alls would hang or corrupt).
+            err = None
             try:
                 self._open_peers()
-                self.transport = "peer"
-            except (OceanWavesError, NotImplementedError):
+            except (OceanWavesError, NotImplementedError) as e:
+                err = f"rank {self.rank}: {e}"
+            errs = [None] * self.world
+            self._dist.all_gather_object(errs, err, group=self.group)
+            failed = [e for e in errs if e]
+            if failed:
                 if self.transport == "peer":
-                    raise
-                self.transport = "alltoall"
+                    raise OceanWavesError("transport='peer' requested but peer mappings failed: " + "; ".join(failed))
+                self.transport = "alltoall"          # decided identically on every rank
+            else:
+                self.transport = "peer"
         elif self.transport == "auto":
             self.transport = "peer"          # world == 1: the "peer" is this rank's own receive buffer
         return True
@@ -227,8 +236,13 @@ class SlabOcean:
         self._peers_ready = True
 
     def _barrier(self):
-        """Stream-ordered barrier: an all-reduce of one element on the stream the kernels run on."""
+        """Stream-ordered barrier: an all-reduce of one element on the stream the kernels run on (NCCL). Under a host-side
+        backend (gloo: the CPU tests, and several ranks sharing one GPU) the stream is drained first and the ranks meet on the host."""
         if self.world == 1:
+            return
+        if self._dist.get_backend(self.group) != "nccl":
+            self.backend.sync(self.backend.current_stream())
+            self._dist.barrier(group=self.group)
             return
         if self._token is None:
             self._token = self.backend.barrier_token()
@@ -269,6 +283,10 @@ class SlabOcean:
         parts = [None] * self.world
         self._dist.all_gather_object(parts, mine, group=self.group)
         return np.concatenate(parts, axis=1)
+
+    def launches_per_frame(self) -> int:
+        """Kernels this rank launches per frame: row, column, normal; above N = 4096 the line decomposition doubles the first two."""
+        return 5 if self.N > 4096 else 3
 
     def exchange_bytes_per_frame(self) -> int:
         """Bytes this rank sends to OTHER ranks per frame (NVLink traffic per direction)."""

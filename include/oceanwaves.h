@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define OW_VERSION 100
+#define OW_VERSION 200
 
 typedef enum ow_status {
     OW_OK = 0,
@@ -54,6 +54,14 @@ typedef struct ow_params {
 #define OW_FLAG_FUSED_NORMALS 0x8u /* experimental (N <= 2048, no Jacobian): produce the normal map as the epilogue of the dy column
                                       tiles instead of a separate kernel. Identical images; measured SLOWER on B200, so off by default */
 
+/* Packed output set for the consumer, in ADDITION to the reference formats: per slot one `displacement`
+ * image RGBA32F (OW_FLAG_PACKED_F32) or RGBA16F (OW_FLAG_PACKED_F16) = (dx, dy, dz, J), J = 1 without OW_FLAG_JACOBIAN, and one
+ * `normal_xz` image RG16_SNORM = (n.x, n.z); the consumer rebuilds n.y = sqrt(1 - n.x^2 - n.z^2) (the normal is a unit vector with
+ * y > 0, normal_map_cs.glsl:53). 20 / 12 B per texel instead of 28 (+4 with the Jacobian). Replaces the four sampler binds of
+ * src/main.cpp:477-487 / grid_tes.glsl:60-64 by two; INTEGRATION.md shows the decode. */
+#define OW_FLAG_PACKED_F32 0x10u
+#define OW_FLAG_PACKED_F16 0x20u
+
 typedef struct ow_ctx ow_ctx;
 
 /* Device pointers to one output set ("slot"); library-owned, valid until ow_destroy. Written by ow_step*.
@@ -67,6 +75,14 @@ typedef struct ow_outputs {
     float* normal;     /* [N*N*4] unit normal xyz, w = 1         */
     float* jacobian;   /* [N*N]   NULL unless OW_FLAG_JACOBIAN   */
 } ow_outputs;
+
+/* Device pointers to one slot's packed images (OW_FLAG_PACKED_*); library-owned, written by ow_step*. */
+typedef struct ow_packed {
+    int32_t N;
+    int32_t displacement_texel_bytes;   /* 16 (RGBA32F) or 8 (RGBA16F) */
+    void* displacement;                 /* [N*N] texels (dx, dy, dz, J) */
+    void* normal_xz;                    /* [N*N] texels RG16_SNORM (n.x, n.z) */
+} ow_packed;
 
 typedef enum ow_image {
     OW_IMG_DY = 0, OW_IMG_DX = 1, OW_IMG_DZ = 2, OW_IMG_NORMAL = 3, OW_IMG_JACOBIAN = 4,
@@ -102,15 +118,21 @@ int ow_set_noise(ow_ctx* ctx, int32_t cascade, const uint8_t* const planes[4], i
 int ow_set_noise_seed(ow_ctx* ctx, int32_t cascade, uint64_t seed);
 /* = tilde_h0_k_cs.glsl for every cascade. Re-callable. Synchronous (like the reference's glFinish). */
 int ow_init_spectrum(ow_ctx* ctx);
-/* Overwrite / read back a cascade's initial spectrum (HOST pointers, N*N*2 floats each). */
+/* The same for ONE cascade: what a GUI edit of one patch's wind/amplitude needs (ow_set_params marks only that cascade
+ * stale; ow_step* refuses to evaluate a stale cascade with OW_ERR_STATE). */
+int ow_init_spectrum_cascade(ow_ctx* ctx, int32_t cascade);
+/* Overwrite a cascade's initial spectrum (HOST pointers, N*N*2 floats each); makes THAT cascade current, no other. */
 int ow_set_h0(ow_ctx* ctx, int32_t cascade, const float* h0k, const float* h0minusk);
 
 /* ---- per frame: replaces tilde_h0_t(); butterfly_fft() x3; generate_normal_map()
  *      (src/main.cpp:240-244, 587-707) ---------------------------------------------------------------- */
 
 /* Slot i <- cascade i at time t, for every cascade. Asynchronous on `stream` (a cudaStream_t passed as
- * void*; NULL = the context's own stream). t replaces float(glfwGetTime()) (src/main.cpp:599). */
+ * void*; NULL = the context's own stream). t replaces float(glfwGetTime()) (src/main.cpp:599).
+ * For N <= 4096 the whole frame is ONE cudaGraphLaunch (built on first use; only the time is patched per call) instead of
+ * the reference's 53 dispatches; ow_set_graph(ctx, 0) falls back to plain launches. */
 int ow_step(ow_ctx* ctx, float t, void* stream);
+int ow_set_graph(ow_ctx* ctx, int32_t enabled);
 /* Slot i <- cascade cascade_of_slot[i] at time time_of_slot[i], i < count <= n_slots (HOST arrays). */
 int ow_step_multi(ow_ctx* ctx, int32_t count, const int32_t* cascade_of_slot, const float* time_of_slot, void* stream);
 /* Same as ow_step_multi but synchronous, with CUDA events around each kernel on `stream`: kernel_ms[0..2] receive
@@ -127,6 +149,11 @@ int ow_download(ow_ctx* ctx, int32_t index, int32_t which /* ow_image */, void* 
  * laid out in that order; used by the headless end-to-end path. */
 int ow_download_frame_async(ow_ctx* ctx, int32_t slot, void* pinned_host, size_t bytes, void* stream);
 size_t ow_frame_bytes(const ow_ctx* ctx);
+/* Packed set (OW_FLAG_PACKED_*): device pointers, bytes per slot (displacement image followed by normal_xz), and the
+ * asynchronous copy of one slot's pair of images into ONE pinned host block of that size. */
+int ow_get_packed(ow_ctx* ctx, int32_t slot, ow_packed* out);
+size_t ow_packed_bytes(const ow_ctx* ctx);
+int ow_download_packed_async(ow_ctx* ctx, int32_t slot, void* pinned_host, size_t bytes, void* stream);
 
 /* Tuning: upper bound on the slots that share one row/column/normal launch group. 0 = automatic (the group's
  * 12 B/texel intermediate <= ~100 MB, slots split evenly into at least as many groups as there are streams). */
@@ -139,6 +166,11 @@ int ow_set_streams(ow_ctx* ctx, int32_t n);
  * groups they formed (a group = the row, column[, normal] kernels of the slots that share launches). */
 int ow_last_launch_count(const ow_ctx* ctx);
 int ow_last_group_count(const ow_ctx* ctx);
+/* Tuning / A-B runs (per context; results do not depend on them): which row kernel runs (0 = the per-N default, 1 = one CTA
+ * per row-pair group, 2 = the persistent software-pipelined kernel), and whether the column kernel drops the consumed
+ * intermediate from L2 without writing it back (discard.global.L2). */
+int ow_set_row_kernel(ow_ctx* ctx, int32_t mode);
+int ow_set_discard_intermediate(ow_ctx* ctx, int32_t on);
 
 /* ---- CUDA-GL interop: replaces the renderer's texture binds (src/main.cpp:477-487) ------------------- */
 
@@ -148,14 +180,16 @@ int ow_gl_register(ow_ctx* ctx, uint32_t tex_dy, uint32_t tex_dx, uint32_t tex_d
 /* ow_step for slot 0 and copy the results into the registered textures (map -> copy -> unmap). */
 int ow_gl_step(ow_ctx* ctx, float t);
 int ow_gl_unregister(ow_ctx* ctx);
+/* The same for the packed set: the caller's RGBA32F/RGBA16F displacement texture and RG16_SNORM normal texture. */
+int ow_gl_register_packed(ow_ctx* ctx, uint32_t tex_displacement, uint32_t tex_normal_xz);
 
 /* ---- one grid over several GPUs (BASELINE config C5): slab-decomposed 2-D IFFT --------------------------
  * Replaces the same reference functions as ow_step (tilde_h0_t; butterfly_fft x3; generate_normal_map,
  * src/main.cpp:240-244) for a grid too large or too slow for one GPU. One process per GPU, one ow_slab per process.
  * Rank r owns row pairs [r*PL, (r+1)*PL) (rows p and N-p, PL = N/2/world) for the row pass and columns
  * [r*XL, (r+1)*XL) (XL = N/world) for the column pass; the transpose between them is the row kernel's store pattern
- * (see ow_slab_rows). Outputs stay column-slabbed. N in [256, 4096] this round (N = 32768 needs a four-step line
- * FFT: not built yet). */
+ * (see ow_slab_rows). Outputs stay column-slabbed. N is a power of two in [256, 32768] with N/world >= 128; above 4096 the
+ * lines use the N = A*B decomposition. */
 typedef struct ow_slab ow_slab;
 
 #define OW_SLAB_IPC_HANDLE_BYTES 64

@@ -13,6 +13,25 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def _have_gpu() -> bool:
+    try:
+        import torch
+        return bool(torch.cuda.is_available())
+    except Exception:  # noqa: BLE001
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    """`pytest tests` on a box without a CUDA device: skip the gpu-marked tests instead of failing them one by one in ow_create.
+    (The product itself still fails loudly there: tests/test_slab_host.py and tests/test_bench_contract.py check that.)"""
+    if _have_gpu():
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device (run with -m gpu on the B200 box)")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def noise():
     import fft_ocean_waves_b200 as fow

@@ -1,6 +1,9 @@
 """torchrun worker for the multi-GPU slab tests: every rank runs SlabOcean over NCCL; rank 0 also runs the single-GPU
 path on the same Philox seed and compares the gathered column slabs with it (same phase functions; agreement to fp32
-round-off, 1e-6 of peak — the single-GPU row kernel is the pipelined variant, so FMA contraction may differ).   torchrun --nproc-per-node P tests/slab_worker.py N [frames]"""
+round-off, 1e-6 of peak — the single-GPU row kernel is the pipelined variant, so FMA contraction may differ).
+    torchrun --nproc-per-node P tests/slab_worker.py N [shared]
+"shared": every rank uses GPU 0 and the process group is gloo — real ow_slab contexts in separate processes, peer stores through CUDA
+IPC mappings of each other's receive buffers, host-side barriers. That is the multi-rank slab path on a box with ONE GPU."""
 import os
 import sys
 
@@ -16,9 +19,13 @@ def main():
     import fft_ocean_waves_b200 as fow
 
     N = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    shared = len(sys.argv) > 2 and sys.argv[2] == "shared"
+    local = 0 if shared else int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if shared:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, world = dist.get_rank(), dist.get_world_size()
     p = fow.OceanParams(L=1000.0, wind_speed=40.0, wind_dir=(1.0, 1.0), amplitude=2.0, suppression=0.1, choppiness=1.0)
     seed, times = 32768, (0.5, 1.0)
@@ -29,7 +36,7 @@ def main():
             one.tilde_h0_k()
             ref = one.frame(times[-1])
     ok = True
-    for transport in ("peer", "alltoall"):
+    for transport in (("peer",) if shared else ("peer", "alltoall")):
         with fow.SlabOcean(N=N, params=p, device=local, jacobian=True, transport=transport) as sim:
             sim.init(seed)
             assert sim.transport == transport
@@ -46,7 +53,7 @@ def main():
                     same = err <= tol
                     print(f"[slab N={N} world={world} {transport}] {k}: max err {err:.3e} (tol {tol:.3e}) {'ok' if same else 'MISMATCH'}", flush=True)
                     ok &= same
-    flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
+    flag = torch.tensor([1.0 if ok else 0.0], device="cpu" if shared else "cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.barrier()
     dist.destroy_process_group()

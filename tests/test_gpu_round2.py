@@ -1,0 +1,200 @@
+"""GPU tests of the round-2 additions, all through the C ABI: the CUDA-graph single-frame path, per-cascade readiness,
+the packed output set, all 64 cascades of BASELINE config C4, and a random-spectrum check of the
+N = A*B line decomposition at N = 16384 against an independent fp64 DFT of sampled output rows and columns."""
+import numpy as np
+import pytest
+
+import fft_ocean_waves_b200 as fow
+from oracle.oracle import OracleSim
+from tests.conftest import rng_noise
+
+pytestmark = pytest.mark.gpu
+C1 = dict(L=1000.0, wind_speed=40.0, wind_dir=(1.0, 1.0), amplitude=2.0, suppression=0.1, choppiness=1.0)
+
+
+def params(**kw):
+    d = dict(C1)
+    d.update(kw)
+    return fow.OceanParams(**d)
+
+
+@pytest.mark.parametrize("N", [256, 1024])
+def test_graph_path_equals_plain_launches(noise, N):
+    """ow_step as ONE cudaGraphLaunch (default) vs the same kernels launched one by one: bit-identical images, and the time
+    patched into the graph's row-kernel node really changes from frame to frame."""
+    times = [0.0, 1.0, 1.0, 7.25, 0.5]
+    with fow.FFTOceanWaves(N=N, cascades=[params()], jacobian=True) as sim:
+        sim.init(noise)
+        sim.set_graph(False)
+        plain = [sim.frame(t) for t in times]
+        sim.set_graph(True)
+        graph = [sim.frame(t) for t in times]
+        assert sim.last_launch_count() == 3 and sim.last_group_count() == 1
+    for a, b, t in zip(plain, graph, times):
+        for k in ("dy", "dx", "dz", "normal", "jacobian"):
+            assert np.array_equal(a[k], b[k]), (k, t)
+    assert np.array_equal(graph[1]["dy"], graph[2]["dy"]) and not np.array_equal(graph[0]["dy"], graph[1]["dy"])
+    ref = OracleSim(N, 1000.0, 40.0, (1.0, 1.0), 2.0, 0.1, noise, threads=8).frame(np.float32(7.25), choppiness=1.0)
+    for k in ("dy", "dx", "dz"):
+        assert np.abs(graph[3][k] - ref[k]).max() <= 1e-4 * np.abs(ref[k]).max()     # parity tolerance: 1e-4 of peak
+
+
+def test_graph_with_several_cascades_and_large_time(noise):
+    """Several cascades in one graph (one chain of nodes per launch group), and the automatic switch to the full-range sincos
+    variant (its own graph) when |w t| leaves the fast path's range."""
+    ps = [params(), params(L=400.0, wind_speed=25.0, wind_dir=(0.3, -1.0))]
+    with fow.FFTOceanWaves(N=512, cascades=ps) as sim:
+        sim.init(noise)
+        for t in (2.0, 40000.0, 3.0):
+            sim.set_graph(True)
+            sim.update(t)
+            sim.sync()
+            g = [{k: sim.download(k, i) for k in ("dy", "dz", "normal")} for i in range(2)]
+            sim.set_graph(False)
+            sim.update(t)
+            sim.sync()
+            for i in range(2):
+                for k in ("dy", "dz", "normal"):
+                    assert np.array_equal(g[i][k], sim.download(k, i)), (t, i, k)
+
+
+def test_readiness_is_per_cascade(noise):
+    """ow_set_params / ow_set_h0 touch ONE cascade: the others stay usable, and a stale cascade is refused (OW_ERR_STATE)."""
+    ps = [params(), params(wind_speed=60.0)]
+    with fow.FFTOceanWaves(N=256, cascades=ps, n_slots=2) as sim:
+        a = np.zeros((256, 256, 2), np.float32)
+        a[128, 128, 0] = 1.0
+        sim.set_h0(a, np.zeros_like(a), cascade=0)           # only cascade 0 has a spectrum now
+        sim.update_multi([0], [0.0])
+        sim.sync()
+        assert np.allclose(sim.download("dy", 0), 1.0 / 65536, rtol=1e-6)
+        with pytest.raises(fow.OceanWavesError):
+            sim.update_multi([0, 1], [0.0, 0.0])             # cascade 1 was never initialised
+        with pytest.raises(fow.OceanWavesError):
+            sim.update(0.0)
+        sim.init(noise)
+        d1 = sim.frame(1.0, slot=1)["dy"]
+        sim.set_params(1, params(wind_speed=20.0))
+        sim.update_multi([0], [1.0])                          # cascade 0 is untouched by cascade 1's edit
+        with pytest.raises(fow.OceanWavesError):
+            sim.update_multi([1], [1.0])
+        sim.tilde_h0_k_cascade(1)                             # re-generate just that cascade
+        d1b = sim.frame(1.0, slot=1)["dy"]
+    ref = OracleSim(256, 1000.0, 20.0, (1.0, 1.0), 2.0, 0.1, noise, threads=8).frame(1.0)["dy"]
+    assert np.abs(d1b - ref).max() <= 1e-4 * np.abs(ref).max() and not np.allclose(d1, d1b)
+
+
+@pytest.mark.parametrize("mode,N,jac", [("f32", 512, True), ("f16", 512, True), ("f16", 2048, False)])
+def test_packed_outputs_decode_to_the_reference_formats(noise, mode, N, jac):
+    """OW_FLAG_PACKED_*: (dx,dy,dz,J) RGBA32F/RGBA16F + RG16_SNORM normal.xz, decoded the way the consumer's shader does
+    (INTEGRATION.md), against the default R32F / RGBA32F outputs of the same frame. Stated tolerances:
+      f32 displacement: exact.  f16 displacement: 1e-3 of the channel's peak (half precision: 2^-11 relative).
+      normal: 1e-4 absolute per component (SNORM16 step 3.1e-5; y rebuilt from x, z)."""
+    with fow.FFTOceanWaves(N=N, cascades=[params()], jacobian=jac, packed=mode) as sim:
+        sim.init(noise)
+        full = sim.frame(1.0)                                  # the reference formats are still produced
+        dec = sim.decode_packed(sim.download_packed(0))
+        assert sim.last_launch_count() == 4                    # row, column, normal, pack
+        assert sim.packed_bytes() == N * N * ((16 if mode == "f32" else 8) + 4)
+    for k in ("dx", "dy", "dz"):
+        if mode == "f32":
+            assert np.array_equal(dec[k], full[k]), k
+        else:
+            assert np.abs(dec[k] - full[k]).max() <= 1e-3 * np.abs(full[k]).max(), k
+    if jac:
+        assert np.abs(dec["jacobian"] - full["jacobian"]).max() <= (0.0 if mode == "f32" else 1e-3 * np.abs(full["jacobian"]).max())
+    else:
+        assert np.all(dec["jacobian"] == 1.0)
+    assert np.abs(dec["normal"] - full["normal"]).max() <= 1e-4
+
+
+def test_packed_api_errors(noise):
+    with fow.FFTOceanWaves(N=256, cascades=[params()]) as sim:
+        sim.init(noise)
+        assert sim.packed_bytes() == 0
+        with pytest.raises(fow.OceanWavesError):
+            sim.download_packed_async(0, 0x1000, 16)
+        lib = fow.load_library()
+        assert lib.ow_gl_register_packed(sim._h, 1, 2) == 3      # OW_ERR_STATE: no packed set in this context
+    with pytest.raises(fow.OceanWavesError):
+        import ctypes as C
+        h = C.c_void_p()
+        p = params().to_c()
+        rc = fow.load_library().ow_create(256, 1, 1, C.byref(p), 0, 0x10 | 0x20, C.byref(h))
+        if rc != 0:
+            raise fow.OceanWavesError("both packed flags")
+
+
+def c4_cascade(c):
+    ang = 2 * np.pi * c / 64
+    return params(L=float(100.0 * 1.08 ** c), wind_speed=float(10 + 0.5 * c), wind_dir=(float(np.cos(ang)), float(np.sin(ang))))
+
+
+def test_c4_all_64_cascades():
+    """BASELINE config C4 complete: 64 cascades N=1024 in ONE context and one ow_step, every cascade against its own oracle."""
+    N = 1024
+    ps = [c4_cascade(c) for c in range(64)]
+    with fow.FFTOceanWaves(N=N, cascades=ps) as sim:
+        for c in range(64):
+            sim.set_noise(rng_noise(1024 + c, N), cascade=c)
+        sim.tilde_h0_k()
+        sim.update(1.0)
+        sim.sync()
+        for c in range(64):
+            ref = OracleSim(N, ps[c].L, ps[c].wind_speed, ps[c].wind_dir, ps[c].amplitude, ps[c].suppression, rng_noise(1024 + c, N), threads=16).frame(1.0)
+            for k in ("dy", "dx", "dz"):
+                got = sim.download(k, c)
+                peak = float(np.abs(ref[k]).max())
+                assert np.abs(got - ref[k]).max() <= 1e-4 * peak, (c, k)
+            assert np.abs(sim.download("normal", c) - ref["normal"]).max() < 1e-4, c
+
+
+def test_n16384_random_spectrum_vs_fp64_dft_of_sampled_lines():
+    """N = 16384 (line decomposition A = 8): sampled output rows AND columns of dy, dx, dz against a direct fp64 evaluation of
+    D = Re(ifft2(ifftshift(H))) on the GPU's own h0 (Philox noise) — independent of every FFT in this repository.
+    Tolerance: 1e-4 of the channel's peak, as everywhere."""
+    import torch
+    N, t, L = 16384, 1.0, 1000.0
+    if torch.cuda.mem_get_info()[0] < 40e9:
+        pytest.skip("not enough device memory")
+    ys = np.array([0, 1, 4097, N // 2, N - 3])
+    xs = np.array([0, 2, 5000, N // 2 + 1, N - 1])
+    with fow.FFTOceanWaves(N=N, cascades=[params()]) as sim:
+        sim.set_noise_seed(16384)
+        sim.tilde_h0_k()
+        sim.update(t)
+        sim.sync()
+        got = {k: sim.download(k) for k in ("dy", "dx", "dz")}
+        h0k, h0m = sim.download("h0k"), sim.download("h0minusk")
+    idx = np.arange(N) - N / 2.0
+    k1 = ((2.0 * np.float32(np.pi) * idx.astype(np.float32)) / np.float32(L)).astype(np.float64)      # the shader's fp32 k, then fp64
+    sh = (np.arange(N) + N // 2) % N                           # ifftshift: spectrum index a' = (a + N/2) mod N sits at DFT index a
+    pos = np.empty(N, np.int64); pos[sh] = np.arange(N)        # DFT index of texel index i
+    Trow = {k: np.zeros((len(ys), N), np.complex128) for k in got}   # T_y[b] = sum_a H'[a][b] e^{2 pi i a y/N}
+    col = {k: np.zeros((N, len(xs)), np.complex128) for k in got}    # T_x[a] = sum_b H'[a][b] e^{2 pi i b x/N}, per texel row
+    ex = np.exp(2j * np.pi * np.outer(pos, xs) / N)             # [texel column u][x]
+    CH = 1024
+    for r0 in range(0, N, CH):
+        v = slice(r0, r0 + CH)
+        A = h0k[v, :, 0].astype(np.float64) + 1j * h0k[v, :, 1]
+        B = h0m[v, :, 0].astype(np.float64) + 1j * h0m[v, :, 1]
+        kx, ky = k1[None, :], k1[v, None]
+        km = np.maximum(np.sqrt(kx * kx + ky * ky), 1e-5)
+        ph = np.sqrt(9.81 * km) * t
+        e = np.cos(ph) + 1j * np.sin(ph)
+        H = {"dy": A * e + B * np.conj(e)}
+        H["dx"] = -1j * (kx / km) * H["dy"]
+        H["dz"] = -1j * (ky / km) * H["dy"]
+        ey = np.exp(2j * np.pi * np.outer(ys, pos[v]) / N)      # [y][texel row]
+        for k in got:
+            Trow[k] += ey @ H[k]
+            col[k][v] = H[k] @ ex
+    for k in got:
+        peak = float(np.abs(got[k]).max())
+        # rows: D[y][x] = Re( (1/N^2) sum_b T_y[b] e^{2 pi i b x/N} ), b = DFT index of texel column u
+        Ty = np.zeros_like(Trow[k]); Ty[:, pos] = Trow[k]
+        rows = np.real(np.fft.ifft(Ty, axis=1)) / N
+        assert np.abs(got[k][ys, :] - rows).max() <= 1e-4 * peak, (k, "rows")
+        Tx = np.zeros_like(col[k]); Tx[pos, :] = col[k]
+        cols = np.real(np.fft.ifft(Tx, axis=0)) / N
+        assert np.abs(got[k][:, xs] - cols).max() <= 1e-4 * peak, (k, "columns")

@@ -56,7 +56,8 @@ def test_single_rank_slab_equals_single_gpu_path(N, transport):
             sim.sync()
             for k in NAMES:
                 got = sim.download(k)
-                assert np.abs(got - ref[k]).max() <= 1e-6 * max(1.0, 0.0) * max(np.abs(ref[k]).max(), 1e-30) + (2e-6 if k in ("normal", "jacobian") else 0.0), (k, t)
+                tol = 1e-6 * float(np.abs(ref[k]).max()) + (2e-6 if k in ("normal", "jacobian") else 0.0)   # fp32 round-off of peak (+2 ulp-ish for O(1) images)
+                assert np.abs(got - ref[k]).max() <= tol, (k, t)
 
 
 def test_c5_full_size_slab_equals_single_gpu_path():
@@ -100,6 +101,25 @@ def test_slab_api_errors():
         assert lib.ow_slab_rows(sim.backend._h, 0.0, 7, None) == 1    # unknown transport -> OW_ERR_INVALID
 
 
+def _torchrun(world, *worker_args, timeout=900):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "slab_worker.py"), *[str(a) for a in worker_args]]
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+
+
+@pytest.mark.parametrize("N,world", [(1024, 2), (4096, 4), (8192, 2)])
+def test_multi_rank_slab_on_one_gpu(N, world):
+    """Runs on ANY GPU box, also one with a single device: `world` processes, each with its own ow_slab context on GPU 0, row results
+    stored into each other's receive buffers through CUDA IPC peer mappings (the same ow_slab_rows(OW_SLAB_PEER_STORES) code that
+    crosses NVLink between devices), ordered by host-side barriers over gloo; rank 0 compares the gathered column slabs with the
+    single-GPU path. N = 8192 exercises the N = A*B line decomposition under the slab geometry."""
+    r = _torchrun(world, N, "shared")
+    assert r.returncode == 0 and "SLAB OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
 @pytest.mark.parametrize("N", [1024, 4096, 8192])
 def test_multi_rank_slab_over_nvlink(N):
     """2 (or 4/8 when present) ranks under torchrun: peer-store and all-to-all transports vs the single-GPU path."""
@@ -108,10 +128,5 @@ def test_multi_rank_slab_over_nvlink(N):
     if ngpu < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
     world = 8 if ngpu >= 8 else 4 if ngpu >= 4 else 2
-    with socket.socket() as s:
-        s.bind(("127.0.0.1", 0))
-        port = s.getsockname()[1]
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", str(port), os.path.join(ROOT, "tests", "slab_worker.py"), str(N)]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    r = _torchrun(world, N)
     assert r.returncode == 0 and "SLAB OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
