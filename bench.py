@@ -347,6 +347,8 @@ def measure_patch(env, args, name, steps, warmup, full):
         sim.set_streams(args.streams)
     if args.row_kernel:
         sim.set_row_kernel(args.row_kernel)
+    if args.col_kernel or args.fused >= 0:
+        sim.set_column_kernel(args.col_kernel, args.fused)
     if args.discard:
         sim.set_discard_intermediate(True)
     sp, stream = env.sp, env.stream
@@ -395,14 +397,16 @@ def measure_patch(env, args, name, steps, warmup, full):
     clocks = sampler.stop() if sampler else None
     kms /= prof_sweeps                                      # ms per sweep per kernel
     groups_per_sweep = groups[0] / steps
-    fused = kms[2] == 0.0                                   # normal map (+ Jacobian) produced by the column kernel's epilogue (no separate kernel)
+    modes = sim.kernel_modes()
+    fused = modes["fused"]                                  # normal map produced by the column kernel's epilogue; the third slot is then the seam (+ Jacobian) pass
     peak, peak_src = measured_peak()
     texels = float(N) * N
     kb = dict(KERNEL_BYTES_PER_TEXEL)
     if w["jacobian"]:
         kb["ow_normal_kernel"] += 8 + 4                     # + read dx,dz, write J
     if fused:
-        kb["ow_col_kernel"] += 16 + (4 if w["jacobian"] else 0)   # the fused column kernel also writes the normal map (+ J) and never re-reads dy
+        kb["ow_col_kernel"] += 12                           # the fused column kernel also writes 3/4 of the normal map and never re-reads dy
+        kb["ow_normal_kernel"] = 4 + 4 + (8 + 4 if w["jacobian"] else 0)   # seam quads (a quarter of the normals) + the Jacobian pass
     per_kernel = []
     for i, k in enumerate(KERNELS):
         if kms[i] == 0.0:
@@ -438,7 +442,7 @@ def measure_patch(env, args, name, steps, warmup, full):
                              f"({frames * sim.frame_bytes() / 1e9:.2f} GB) stream through L2, the folded spectrum ({8 * texels * len(w['cascades']) / 1e6:.1f} MB) is re-read every frame",
                        "parallelism": (f"64 cascades sharded {frames} per GPU over {world} GPUs, no communication" if sharded
                                        else f"{world} x independent patch per GPU, no communication"),
-                       "wall_s_timed_region": t_wall},
+                       "kernels": modes, "wall_s_timed_region": t_wall},
             "clocks": clocks, "gpu_launches": int(timed_launches), "roofline": roofline}
 
     # ---- the drop-in call itself: ONE frame per ow_step (what FFTOceanWaves::update() does, src/main.cpp:240-244) ---------------
@@ -501,31 +505,40 @@ def measure_patch(env, args, name, steps, warmup, full):
 def single_frame_numbers(env, sim, w):
     """ow_step(t), one frame per call into slot 0 — the call that replaces the reference's update() chain. With the CUDA
     graph (default) and with plain launches: frames/s back to back (no host sync between frames: throughput of the call path) and
-    the latency of one synchronous frame (ow_step + ow_sync, host clock)."""
+    the latency of one synchronous frame (ow_step + ow_sync, host clock). The loop calls the C ABI through pre-built ctypes
+    arguments, so what is timed is the library and the GPU, not Python argument marshalling."""
+    import ctypes as C
     torch = env.torch
     out = {}
     nseq = min(len(w["times"]), 200)
+    lib, h, stp = sim._lib, sim._h, C.c_void_p(env.sp)
+    ts = [C.c_float(t) for t in w["times"][:max(nseq, 50)]]
+    step, sync = lib.ow_step, lib.ow_sync
     for label, on in (("graph", True), ("launches", False)):
         sim.set_graph(on)
         for f in range(10):
-            sim.update(w["times"][f % len(w["times"])], stream=env.sp)
+            assert step(h, ts[f % len(ts)], stp) == 0
         torch.cuda.synchronize()
         a, b = env.event(), env.event()
         a.record(env.stream)
+        t0 = time.perf_counter()
         for f in range(nseq):
-            sim.update(w["times"][f], stream=env.sp)
+            step(h, ts[f], stp)
+        host_us = (time.perf_counter() - t0) * 1e6 / nseq
         b.record(env.stream)
         torch.cuda.synchronize()
         fps = nseq / (a.elapsed_time(b) * 1e-3)
         lat = []
         for f in range(50):
             t0 = time.perf_counter()
-            sim.update(w["times"][f % len(w["times"])], stream=env.sp)
-            sim.sync(stream=env.sp)
+            step(h, ts[f % len(ts)], stp)
+            sync(h, stp)
             lat.append(time.perf_counter() - t0)
-        out[label] = {"back_to_back_fps": fps, "sync_latency_us_median": float(np.median(lat) * 1e6), "frames": nseq}
+        out[label] = {"back_to_back_fps": fps, "sync_latency_us_median": float(np.median(lat) * 1e6), "host_us_per_call": host_us, "frames": nseq}
     sim.set_graph(True)
-    out["what"] = "sim.update(t) = ow_step: slot 0 <- cascade 0 at time t, one call per frame (the reference's update(), src/main.cpp:240-244)"
+    out["what"] = ("ow_step(ctx, t, stream): slot 0 <- cascade 0 at time t, one call per frame (the reference's update(), src/main.cpp:240-244). "
+                   "Consecutive frames write the same output slot, so they run one after the other on the GPU: the rate is set by the "
+                   "latency of the frame's dependent kernels, not by throughput")
     return out
 
 
@@ -853,7 +866,9 @@ def main():
     ap.add_argument("--slots", type=int, default=0, help="frames evaluated per ow_step_multi call (0 = 128 for c2, 32 for c3, 64 for c4)")
     ap.add_argument("--group", type=int, default=0, help="slots per launch group (0 = library default)")
     ap.add_argument("--streams", type=int, default=0, help="internal streams the launch groups are spread over (0 = library default)")
-    ap.add_argument("--row-kernel", type=int, default=0, help="ow_set_row_kernel mode (0 = per-N default, 1 = classic, 2 = persistent pipelined)")
+    ap.add_argument("--row-kernel", type=int, default=0, help="ow_set_row_kernel mode (0 = per-N default, 1 = classic, 2 = persistent register-pipelined, 3 = persistent bulk-async staged)")
+    ap.add_argument("--col-kernel", type=int, default=0, help="ow_set_column_kernel mode (0 = per-N default, 1 = ow_col_kernel, 2 = ow_col2_kernel, 3 = ow_col2_kernel TMA-staged)")
+    ap.add_argument("--fused", type=int, default=-1, help="normal map as the column kernel's epilogue: -1 = per-N default, 0 = off, 1 = on")
     ap.add_argument("--discard", action="store_true", help="ow_set_discard_intermediate(1)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-compare", action="store_true", help="skip the cuFFT comparison leg")

@@ -26,7 +26,7 @@ SOURCES = [
     ("ow_api.cu", []),
     ("ow_slab.cu", []),
 ]
-HEADERS = ["ow_fft.cuh", "ow_kernels.cuh", "ow_config.cuh", "ow_frame_kernels.cuh", "ow_internal.h", os.path.join("..", "..", "include", "oceanwaves.h")]
+HEADERS = ["ow_fft.cuh", "ow_kernels.cuh", "ow_config.cuh", "ow_frame_kernels.cuh", "ow_async.cuh", "ow_internal.h", os.path.join("..", "..", "include", "oceanwaves.h")]
 
 
 def _nvcc() -> str:
@@ -43,7 +43,13 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, defines=(), tag: str = "") -> str:
+    """defines/tag: a VARIANT build for A/B runs (tools/): extra -D flags, objects and library suffixed with `tag`
+    (lib/liboceanwaves_<tag>.so; select it with OCEANWAVES_LIB). The product build has neither."""
+    global OBJDIR, LIB
+    if tag:
+        OBJDIR = os.path.join(HERE, "build", tag)
+        LIB = os.path.join(LIBDIR, f"liboceanwaves_{tag}.so")
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
     nvcc = _nvcc()
@@ -54,7 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(OBJDIR, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            cmd = [nvcc, *ARCH, *COMMON, *extra, "-c", s, "-o", o]
+            cmd = [nvcc, *ARCH, *COMMON, *extra, *[f"-D{d}" for d in defines], "-c", s, "-o", o]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
                 print(" ".join(cmd))
@@ -72,4 +78,6 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    tags = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--tag=")]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defines=defs, tag=tags[0] if tags else ""))

@@ -50,6 +50,10 @@ struct ow_ctx {
     std::string err;
     KernelConfig kcfg;            // per-context (device) launch facts: SM count, persistent-kernel occupancy
     int row_mode = 0;             // ow_set_row_kernel
+    int col_mode = 0, fuse_mode = -1;   // ow_set_column_kernel
+    int* d_seam = nullptr;        // [n_slots][N/16] seam counters of the fused normal map
+    alignas(64) unsigned char inter_tmap[128];   // CUtensorMap over d_inter (64 bytes used) for the TMA-staged column kernel
+    bool have_tmap = false;
     int discard_inter = 0;        // ow_set_discard_intermediate
     // ow_step (slot i <- cascade i at ONE time t) as a CUDA graph: [exact sincos, fast sincos]; rebuilt when a tuning knob changes
     bool graph_enabled = true;
@@ -109,8 +113,17 @@ FrameBuffers buffers(const ow_ctx* c) {
     fb.discard_inter = c->discard_inter;
     fb.four_step = (c->flags & OW_FLAG_FOUR_STEP) ? 1 : 0;
     fb.scratch = c->d_scratch;
-    fb.fuse_normals = (c->flags & OW_FLAG_FUSED_NORMALS) && !(c->flags & OW_FLAG_JACOBIAN) && c->N <= 2048 ? 1 : 0;
     fb.row_mode = c->row_mode;
+    fb.col_mode = c->col_mode;
+    fb.fuse_mode = c->fuse_mode;
+    if (c->flags & OW_FLAG_FUSED_NORMALS) {          // force the fused epilogue whatever the per-N default is
+        fb.fuse_mode = 1;
+        if (fb.col_mode <= 1) fb.col_mode = c->have_tmap ? 3 : 2;
+    }
+    fb.seam = c->d_seam;
+    fb.inter_tmap = c->have_tmap ? c->inter_tmap : nullptr;
+    fb.row_bulk_ctas[0] = c->kcfg.row_bulk_ctas[0]; fb.row_bulk_ctas[1] = c->kcfg.row_bulk_ctas[1];
+    fb.col2_ctas[0] = c->kcfg.col2_ctas[0]; fb.col2_ctas[1] = c->kcfg.col2_ctas[1];
     fb.sm_count = c->kcfg.sm_count;
     fb.row_pipe_ctas[0] = c->kcfg.row_pipe_ctas[0]; fb.row_pipe_ctas[1] = c->kcfg.row_pipe_ctas[1];
     return fb;
@@ -160,7 +173,7 @@ void release(ow_ctx* c) {
     c->gl_registered = false;
     cudaFree(c->d_noise); cudaFree(c->d_h0); cudaFree(c->d_hp); cudaFree(c->d_nyq); cudaFree(c->d_ktab); cudaFree(c->d_casc); cudaFree(c->d_inter);
     drop_plans(c);
-    cudaFree(c->d_disp); cudaFree(c->d_normal); cudaFree(c->d_jac); cudaFree(c->d_tmp); cudaFree(c->d_scratch); cudaFree(c->d_packed);
+    cudaFree(c->d_disp); cudaFree(c->d_normal); cudaFree(c->d_jac); cudaFree(c->d_tmp); cudaFree(c->d_scratch); cudaFree(c->d_packed); cudaFree(c->d_seam);
     if (c->stream) cudaStreamDestroy(c->stream);
     for (auto& s : c->aux) if (s) cudaStreamDestroy(s);
     for (auto& e : c->ev_join) if (e) cudaEventDestroy(e);
@@ -232,7 +245,10 @@ int ow_create(int32_t N, int32_t n_cascades, int32_t n_slots, const ow_params* c
         OW_TRY(cudaMalloc(&c->d_packed, c->pk.slot_bytes * n_slots));
         c->pk.base = c->d_packed;
     }
+    OW_TRY(cudaMalloc(&c->d_seam, (size_t)n_slots * (N / 16) * sizeof(int)));
+    OW_TRY(cudaMemsetAsync(c->d_seam, 0, (size_t)n_slots * (N / 16) * sizeof(int), c->stream));
     OW_TRY(configure_frame_kernels(N, &c->kcfg));
+    c->have_tmap = make_inter_tensor_map(c->inter_tmap, c->d_inter, N, n_slots);
 #undef OW_TRY
     *out = c;
     return OW_OK;
@@ -511,9 +527,28 @@ int ow_set_graph(ow_ctx* c, int32_t enabled) {
 
 int ow_set_row_kernel(ow_ctx* c, int32_t mode) {
     if (!c) return OW_ERR_INVALID;
-    if (mode < 0 || mode > 2) return fail(c, OW_ERR_INVALID, "ow_set_row_kernel: mode must be 0 (per-N default), 1 (one CTA per row-pair group) or 2 (persistent pipelined)");
+    if (mode < 0 || mode > 3)
+        return fail(c, OW_ERR_INVALID, "ow_set_row_kernel: mode must be 0 (per-N default), 1 (one CTA per row-pair group), 2 (persistent, register-pipelined) or 3 (persistent, bulk-async staged)");
     c->row_mode = mode;
     drop_plans(c);
+    return OW_OK;
+}
+
+int ow_set_column_kernel(ow_ctx* c, int32_t mode, int32_t fused) {
+    if (!c) return OW_ERR_INVALID;
+    if (mode < 0 || mode > 3 || fused < -1 || fused > 1)
+        return fail(c, OW_ERR_INVALID, "ow_set_column_kernel: mode in 0..3 (0 = per-N default, 1 = ow_col_kernel, 2 = ow_col2_kernel, 3 = ow_col2_kernel TMA-staged), fused in -1..1");
+    c->col_mode = mode;
+    c->fuse_mode = fused;
+    drop_plans(c);
+    return OW_OK;
+}
+
+int ow_get_kernel_modes(ow_ctx* c, int32_t* row, int32_t* column, int32_t* fused) {
+    if (!c || !row || !column || !fused) return OW_ERR_INVALID;
+    int r, k, f;
+    effective_modes(buffers(c), &r, &k, &f);
+    *row = r; *column = k; *fused = f;
     return OW_OK;
 }
 

@@ -7,14 +7,37 @@ namespace ow {
 // ---------------------------------------------------------------------------------------------------
 // Per-N configuration. Row plans have R2 = 16 so that 16 consecutive butterfly ids of stages 0 and 1 walk
 // the unit-stride digit; pads (P1,P0) make stage 2 conflict-free for 8-byte accesses (16-lane phases).
-// ROW_PIPE selects the persistent software-pipelined row kernel (ow_row_pipe_kernel) instead of one CTA per ROW_PAIRS
-// row pairs; chosen per N from whole-frame throughput in multi-stream sweeps (tools/tune/tune.cu -DTUNE_SWEEP), where a
-// variant that wins in isolation does not always win (profiles/r01d_tune_sweep_*.txt).
-// COL_FUSE: ow_col_fused_kernel (normal map as the epilogue of the dy column tiles) is available for this N (needs COL_G == 8);
-// used only when the context asks for it (OW_FLAG_FUSED_NORMALS): on B200 it is slower than the two separate kernels.
+// ROW_MODE: 1 = one CTA per ROW_PAIRS row pairs (ow_row_kernel), 2 = persistent register-pipelined kernel (ow_row_pipe_kernel),
+// 3 = persistent kernel with bulk-async staging (ow_row_bulk_kernel); chosen per N from whole-frame throughput (bench.py
+// --row-kernel; profiles/r02*), where a variant that wins in isolation does not always win.
+// COL_FUSE: ow_col2_kernel (16-column tiles, optional TMA staging, normal map as the epilogue of the dy tiles) is available for
+// this N (needs COL_G == 8). COL_MODE: 1 = ow_col_kernel, 2 = ow_col2_kernel with direct loads, 3 = ow_col2_kernel TMA-staged.
+// COL_FUSED: the normal map comes out of the column kernel (no separate normal kernel) by default.
 // Normal kernel: NRM_RY output rows per thread walk, NRM_WARPS warps per CTA, NRM_MINB resident CTAs per SM.
 // Column plans interleave G jobs in the lane index, need S0 odd and a job stride == 16/G (mod 16).
 // ---------------------------------------------------------------------------------------------------
+#ifndef OW_C2MB_SMALL
+#define OW_C2MB_SMALL 3     // resident ow_col2_kernel CTAs per SM the register allocation aims at, N <= 512 (80 registers, 4 B of spills)
+#endif
+#ifndef OW_C2MB_1024
+#define OW_C2MB_1024 1
+#endif
+// A/B knobs of tools/ variant builds (build.py -D... --tag=...): N = 512 row-pair groups per CTA / padding, column and normal kernel residency
+#ifndef OW_COLMB_512
+#define OW_COLMB_512 2
+#endif
+#ifndef OW_NRM_MINB
+#define OW_NRM_MINB 4
+#endif
+#ifndef OW_ROW512_T
+#define OW_ROW512_T 32
+#endif
+#ifndef OW_ROW512_PAIRS
+#define OW_ROW512_PAIRS 4
+#endif
+#ifndef OW_ROW512_MINB
+#define OW_ROW512_MINB 3
+#endif
 template <int N>
 struct Cfg;
 
@@ -22,50 +45,65 @@ template <>
 struct Cfg<256> {
     using Row = Plan<256, 4, 4, 16, 32, 1, 0>;
     static constexpr int ROW_PAIRS = 4, ROW_MINB = 4;
-    static constexpr bool ROW_PIPE = false;
+    static constexpr int ROW_MODE = 1;
     using Col = Plan<256, 4, 4, 16, 32, 0, 1>;
     static constexpr int COL_G = 8, COL_MINB = 2;
+    static constexpr int COL2_MINB = OW_C2MB_SMALL;
     static constexpr bool COL_FUSE = true;
+    static constexpr int COL_MODE = 1;
+    static constexpr bool COL_FUSED = false;
     static constexpr int NRM_RY = 8, NRM_WARPS = 4, NRM_MINB = 4;
 };
 template <>
 struct Cfg<512> {
-    using Row = Plan<512, 8, 4, 16, 32, 1, 14>;
-    static constexpr int ROW_PAIRS = 4, ROW_MINB = 3;
-    static constexpr bool ROW_PIPE = false;
+    using Row = Plan<512, 8, 4, 16, OW_ROW512_T, 1, 14>;
+    static constexpr int ROW_PAIRS = OW_ROW512_PAIRS, ROW_MINB = OW_ROW512_MINB;
+    static constexpr int ROW_MODE = 1;
     using Col = Plan<512, 8, 4, 16, 32, 0, 1>;
-    static constexpr int COL_G = 8, COL_MINB = 2;
+    static constexpr int COL_G = 8, COL_MINB = OW_COLMB_512;
+    static constexpr int COL2_MINB = OW_C2MB_SMALL;
     static constexpr bool COL_FUSE = true;
-    static constexpr int NRM_RY = 8, NRM_WARPS = 4, NRM_MINB = 4;
+    static constexpr int COL_MODE = 1;
+    static constexpr bool COL_FUSED = false;
+    static constexpr int NRM_RY = 8, NRM_WARPS = 4, NRM_MINB = OW_NRM_MINB;
 };
 template <>
 struct Cfg<1024> {
     using Row = Plan<1024, 8, 8, 16, 64, 1, 10>;
     static constexpr int ROW_PAIRS = 2, ROW_MINB = 3;
-    static constexpr bool ROW_PIPE = true;
+    static constexpr int ROW_MODE = 2;
     using Col = Plan<1024, 8, 8, 16, 64, 0, 1>;
     static constexpr int COL_G = 8, COL_MINB = 2;
+    static constexpr int COL2_MINB = OW_C2MB_1024;
     static constexpr bool COL_FUSE = true;
+    static constexpr int COL_MODE = 1;
+    static constexpr bool COL_FUSED = false;
     static constexpr int NRM_RY = 8, NRM_WARPS = 4, NRM_MINB = 4;
 };
 template <>
 struct Cfg<2048> {
     using Row = Plan<2048, 8, 16, 16, 256, 1, 2>;      // 256 threads per row pair: one stage-0 butterfly per thread
     static constexpr int ROW_PAIRS = 1, ROW_MINB = 3;
-    static constexpr bool ROW_PIPE = false;
+    static constexpr int ROW_MODE = 1;
     using Col = Plan<2048, 8, 16, 16, 64, 0, 1>;
     static constexpr int COL_G = 8, COL_MINB = 1;
+    static constexpr int COL2_MINB = 1;
     static constexpr bool COL_FUSE = true;
+    static constexpr int COL_MODE = 1;
+    static constexpr bool COL_FUSED = false;
     static constexpr int NRM_RY = 8, NRM_WARPS = 4, NRM_MINB = 4;
 };
 template <>
 struct Cfg<4096> {
     using Row = Plan<4096, 16, 16, 16, 256, 0, 1>;
     static constexpr int ROW_PAIRS = 1, ROW_MINB = 1;
-    static constexpr bool ROW_PIPE = false;
+    static constexpr int ROW_MODE = 1;
     using Col = Plan<4096, 16, 16, 16, 128, 0, 1>;
     static constexpr int COL_G = 4, COL_MINB = 1;
+    static constexpr int COL2_MINB = 1;
     static constexpr bool COL_FUSE = false;
+    static constexpr int COL_MODE = 1;
+    static constexpr bool COL_FUSED = false;
     static constexpr int NRM_RY = 8, NRM_WARPS = 4, NRM_MINB = 4;
 };
 

@@ -33,16 +33,30 @@ cudaError_t configure_n(KernelConfig* cfg) {
     if ((e = opt_in_smem(ow_row_slab_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true>, rs)) != cudaSuccess) return e;
     if ((e = opt_in_smem(ow_col_kernel<K, C::COL_G, C::COL_MINB>, cs)) != cudaSuccess) return e;
     if ((e = opt_in_smem(ow_col_slab_kernel<K, C::COL_G, C::COL_MINB>, cs)) != cudaSuccess) return e;
-    if constexpr (C::COL_FUSE) {
-        if ((e = opt_in_smem(ow_col_fused_kernel<K, C::COL_G, C::COL_MINB, C::NRM_RY>, cs)) != cudaSuccess) return e;
-    }
-    // resident CTAs per SM of the persistent row kernel ON THIS DEVICE (the grid of ow_row_pipe_kernel)
+    constexpr size_t rbs = row_bulk_smem<R, C::ROW_PAIRS>();
+    if ((e = opt_in_smem(ow_row_bulk_kernel<R, C::ROW_PAIRS, C::ROW_MINB, false>, rbs)) != cudaSuccess) return e;
+    if ((e = opt_in_smem(ow_row_bulk_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true>, rbs)) != cudaSuccess) return e;
+    // resident CTAs per SM of the persistent kernels ON THIS DEVICE (their grids)
     for (int fast = 0; fast < 2; ++fast) {
         int n = 0;
         e = fast ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ow_row_pipe_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true>, R::T * C::ROW_PAIRS, rs)
                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ow_row_pipe_kernel<R, C::ROW_PAIRS, C::ROW_MINB, false>, R::T * C::ROW_PAIRS, rs);
         if (e != cudaSuccess) return e;
         cfg->row_pipe_ctas[fast] = n > 0 ? n : 1;
+        e = fast ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ow_row_bulk_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true>, R::T * C::ROW_PAIRS, rbs)
+                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ow_row_bulk_kernel<R, C::ROW_PAIRS, C::ROW_MINB, false>, R::T * C::ROW_PAIRS, rbs);
+        if (e != cudaSuccess) return e;
+        cfg->row_bulk_ctas[fast] = n > 0 ? n : 1;
+    }
+    if constexpr (C::COL_FUSE) {
+        constexpr size_t c2d = Col2Smem<K, C::COL_G, false>::BYTES, c2s = Col2Smem<K, C::COL_G, true>::BYTES;
+        if ((e = opt_in_smem(ow_col2_kernel<K, C::COL_G, C::COL2_MINB, C::NRM_RY, false>, c2d)) != cudaSuccess) return e;
+        if ((e = opt_in_smem(ow_col2_kernel<K, C::COL_G, C::COL2_MINB, C::NRM_RY, true>, c2s)) != cudaSuccess) return e;
+        int n = 0;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ow_col2_kernel<K, C::COL_G, C::COL2_MINB, C::NRM_RY, false>, K::T * C::COL_G, c2d)) != cudaSuccess) return e;
+        cfg->col2_ctas[0] = n > 0 ? n : 1;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ow_col2_kernel<K, C::COL_G, C::COL2_MINB, C::NRM_RY, true>, K::T * C::COL_G, c2s)) != cudaSuccess) return e;
+        cfg->col2_ctas[1] = n > 0 ? n : 1;
     }
     return cudaSuccess;
 }
@@ -96,38 +110,99 @@ int launch_n(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_
     using R = typename C::Row;
     using K = typename C::Col;
     constexpr size_t rs = row_smem<R, C::ROW_PAIRS>(), cs = ColLayout<K, C::COL_G>::SMEM;
+    const int fi = fast_phase ? 1 : 0;
     if (ev) cudaEventRecord(ev[0], L.st);
+    // ---- spectrum + row IFFT --------------------------------------------------------------------------------------------
+    const int row_mode = fb.row_mode ? fb.row_mode : C::ROW_MODE;
+    const int n_cta_items = count * (N / 2 / C::ROW_PAIRS);
     L.reads_time = true;
-    if (fb.row_mode == 1 || (fb.row_mode == 0 && !C::ROW_PIPE)) {
+    if (row_mode == 1) {
         const dim3 rgrid(N / 2 / C::ROW_PAIRS, count);
         if (fast_phase) L(ow_row_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true>, rgrid, R::T * C::ROW_PAIRS, rs, fb, tab);
         else L(ow_row_kernel<R, C::ROW_PAIRS, C::ROW_MINB, false>, rgrid, R::T * C::ROW_PAIRS, rs, fb, tab);
-    } else {
-        const int n_cta_items = count * (N / 2 / C::ROW_PAIRS);
-        const int resident = fb.sm_count * fb.row_pipe_ctas[fast_phase ? 1 : 0];
+    } else if (row_mode == 2) {
+        const int resident = fb.sm_count * fb.row_pipe_ctas[fi];
         const int grid = n_cta_items < resident ? n_cta_items : resident;
         if (fast_phase) L(ow_row_pipe_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true>, grid, R::T * C::ROW_PAIRS, rs, fb, tab, n_cta_items);
         else L(ow_row_pipe_kernel<R, C::ROW_PAIRS, C::ROW_MINB, false>, grid, R::T * C::ROW_PAIRS, rs, fb, tab, n_cta_items);
+    } else {
+        constexpr size_t rbs = row_bulk_smem<R, C::ROW_PAIRS>();
+        const int resident = fb.sm_count * fb.row_bulk_ctas[fi];
+        const int grid = n_cta_items < resident ? n_cta_items : resident;
+        if (fast_phase) L(ow_row_bulk_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true>, grid, R::T * C::ROW_PAIRS, rbs, fb, tab, n_cta_items);
+        else L(ow_row_bulk_kernel<R, C::ROW_PAIRS, C::ROW_MINB, false>, grid, R::T * C::ROW_PAIRS, rbs, fb, tab, n_cta_items);
     }
     if (ev) cudaEventRecord(ev[1], L.st);
+    // ---- column IFFT + inversion (+ normal map as its epilogue) ----------------------------------------------------------
     const float scale = 0.5f / ((float)N * (float)N);   // 1/2 from the Hermitian split, 1/N^2 from inversion_cs.glsl:36
+    int col_mode = fb.col_mode ? fb.col_mode : C::COL_MODE;
+    if (!C::COL_FUSE) col_mode = 1;
+    if (col_mode == 3 && !fb.inter_tmap) col_mode = 2;
+    bool fused = false;
+    int launches = 1;
     if constexpr (C::COL_FUSE) {
-        if (!with_jac && fb.fuse_normals) {
-            // normal map fused into the dy tiles: 6 output pairs per dy tile, ordinary 8-pair tiles for dx and dz
-            const int ndy = (N / 2 + 5) / 6;
-            L(ow_col_fused_kernel<K, C::COL_G, C::COL_MINB, C::NRM_RY>, dim3(ndy + 2 * (N / (2 * C::COL_G)), count), K::T * C::COL_G, cs, fb, tab, scale, ndy);
-            if (ev) { cudaEventRecord(ev[2], L.st); cudaEventRecord(ev[3], L.st); }
-            return launches_ok() && L.err == cudaSuccess ? 2 : -1;
+        if (col_mode != 1) {
+            fused = fb.fuse_mode < 0 ? C::COL_FUSED : fb.fuse_mode != 0;
+            const int total = 3 * (N / (2 * C::COL_G)) * count;
+            if (col_mode == 3) {
+                const int resident = fb.sm_count * fb.col2_ctas[1];
+                L(ow_col2_kernel<K, C::COL_G, C::COL2_MINB, C::NRM_RY, true>, total < resident ? total : resident, K::T * C::COL_G,
+                  Col2Smem<K, C::COL_G, true>::BYTES, *static_cast<const CUtensorMap*>(fb.inter_tmap), fb, tab, scale, total, fused ? 1 : 0);
+            } else {
+                CUtensorMap none{};
+                L(ow_col2_kernel<K, C::COL_G, C::COL2_MINB, C::NRM_RY, false>, total, K::T * C::COL_G, Col2Smem<K, C::COL_G, false>::BYTES, none, fb, tab,
+                  scale, total, fused ? 1 : 0);
+            }
         }
     }
-    L(ow_col_kernel<K, C::COL_G, C::COL_MINB>, dim3(N / (2 * C::COL_G), 3, count), K::T * C::COL_G, cs, fb, tab, scale);
+    if (col_mode == 1) L(ow_col_kernel<K, C::COL_G, C::COL_MINB>, dim3(N / (2 * C::COL_G), 3, count), K::T * C::COL_G, cs, fb, tab, scale);
     if (ev) cudaEventRecord(ev[2], L.st);
+    // ---- normal map (+ Jacobian) ------------------------------------------------------------------------------------------
     const dim3 ngrid(N / 128, N / (C::NRM_WARPS * C::NRM_RY), count);
-    if (with_jac) L(ow_normal_kernel<N, true, C::NRM_RY, C::NRM_WARPS, C::NRM_MINB>, ngrid, dim3(32, C::NRM_WARPS), 0, fb, tab);
-    else L(ow_normal_kernel<N, false, C::NRM_RY, C::NRM_WARPS, C::NRM_MINB>, ngrid, dim3(32, C::NRM_WARPS), 0, fb, tab);
+    if (!fused) {
+        if (with_jac) L(ow_normal_kernel<N, true, C::NRM_RY, C::NRM_WARPS, C::NRM_MINB>, ngrid, dim3(32, C::NRM_WARPS), 0, fb, tab);
+        else L(ow_normal_kernel<N, false, C::NRM_RY, C::NRM_WARPS, C::NRM_MINB>, ngrid, dim3(32, C::NRM_WARPS), 0, fb, tab);
+        ++launches;
+    } else {
+        constexpr int SRY = 4;        // rows per seam thread
+        L(ow_seam_kernel<N, SRY>, dim3((N / SRY + 127) / 128, N / 16, count), 128, 0, fb, tab);
+        ++launches;
+        if (with_jac) {
+            L(ow_jac_kernel<N, C::NRM_RY, C::NRM_WARPS, C::NRM_MINB>, ngrid, dim3(32, C::NRM_WARPS), 0, fb, tab);
+            ++launches;
+        }
+    }
     if (ev) cudaEventRecord(ev[3], L.st);
     if (L.err != cudaSuccess) stash_launch_error(L.err);
-    return launches_ok() && L.err == cudaSuccess ? 3 : -1;
+    return launches_ok() && L.err == cudaSuccess ? 1 + launches : -1;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
+bool make_inter_tensor_map(void* out, const float2* inter, int N, int n_slots) {
+    int T = 0;
+    switch (N) {
+        case 256: T = Cfg<256>::Col::T; break;
+        case 512: T = Cfg<512>::Col::T; break;
+        case 1024: T = Cfg<1024>::Col::T; break;
+        case 2048: T = Cfg<2048>::Col::T; break;
+        default: return false;
+    }
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        cudaGetLastError();
+        return false;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)2 * N, (cuuint64_t)n_slots * 3 * (N / 2)};      // innermost first: floats per row, rows
+    const cuuint64_t strides[1] = {(cuuint64_t)N * sizeof(float2)};                          // bytes between rows
+    const cuuint32_t box[2] = {32u, (cuuint32_t)T};                                          // 16 columns of float2 x T rows
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult r = reinterpret_cast<EncodeFn>(fn)(static_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float2*>(inter), dims,
+                                                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
 }
 
 bool frame_supported(int N) { return N == 256 || N == 512 || N == 1024 || N == 2048 || N == 4096 || big_supported(N, false); }
@@ -193,6 +268,31 @@ int launch_slab_cols(const SlabGeom& g, const float2* recv, float* disp_loc, flo
         case 4096: return slab_cols_n<4096>(g, recv, disp_loc, normal_loc, jac_loc, jac_scale, st);
     }
     return -1;
+}
+
+template <int N>
+void modes_n(const FrameBuffers& fb, int* row, int* col, int* fused) {
+    using C = Cfg<N>;
+    *row = fb.row_mode ? fb.row_mode : C::ROW_MODE;
+    int cm = fb.col_mode ? fb.col_mode : C::COL_MODE;
+    if (!C::COL_FUSE) cm = 1;
+    if (cm == 3 && !fb.inter_tmap) cm = 2;
+    *col = cm;
+    *fused = cm == 1 ? 0 : (fb.fuse_mode < 0 ? (C::COL_FUSED ? 1 : 0) : (fb.fuse_mode != 0 ? 1 : 0));
+}
+
+// The kernels launch_frame will actually use for this context (per-N defaults resolved; the line decomposition has its own).
+void effective_modes(const FrameBuffers& fb, int* row, int* col, int* fused) {
+    *row = *col = 1;
+    *fused = 0;
+    if (!frame_graphable(fb)) return;
+    switch (fb.N) {
+        case 256: return modes_n<256>(fb, row, col, fused);
+        case 512: return modes_n<512>(fb, row, col, fused);
+        case 1024: return modes_n<1024>(fb, row, col, fused);
+        case 2048: return modes_n<2048>(fb, row, col, fused);
+        case 4096: return modes_n<4096>(fb, row, col, fused);
+    }
 }
 
 bool frame_graphable(const FrameBuffers& fb) { return !big_supported(fb.N, false) && !(fb.four_step && big_supported(fb.N, true)); }

@@ -5,6 +5,7 @@
 #include "ow_internal.h"
 #include "ow_kernels.cuh"
 #include "ow_config.cuh"
+#include "ow_async.cuh"
 
 namespace ow {
 
@@ -149,6 +150,110 @@ __global__ void __launch_bounds__(P::T* PAIRS, MINB) ow_row_pipe_kernel(FrameBuf
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Persistent row kernel with bulk-async staging. Same walk over (slot entry, row pair) items as ow_row_pipe_kernel, but the
+// folded spectrum row of the NEXT item (N float4, contiguous) is fetched by ONE cp.async.bulk per item into a per-group
+// shared-memory buffer, signalled through the group's mbarrier: no registers hold data in flight, the copy is issued the moment
+// stage 0 has consumed the previous row and lands during stages 1 and 2 and their stores. Groups (T threads, one row pair each)
+// never wait for each other: warp barriers for T = 32, named barriers otherwise. Pair 0 (rows 0 and N/2) takes the literal
+// out-of-line path from global memory.
+// ---------------------------------------------------------------------------------------------------
+template <class P>
+struct RowBulkSmem {
+    static constexpr size_t GROUP = (((size_t)P::N * 16 + (size_t)3 * P::LINE * 8) + 127) / 128 * 128;   // staged row + the three lines
+};
+template <class P, int PAIRS>
+constexpr size_t row_bulk_smem() { return PAIRS * RowBulkSmem<P>::GROUP; }
+
+template <int T, int PAIRS>
+__device__ __forceinline__ void row_group_sync(int g) {
+    if (T == 32) __syncwarp();
+    else if (PAIRS == 1) __syncthreads();
+    else named_barrier(1 + g, T);
+}
+
+template <class P, int PAIRS, int MINB, bool FAST>
+__global__ void __launch_bounds__(P::T* PAIRS, MINB) ow_row_bulk_kernel(FrameBuffers fb, SlotTable tab, int n_cta_items) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bars[PAIRS];
+    constexpr int N = P::N, R0 = P::R0, HP = N / 2, C0 = P::C0, T = P::T;
+    static_assert(P::M % P::T == 0, "whole stage-0 batches");
+    const int ft = threadIdx.x % T, g = threadIdx.x / T;
+    unsigned char* mine = smem_raw + (size_t)g * RowBulkSmem<P>::GROUP;
+    const float4* stg = reinterpret_cast<const float4*>(mine);
+    const SmemDirect sm{reinterpret_cast<float2*>(mine + (size_t)N * 16)};
+    uint64_t* bar = &bars[g];
+
+    auto item_of = [&](int ci) {
+        const int item = ci * PAIRS + g, e = item / HP;
+        RowItem<N> it;
+        it.p = item - e * HP;
+        const int cascade = tab.cascade[e];
+        it.rows = FullRows<N>{fb.h0 + (size_t)cascade * N * N, fb.hp + (size_t)cascade * HP * N, fb.nyq + (size_t)cascade * HP};
+        it.prow = it.rows.pair_row(it.p);
+        it.ktab = fb.ktab + (size_t)cascade * N;
+        it.inter = fb.inter + (size_t)tab.slot[e] * 3 * HP * N;
+        it.t = tab.time[e];
+        return it;
+    };
+    auto issue = [&](const RowItem<N>& it) {      // one thread of the group
+        mbar_arrive_expect_tx(bar, (unsigned)N * 16u);
+        bulk_load(mine, it.prow, (unsigned)N * 16u, bar, l2_policy_evict_first());
+    };
+
+    int ci = blockIdx.x;
+    if (ci >= n_cta_items) return;
+    if (ft == 0) {
+        mbar_init(bar, 1);
+        mbar_init_fence();
+    }
+    __syncthreads();
+    RowItem<N> cur = item_of(ci);
+    if (cur.p != 0 && ft == 0) issue(cur);
+    unsigned phase = 0;
+    for (; ci < n_cta_items; ci += gridDim.x) {
+        const int cn = ci + gridDim.x;
+        const bool has_next = cn < n_cta_items;
+        RowItem<N> nx = cur;
+        if (has_next) nx = item_of(cn);
+        if (cur.p == 0) {
+            row_phase0_pair0<P, FAST>(sm, ft, cur.rows, cur.ktab, cur.t);
+        } else {
+            const float ky = OW_LDG(cur.ktab + cur.p);
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+#pragma unroll 1
+            for (int c = 0; c < C0; ++c) {
+                const int b = ft + T * c;
+                float2 vy[R0], vx[R0], vz[R0];
+                FoldedPair fp[R0];
+#pragma unroll
+                for (int d0 = 0; d0 < R0; ++d0) {
+                    fp[d0].f = stg[d0 * P::M + b];
+                    fp[d0].kx = OW_LDG(cur.ktab + d0 * P::M + b);
+                }
+#pragma unroll
+                for (int d0 = 0; d0 < R0; ++d0) {
+                    const Sym3 s = spectrum_folded<FAST>(fp[d0], ky, cur.t, (d0 == 0 && b == 0) ? cur.rows.nyq_of(cur.p) : nullptr);
+                    vy[d0] = s.y; vx[d0] = s.x; vz[d0] = s.z;
+                }
+                float2 tw[R0];
+                twiddle_powers<R0>(unit_root(b, N), tw);
+                stage0_finish<P>(sm, 0 * P::LINE, b, vy, tw);
+                stage0_finish<P>(sm, 1 * P::LINE, b, vx, tw);
+                stage0_finish<P>(sm, 2 * P::LINE, b, vz, tw);
+            }
+        }
+        row_group_sync<T, PAIRS>(g);      // stage-0 results visible; the staged row is consumed
+        if (has_next && nx.p != 0 && ft == 0) issue(nx);
+        row_phase1<P>(sm, ft);
+        row_group_sync<T, PAIRS>(g);
+        row_phase2<P>(sm, ft, cur.p, FullSink<N>{cur.inter});
+        row_group_sync<T, PAIRS>(g);      // the next pair's stage-0 stores reuse the lines
+        cur = nx;
+    }
+}
+
 // Slab variant (one grid over several GPUs): this rank's row pairs [p0, p0 + PL), results stored straight into the
 // column owners' receive buffers (peer mappings over NVLink) or into the local send buffer (see SlabSink).
 template <class P, int PAIRS, int MINB, bool FAST>
@@ -189,46 +294,133 @@ __global__ void __launch_bounds__(P::T* G, MINB) ow_col_kernel(FrameBuffers fb, 
     col_phase2<P>(sm, base, ft, dst, scale, geom);
 }
 
-// Column kernel with the normal map fused into the dy tiles (see "COLUMN KERNEL WITH THE NORMAL MAP AS ITS EPILOGUE").
-// grid.x = ndy dy tiles (6 output pairs + 2 halo pairs each) followed by 2 * N/16 ordinary tiles for dx and dz; grid.y = slot entries.
-template <class P, int G, int MINB, int RY>
-__global__ void __launch_bounds__(P::T* G, MINB) ow_col_fused_kernel(FrameBuffers fb, SlotTable tab, float scale, int ndy) {
-    static_assert(G == 8, "dy tiles are 6 output pairs + 2 halo pairs");
-    extern __shared__ __align__(16) float2 smem[];
-    constexpr int N = P::N, HP = N / 2;
+// ---------------------------------------------------------------------------------------------------
+// Column kernel, second generation: persistent CTAs walking (slot entry, channel, 16-column tile) work items, optionally
+//   STAGED  the tile's input rows arrive through 2-D TMA copies (ColStage in ow_kernels.cuh) into a shared-memory staging buffer
+//           behind an mbarrier; the copy of the NEXT step (or of the next tile's first step) is issued as soon as every thread has
+//           taken the current step into registers, so it is in flight during stage-0 math, stages 1-2, the stores and the epilogue;
+//   fuse    dy tiles keep their final heights in shared memory and produce the normal map of their three interior column quads as
+//           their epilogue (see "COLUMN KERNEL WITH THE NORMAL MAP AS ITS EPILOGUE"); the seam quads between tiles are left to
+//           ow_seam_kernel, a light pass over the stored heights.
+// Work order inside a frame: dy tiles first (they are the long ones), then dx, then dz.
+// ---------------------------------------------------------------------------------------------------
+template <class P, int G, bool STAGED>
+struct Col2Smem {
     using LY = ColLayout<P, G>;
-    const int job = threadIdx.x % G, ft = threadIdx.x / G;
-    const int slot = tab.slot[blockIdx.y];
-    const SmemDirect sm{smem};
+    using CS = ColStage<P, G>;
+    static constexpr size_t STAGE = STAGED ? ((CS::BYTES + 127) / 128) * 128 : 0;
+    static constexpr size_t BYTES = STAGE + LY::SMEM;
+};
+
+template <class P, int G, int MINB, int RY, bool STAGED>
+__global__ void __launch_bounds__(P::T* G, MINB) ow_col2_kernel(const __grid_constant__ CUtensorMap tmap, FrameBuffers fb, SlotTable tab, float scale,
+                                                                int total, int fuse) {
+    static_assert(G == 8, "tiles are 16 columns: three interior quads + one seam quad");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    constexpr int N = P::N, HP = N / 2, NT = N / (2 * G), TPF = 3 * NT, H = P::R0 / 2, NTHREADS = P::T * G;
+    using LY = ColLayout<P, G>;
+    using CS = ColStage<P, G>;
+    using SM_ = Col2Smem<P, G, STAGED>;
+    float4* staging = reinterpret_cast<float4*>(smem_raw);
+    const SmemDirect sm{reinterpret_cast<float2*>(smem_raw + SM_::STAGE)};
+    const int tid = threadIdx.x, job = tid % G, ft = tid / G;
     const int base = job * LY::SJ;
     const FullColGeom<N> geom{};
-    const bool dy_tile = (int)blockIdx.x < ndy;
-    int f, pair;
-    bool store = true;
-    if (dy_tile) {
-        f = 0;
-        pair = (6 * (int)blockIdx.x - 1 + job) & (HP - 1);
-        store = job >= 1 && job <= 6 && 6 * (int)blockIdx.x + job - 1 < HP;
-    } else {
-        const int r = (int)blockIdx.x - ndy;
-        f = 1 + r / (HP / G);
-        pair = (r % (HP / G)) * G + job;
+    int w = blockIdx.x;
+    if (w >= total) return;
+
+    // one elected thread: arm the barrier with the byte count of step s of work item wi and issue its copies
+    auto issue = [&](int wi, int s) {
+        const int e = wi / TPF, r = wi - e * TPF, f = r / NT, tile = r - f * NT;
+        const int row_base = (tab.slot[e] * 3 + f) * HP;
+        const uint64_t pol = l2_policy_evict_first();        // the intermediate is read exactly once
+        mbar_arrive_expect_tx(&bar, CS::STEP_TX_BYTES + (s == 0 ? CS::EXTRA_TX_BYTES : 0u));
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+            tma_load_2d(staging + (2 * i + 0) * CS::BOX_F4, &tmap, 4 * tile * G, row_base + CS::fwd_row0(i, s), &bar, pol);
+            tma_load_2d(staging + (2 * i + 1) * CS::BOX_F4, &tmap, 4 * tile * G, row_base + CS::mir_row0(i, s), &bar, pol);
+        }
+        if (s == 0) {
+#pragma unroll
+            for (int i = 0; i < H; ++i)
+                bulk_load(staging + CS::EXTRA_F4 + i * G, fb.inter + ((size_t)(row_base + CS::extra_row(i)) * N + 2 * tile * G), G * 16, &bar, pol);
+        }
+    };
+
+    unsigned phase = 0;
+    if (STAGED) {
+        if (tid == 0) {
+            mbar_init(&bar, 1);
+            mbar_init_fence();
+            tma_prefetch_descriptor(&tmap);
+        }
+        __syncthreads();
+        if (tid == 0) issue(w, 0);
     }
-    const int x = 2 * pair;
-    const float2* src = fb.inter + ((size_t)slot * 3 + f) * HP * N + x;
-    float* dst = fb.disp + ((size_t)slot * 3 + f) * N * N + x;
+    for (; w < total; w += gridDim.x) {
+        const int e = w / TPF, r = w - e * TPF, f = r / NT, tile = r - f * NT;
+        const int slot = tab.slot[e];
+        const int x = 2 * (tile * G + job);
+        float* dst = fb.disp + ((size_t)slot * 3 + f) * N * N + x;
+        if (STAGED) {
 #pragma unroll 1
-    for (int j = ft; j < P::M / 2; j += P::T) col_phase0<P>(sm, base, j, src, geom);
-    __syncthreads();
-    col_phase1<P>(sm, base, ft);
-    __syncthreads();
-    if (!dy_tile) {
-        col_phase2<P>(sm, base, ft, dst, scale, geom);
-        return;
+            for (int s = 0; s < CS::STEPS; ++s) {
+                float4 la[H], lb[H];
+                mbar_wait(&bar, phase);
+                phase ^= 1u;
+                col_stage_read<P, G>(staging, job, ft, s, la, lb);
+                __syncthreads();          // the step is in registers everywhere (and the previous tile's epilogue is done with the lines)
+                if (tid == 0) {
+                    if (s + 1 < CS::STEPS) issue(w, s + 1);
+                    else if (w + (int)gridDim.x < total) issue(w + gridDim.x, 0);
+                }
+                col_phase0_math<P>(sm, base, s * P::T + ft, la, lb);
+            }
+        } else {
+            const float2* src = fb.inter + ((size_t)slot * 3 + f) * HP * N + x;
+            const bool discard = job == 0 && fb.discard_inter;
+#pragma unroll 1
+            for (int j = ft; j < P::M / 2; j += P::T) col_phase0<P>(sm, base, j, src, geom, discard);
+        }
+        __syncthreads();
+        col_phase1<P>(sm, base, ft);
+        __syncthreads();
+        if (f == 0 && fuse) {
+            col_phase2_keep<P>(sm, base, ft, dst, scale, geom, true);
+            __syncthreads();
+            float4* normal = fb.normal + (size_t)slot * N * N;
+            col_normals_phase<P, RY>(sm, tid, NTHREADS, LY::SJ, 16 * tile + 2, normal);
+        } else {
+            col_phase2<P>(sm, base, ft, dst, scale, geom);
+        }
+        if (!STAGED) __syncthreads();     // the next tile's stage-0 stores reuse the lines
     }
-    col_phase2_keep<P>(sm, base, ft, dst, scale, geom, store);
-    __syncthreads();
-    col_normals_phase<P, RY>(sm, threadIdx.x, P::T * G, LY::SJ, 12 * (int)blockIdx.x, fb.normal + (size_t)slot * N * N);
+}
+
+// The seam quads of the fused normal map: columns 16k+14 .. 16k+17 of every slot entry, from the stored heights (L2). One thread walks
+// RY rows of one seam; consecutive lanes take consecutive row chunks. A quarter of the normal map's texels, none of its FFT work.
+template <int N, int RY>
+__global__ void __launch_bounds__(128) ow_seam_kernel(FrameBuffers fb, SlotTable tab) {
+    const int k = blockIdx.y, slot = tab.slot[blockIdx.z];
+    const float* dy = fb.disp + (size_t)slot * 3 * N * N;
+    float4* normal = fb.normal + (size_t)slot * N * N;
+    const int cA = 16 * k + 12, cB = (16 * (k + 1)) & (N - 1);
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < N / RY) normal_quad_walk_src<N, RY, false>(SeamRowSrc{dy, (size_t)N, cA, cB}, w * RY, 0.f, EmitSeam{normal, (size_t)N, cA, cB});
+}
+
+// Jacobian/foam map alone (frames whose normal map came out of ow_col2_kernel). Lanes run along x: 128 columns per warp.
+template <int N, int RY, int WARPS, int MINB>
+__global__ void __launch_bounds__(32 * WARPS, MINB) ow_jac_kernel(FrameBuffers fb, SlotTable tab) {
+    const int lane = threadIdx.x, w = threadIdx.y;
+    const int x0 = blockIdx.x * 128 + 4 * lane, y0 = (blockIdx.y * WARPS + w) * RY;
+    const int e = blockIdx.z, slot = tab.slot[e];
+    const CascadeDev c = fb.casc[tab.cascade[e]];
+    const float s = c.choppiness * ((float)N / (2.0f * c.L));
+    float* jac = fb.jacobian + (size_t)slot * N * N;
+    jac_quad_walk<N, RY>(fb.disp + (size_t)slot * 3 * N * N, FullNrmGeom<N>{}, x0, y0, s,
+                         [=](int y, float4 J) { __stcs(reinterpret_cast<float4*>(jac + (size_t)y * N + x0), J); });
 }
 
 // Slab variant: the column slab's receive buffer [p][c][XH] (row stride 3*XH) -> disp_loc[c][y][XH].

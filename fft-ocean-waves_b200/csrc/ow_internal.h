@@ -37,17 +37,25 @@ struct FrameBuffers {
     float* jacobian;       // [slot][N][N] or nullptr
     int discard_inter;     // column kernel drops the intermediate's lines from L2 after reading them (no DRAM write-back)
     float2* scratch;       // N = A*B decomposition only: one frame of radix-A sums, 12 B/texel (ow_big_kernels.cu)
-    int fuse_normals;      // OW_FLAG_FUSED_NORMALS: normal map as the epilogue of the dy column tiles (ow_col_fused_kernel)
     int four_step;         // force the N = A*B line decomposition (ow_big_kernels.cu) on a grid the direct kernels could do
-    int row_mode;          // 0 = the per-N choice Cfg<N>::ROW_PIPE, 1 = one CTA per ROW_PAIRS row pairs, 2 = persistent pipelined kernel (ow_set_row_kernel)
+    int row_mode;          // 0 = the per-N choice Cfg<N>::ROW_MODE, 1 = one CTA per ROW_PAIRS row pairs, 2 = persistent register-pipelined kernel,
+                           // 3 = persistent kernel with bulk-async (cp.async.bulk + mbarrier) staging of the spectrum rows (ow_set_row_kernel)
+    int col_mode;          // 0 = the per-N choice Cfg<N>::COL_MODE, 1 = ow_col_kernel, 2 = ow_col2_kernel with direct loads, 3 = ow_col2_kernel with TMA staging
+    int fuse_mode;         // -1 = the per-N choice Cfg<N>::COL_FUSED, 0 = separate normal kernel, 1 = normal map as the column kernel's epilogue (col_mode 2/3)
+    int* seam;             // [slot][N/16] arrival counters of the seams between neighbouring dy tiles (fused normal map), all zero between launches
+    const void* inter_tmap;   // host pointer to the CUtensorMap over `inter` ([n_slots*3*N/2 rows][2N floats], box = 32 floats x T rows), or nullptr
     int sm_count;          // of the context's device (grid size of the persistent kernels)
-    int row_pipe_ctas[2];  // resident CTAs per SM of the persistent row kernel on that device: [exact sincos, fast sincos]
+    int row_pipe_ctas[2];  // resident CTAs per SM of the persistent row kernels on that device: [exact sincos, fast sincos]
+    int row_bulk_ctas[2];
+    int col2_ctas[2];      // resident CTAs per SM of ow_col2_kernel: [direct loads, TMA staged]
 };
 
 // What configure_frame_kernels found out about the device the calling context lives on (kept per context: no process-global state).
 struct KernelConfig {
     int sm_count = 148;
     int row_pipe_ctas[2] = {1, 1};
+    int row_bulk_ctas[2] = {1, 1};     // ow_row_bulk_kernel, [exact, fast]
+    int col2_ctas[2] = {1, 1};         // ow_col2_kernel, [direct loads, TMA staged]
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -135,7 +143,11 @@ int launch_big_frame(const FrameBuffers& fb, const SlotTable& tab, int count, bo
 int launch_frame(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_jacobian, bool fast_phase,
                  Launcher& L, cudaEvent_t* ev = nullptr);
 constexpr float kFastPhaseLimit = 2.0e4f;
-bool frame_graphable(const FrameBuffers& fb);   // launch_frame can build graph nodes for this context (direct kernels, N <= 4096)
+bool frame_graphable(const FrameBuffers& fb);
+void effective_modes(const FrameBuffers& fb, int* row, int* col, int* fused);   // launch_frame can build graph nodes for this context (direct kernels, N <= 4096)
+// Tensor map over the row->column intermediate for the TMA-staged column kernel (64 bytes, 64-byte aligned, at `out`).
+// Returns false when the driver entry point is missing or N has no staged kernel; the context then runs without staging.
+bool make_inter_tensor_map(void* out, const float2* inter, int N, int n_slots);
 cudaError_t configure_frame_kernels(int N, KernelConfig* cfg);   // opt-in shared memory sizes + occupancy queries; call once per context
 // The launchers below return a launch count (< 0: error) and have then already consumed the CUDA error; it is kept here
 // (per thread) so the API layer can report what actually went wrong. cudaSuccess when the failure was not a CUDA error.

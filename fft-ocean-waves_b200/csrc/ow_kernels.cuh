@@ -29,17 +29,29 @@ namespace ow {
 #define OW_SQRT(a) __fsqrt_rn((a))
 #define OW_RCP(a) __fdividef(1.0f, (a))
 #define OW_LDG(p) __ldg(p)
+// Loads of data PRODUCED on the device (the row->column intermediate, the displacement planes). Between separate kernels the
+// read-only path is fine; the frame-pipelined kernel (ow_mega_kernels.cu) reads what other CTAs of the SAME launch wrote, so there
+// they must come from L2 (ld.global.cg), never from the non-coherent L1 path.
+#ifdef OW_COHERENT_LOADS
+#define OW_LDP(p) __ldcg(p)
+#else
+#define OW_LDP(p) __ldg(p)
+#endif
 // Drop a 128-byte line from L2 WITHOUT writing it back (its contents become undefined). Used on the row->column
 // intermediate once the column kernel has consumed it: nobody reads it again before the next frame's row kernel
 // rewrites the whole line, so the dirty data never has to travel to DRAM.
 #define OW_DISCARD_L2(p) asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory")
+// A data dependency on two loaded values, ordered (volatile) before the volatile asm statements that follow it.
+#define OW_USE_BEFORE(a, b) asm volatile("" ::"f"(a), "f"(b) : "memory")
 #else
 #define OW_DISCARD_L2(p) ((void)(p))
+#define OW_USE_BEFORE(a, b) ((void)(a), (void)(b))
 #define OW_MUL(a, b) ((a) * (b))
 #define OW_ADD(a, b) ((a) + (b))
 #define OW_SQRT(a) sqrtf((a))
 #define OW_RCP(a) (1.0f / (a))
 #define OW_LDG(p) (*(p))
+#define OW_LDP(p) (*(p))
 #endif
 
 constexpr float kGravity = 9.81f;   // tilde_h0_t_cs.glsl:58
@@ -333,11 +345,24 @@ OW_HD void row_phase0(const Smem& sm, int ft, int p, const Rows& rows, const flo
     }
 }
 
+// Stages 1 and 2 of the three lines of a row pair. When a line has fewer stage butterflies than the group has threads (N = 2048:
+// 128 butterflies, 256 threads) the 3 x B butterflies of the pair are dealt out as ONE list over all threads (task = line * B + id),
+// so nobody idles through two thirds of the kernel; otherwise every thread does its butterflies of all three lines.
 template <class P, class Smem>
 OW_HD void row_phase1(const Smem& sm, int ft) {
 #if OW_ABLATE & 4
     return;
 #endif
+    if (P::B1 < P::T) {
+#pragma unroll 1
+        for (int task = ft; task < 3 * P::B1; task += P::T) {
+            const int f = task / P::B1, q = task - f * P::B1;
+            float2 tw[P::R1];
+            stage1_twiddles<P>(q, tw);
+            stage1<P>(sm, f * P::LINE, q, tw);
+        }
+        return;
+    }
     // d2 = q % R2 is the same for every butterfly q = ft + T*c of this thread when R2 divides T
     constexpr bool kSameTw = (P::T % P::R2 == 0);
     float2 tw[P::R1];
@@ -353,28 +378,39 @@ OW_HD void row_phase1(const Smem& sm, int ft) {
 }
 
 template <class P, class Smem, class Sink>
+OW_HD void row_phase2_line(const Smem& sm, int f, int bp, int p, const Sink& sink) {
+    float2 v[P::R2];
+#if OW_ABLATE & 4
+#pragma unroll
+    for (int d2 = 0; d2 < P::R2; ++d2) v[d2] = sm.ld(f * P::LINE + P::addr(bp % P::R0, bp / P::R0, d2));
+#else
+    stage2<P>(sm, f * P::LINE, bp, v);
+#endif
+#if OW_ABLATE & 8
+#pragma unroll
+    for (int k2 = 0; k2 < P::R2; ++k2) if (v[k2].x == 12345.678f) sink.put(f, p, bp + k2 * P::B2, v[k2]);
+#else
+#pragma unroll
+    for (int k2 = 0; k2 < P::R2; ++k2) sink.put(f, p, bp + k2 * P::B2, v[k2]);
+#endif
+}
+
+template <class P, class Smem, class Sink>
 OW_HD void row_phase2(const Smem& sm, int ft, int p, const Sink& sink) {
+    if (P::B2 < P::T) {           // see row_phase1
+#pragma unroll 1
+        for (int task = ft; task < 3 * P::B2; task += P::T) {
+            const int f = task / P::B2;
+            row_phase2_line<P>(sm, f, task - f * P::B2, p, sink);
+        }
+        return;
+    }
 #pragma unroll 1
     for (int c = 0; c < P::C2; ++c) {
         const int bp = ft + P::T * c;
         if (bp >= P::B2) break;
 #pragma unroll 1
-        for (int f = 0; f < 3; ++f) {
-            float2 v[P::R2];
-#if OW_ABLATE & 4
-#pragma unroll
-            for (int d2 = 0; d2 < P::R2; ++d2) v[d2] = sm.ld(f * P::LINE + P::addr(bp % P::R0, bp / P::R0, d2));
-#else
-            stage2<P>(sm, f * P::LINE, bp, v);
-#endif
-#if OW_ABLATE & 8
-#pragma unroll
-            for (int k2 = 0; k2 < P::R2; ++k2) if (v[k2].x == 12345.678f) sink.put(f, p, bp + k2 * P::B2, v[k2]);
-#else
-#pragma unroll
-            for (int k2 = 0; k2 < P::R2; ++k2) sink.put(f, p, bp + k2 * P::B2, v[k2]);
-#endif
-        }
+        for (int f = 0; f < 3; ++f) row_phase2_line<P>(sm, f, bp, p, sink);
     }
 }
 
@@ -392,19 +428,12 @@ OW_HD void row_phase2(const Smem& sm, int ft, int p, const Sink& sink) {
 OW_HD float2 pack_fwd(float4 r) { return make_float2(r.x - r.w, r.y + r.z); }   // P1 + i*P2
 OW_HD float2 pack_cnj(float4 r) { return make_float2(r.x + r.w, r.z - r.y); }   // conj(P1) + i*conj(P2)
 
-template <class P, class Smem, class Geom>
-OW_HD void col_phase0(const Smem& sm, int base, int j /* pair id in [0, M/2) */, const float2* __restrict__ src /* inter[c] + x */,
-                      const Geom& geom, bool discard_line = false /* this thread drops the 128-B lines it read (job 0 of a G=8 tile) */) {
+// Stage 0 of pair id j given its 2*H loaded rows: la[i] = row i*M + bA, lb[i] = row i*M + bB (bA = j, bB = M - j; j == 0: bB = M/2).
+template <class P, class Smem>
+OW_HD void col_phase0_math(const Smem& sm, int base, int j, const float4 (&la)[P::R0 / 2], const float4 (&lb)[P::R0 / 2]) {
     constexpr int N = P::N, R0 = P::R0, M = P::M, H = R0 / 2;
-    const size_t ss = geom.src_stride();
     const int bA = j, bB = (j == 0) ? M / 2 : M - j;
     float2 qa[R0], qb[R0];
-    float4 la[H], lb[H];
-#pragma unroll
-    for (int i = 0; i < H; ++i) {
-        la[i] = OW_LDG(reinterpret_cast<const float4*>(src + (size_t)(i * M + bA) * ss));
-        lb[i] = OW_LDG(reinterpret_cast<const float4*>(src + (size_t)(i * M + bB) * ss));
-    }
     if (j != 0) {
 #pragma unroll
         for (int i = 0; i < H; ++i) {
@@ -419,13 +448,6 @@ OW_HD void col_phase0(const Smem& sm, int base, int j /* pair id in [0, M/2) */,
 #pragma unroll
         for (int i = 0; i < H; ++i) { qb[i] = pack_fwd(lb[i]); qb[R0 - 1 - i] = pack_cnj(lb[i]); }   // v = i*M+M/2
     }
-    if (discard_line) {     // after the first use of the loaded values: every lane's piece of these lines has arrived
-#pragma unroll
-        for (int i = 0; i < H; ++i) {
-            OW_DISCARD_L2(src + (size_t)(i * M + bA) * ss);
-            OW_DISCARD_L2(src + (size_t)(i * M + bB) * ss);
-        }
-    }
     float2 tw[R0];
     twiddle_powers<R0>(unit_root(bA, N), tw);
     stage0_finish<P>(sm, base, bA, qa, tw);
@@ -437,6 +459,68 @@ OW_HD void col_phase0(const Smem& sm, int base, int j /* pair id in [0, M/2) */,
         twiddle_powers<R0>(unit_root(bB, N), tw);
     }
     stage0_finish<P>(sm, base, bB, qb, tw);
+}
+
+template <class P, class Smem, class Geom>
+OW_HD void col_phase0(const Smem& sm, int base, int j /* pair id in [0, M/2) */, const float2* __restrict__ src /* inter[c] + x */,
+                      const Geom& geom, bool discard_line = false /* this thread drops the 128-B lines it read (job 0 of a G=8 tile) */) {
+    constexpr int R0 = P::R0, M = P::M, H = R0 / 2;
+    const size_t ss = geom.src_stride();
+    const int bA = j, bB = (j == 0) ? M / 2 : M - j;
+    float4 la[H], lb[H];
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+        la[i] = OW_LDP(reinterpret_cast<const float4*>(src + (size_t)(i * M + bA) * ss));
+        lb[i] = OW_LDP(reinterpret_cast<const float4*>(src + (size_t)(i * M + bB) * ss));
+    }
+    if (discard_line) {     // only AFTER the loaded values exist in registers: then every lane's piece of these lines has arrived
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+            OW_USE_BEFORE(la[i].x, lb[i].x);
+            OW_DISCARD_L2(src + (size_t)(i * M + bA) * ss);
+            OW_DISCARD_L2(src + (size_t)(i * M + bB) * ss);
+        }
+    }
+    col_phase0_math<P>(sm, base, j, la, lb);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// TMA staging of a column tile (ow_col2_kernel). One STEP = the rows the T pair ids j = s*T + ft (ft < T) of every job need:
+// for each i < H a "forward" box of T consecutive rows starting at i*M + s*T (row of bA = j) and a "mirror" box of T consecutive
+// rows starting at i*M + M - s*T - T + 1 (row of bB = M - j sits at box row T-1-ft). Every box row is the tile's G column pairs =
+// G*16 contiguous bytes of one intermediate row, so a box is one 2-D TMA copy (T rows x G*16 B) and lands densely:
+//   staging[(2*i + which) * T + r][job]  (float4).       Lane order is job-fastest, so a warp's LDS.128 covers whole box rows.
+// The one row no box covers is i*M + M/2 (bB of j == 0, step 0): H extra rows behind the boxes, fetched by 1-D bulk copies.
+// (The mirror box of step 0 ends at row i*M + M, which nobody reads: for i = H-1 it belongs to the next channel or is out of bounds
+// and zero-filled.)
+// ---------------------------------------------------------------------------------------------------
+template <class P, int G>
+struct ColStage {
+    static constexpr int H = P::R0 / 2, T = P::T;
+    static constexpr int STEPS = (P::M / 2) / T;
+    static constexpr int BOX_F4 = T * G;                    // float4 elements per box
+    static constexpr int EXTRA_F4 = 2 * H * BOX_F4;         // offset of the H extra rows
+    static constexpr int TOTAL_F4 = EXTRA_F4 + H * G;
+    static constexpr size_t BYTES = (size_t)TOTAL_F4 * sizeof(float4);
+    static constexpr unsigned STEP_TX_BYTES = 2u * H * BOX_F4 * 16u;       // bytes the boxes of one step deliver
+    static constexpr unsigned EXTRA_TX_BYTES = (unsigned)H * G * 16u;      // + the extra rows (step 0 only)
+    static_assert((P::M / 2) % T == 0, "whole steps");
+    static OW_HD int fwd_row0(int i, int s) { return i * P::M + s * T; }
+    static OW_HD int mir_row0(int i, int s) { return i * P::M + P::M - s * T - T + 1; }
+    static OW_HD int extra_row(int i) { return i * P::M + P::M / 2; }
+};
+
+// The 2*H rows pair id j = s*T + ft of `job` needs, out of the staging buffer (then: col_phase0_math).
+template <class P, int G>
+OW_HD void col_stage_read(const float4* __restrict__ staging, int job, int ft, int s, float4 (&la)[P::R0 / 2], float4 (&lb)[P::R0 / 2]) {
+    using CS = ColStage<P, G>;
+    constexpr int H = CS::H, T = CS::T;
+    const int j = s * T + ft;
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+        la[i] = staging[((2 * i + 0) * T + ft) * G + job];
+        lb[i] = (j == 0) ? staging[CS::EXTRA_F4 + i * G + job] : staging[((2 * i + 1) * T + (T - 1 - ft)) * G + job];
+    }
 }
 
 template <class P, class Smem>
@@ -694,19 +778,19 @@ OW_HD NormalRowIn normal_row_load(const float* __restrict__ disp, const Geom& ge
     const int xl2 = (x0 - 2) & MSK, xl1 = (x0 - 1) & MSK, xr = (x0 + 4) & MSK;
     const float* r = disp + (size_t)rr * geom.row_stride();
     NormalRowIn in;
-    in.l = OW_LDG(reinterpret_cast<const float2*>(r + xl2));
-    in.m = OW_LDG(reinterpret_cast<const float4*>(r + x0));
-    in.e = OW_LDG(r + xr);
+    in.l = OW_LDP(reinterpret_cast<const float2*>(r + xl2));
+    in.m = OW_LDP(reinterpret_cast<const float4*>(r + x0));
+    in.e = OW_LDP(r + xr);
     in.a = in.b = make_float4(0.f, 0.f, 0.f, 0.f);
     in.al = in.ar = in.bl = in.br = 0.f;
     if (JAC && want_xz) {
         const float* rx = r + geom.plane_stride();
         const float* rz = r + 2 * geom.plane_stride();
-        in.a = OW_LDG(reinterpret_cast<const float4*>(rx + x0));
-        in.b = OW_LDG(reinterpret_cast<const float4*>(rz + x0));
+        in.a = OW_LDP(reinterpret_cast<const float4*>(rx + x0));
+        in.b = OW_LDP(reinterpret_cast<const float4*>(rz + x0));
         if (want_dd) {
-            in.al = OW_LDG(rx + xl1); in.ar = OW_LDG(rx + xr);
-            in.bl = OW_LDG(rz + xl1); in.br = OW_LDG(rz + xr);
+            in.al = OW_LDP(rx + xl1); in.ar = OW_LDP(rx + xr);
+            in.bl = OW_LDP(rz + xl1); in.br = OW_LDP(rz + xr);
         }
     }
     return in;
@@ -789,14 +873,16 @@ OW_HD void normal_quad_walk_src(const Src& src, int y0, float s, const Emit& emi
 }
 
 // ---------------------------------------------------------------------------------------------------
-// COLUMN KERNEL WITH THE NORMAL MAP AS ITS EPILOGUE (no Jacobian; tiles of G = 8 column pairs).
-// A dy tile carries one halo pair either side: jobs 0..7 = pairs 6t-1 .. 6t+6 (mod N/2), of which jobs 1..6 are the tile's
-// OUTPUT pairs (columns 12t .. 12t+11). After stage 2 every job's final heights are written back IN PLACE into its line
-// (row y = k0 + R0 k1 + R0 R1 k2 at addr(k0,k1,k2); .x = even column, .y = odd column), the tile syncs, and the same
-// sliding-window stencil as the stand-alone normal kernel runs out of shared memory: one thread per (column quad, RY rows),
-// lanes spread over the unit-stride digit k2 so that every LDS.64 phase is conflict-free. The heights never make the
-// round trip through L2/HBM, and the normal map's HBM writes overlap the FFT work of the other resident tiles.
-// Cost: 8 transformed pairs per 6 output pairs on the dy channel (+11 % column FFT work overall).
+// COLUMN KERNEL WITH THE NORMAL MAP AS ITS EPILOGUE (ow_col2_kernel; tiles of G = 8 column pairs = 16 columns).
+// After stage 2 a dy tile writes its final heights back IN PLACE into its lines (row y = k0 + R0 k1 + R0 R1 k2 at addr(k0,k1,k2);
+// .x = even column, .y = odd column), the tile syncs, and the same sliding-window stencil as the stand-alone normal kernel runs
+// out of shared memory for the three column quads whose 4x4 neighbourhoods lie inside the tile: columns c0+2 .. c0+13 (c0 = first
+// column of the tile; a quad at x0 needs columns x0-2 .. x0+4). One thread per (column quad, RY rows), lanes spread over the
+// unit-stride digit k2 so that every LDS.64 phase is conflict-free. Those heights never make the round trip through L2/HBM.
+// The fourth quad of every 16 columns, c0+14 .. c0+17, straddles two tiles: a SEAM. It is computed from global memory (L2) by
+// whichever of the two neighbouring tiles finishes LAST (an atomic counter per seam: no waiting, no ordering assumption between
+// CTAs), with the same walk on the same stored heights - so the image is bit-identical to the separate normal kernel's.
+// No column is transformed twice (the round-1 variant re-transformed 2 halo pairs per 6 output pairs).
 // ---------------------------------------------------------------------------------------------------
 template <class P, class Smem, class Geom>
 OW_HD void col_phase2_keep(const Smem& sm, int base, int ft, float* __restrict__ dst /* out[c] + x */, float scale, const Geom& geom, bool store) {
@@ -888,6 +974,109 @@ OW_HD void col_normals_phase(const Smem& sm, int tid, int nthreads, int SJ, int 
         if (j == 3 || x0 >= N) continue;                        // idle quad slot / wrapped duplicate pairs of the last tile
         const SmemRowSrc<P, Smem> src{sm, 2 * j * SJ, SJ};
         normal_quad_walk_src<N, RY, false>(src, LOW * k2 + RY * w, 0.f, EmitQuad{normal, (size_t)N, x0, c, LOW});
+    }
+}
+
+// Seam quad k of a slot: output columns cA+2, cA+3 (the last two of tile k) and cB, cB+1 (the first two of tile k+1, wrapping),
+// cA = 16k+12, cB = 16(k+1) mod N. The seven heights of a row are two aligned float4 loads from L2 (never L1: the neighbour tile
+// was written by another SM during this kernel).
+struct SeamRowSrc {
+    const float* dy;        // slot's dy plane [N][N]
+    size_t stride;
+    int cA, cB;
+    OW_HD NormalRowIn load(int rr, bool, bool) const {
+        const float* r = dy + (size_t)rr * stride;
+#ifdef __CUDA_ARCH__
+        const float4 A = __ldcg(reinterpret_cast<const float4*>(r + cA)), B = __ldcg(reinterpret_cast<const float4*>(r + cB));
+#else
+        const float4 A = *reinterpret_cast<const float4*>(r + cA), B = *reinterpret_cast<const float4*>(r + cB);
+#endif
+        NormalRowIn in;
+        in.l = make_float2(A.x, A.y); in.m = make_float4(A.z, A.w, B.x, B.y); in.e = B.z;
+        in.a = in.b = make_float4(0.f, 0.f, 0.f, 0.f);
+        in.al = in.ar = in.bl = in.br = 0.f;
+        return in;
+    }
+};
+
+struct EmitSeam {
+    float4* normal;         // slot base, [N][N]
+    size_t ostride;
+    int cA, cB;
+    OW_HD void operator()(int y, const float4 (&n)[4], float4) const {
+        float4* d = normal + (size_t)y * ostride;
+#ifdef __CUDA_ARCH__
+        __stcs(d + cA + 2, n[0]); __stcs(d + cA + 3, n[1]); __stcs(d + cB, n[2]); __stcs(d + cB + 1, n[3]);
+#else
+        d[cA + 2] = n[0]; d[cA + 3] = n[1]; d[cB] = n[2]; d[cB + 1] = n[3];
+#endif
+    }
+};
+
+// All N rows of seam k, RY rows per thread.
+template <int N, int RY>
+OW_HD void col_seam_phase(const float* __restrict__ dy, float4* __restrict__ normal, int k, int tid, int nthreads) {
+    const int cA = 16 * k + 12, cB = (16 * (k + 1)) & (N - 1);
+    const SeamRowSrc src{dy, (size_t)N, cA, cB};
+    const EmitSeam emit{normal, (size_t)N, cA, cB};
+#pragma unroll 1
+    for (int w = tid; w < N / RY; w += nthreads) normal_quad_walk_src<N, RY, false>(src, w * RY, 0.f, emit);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// JACOBIAN ALONE (extension) for frames whose normal map came out of the column kernel: the same expression, in the
+// same operation order, as the Jacobian that rides normal_quad_walk_src, so both paths give identical images. One thread owns four
+// adjacent columns and walks down RY rows; row r of Dx and Dz is loaded one iteration ahead of its use.
+//   J = (1 - s (Dx[y][x+1] - Dx[y][x-1])) (1 - s (Dz[y+1][x] - Dz[y-1][x])) - (s (Dx[y+1][x] - Dx[y-1][x])) (s (Dz[y][x+1] - Dz[y][x-1]))
+// ---------------------------------------------------------------------------------------------------
+struct JacRowIn {
+    float4 a, b;            // Dx[x0 .. x0+3], Dz[x0 .. x0+3]
+    float al, ar, bl, br;   // Dx[x0-1], Dx[x0+4], Dz[x0-1], Dz[x0+4]
+};
+
+template <class Geom>
+OW_HD JacRowIn jac_row_load(const float* __restrict__ disp, const Geom& geom, int x0, int rr, bool want_dd) {
+    const int MSK = geom.xmask();
+    const int xl1 = (x0 - 1) & MSK, xr = (x0 + 4) & MSK;
+    const float* rx = disp + (size_t)rr * geom.row_stride() + geom.plane_stride();
+    const float* rz = rx + geom.plane_stride();
+    JacRowIn in;
+    in.a = OW_LDP(reinterpret_cast<const float4*>(rx + x0));
+    in.b = OW_LDP(reinterpret_cast<const float4*>(rz + x0));
+    in.al = in.ar = in.bl = in.br = 0.f;
+    if (want_dd) {
+        in.al = OW_LDP(rx + xl1); in.ar = OW_LDP(rx + xr);
+        in.bl = OW_LDP(rz + xl1); in.br = OW_LDP(rz + xr);
+    }
+    return in;
+}
+
+template <int N, int RY, class Geom, class Emit>
+OW_HD void jac_quad_walk(const float* __restrict__ disp /* dy,dx,dz planes */, const Geom& geom, int x0, int y0, float s, const Emit& emit) {
+    constexpr int MSK = N - 1;
+    float xc_m1[4], xc_0[4], zc_m1[4], zc_0[4], ddx_0[4], ddz_0[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) xc_m1[j] = xc_0[j] = zc_m1[j] = zc_0[j] = ddx_0[j] = ddz_0[j] = 0.f;
+    JacRowIn nxt = jac_row_load(disp, geom, x0, (y0 - 1) & MSK, false);
+#pragma unroll
+    for (int i = -1; i <= RY; ++i) {              // row r = y0 + i ; emits output row r - 1 once i >= 1
+        const JacRowIn in = nxt;
+        if (i < RY) nxt = jac_row_load(disp, geom, x0, (y0 + i + 1) & MSK, i + 1 < RY);
+        const float4 a = in.a, b = in.b;
+        const float xc[4] = {a.x, a.y, a.z, a.w}, zc[4] = {b.x, b.y, b.z, b.w};
+        const float ddx[4] = {a.y - in.al, a.z - a.x, a.w - a.y, in.ar - a.z};
+        const float ddz[4] = {b.y - in.bl, b.z - b.x, b.w - b.y, in.br - b.z};
+        if (i >= 1) {
+            float J[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                J[j] = fmaf(-s, ddx_0[j], 1.0f) * fmaf(-s, zc[j] - zc_m1[j], 1.0f) - (s * (xc[j] - xc_m1[j])) * (s * ddz_0[j]);
+            emit(y0 + i - 1, make_float4(J[0], J[1], J[2], J[3]));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            xc_m1[j] = xc_0[j]; xc_0[j] = xc[j]; zc_m1[j] = zc_0[j]; zc_0[j] = zc[j]; ddx_0[j] = ddx[j]; ddz_0[j] = ddz[j];
+        }
     }
 }
 

@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = [
     "ow_step", "ow_step_multi", "ow_step_multi_timed", "ow_sync", "ow_get_outputs", "ow_download", "ow_download_frame_async",
     "ow_frame_bytes", "ow_set_group_size", "ow_set_streams", "ow_last_launch_count", "ow_gl_register", "ow_gl_step", "ow_gl_unregister",
     "ow_set_noise_seed", "ow_last_group_count", "ow_init_spectrum_cascade", "ow_set_graph", "ow_get_packed", "ow_packed_bytes",
-    "ow_download_packed_async", "ow_set_row_kernel", "ow_set_discard_intermediate", "ow_gl_register_packed",
+    "ow_download_packed_async", "ow_set_row_kernel", "ow_set_discard_intermediate", "ow_gl_register_packed", "ow_set_column_kernel", "ow_get_kernel_modes",
     "ow_slab_create", "ow_slab_destroy", "ow_slab_last_error", "ow_slab_get_info", "ow_slab_init_spectrum_seeded", "ow_slab_ipc_handle",
     "ow_slab_open_peers", "ow_slab_rows", "ow_slab_cols", "ow_slab_local_exchange", "ow_slab_sync", "ow_slab_download",
 ]
@@ -141,6 +141,8 @@ def load_library():
     L.ow_download_packed_async.argtypes = [vp, i32, vp, C.c_size_t, vp]
     L.ow_set_row_kernel.argtypes = [vp, i32]
     L.ow_set_discard_intermediate.argtypes = [vp, i32]
+    L.ow_set_column_kernel.argtypes = [vp, i32, i32]
+    L.ow_get_kernel_modes.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.ow_gl_register_packed.argtypes = [vp, u32, u32]
     L.ow_slab_create.argtypes = [i32, i32, i32, C.POINTER(_Params), i32, u32, C.POINTER(vp)]
     L.ow_slab_destroy.argtypes = [vp]
@@ -281,6 +283,14 @@ class FFTOceanWaves:
 
     def set_row_kernel(self, mode: int):
         self._check(self._lib.ow_set_row_kernel(self._h, int(mode)), "ow_set_row_kernel")
+
+    def set_column_kernel(self, mode: int, fused: int = -1):
+        self._check(self._lib.ow_set_column_kernel(self._h, int(mode), int(fused)), "ow_set_column_kernel")
+
+    def kernel_modes(self) -> dict:
+        r, k, f = C.c_int32(), C.c_int32(), C.c_int32()
+        self._check(self._lib.ow_get_kernel_modes(self._h, C.byref(r), C.byref(k), C.byref(f)), "ow_get_kernel_modes")
+        return {"row": r.value, "column": k.value, "fused": bool(f.value)}
 
     def set_discard_intermediate(self, on: bool):
         self._check(self._lib.ow_set_discard_intermediate(self._h, int(bool(on))), "ow_set_discard_intermediate")

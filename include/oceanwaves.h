@@ -51,8 +51,8 @@ typedef struct ow_params {
 #define OW_FLAG_FOUR_STEP 0x4u   /* N = 1024 / 2048 only: run the N = A*B line decomposition that N > 4096 uses (A = 4), for
                                     testing that code path against the direct kernels; slower, same results to round-off */
 
-#define OW_FLAG_FUSED_NORMALS 0x8u /* experimental (N <= 2048, no Jacobian): produce the normal map as the epilogue of the dy column
-                                      tiles instead of a separate kernel. Identical images; measured SLOWER on B200, so off by default */
+#define OW_FLAG_FUSED_NORMALS 0x8u /* N <= 2048: force the normal map to be produced as the epilogue of the dy column tiles (ow_col2_kernel)
+                                      instead of by a separate kernel, whatever the per-N default is. Identical images */
 
 /* Packed output set for the consumer, in ADDITION to the reference formats: per slot one `displacement`
  * image RGBA32F (OW_FLAG_PACKED_F32) or RGBA16F (OW_FLAG_PACKED_F16) = (dx, dy, dz, J), J = 1 without OW_FLAG_JACOBIAN, and one
@@ -166,10 +166,16 @@ int ow_set_streams(ow_ctx* ctx, int32_t n);
  * groups they formed (a group = the row, column[, normal] kernels of the slots that share launches). */
 int ow_last_launch_count(const ow_ctx* ctx);
 int ow_last_group_count(const ow_ctx* ctx);
-/* Tuning / A-B runs (per context; results do not depend on them): which row kernel runs (0 = the per-N default, 1 = one CTA
- * per row-pair group, 2 = the persistent software-pipelined kernel), and whether the column kernel drops the consumed
- * intermediate from L2 without writing it back (discard.global.L2). */
+/* Tuning / A-B runs (per context; results agree to fp32 round-off): which row kernel runs (0 = the per-N default, 1 = one CTA
+ * per row-pair group, 2 = persistent, next row prefetched into registers, 3 = persistent, next row staged by cp.async.bulk behind an
+ * mbarrier); which column kernel (0 = per-N default, 1 = ow_col_kernel, 2 = ow_col2_kernel with direct loads, 3 = ow_col2_kernel with
+ * TMA-staged tiles) and whether the normal map is its epilogue (fused: -1 = per-N default, 0 = separate normal kernel, 1 = fused;
+ * needs mode 2 or 3 and N <= 2048); and whether the column kernel drops the consumed intermediate from L2 without writing it back
+ * (discard.global.L2). */
 int ow_set_row_kernel(ow_ctx* ctx, int32_t mode);
+int ow_set_column_kernel(ow_ctx* ctx, int32_t mode, int32_t fused);
+/* The kernels this context will actually run (per-N defaults resolved): row 1..3, column 1..3, fused 0/1. */
+int ow_get_kernel_modes(ow_ctx* ctx, int32_t* row, int32_t* column, int32_t* fused);
 int ow_set_discard_intermediate(ow_ctx* ctx, int32_t on);
 
 /* ---- CUDA-GL interop: replaces the renderer's texture binds (src/main.cpp:477-487) ------------------- */

@@ -40,12 +40,12 @@ public:
     OceanSim& operator=(const OceanSim&) = delete;
     ~OceanSim() { destroy(); }
 
-    // = create_textures() for the sim resources. with_jacobian adds the foam map (extension).
-    bool create(int N, const Params& p, int device = 0, bool with_jacobian = false) {
+    // = create_textures() for the sim resources. with_jacobian adds the foam map (extension); extra_flags e.g. OW_FLAG_PACKED_F16.
+    bool create(int N, const Params& p, int device = 0, bool with_jacobian = false, uint32_t extra_flags = 0u) {
         destroy();
         n_ = N;
         const ow_params c = to_c(p);
-        const int rc = ow_create(N, 1, 1, &c, device, with_jacobian ? OW_FLAG_JACOBIAN : 0u, &ctx_);
+        const int rc = ow_create(N, 1, 1, &c, device, (with_jacobian ? OW_FLAG_JACOBIAN : 0u) | extra_flags, &ctx_);
         if (rc != OW_OK) { err_ = ow_last_error(nullptr); ctx_ = nullptr; return false; }
         return true;
     }
@@ -75,6 +75,10 @@ public:
     // = tilde_h0_t(); butterfly_fft(dy); butterfly_fft(dx); butterfly_fft(dz); generate_normal_map();
     // t replaces float(glfwGetTime()) (:599). Asynchronous on `stream` (cudaStream_t as void*, NULL = own stream).
     bool update(float t, void* stream = nullptr) { return ok(ow_step(ctx_, t, stream)); }
+    // The demo's clock: t = float(glfwGetTime()) (:599). time_scale / time_offset let the app slow, speed up, pause (scale 0) or
+    // scrub the sea without touching the sim (the reference has no such control; a GUI slider next to the ones at :348-358 would set them).
+    float time_scale = 1.0f, time_offset = 0.0f;
+    bool update_wall_clock(double wall_seconds, void* stream = nullptr) { return update(time_offset + time_scale * float(wall_seconds), stream); }
     bool sync(void* stream = nullptr) { return ok(ow_sync(ctx_, stream)); }
 
     // Device pointers (row-major [y][x], the layout of the reference's R32F / RGBA32F textures).
@@ -87,6 +91,13 @@ public:
     // CUDA-GL interop: ids of the app's own m_dy/m_dx/m_dz (R32F) and m_normal_map (RGBA32F) textures.
     bool gl_register(uint32_t dy, uint32_t dx, uint32_t dz, uint32_t normal) { return ok(ow_gl_register(ctx_, dy, dx, dz, normal)); }
     bool gl_update(float t) { return ok(ow_gl_step(ctx_, t)); }
+    // Packed set (context created with OW_FLAG_PACKED_F16 / _F32): the app's RGBA16F/RGBA32F displacement and RG16_SNORM normal textures.
+    bool gl_register_packed(uint32_t displacement, uint32_t normal_xz) { return ok(ow_gl_register_packed(ctx_, displacement, normal_xz)); }
+    ow_packed packed() {
+        ow_packed p{};
+        if (ctx_) ow_get_packed(ctx_, 0, &p);
+        return p;
+    }
 
     // Headless dump (tests, tools): which = OW_IMG_*.
     bool download(int which, void* host, size_t bytes) { return ok(ow_download(ctx_, 0, which, host, bytes, nullptr)); }

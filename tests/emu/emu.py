@@ -33,7 +33,7 @@ def lib():
         fp = C.POINTER(C.c_float)
         L.emu_frame.argtypes = [C.c_int, fp, fp, C.c_float, C.c_float, C.c_float, fp, fp, fp, fp, C.POINTER(C.c_long)]
         L.emu_dft.argtypes = [C.c_int, fp, fp]
-        L.emu_frame_fused.argtypes = [C.c_int, fp, fp, C.c_float, C.c_float, fp, fp, C.POINTER(C.c_long)]
+        L.emu_frame_fused.argtypes = [C.c_int, fp, fp, C.c_float, C.c_float, C.c_float, C.c_int, fp, fp, fp, C.POINTER(C.c_long)]
         L.emu_big_frame.argtypes = [C.c_int, C.c_int, fp, fp, C.c_float, C.c_float, C.c_float, fp, fp, fp]
         L.emu_slab_frame.argtypes = [C.c_int, C.c_int, fp, fp, C.c_float, C.c_float, C.c_float, fp, fp, fp]
         _lib = L
@@ -96,15 +96,19 @@ def big_frame(N, A, h0k, h0minusk, L, t, choppiness=1.0):
     return dict(dy=disp[0], dx=disp[1], dz=disp[2], normal=nm, jacobian=jac)
 
 
-def frame_fused(N, h0k, h0minusk, L, t):
-    """The frame without the Jacobian as the product runs it: normal map fused into the dy column tiles (ow_col_fused_kernel)."""
+def frame_fused(N, h0k, h0minusk, L, t, choppiness=1.0, staged=False):
+    """The frame through ow_col2_kernel's phases: normal map as the epilogue of the dy column tiles (interior quads out of shared
+    memory, seam quads from the stored heights), Jacobian from ow_jac_kernel's walk; staged=True feeds stage 0 from an emulated TMA
+    staging buffer."""
     a = np.ascontiguousarray(h0k, np.float32)
     b = np.ascontiguousarray(h0minusk, np.float32)
     disp = np.empty((3, N, N), np.float32)
     nm = np.full((N, N, 4), np.nan, np.float32)
+    jac = np.full((N, N), np.nan, np.float32)
     stats = np.zeros(14, np.int64)
-    rc = lib().emu_frame_fused(N, _p(a), _p(b), float(L), float(t), _p(disp), _p(nm), stats.ctypes.data_as(C.POINTER(C.c_long)))
+    rc = lib().emu_frame_fused(N, _p(a), _p(b), float(L), float(t), float(choppiness), int(bool(staged)), _p(disp), _p(nm), _p(jac),
+                               stats.ctypes.data_as(C.POINTER(C.c_long)))
     assert rc == 0, rc
-    out = dict(dy=disp[0], dx=disp[1], dz=disp[2], normal=nm)
+    out = dict(dy=disp[0], dx=disp[1], dz=disp[2], normal=nm, jacobian=jac)
     out["conflicts"] = {n: (int(stats[2 * i]), int(stats[2 * i + 1])) for i, n in enumerate(PHASES + ["col_normals"])}
     return out

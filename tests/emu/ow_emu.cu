@@ -162,37 +162,69 @@ int emu_frame_n(const float* h0k, const float* h0minusk, float L, float t, float
     return 0;
 }
 
-// ow_col_fused_kernel thread by thread: dy tiles of 6 output + 2 halo pairs with the normal map as their epilogue, ordinary
-// tiles for dx and dz. st.req/wf[3..5] = the three FFT phases of the dy tiles, stats6 = the stencil phase out of shared memory.
+// ow_col2_kernel thread by thread: 16-column tiles; dy tiles keep their heights in the lines and run the normal-map epilogue for
+// their three interior quads; the seam quads are walked afterwards from the stored heights (on the GPU: by the last of the two
+// neighbouring tiles to finish). staged = true routes stage 0 through a host copy of the TMA staging buffer, filled box by box the
+// way ow_col2_kernel's issue() asks the copy engine to (ColStage), so the box/row/extra-row algebra is checked here too.
+// st.req/wf[3..5] = the three FFT phases of the dy tiles, stats6 = the stencil phase out of shared memory, stats6[2..3] = the
+// staging reads of stage 0.
 template <int N>
-void emu_cols_fused(const float2* inter, float* disp, float4* normal, Stats& st, long* stats6) {
+void emu_cols2(const float2* inter, float* disp, float4* normal, bool staged, bool fuse, Stats& st, long* stats6) {
     using C = Cfg<N>;
     using P = typename C::Col;
-    constexpr int G = C::COL_G, NT = P::T * G, HP = N / 2, RY = C::NRM_RY;
+    constexpr int G = C::COL_G, NT_ = P::T * G, HP = N / 2, RY = C::NRM_RY, NTILES = N / (2 * G), H = P::R0 / 2;
     using LY = ColLayout<P, G>;
+    using CS = ColStage<P, G>;
     std::vector<float2> smem((size_t)G * LY::SJ);
+    std::vector<float4> staging(CS::TOTAL_F4);
     const float scale = 0.5f / ((float)N * (float)N);
     const FullColGeom<N> geom{};
     Recorder rec;
-    const int ndy = (HP + 5) / 6, nblk = ndy + 2 * (HP / G);
-    for (int blk = 0; blk < nblk; ++blk) {
-        const bool dy_tile = blk < ndy;
-        for (int phase = 0; phase < 4; ++phase) {
+    auto inter_row = [&](int f, long row, int tile, float4* dstrow) {     // G float4 = the tile's 16 columns of one intermediate row
+        const long total_rows = 3L * HP;
+        const long gr = (long)f * HP + row;
+        for (int g = 0; g < G; ++g) {
+            if (gr < 0 || gr >= total_rows) { dstrow[g] = make_float4(0, 0, 0, 0); continue; }           // TMA zero-fills out-of-bounds rows
+            const float2* p = inter + (size_t)gr * N + 2 * (tile * G + g);
+            dstrow[g] = make_float4(p[0].x, p[0].y, p[1].x, p[1].y);
+        }
+    };
+    for (int blk = 0; blk < 3 * NTILES; ++blk) {
+        const int f = blk / NTILES, tile = blk % NTILES;
+        const bool dy_tile = f == 0 && fuse;
+        // phase 0
+        if (staged) {
+            for (int s = 0; s < CS::STEPS; ++s) {
+                for (int i = 0; i < H; ++i)
+                    for (int r = 0; r < P::T; ++r) {
+                        inter_row(f, CS::fwd_row0(i, s) + r, tile, staging.data() + ((2 * i + 0) * P::T + r) * G);
+                        inter_row(f, CS::mir_row0(i, s) + r, tile, staging.data() + ((2 * i + 1) * P::T + r) * G);
+                    }
+                if (s == 0) for (int i = 0; i < H; ++i) inter_row(f, CS::extra_row(i), tile, staging.data() + CS::EXTRA_F4 + i * G);
+                rec.begin(NT_);
+                for (int tid = 0; tid < NT_; ++tid) {
+                    const int job = tid % G, ft = tid / G;
+                    const SmemEmu sm{smem.data(), &rec.seq[tid]};
+                    float4 la[H], lb[H];
+                    col_stage_read<P, G>(staging.data(), job, ft, s, la, lb);
+                    col_phase0_math<P>(sm, job * LY::SJ, s * P::T + ft, la, lb);
+                }
+                if (blk < 2) { rec.requests = rec.wavefronts = 0; rec.end(); st.req[3] += rec.requests; st.wf[3] += rec.wavefronts; }
+            }
+        }
+        for (int phase = staged ? 1 : 0; phase < 4; ++phase) {
             if (phase == 3 && !dy_tile) break;
-            rec.begin(NT);
-            for (int tid = 0; tid < NT; ++tid) {
+            rec.begin(NT_);
+            for (int tid = 0; tid < NT_; ++tid) {
                 const int job = tid % G, ft = tid / G, base = job * LY::SJ;
-                int f, pair;
-                bool store = true;
-                if (dy_tile) { f = 0; pair = (6 * blk - 1 + job) & (HP - 1); store = job >= 1 && job <= 6 && 6 * blk + job - 1 < HP; }
-                else { const int r = blk - ndy; f = 1 + r / (HP / G); pair = (r % (HP / G)) * G + job; }
+                const int pair = tile * G + job;
                 const SmemEmu sm{smem.data(), &rec.seq[tid]};
                 const float2* src = inter + (size_t)f * HP * N + 2 * pair;
                 float* dst = disp + (size_t)f * N * N + 2 * pair;
                 if (phase == 0) for (int j = ft; j < P::M / 2; j += P::T) col_phase0<P>(sm, base, j, src, geom);
                 if (phase == 1) col_phase1<P>(sm, base, ft);
-                if (phase == 2) { if (dy_tile) col_phase2_keep<P>(sm, base, ft, dst, scale, geom, store); else col_phase2<P>(sm, base, ft, dst, scale, geom); }
-                if (phase == 3) col_normals_phase<P, RY>(sm, tid, NT, LY::SJ, 12 * blk, normal);
+                if (phase == 2) { if (dy_tile) col_phase2_keep<P>(sm, base, ft, dst, scale, geom, true); else col_phase2<P>(sm, base, ft, dst, scale, geom); }
+                if (phase == 3) col_normals_phase<P, RY>(sm, tid, NT_, LY::SJ, 16 * tile + 2, normal);
             }
             if (blk < 2) {
                 rec.requests = rec.wavefronts = 0; rec.end();
@@ -201,10 +233,14 @@ void emu_cols_fused(const float2* inter, float* disp, float4* normal, Stats& st,
             }
         }
     }
+    if (fuse)
+        for (int k = 0; k < NTILES; ++k)
+            for (int tid = 0; tid < NT_; ++tid) col_seam_phase<N, 4>(disp, normal, k, tid, NT_);
 }
 
 template <int N>
-int emu_frame_fused_n(const float* h0k, const float* h0minusk, float L, float t, float* disp, float* normal, long* stats) {
+int emu_frame_fused_n(const float* h0k, const float* h0minusk, float L, float t, float lambda, int staged, float* disp, float* normal, float* jac,
+                      long* stats) {
     std::vector<float4> h0((size_t)N * N), hp, nyq;
     for (size_t i = 0; i < (size_t)N * N; ++i) h0[i] = make_float4(h0k[2 * i], h0k[2 * i + 1], h0minusk[2 * i], h0minusk[2 * i + 1]);
     fold_full<N>(h0, hp, nyq);
@@ -215,7 +251,14 @@ int emu_frame_fused_n(const float* h0k, const float* h0minusk, float L, float t,
     Stats st;
     long s6[2] = {0, 0};
     emu_rows<N>(FullRows<N>{h0.data(), hp.data(), nyq.data()}, ktab.data(), t, FullSink<N>{inter.data()}, 0, N / 2, st);
-    emu_cols_fused<N>(inter.data(), disp, reinterpret_cast<float4*>(normal), st, s6);
+    emu_cols2<N>(inter.data(), disp, reinterpret_cast<float4*>(normal), staged != 0, true, st, s6);
+    if (jac) {       // ow_jac_kernel: the Jacobian alone, from the stored dx/dz planes
+        const float s = lambda * ((float)N / (2.0f * L));
+        for (int y0 = 0; y0 < N; y0 += 8)
+            for (int x0 = 0; x0 < N; x0 += 4)
+                jac_quad_walk<N, 8>(disp, FullNrmGeom<N>{}, x0, y0, s,
+                                    [&](int y, float4 J) { *reinterpret_cast<float4*>(jac + (size_t)y * N + x0) = J; });
+    }
     if (stats) { for (int i = 0; i < 6; ++i) { stats[2 * i] = st.req[i]; stats[2 * i + 1] = st.wf[i]; } stats[12] = s6[0]; stats[13] = s6[1]; }
     return 0;
 }
@@ -357,12 +400,13 @@ int emu_big_frame_n(const float* h0k, const float* h0minusk, float L, float t, f
     return 0;
 }
 
-extern "C" int emu_frame_fused(int N, const float* h0k, const float* h0minusk, float L, float t, float* disp, float* normal, long* stats) {
+extern "C" int emu_frame_fused(int N, const float* h0k, const float* h0minusk, float L, float t, float lambda, int staged, float* disp,
+                               float* normal, float* jac, long* stats) {
     switch (N) {
-        case 256: return emu_frame_fused_n<256>(h0k, h0minusk, L, t, disp, normal, stats);
-        case 512: return emu_frame_fused_n<512>(h0k, h0minusk, L, t, disp, normal, stats);
-        case 1024: return emu_frame_fused_n<1024>(h0k, h0minusk, L, t, disp, normal, stats);
-        case 2048: return emu_frame_fused_n<2048>(h0k, h0minusk, L, t, disp, normal, stats);
+        case 256: return emu_frame_fused_n<256>(h0k, h0minusk, L, t, lambda, staged, disp, normal, jac, stats);
+        case 512: return emu_frame_fused_n<512>(h0k, h0minusk, L, t, lambda, staged, disp, normal, jac, stats);
+        case 1024: return emu_frame_fused_n<1024>(h0k, h0minusk, L, t, lambda, staged, disp, normal, jac, stats);
+        case 2048: return emu_frame_fused_n<2048>(h0k, h0minusk, L, t, lambda, staged, disp, normal, jac, stats);
     }
     return -1;
 }

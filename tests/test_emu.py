@@ -99,17 +99,25 @@ def test_emulated_line_decomposition_matches_oracle_and_direct_kernels(noise, N,
     assert np.abs(big["jacobian"] - ref["jacobian"]).max() < 1e-4
 
 
-@pytest.mark.parametrize("N", [256, 512, 1024])
-def test_emulated_fused_column_normal_kernel_equals_separate_kernels(noise, N):
-    """Frames without the Jacobian run the normal map as the epilogue of the dy column tiles (6 output pairs + 2 halo pairs per
-    tile, heights kept in the tile's shared-memory lines). Same stencil code, same inputs: the result must be bit-identical to
-    the column kernel + stand-alone normal kernel, every texel written exactly once, and the stencil's LDS phases conflict-free."""
-    s = OracleSim(N, 1000.0, 40.0, (1.0, 1.0), 2.0, 0.1, noise, threads=4)
-    a, b = s.h0()
+@pytest.mark.parametrize("N,staged", [(256, False), (256, True), (512, True), (1024, False), (1024, True), (2048, True)])
+def test_emulated_fused_column_normal_kernel_equals_separate_kernels(noise, N, staged):
+    """ow_col2_kernel: the normal map as the epilogue of the dy column tiles (three interior quads per 16-column tile out of the tile's
+    shared-memory lines, the seam quad between two tiles from the stored heights), the Jacobian from its own walk, and - staged - stage 0
+    fed from the TMA staging buffer (box layout of ColStage, incl. the extra row of pair id 0 and the zero-filled out-of-bounds row).
+    Same stencil code on the same heights: bit-identical to the column kernel + stand-alone normal kernel, every texel written, and
+    every shared-memory phase conflict-free."""
+    if N == 2048:
+        rngn = np.random.default_rng(2048).integers(0, 256, (4, N, N), dtype=np.uint8)
+        ak, bk = R.h0_fields(N, 1000.0, 40.0, (1, 1), 2.0, 0.1, rngn)
+        a = np.stack([ak.real, ak.imag], -1).astype(np.float32)
+        b = np.stack([bk.real, bk.imag], -1).astype(np.float32)
+    else:
+        s = OracleSim(N, 1000.0, 40.0, (1.0, 1.0), 2.0, 0.1, noise, threads=4)
+        a, b = s.h0()
     sep = emu.frame(N, a, b, 1000.0, 1.0, 1.0)
-    fused = emu.frame_fused(N, a, b, 1000.0, 1.0)
-    assert not np.isnan(fused["normal"]).any()
-    for k in ("dy", "dx", "dz", "normal"):
+    fused = emu.frame_fused(N, a, b, 1000.0, 1.0, 1.0, staged=staged)
+    assert not np.isnan(fused["normal"]).any() and not np.isnan(fused["jacobian"]).any()
+    for k in ("dy", "dx", "dz", "normal", "jacobian"):
         assert np.array_equal(fused[k], sep[k]), k
     for phase, (req, wf) in fused["conflicts"].items():
         assert req > 0 and wf == req, f"{phase}: {wf} wavefronts for {req} requests (bank conflicts)"

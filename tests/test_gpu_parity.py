@@ -277,18 +277,19 @@ def test_set_params_requires_reinit(noise):
 
 @pytest.mark.parametrize("N", [256, 512, 1024, 2048])
 def test_fused_normal_epilogue_equals_separate_normal_kernel(noise, N):
-    """OW_FLAG_FUSED_NORMALS (experimental): the normal map out of the column kernel's dy tiles (ow_col_fused_kernel) instead of
-    the stand-alone normal kernel. Same stencil on the same heights: identical displacement and normal images, every texel written."""
+    """OW_FLAG_FUSED_NORMALS: the normal map out of the column kernel's dy tiles (ow_col2_kernel: interior quads from shared memory,
+    seam quads by the last-arriving neighbour tile) instead of the stand-alone normal kernel. Same column kernel, same stencil on the
+    same heights: identical displacement and normal images, every texel written."""
     with fow.FFTOceanWaves(N=N, cascades=[params()]) as sim:
         sim.init(noise)
+        sim.set_column_kernel(3, 0)          # the same column kernel, normal map by the separate kernel
         sep = sim.frame(2.0)
         assert sim.last_launch_count() == 3
     with fow.FFTOceanWaves(N=N, cascades=[params()], fused_normals=True) as sim:
         sim.init(noise)
-        lib = fow.load_library()
         sim.update(0.0)                      # fill the normal buffer with another frame first: stale texels would show
         fused = sim.frame(2.0)
-        assert sim.last_launch_count() == 2
+        assert sim.last_launch_count() == 3          # row, column + interior normals, seam quads
     for k in ("dy", "dx", "dz", "normal"):
         assert np.array_equal(fused[k], sep[k]), k
     check_frame(fused, oracle_for(N, noise).frame(2.0), f"fused N={N} ")

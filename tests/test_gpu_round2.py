@@ -198,3 +198,66 @@ def test_n16384_random_spectrum_vs_fp64_dft_of_sampled_lines():
         Tx = np.zeros_like(col[k]); Tx[pos, :] = col[k]
         cols = np.real(np.fft.ifft(Tx, axis=0)) / N
         assert np.abs(got[k][:, xs] - cols).max() <= 1e-4 * peak, (k, "columns")
+
+
+@pytest.mark.parametrize("N", [256, 512, 1024, 2048])
+def test_row_and_column_kernel_variants_agree(noise, N):
+    """Every row kernel (1 = CTA per row-pair group, 2 = persistent + register prefetch, 3 = persistent + cp.async.bulk/mbarrier staging)
+    with every column kernel (1 = ow_col_kernel, 2 = ow_col2_kernel direct loads, 3 = ow_col2_kernel TMA-staged), normal map fused
+    into the column kernel or not. All of them must sit inside the parity tolerance of the oracle; variants differ only by fp32 round-off
+    (2e-6 of peak); and for a FIXED (row, column) pair the fused normal map (interior quads out of shared memory + seams by the last
+    arriving tile) must be bit-identical to the separate normal kernel's, the Jacobian (ow_jac_kernel) within round-off."""
+    t = 2.0
+    ref = OracleSim(N, 1000.0, 40.0, (1.0, 1.0), 2.0, 0.1, noise, threads=8).frame(np.float32(t), choppiness=1.0)
+    with fow.FFTOceanWaves(N=N, cascades=[params()], jacobian=True, n_slots=5) as sim:
+        sim.init(noise)
+        base = None
+        for rm in (1, 2, 3):
+            sim.set_row_kernel(rm)
+            for cm in (1, 2, 3):
+                sim.set_column_kernel(cm, 0)
+                sep = sim.frame(t)
+                assert sim.last_launch_count() == 3
+                for k in ("dy", "dx", "dz"):
+                    peak = float(np.abs(ref[k]).max())
+                    assert np.abs(sep[k] - ref[k]).max() <= 1e-4 * peak, (rm, cm, k)
+                    if base is not None:
+                        assert np.abs(sep[k] - base[k]).max() <= 2e-6 * peak, (rm, cm, k)
+                assert np.abs(sep["normal"] - ref["normal"]).max() < 1e-4 and np.abs(sep["jacobian"] - ref["jacobian"]).max() < 1e-4
+                base = base or sep
+                if cm == 1:
+                    continue
+                sim.set_column_kernel(cm, 1)
+                sim.update(0.0)                      # another frame first: stale texels / seam counters would show
+                fused = sim.frame(t)
+                assert sim.last_launch_count() == 4  # row, column(+ interior normals), seam quads, Jacobian
+                for k in ("dy", "dx", "dz", "normal"):
+                    assert np.array_equal(fused[k], sep[k]), (rm, cm, k)
+                assert np.abs(fused["jacobian"] - sep["jacobian"]).max() <= 2e-6, (rm, cm)
+        # several slots per launch, twice in a row (persistent loops over many tiles; seam counters re-armed between frames)
+        sim.set_row_kernel(3)
+        sim.set_column_kernel(3, 1)
+        times = [0.0, 0.5, 2.0, 9.98, 2.0]
+        for _ in range(2):
+            sim.update_multi([0] * 5, times)
+            sim.sync()
+            assert np.array_equal(sim.download("dy", 2), sim.download("dy", 4))
+            assert np.array_equal(sim.download("normal", 2), sim.download("normal", 4))
+            assert np.abs(sim.download("dy", 2) - ref["dy"]).max() <= 1e-4 * np.abs(ref["dy"]).max()
+            assert np.abs(sim.download("normal", 4) - ref["normal"]).max() < 1e-4
+
+
+def test_fused_normals_without_jacobian(noise):
+    with fow.FFTOceanWaves(N=512, cascades=[params()]) as sim:
+        sim.init(noise)
+        sim.set_column_kernel(1, 0)
+        sep = sim.frame(1.0)
+        sim.set_column_kernel(3, 1)
+        fused = sim.frame(1.0)
+        assert sim.last_launch_count() == 3 and sim.kernel_modes() == {"row": sim.kernel_modes()["row"], "column": 3, "fused": True}
+        sim.set_graph(False)
+        fused2 = sim.frame(1.0)
+    for k in ("dy", "dx", "dz"):
+        assert np.abs(fused[k] - sep[k]).max() <= 2e-6 * np.abs(sep[k]).max()
+        assert np.array_equal(fused[k], fused2[k])
+    assert np.abs(fused["normal"] - sep["normal"]).max() < 2e-6 and np.array_equal(fused["normal"], fused2["normal"])
