@@ -55,6 +55,12 @@ struct ow_ctx {
     alignas(64) unsigned char inter_tmap[128];   // CUtensorMap over d_inter (64 bytes used) for the TMA-staged column kernel
     bool have_tmap = false;
     int discard_inter = 0;        // ow_set_discard_intermediate
+    // L2 residency of the folded spectrum: a time sweep re-reads the same cascade's block every frame, so when all blocks together fit the
+    // device's persisting-L2 carve-out the launch streams carry an access-policy window over d_hp (ow_set_l2_persist). OFF by default: measured on B200 at N = 2048 the carve-out costs the streaming data more than the spectrum's hits save (profiles/r02_l2_persist_ab.txt)
+    int l2_persist = 0;
+    bool l2_window_on = false;
+    cudaStream_t l2_user_stream = nullptr;   // last caller stream the window was applied to
+    int cap_row = 0, cap_col = 0; // ow_set_resident_ctas: CTAs per SM of the persistent row / column kernels (0 = what fits)
     // ow_step (slot i <- cascade i at ONE time t) as a CUDA graph: [exact sincos, fast sincos]; rebuilt when a tuning knob changes
     bool graph_enabled = true;
     std::unique_ptr<GraphPlan> plan[2];
@@ -126,10 +132,45 @@ FrameBuffers buffers(const ow_ctx* c) {
     fb.col2_ctas[0] = c->kcfg.col2_ctas[0]; fb.col2_ctas[1] = c->kcfg.col2_ctas[1];
     fb.sm_count = c->kcfg.sm_count;
     fb.row_pipe_ctas[0] = c->kcfg.row_pipe_ctas[0]; fb.row_pipe_ctas[1] = c->kcfg.row_pipe_ctas[1];
+    for (int i = 0; i < 2; ++i) {
+        if (c->cap_row > 0) { fb.row_pipe_ctas[i] = std::min(fb.row_pipe_ctas[i], c->cap_row); fb.row_bulk_ctas[i] = std::min(fb.row_bulk_ctas[i], c->cap_row); }
+        if (c->cap_col > 0) fb.col2_ctas[i] = std::min(fb.col2_ctas[i], c->cap_col);
+    }
+    fb.col_pipe_ctas = c->cap_col > 0 ? std::min(c->kcfg.col_pipe_ctas, c->cap_col) : c->kcfg.col_pipe_ctas;
     return fb;
 }
 
 void drop_plans(ow_ctx* c) { c->plan[0].reset(); c->plan[1].reset(); }
+
+size_t hp_bytes(const ow_ctx* c) { return hp_block_elems(c->N / 2, c->N) * c->n_cascades * sizeof(float4); }
+
+// Access-policy window over the folded spectrum on one stream (hits persist in the L2 carve-out, everything else streams).
+void apply_l2_window(ow_ctx* c, cudaStream_t st, bool on) {
+    cudaStreamAttrValue v{};
+    v.accessPolicyWindow.base_ptr = on ? static_cast<void*>(c->d_hp) : nullptr;
+    v.accessPolicyWindow.num_bytes = on ? hp_bytes(c) : 0;
+    v.accessPolicyWindow.hitRatio = on ? 1.0f : 0.0f;
+    v.accessPolicyWindow.hitProp = on ? cudaAccessPropertyPersisting : cudaAccessPropertyNormal;
+    v.accessPolicyWindow.missProp = on ? cudaAccessPropertyStreaming : cudaAccessPropertyNormal;
+    if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();   // a hint: never fatal
+}
+
+// (Re)decides whether the window is used and applies it to the context's own streams.
+void configure_l2(ow_ctx* c) {
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c->device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
+    const size_t bytes = hp_bytes(c);
+    // automatic: only when every cascade's block fits at once and leaves at least a third of the carve-out's budget to the streaming data
+    bool on = c->l2_persist > 0 || (c->l2_persist < 0 && bytes <= (size_t)max_persist * 2 / 3);
+    if (bytes > (size_t)max_persist || bytes > (size_t)max_window) on = false;
+    if (on && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes) != cudaSuccess) { cudaGetLastError(); on = false; }
+    if (!on && c->l2_window_on) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0); cudaGetLastError(); }    // give the carve-out back
+    c->l2_window_on = on;
+    c->l2_user_stream = nullptr;
+    apply_l2_window(c, c->stream, on);
+    for (auto& s : c->aux) apply_l2_window(c, s, on);
+}
 
 bool all_ready(const ow_ctx* c) {
     for (char r : c->h0_ready) if (!r) return false;
@@ -154,7 +195,8 @@ int pick_group(const ow_ctx* c, int count) {
     } else {
         // small grids: a launch has to be long enough to amortise its ramp-up and tail (measured at N=512: 11 frames per
         // group 301 k fps, 21 per group 326 k fps), so the budget is larger there
-        gmax = (int)((c->N <= 512 ? 400.0e6 : 100.0e6) / (12.0 * c->N * (double)c->N));
+        // ... and at N = 2048 three frames per launch beat one (17.8 k vs 17.2 k frames/s: the row kernel's 2.3 waves of CTAs per frame)
+        gmax = (int)((c->N <= 512 ? 400.0e6 : c->N >= 2048 ? 160.0e6 : 100.0e6) / (12.0 * c->N * (double)c->N));
         if (gmax < 1) gmax = 1;
     }
     if (gmax > kMaxGroup) gmax = kMaxGroup;
@@ -221,14 +263,16 @@ int ow_create(int32_t N, int32_t n_cascades, int32_t n_slots, const ow_params* c
     OW_TRY(cudaSetDevice(device));
     OW_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int i = 0; i < ow_ctx::kMaxAux; ++i) {
+        // (graded priorities on these streams, so that the chains of one call run staggered instead of in phase, were measured and are
+        // slower: C2 336 k vs 362 k frames/s, C4 75 k vs 80 k - profiles/r02_experiments.md)
         OW_TRY(cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
         OW_TRY(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
     }
     OW_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     OW_TRY(cudaMalloc(&c->d_h0, nn * n_cascades * sizeof(float4)));
-    OW_TRY(cudaMalloc(&c->d_hp, nn / 2 * n_cascades * sizeof(float4)));
+    OW_TRY(cudaMalloc(&c->d_hp, hp_block_elems(N / 2, N) * n_cascades * sizeof(float4)));   // per cascade: [N/2][N] float4 (+ [N/2][N] float2, N <= 512)
     OW_TRY(cudaMalloc(&c->d_nyq, (size_t)(N / 2) * n_cascades * sizeof(float4)));
-    OW_TRY(cudaMemsetAsync(c->d_hp, 0, nn / 2 * n_cascades * sizeof(float4), c->stream));
+    OW_TRY(cudaMemsetAsync(c->d_hp, 0, hp_block_elems(N / 2, N) * n_cascades * sizeof(float4), c->stream));
     OW_TRY(cudaMemsetAsync(c->d_nyq, 0, (size_t)(N / 2) * n_cascades * sizeof(float4), c->stream));
     OW_TRY(cudaMalloc(&c->d_ktab, (size_t)N * n_cascades * sizeof(float)));
     OW_TRY(cudaMalloc(&c->d_casc, n_cascades * sizeof(CascadeDev)));
@@ -248,6 +292,7 @@ int ow_create(int32_t N, int32_t n_cascades, int32_t n_slots, const ow_params* c
     OW_TRY(cudaMalloc(&c->d_seam, (size_t)n_slots * (N / 16) * sizeof(int)));
     OW_TRY(cudaMemsetAsync(c->d_seam, 0, (size_t)n_slots * (N / 16) * sizeof(int), c->stream));
     OW_TRY(configure_frame_kernels(N, &c->kcfg));
+    configure_l2(c);
     c->have_tmap = make_inter_tensor_map(c->inter_tmap, c->d_inter, N, n_slots);
 #undef OW_TRY
     *out = c;
@@ -333,7 +378,7 @@ static int init_range(ow_ctx* c, int lo, int hi, const char* who) {
         OW_CUDA(c, launch_ktab(c->d_ktab + (size_t)i * c->N, c->N, c->params[i].L, c->stream));
         OW_CUDA(c, launch_h0(c->d_h0 + (size_t)i * nn, c->d_noise + (size_t)i * 4 * plane, c->noise_w, c->noise_h, c->N,
                              c->casc_host[i], c->stream));
-        OW_CUDA(c, launch_fold(c->d_h0 + (size_t)i * nn, c->d_hp + (size_t)i * (nn / 2), c->d_nyq + (size_t)i * (c->N / 2), c->N, c->stream));
+        OW_CUDA(c, launch_fold(c->d_h0 + (size_t)i * nn, c->d_hp + (size_t)i * hp_block_elems(c->N / 2, c->N), c->d_nyq + (size_t)i * (c->N / 2), c->d_ktab + (size_t)i * c->N, c->N, c->stream));
     }
     for (int i = 0; i < c->n_cascades; ++i) c->casc_host[i] = to_dev(c->params[i]);
     OW_CUDA(c, cudaMemcpyAsync(c->d_casc, c->casc_host.data(), c->n_cascades * sizeof(CascadeDev), cudaMemcpyHostToDevice, c->stream));
@@ -362,9 +407,10 @@ int ow_set_h0(ow_ctx* c, int32_t cascade, const float* h0k, const float* h0minus
     OW_CUDA(c, cudaMemcpyAsync(c->d_tmp, h0k, nn * 2 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     OW_CUDA(c, cudaMemcpyAsync(c->d_tmp + nn * 2, h0minusk, nn * 2 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     OW_CUDA(c, launch_merge_h0(c->d_h0 + (size_t)cascade * nn, c->d_tmp, c->d_tmp + nn * 2, (int)nn, c->stream));
-    OW_CUDA(c, launch_fold(c->d_h0 + (size_t)cascade * nn, c->d_hp + (size_t)cascade * (nn / 2), c->d_nyq + (size_t)cascade * (c->N / 2), c->N, c->stream));
     // this cascade's k table and the cascade constants follow the CURRENT parameters (h0 itself is the caller's)
     OW_CUDA(c, launch_ktab(c->d_ktab + (size_t)cascade * c->N, c->N, c->params[cascade].L, c->stream));
+    OW_CUDA(c, launch_fold(c->d_h0 + (size_t)cascade * nn, c->d_hp + (size_t)cascade * hp_block_elems(c->N / 2, c->N), c->d_nyq + (size_t)cascade * (c->N / 2),
+                           c->d_ktab + (size_t)cascade * c->N, c->N, c->stream));
     for (int i = 0; i < c->n_cascades; ++i) c->casc_host[i] = to_dev(c->params[i]);
     OW_CUDA(c, cudaMemcpyAsync(c->d_casc, c->casc_host.data(), c->n_cascades * sizeof(CascadeDev), cudaMemcpyHostToDevice, c->stream));
     OW_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -398,6 +444,10 @@ static int step_impl(ow_ctx* c, int32_t count, const int32_t* cascade_of_slot, c
     }
     OW_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = pick(c, stream);
+    if (c->l2_window_on && st != c->stream && st != c->l2_user_stream) {      // a caller-owned stream: give it the window once
+        apply_l2_window(c, st, true);
+        c->l2_user_stream = st;
+    }
     const FrameBuffers fb = buffers(c);
     const int group = pick_group(c, count);
     int launches = 0;
@@ -536,8 +586,8 @@ int ow_set_row_kernel(ow_ctx* c, int32_t mode) {
 
 int ow_set_column_kernel(ow_ctx* c, int32_t mode, int32_t fused) {
     if (!c) return OW_ERR_INVALID;
-    if (mode < 0 || mode > 3 || fused < -1 || fused > 1)
-        return fail(c, OW_ERR_INVALID, "ow_set_column_kernel: mode in 0..3 (0 = per-N default, 1 = ow_col_kernel, 2 = ow_col2_kernel, 3 = ow_col2_kernel TMA-staged), fused in -1..1");
+    if (mode < 0 || mode > 4 || fused < -1 || fused > 1)
+        return fail(c, OW_ERR_INVALID, "ow_set_column_kernel: mode in 0..4 (0 = per-N default, 1 = ow_col_kernel, 2 = ow_col2_kernel, 3 = ow_col2_kernel TMA-staged, 4 = ow_col_pipe_kernel), fused in -1..1");
     c->col_mode = mode;
     c->fuse_mode = fused;
     drop_plans(c);
@@ -549,6 +599,23 @@ int ow_get_kernel_modes(ow_ctx* c, int32_t* row, int32_t* column, int32_t* fused
     int r, k, f;
     effective_modes(buffers(c), &r, &k, &f);
     *row = r; *column = k; *fused = f;
+    return OW_OK;
+}
+
+int ow_set_resident_ctas(ow_ctx* c, int32_t row_per_sm, int32_t col_per_sm) {
+    if (!c || row_per_sm < 0 || col_per_sm < 0) return OW_ERR_INVALID;
+    c->cap_row = row_per_sm;
+    c->cap_col = col_per_sm;
+    drop_plans(c);
+    return OW_OK;
+}
+
+int ow_set_l2_persist(ow_ctx* c, int32_t mode) {
+    if (!c || mode < -1 || mode > 1) return OW_ERR_INVALID;
+    OW_CUDA(c, cudaSetDevice(c->device));
+    if (c->l2_user_stream) apply_l2_window(c, c->l2_user_stream, false);
+    c->l2_persist = mode;
+    configure_l2(c);
     return OW_OK;
 }
 

@@ -59,7 +59,7 @@ struct Big {
         const int cascade = tab.cascade[0], slot = tab.slot[0];
         const size_t nn = (size_t)N * N;
         if (ev) cudaEventRecord(ev[0], st);
-        const FullRows<N> rows{fb.h0 + (size_t)cascade * nn, fb.hp + (size_t)cascade * (nn / 2), fb.nyq + (size_t)cascade * (N / 2)};
+        const FullRows<N> rows{fb.h0 + (size_t)cascade * nn, fb.hp + (size_t)cascade * hp_block_f4(N / 2, N), fb.nyq + (size_t)cascade * (N / 2)};
         float2* inter = fb.inter + (size_t)slot * 3 * (nn / 2);
         rows_pass(rows, fb.ktab + (size_t)cascade * N, 0, N / 2, tab.time[0], fast, fb.scratch, FullSink<N>{inter}, st);
         if (ev) cudaEventRecord(ev[1], st);

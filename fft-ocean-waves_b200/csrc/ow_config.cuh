@@ -11,7 +11,9 @@ namespace ow {
 // 3 = persistent kernel with bulk-async staging (ow_row_bulk_kernel); chosen per N from whole-frame throughput (bench.py
 // --row-kernel; profiles/r02*), where a variant that wins in isolation does not always win.
 // COL_FUSE: ow_col2_kernel (16-column tiles, optional TMA staging, normal map as the epilogue of the dy tiles) is available for
-// this N (needs COL_G == 8). COL_MODE: 1 = ow_col_kernel, 2 = ow_col2_kernel with direct loads, 3 = ow_col2_kernel TMA-staged.
+// this N (needs COL_G == 8). COL_MODE: 1 = ow_col_kernel, 2 = ow_col2_kernel with direct loads, 3 = ow_col2_kernel TMA-staged,
+// 4 = ow_col_pipe_kernel (persistent, register-pipelined loads).
+// COLP_MINB: resident CTAs per SM the register allocation of ow_col_pipe_kernel (COL_MODE 4) aims at.
 // COL_FUSED: the normal map comes out of the column kernel (no separate normal kernel) by default.
 // Normal kernel: NRM_RY output rows per thread walk, NRM_WARPS warps per CTA, NRM_MINB resident CTAs per SM.
 // Column plans interleave G jobs in the lane index, need S0 odd and a job stride == 16/G (mod 16).
@@ -23,6 +25,9 @@ namespace ow {
 #define OW_C2MB_1024 1
 #endif
 // A/B knobs of tools/ variant builds (build.py -D... --tag=...): N = 512 row-pair groups per CTA / padding, column and normal kernel residency
+#ifndef OW_COLP_1024
+#define OW_COLP_1024 1    // resident ow_col_pipe_kernel CTAs per SM at N = 1024 (2 forces 64 registers: spills)
+#endif
 #ifndef OW_COLMB_512
 #define OW_COLMB_512 2
 #endif
@@ -49,6 +54,7 @@ struct Cfg<256> {
     using Col = Plan<256, 4, 4, 16, 32, 0, 1>;
     static constexpr int COL_G = 8, COL_MINB = 2;
     static constexpr int COL2_MINB = OW_C2MB_SMALL;
+    static constexpr int COLP_MINB = 2;
     static constexpr bool COL_FUSE = true;
     static constexpr int COL_MODE = 1;
     static constexpr bool COL_FUSED = false;
@@ -62,6 +68,7 @@ struct Cfg<512> {
     using Col = Plan<512, 8, 4, 16, 32, 0, 1>;
     static constexpr int COL_G = 8, COL_MINB = OW_COLMB_512;
     static constexpr int COL2_MINB = OW_C2MB_SMALL;
+    static constexpr int COLP_MINB = 2;
     static constexpr bool COL_FUSE = true;
     static constexpr int COL_MODE = 1;
     static constexpr bool COL_FUSED = false;
@@ -75,6 +82,7 @@ struct Cfg<1024> {
     using Col = Plan<1024, 8, 8, 16, 64, 0, 1>;
     static constexpr int COL_G = 8, COL_MINB = 2;
     static constexpr int COL2_MINB = OW_C2MB_1024;
+    static constexpr int COLP_MINB = OW_COLP_1024;
     static constexpr bool COL_FUSE = true;
     static constexpr int COL_MODE = 1;
     static constexpr bool COL_FUSED = false;
@@ -88,8 +96,9 @@ struct Cfg<2048> {
     using Col = Plan<2048, 8, 16, 16, 64, 0, 1>;
     static constexpr int COL_G = 8, COL_MINB = 1;
     static constexpr int COL2_MINB = 1;
+    static constexpr int COLP_MINB = 1;
     static constexpr bool COL_FUSE = true;
-    static constexpr int COL_MODE = 1;
+    static constexpr int COL_MODE = 4;
     static constexpr bool COL_FUSED = false;
     static constexpr int NRM_RY = 8, NRM_WARPS = 4, NRM_MINB = 4;
 };
@@ -101,6 +110,7 @@ struct Cfg<4096> {
     using Col = Plan<4096, 16, 16, 16, 128, 0, 1>;
     static constexpr int COL_G = 4, COL_MINB = 1;
     static constexpr int COL2_MINB = 1;
+    static constexpr int COLP_MINB = 1;
     static constexpr bool COL_FUSE = false;
     static constexpr int COL_MODE = 1;
     static constexpr bool COL_FUSED = false;

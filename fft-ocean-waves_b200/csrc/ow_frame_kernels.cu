@@ -33,6 +33,12 @@ cudaError_t configure_n(KernelConfig* cfg) {
     if ((e = opt_in_smem(ow_row_slab_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true>, rs)) != cudaSuccess) return e;
     if ((e = opt_in_smem(ow_col_kernel<K, C::COL_G, C::COL_MINB>, cs)) != cudaSuccess) return e;
     if ((e = opt_in_smem(ow_col_slab_kernel<K, C::COL_G, C::COL_MINB>, cs)) != cudaSuccess) return e;
+    if ((e = opt_in_smem(ow_col_pipe_kernel<K, C::COL_G, C::COLP_MINB>, cs)) != cudaSuccess) return e;
+    {
+        int n = 0;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ow_col_pipe_kernel<K, C::COL_G, C::COLP_MINB>, K::T * C::COL_G, cs)) != cudaSuccess) return e;
+        cfg->col_pipe_ctas = n > 0 ? n : 1;
+    }
     constexpr size_t rbs = row_bulk_smem<R, C::ROW_PAIRS>();
     if ((e = opt_in_smem(ow_row_bulk_kernel<R, C::ROW_PAIRS, C::ROW_MINB, false>, rbs)) != cudaSuccess) return e;
     if ((e = opt_in_smem(ow_row_bulk_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true>, rbs)) != cudaSuccess) return e;
@@ -136,12 +142,16 @@ int launch_n(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_
     // ---- column IFFT + inversion (+ normal map as its epilogue) ----------------------------------------------------------
     const float scale = 0.5f / ((float)N * (float)N);   // 1/2 from the Hermitian split, 1/N^2 from inversion_cs.glsl:36
     int col_mode = fb.col_mode ? fb.col_mode : C::COL_MODE;
-    if (!C::COL_FUSE) col_mode = 1;
+    if (!C::COL_FUSE && col_mode != 4) col_mode = 1;
     if (col_mode == 3 && !fb.inter_tmap) col_mode = 2;
     bool fused = false;
     int launches = 1;
+    if (col_mode == 4) {
+        const int total = 3 * (N / (2 * C::COL_G)) * count, resident = fb.sm_count * fb.col_pipe_ctas;
+        L(ow_col_pipe_kernel<K, C::COL_G, C::COLP_MINB>, total < resident ? total : resident, K::T * C::COL_G, cs, fb, tab, scale, total);
+    }
     if constexpr (C::COL_FUSE) {
-        if (col_mode != 1) {
+        if (col_mode == 2 || col_mode == 3) {
             fused = fb.fuse_mode < 0 ? C::COL_FUSED : fb.fuse_mode != 0;
             const int total = 3 * (N / (2 * C::COL_G)) * count;
             if (col_mode == 3) {
@@ -204,6 +214,8 @@ bool make_inter_tensor_map(void* out, const float2* inter, int N, int n_slots) {
                                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
+
+size_t hp_block_elems(int npairs, int N) { return hp_block_f4(npairs, N); }
 
 bool frame_supported(int N) { return N == 256 || N == 512 || N == 1024 || N == 2048 || N == 4096 || big_supported(N, false); }
 
@@ -275,10 +287,10 @@ void modes_n(const FrameBuffers& fb, int* row, int* col, int* fused) {
     using C = Cfg<N>;
     *row = fb.row_mode ? fb.row_mode : C::ROW_MODE;
     int cm = fb.col_mode ? fb.col_mode : C::COL_MODE;
-    if (!C::COL_FUSE) cm = 1;
+    if (!C::COL_FUSE && cm != 4) cm = 1;
     if (cm == 3 && !fb.inter_tmap) cm = 2;
     *col = cm;
-    *fused = cm == 1 ? 0 : (fb.fuse_mode < 0 ? (C::COL_FUSED ? 1 : 0) : (fb.fuse_mode != 0 ? 1 : 0));
+    *fused = (cm == 1 || cm == 4) ? 0 : (fb.fuse_mode < 0 ? (C::COL_FUSED ? 1 : 0) : (fb.fuse_mode != 0 ? 1 : 0));
 }
 
 // The kernels launch_frame will actually use for this context (per-N defaults resolved; the line decomposition has its own).

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(P::T* PAIRS, MINB) ow_row_kernel(FrameBuffers 
     const float t = tab.time[e];
     const int slot = tab.slot[e];
     const SmemDirect sm{smem + (size_t)g * 3 * P::LINE};
-    const FullRows<N> rows{fb.h0 + (size_t)cascade * N * N, fb.hp + (size_t)cascade * (N / 2) * N, fb.nyq + (size_t)cascade * (N / 2)};
+    const FullRows<N> rows{fb.h0 + (size_t)cascade * N * N, fb.hp + (size_t)cascade * hp_block_f4(N / 2, N), fb.nyq + (size_t)cascade * (N / 2)};
     const float* ktab = fb.ktab + (size_t)cascade * N;
     float2* inter = fb.inter + (size_t)slot * 3 * (N / 2) * N;
     OW_STAMP(blockIdx.x, 0); OW_STAMP(blockIdx.x, 1);
@@ -76,6 +76,7 @@ template <int N>
 struct RowItem {
     FullRows<N> rows;
     const float4* prow;   // folded pair row of this item
+    const float2* wrow;   // its (w, 1/|k|) row
     const float* ktab;
     float2* inter;
     float t;
@@ -95,8 +96,9 @@ __global__ void __launch_bounds__(P::T* PAIRS, MINB) ow_row_pipe_kernel(FrameBuf
         RowItem<N> it;
         it.p = item - e * HP;
         const int cascade = tab.cascade[e];
-        it.rows = FullRows<N>{fb.h0 + (size_t)cascade * N * N, fb.hp + (size_t)cascade * HP * N, fb.nyq + (size_t)cascade * HP};
+        it.rows = FullRows<N>{fb.h0 + (size_t)cascade * N * N, fb.hp + (size_t)cascade * hp_block_f4(HP, N), fb.nyq + (size_t)cascade * HP};
         it.prow = it.rows.pair_row(it.p);
+        it.wrow = it.rows.wk_row(it.p);
         it.ktab = fb.ktab + (size_t)cascade * N;
         it.inter = fb.inter + (size_t)tab.slot[e] * 3 * HP * N;
         it.t = tab.time[e];
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(P::T* PAIRS, MINB) ow_row_pipe_kernel(FrameBuf
     auto issue = [&](const RowItem<N>& it, int c, FoldedPair (&fp)[R0]) {
         const int b = ft + P::T * c;
 #pragma unroll
-        for (int d0 = 0; d0 < R0; ++d0) fp[d0] = load_folded(it.prow, it.ktab, d0 * P::M + b);
+        for (int d0 = 0; d0 < R0; ++d0) fp[d0] = load_folded<kUseWk<N>>(it.prow, it.wrow, it.ktab, d0 * P::M + b);
     };
 
     FoldedPair nxt[R0];
@@ -129,7 +131,7 @@ __global__ void __launch_bounds__(P::T* PAIRS, MINB) ow_row_pipe_kernel(FrameBuf
                 float2 vy[R0], vx[R0], vz[R0];
 #pragma unroll
                 for (int d0 = 0; d0 < R0; ++d0) {
-                    const Sym3 s = spectrum_folded<FAST>(nxt[d0], ky, cur.t, (d0 == 0 && b == 0) ? cur.rows.nyq_of(cur.p) : nullptr);
+                    const Sym3 s = spectrum_folded<FAST, kUseWk<N>>(nxt[d0], ky, cur.t, (d0 == 0 && b == 0) ? cur.rows.nyq_of(cur.p) : nullptr);
                     vy[d0] = s.y; vx[d0] = s.x; vz[d0] = s.z;
                 }
                 if (c + 1 < C0) issue(cur, c + 1, nxt);                       // next batch of this pair
@@ -189,8 +191,9 @@ __global__ void __launch_bounds__(P::T* PAIRS, MINB) ow_row_bulk_kernel(FrameBuf
         RowItem<N> it;
         it.p = item - e * HP;
         const int cascade = tab.cascade[e];
-        it.rows = FullRows<N>{fb.h0 + (size_t)cascade * N * N, fb.hp + (size_t)cascade * HP * N, fb.nyq + (size_t)cascade * HP};
+        it.rows = FullRows<N>{fb.h0 + (size_t)cascade * N * N, fb.hp + (size_t)cascade * hp_block_f4(HP, N), fb.nyq + (size_t)cascade * HP};
         it.prow = it.rows.pair_row(it.p);
+        it.wrow = it.rows.wk_row(it.p);
         it.ktab = fb.ktab + (size_t)cascade * N;
         it.inter = fb.inter + (size_t)tab.slot[e] * 3 * HP * N;
         it.t = tab.time[e];
@@ -230,11 +233,12 @@ __global__ void __launch_bounds__(P::T* PAIRS, MINB) ow_row_bulk_kernel(FrameBuf
 #pragma unroll
                 for (int d0 = 0; d0 < R0; ++d0) {
                     fp[d0].f = stg[d0 * P::M + b];
+                    fp[d0].wk = kUseWk<N> ? OW_LDG(cur.wrow + d0 * P::M + b) : make_float2(0.f, 0.f);
                     fp[d0].kx = OW_LDG(cur.ktab + d0 * P::M + b);
                 }
 #pragma unroll
                 for (int d0 = 0; d0 < R0; ++d0) {
-                    const Sym3 s = spectrum_folded<FAST>(fp[d0], ky, cur.t, (d0 == 0 && b == 0) ? cur.rows.nyq_of(cur.p) : nullptr);
+                    const Sym3 s = spectrum_folded<FAST, kUseWk<N>>(fp[d0], ky, cur.t, (d0 == 0 && b == 0) ? cur.rows.nyq_of(cur.p) : nullptr);
                     vy[d0] = s.y; vx[d0] = s.x; vz[d0] = s.z;
                 }
                 float2 tw[R0];
@@ -286,12 +290,91 @@ __global__ void __launch_bounds__(P::T* G, MINB) ow_col_kernel(FrameBuffers fb, 
     const FullColGeom<N> geom{};
     // a G=8 tile reads whole 128-byte lines of the intermediate (8 jobs x 16 B): job 0 drops them from L2 after use
     const bool discard = (G == 8) && job == 0 && fb.discard_inter;
+#ifdef OW_TRACE
+    const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+#endif
+    OW_STAMP(cta, 0); OW_STAMP(cta, 1);
 #pragma unroll 1
     for (int j = ft; j < P::M / 2; j += P::T) col_phase0<P>(sm, base, j, src, geom, discard);
+    OW_STAMP(cta, 2);
     __syncthreads();
+    OW_STAMP(cta, 3);
     col_phase1<P>(sm, base, ft);
+    OW_STAMP(cta, 4);
     __syncthreads();
+    OW_STAMP(cta, 5);
     col_phase2<P>(sm, base, ft, dst, scale, geom);
+    OW_STAMP(cta, 6);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Persistent, register-pipelined column kernel. The per-CTA timeline of ow_col_kernel (tools/tune/trace.cu, N = 2048:
+// profiles/r02_col_cta_timeline.txt) shows a tile spending 45 % of its life in phase 0, most of it waiting for its global loads
+// with nothing else in flight, and another 10 % between CTAs: a CTA cannot retire (and its successor cannot start) until its
+// stores have drained. Here a CTA walks over many (slot entry, channel, 16-column tile) items and always has the FIRST load batch
+// of its NEXT tile in flight in registers: it is issued as soon as stage 0 of the current tile has consumed the registers and
+// lands during stages 1 and 2; the remaining batches of a tile (N = 2048: one more) are issued at the top of phase 0, before
+// the first batch is transformed. Stores drain while the next tile's stage 0 runs.
+// ---------------------------------------------------------------------------------------------------
+template <class P, int G, int MINB>
+__global__ void __launch_bounds__(P::T* G, MINB) ow_col_pipe_kernel(FrameBuffers fb, SlotTable tab, float scale, int total) {
+    extern __shared__ __align__(16) float2 smem[];
+    constexpr int N = P::N, HP = N / 2, NT = N / (2 * G), TPF = 3 * NT, H = P::R0 / 2, M = P::M;
+    constexpr int C0 = (M / 2) / P::T;
+    static_assert((M / 2) % P::T == 0 && C0 >= 1, "whole stage-0 batches");
+    using LY = ColLayout<P, G>;
+    const int job = threadIdx.x % G, ft = threadIdx.x / G;
+    const SmemDirect sm{smem};
+    const int base = job * LY::SJ;
+    const FullColGeom<N> geom{};
+    int w = blockIdx.x;
+    if (w >= total) return;
+
+    auto src_of = [&](int wi) {
+        const int e = wi / TPF, r = wi - e * TPF, f = r / NT, tile = r - f * NT;
+        return fb.inter + ((size_t)tab.slot[e] * 3 + f) * HP * N + 2 * (tile * G + job);
+    };
+    auto issue = [&](const float2* src, int j, float4 (&la)[H], float4 (&lb)[H]) {
+        const int bA = j, bB = (j == 0) ? M / 2 : M - j;
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+            la[i] = OW_LDP(reinterpret_cast<const float4*>(src + (size_t)(i * M + bA) * N));
+            lb[i] = OW_LDP(reinterpret_cast<const float4*>(src + (size_t)(i * M + bB) * N));
+        }
+    };
+
+    float4 na[H], nb[H];                       // batch 0 of the tile about to be transformed
+    const float2* src = src_of(w);
+    issue(src, ft, na, nb);
+    for (; w < total; w += gridDim.x) {
+        const int e = w / TPF, r = w - e * TPF, f = r / NT, tile = r - f * NT;
+        float* dst = fb.disp + ((size_t)tab.slot[e] * 3 + f) * N * N + 2 * (tile * G + job);
+        const int wn = w + gridDim.x;
+        if (C0 == 1) {
+            col_phase0_math<P>(sm, base, ft, na, nb);
+        } else {
+            float4 la[H], lb[H];
+#pragma unroll
+            for (int i = 0; i < H; ++i) { la[i] = na[i]; lb[i] = nb[i]; }
+#pragma unroll
+            for (int c = 1; c < C0; ++c) {
+                issue(src, ft + c * P::T, na, nb);                 // batch c in flight while batch c-1 is transformed
+                col_phase0_math<P>(sm, base, ft + (c - 1) * P::T, la, lb);
+#pragma unroll
+                for (int i = 0; i < H; ++i) { la[i] = na[i]; lb[i] = nb[i]; }
+            }
+            col_phase0_math<P>(sm, base, ft + (C0 - 1) * P::T, la, lb);
+        }
+        if (wn < total) {
+            src = src_of(wn);
+            issue(src, ft, na, nb);                                // lands during stages 1 and 2
+        }
+        __syncthreads();
+        col_phase1<P>(sm, base, ft);
+        __syncthreads();
+        col_phase2<P>(sm, base, ft, dst, scale, geom);
+        __syncthreads();                                           // the next tile's stage-0 stores reuse the lines
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -27,7 +27,7 @@ struct SlotTable {
 struct FrameBuffers {
     int N;
     const float4* h0;      // [cascade][N][N]   (h0k.re, h0k.im, h0minusk.re, h0minusk.im)
-    const float4* hp;      // [cascade][N/2][N] folded texel pairs (fold_pair in ow_kernels.cuh); what the row kernel streams
+    const float4* hp;      // [cascade] blocks of [N/2][N] float4 folded texel pairs (fold_pair) + [N/2][N] float2 (w, 1/|k|): what the row kernel streams
     const float4* nyq;     // [cascade][N/2]    Nyquist-column extras (fold_pair_nyq)
     const float* ktab;     // [cascade][N]      k(i) = 2*pi*(i - N/2)/L, computed with the shader's operation order
     const CascadeDev* casc;
@@ -40,7 +40,8 @@ struct FrameBuffers {
     int four_step;         // force the N = A*B line decomposition (ow_big_kernels.cu) on a grid the direct kernels could do
     int row_mode;          // 0 = the per-N choice Cfg<N>::ROW_MODE, 1 = one CTA per ROW_PAIRS row pairs, 2 = persistent register-pipelined kernel,
                            // 3 = persistent kernel with bulk-async (cp.async.bulk + mbarrier) staging of the spectrum rows (ow_set_row_kernel)
-    int col_mode;          // 0 = the per-N choice Cfg<N>::COL_MODE, 1 = ow_col_kernel, 2 = ow_col2_kernel with direct loads, 3 = ow_col2_kernel with TMA staging
+    int col_mode;          // 0 = the per-N choice Cfg<N>::COL_MODE, 1 = ow_col_kernel, 2 = ow_col2_kernel with direct loads, 3 = ow_col2_kernel with TMA staging,
+                           // 4 = ow_col_pipe_kernel (persistent, next tile's first load batch in flight in registers)
     int fuse_mode;         // -1 = the per-N choice Cfg<N>::COL_FUSED, 0 = separate normal kernel, 1 = normal map as the column kernel's epilogue (col_mode 2/3)
     int* seam;             // [slot][N/16] arrival counters of the seams between neighbouring dy tiles (fused normal map), all zero between launches
     const void* inter_tmap;   // host pointer to the CUtensorMap over `inter` ([n_slots*3*N/2 rows][2N floats], box = 32 floats x T rows), or nullptr
@@ -48,6 +49,7 @@ struct FrameBuffers {
     int row_pipe_ctas[2];  // resident CTAs per SM of the persistent row kernels on that device: [exact sincos, fast sincos]
     int row_bulk_ctas[2];
     int col2_ctas[2];      // resident CTAs per SM of ow_col2_kernel: [direct loads, TMA staged]
+    int col_pipe_ctas;     // resident CTAs per SM of ow_col_pipe_kernel
 };
 
 // What configure_frame_kernels found out about the device the calling context lives on (kept per context: no process-global state).
@@ -56,6 +58,7 @@ struct KernelConfig {
     int row_pipe_ctas[2] = {1, 1};
     int row_bulk_ctas[2] = {1, 1};     // ow_row_bulk_kernel, [exact, fast]
     int col2_ctas[2] = {1, 1};         // ow_col2_kernel, [direct loads, TMA staged]
+    int col_pipe_ctas = 1;             // ow_col_pipe_kernel
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -131,6 +134,8 @@ private:
     static SlotTable* pick_tab(T*, SlotTable* cur) { return cur; }
 };
 
+// float4 elements of one block of folded pair rows (npairs rows of N texels): hp_block_f4 in ow_kernels.cuh
+size_t hp_block_elems(int npairs, int N);
 bool frame_supported(int N);            // direct kernels (N <= 4096) or the N = A*B decomposition (8192 .. 32768)
 // N = A*B line decomposition (ow_big_kernels.cu). forced: the test-only mapping of N = 1024 / 2048 onto it.
 bool big_supported(int N, bool forced);
@@ -203,8 +208,9 @@ cudaError_t launch_h0(float4* h0, const uint8_t* noise, int noise_w, int noise_h
                       cudaStream_t st);
 // Fold h0 into the per-pair coefficients the row kernel streams. Full grid: pair p uses rows p and N-p of h0[N][N];
 // slab: local rows pl and PL+pl of h0_loc[2*PL][N] (first_pair = rank*PL; pair 0 is skipped in both).
-cudaError_t launch_fold(const float4* h0, float4* hp, float4* nyq, int N, cudaStream_t st);
-cudaError_t launch_fold_slab(const float4* h0_loc, float4* hp_loc, float4* nyq_loc, int N, int first_pair, int PL, cudaStream_t st);
+// hp / hp_loc are blocks of hp_block_f4(npairs, N) float4: the fold coefficients, then (w, 1/|k|) per pair texel (ktab: this cascade's k table).
+cudaError_t launch_fold(const float4* h0, float4* hp, float4* nyq, const float* ktab, int N, cudaStream_t st);
+cudaError_t launch_fold_slab(const float4* h0_loc, float4* hp_loc, float4* nyq_loc, const float* ktab, int N, int first_pair, int PL, cudaStream_t st);
 cudaError_t launch_split_h0(const float4* h0, float* h0k, float* h0minusk, int n, cudaStream_t st);
 cudaError_t launch_merge_h0(float4* h0, const float* h0k, const float* h0minusk, int n, cudaStream_t st);
 

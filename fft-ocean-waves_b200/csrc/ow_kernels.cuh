@@ -128,13 +128,26 @@ constexpr int kHalo = 8;          // halo columns either side of a column slab (
                                   // 16-column CTA tiles and float4 alignment)
 constexpr int kMaxWorld = 8;
 
+// A block of folded pair rows is [npairs][N] float4 (fold_pair), followed - for N <= 512 - by [npairs][N] float2 (w, 1/|k|): the
+// dispersion w = sqrt(g |k|) and 1/|k| of the pair's texel depend on the grid only, so they are tabulated at init (ow_fold_kernel, with
+// the shader's operation order) instead of being re-derived through two IEEE square roots per texel per frame. Measured on B200: +4 %
+// frames/s at N = 512 (a time sweep keeps the cascade's block L2-resident); at N = 1024 neutral in a 64-cascade step and -4 % in an
+// 8-cascade one (every block is read once per step, from DRAM), at N = 2048 slower: the table's extra 4 B/texel come from DRAM every
+// frame and cost more than they save (the frame is DRAM-bound there). So grids above 512 have no table and their kernels
+// re-derive (w, 1/|k|) in registers: w with the same operations (bit-identical), 1/|k| through the fast reciprocal (1 ulp).
+OW_HD bool use_wk(int N) { return N <= 512; }
+template <int N>
+constexpr bool kUseWk = (N <= 512);
+OW_HD size_t hp_block_f4(int npairs, int N) { return (size_t)npairs * N * (use_wk(N) ? 3 : 2) / 2; }    // float4 elements of a block
+
 template <int N>
 struct FullRows {
     const float4* h0;     // [N][N]    full initial spectrum (pair 0 and downloads)
-    const float4* hp;     // [N/2][N]  folded pairs, row p (row 0 unused)
+    const float4* hp;     // [N/2][N]  folded pairs, row p (row 0 unused), then [N/2][N] float2 (w, 1/|k|)
     const float4* nyq;    // [N/2]     Nyquist-column extras
     OW_HD const float4* row(int v) const { return h0 + (size_t)v * N; }
     OW_HD const float4* pair_row(int p) const { return hp + (size_t)p * N; }
+    OW_HD const float2* wk_row(int p) const { return reinterpret_cast<const float2*>(hp + (size_t)(N / 2) * N) + (size_t)p * N; }
     OW_HD const float4* nyq_of(int p) const { return nyq + p; }
 };
 
@@ -147,9 +160,10 @@ struct FullSink {
 template <int N>
 struct SlabRows {
     const float4* h0;   // [2*PL][N]
-    const float4* hp;   // [PL][N]   folded pairs of this rank (local pair index p - p0)
+    const float4* hp;   // [PL][N]   folded pairs of this rank (local pair index p - p0), then [PL][N] float2 (w, 1/|k|)
     const float4* nyq;  // [PL]
     int p0, PL;
+    OW_HD const float2* wk_row(int p) const { return reinterpret_cast<const float2*>(hp + (size_t)PL * N) + (size_t)(p - p0) * N; }
     OW_HD int local(int v) const { return (v < N / 2 ? v : PL + ((N - v) & (N / 2 - 1))) - p0; }
     OW_HD const float4* row(int v) const { return h0 + (size_t)local(v) * N; }
     OW_HD const float4* pair_row(int p) const { return hp + (size_t)(p - p0) * N; }
@@ -228,38 +242,52 @@ OW_HD float4 fold_pair_nyq(float4 A, float4 B) {
     return make_float4(((A.x + A.z) - B.x) - B.z, ((A.w - A.y) - B.w) + B.y, ((A.x - A.z) + B.x) - B.z, ((A.y + A.w) + B.y) + B.w);
 }
 
-// Folded texel pair as loaded: f at (u, p), k_x at u. g (Nyquist column only) is loaded by the one thread that owns u = 0.
+// Folded texel pair as loaded: f and (w, 1/|k|) at (u, p), k_x at u. g (Nyquist column only) is loaded by the one thread that owns u = 0.
 struct FoldedPair {
     float4 f;
+    float2 wk;
     float kx;
 };
 
-OW_HD FoldedPair load_folded(const float4* __restrict__ prow, const float* __restrict__ ktab, int u) {
+template <bool WK = true>
+OW_HD FoldedPair load_folded(const float4* __restrict__ prow, const float2* __restrict__ wrow, const float* __restrict__ ktab, int u) {
     FoldedPair fp;
 #if OW_ABLATE & 1
-    fp.f = make_float4(u * 1e-3f, 1e-3f, u * 2e-3f, 1.0f); fp.kx = (u - 512) * 6.28e-3f;
+    fp.f = make_float4(u * 1e-3f, 1e-3f, u * 2e-3f, 1.0f); fp.kx = (u - 512) * 6.28e-3f; fp.wk = make_float2(1.0f + u * 1e-3f, 0.5f);
     return fp;
 #endif
     fp.f = OW_LDG(prow + u);
+    fp.wk = WK ? OW_LDG(wrow + u) : make_float2(0.f, 0.f);
     fp.kx = OW_LDG(ktab + u);
     return fp;
 }
 
-template <bool FAST>
-OW_HD Sym3 spectrum_folded(const FoldedPair& fp, float ky, float t, const float4* __restrict__ nyq_g /* non-null iff u == 0 */) {
-    const float kx = fp.kx;
-    // tilde_h0_t_cs.glsl:74-79 — same operation order as the shader so w*t matches to the bit.
+// (w, 1/|k|) of the texel (kx, ky): tilde_h0_t_cs.glsl:74-79 with the shader's operation order (the init kernels are compiled
+// without FMA contraction), so w*t in the row kernel matches the oracle's to the bit.
+OW_HD float2 dispersion_of(float kx, float ky) {
     float km = OW_SQRT(OW_ADD(OW_MUL(kx, kx), OW_MUL(ky, ky)));
     if (km < 0.00001f) km = 0.00001f;
-    const float w = OW_SQRT(OW_MUL(kGravity, km));
+    return make_float2(OW_SQRT(OW_MUL(kGravity, km)), 1.0f / km);
+}
+OW_HD float2 dispersion_fast(float kx, float ky) {      // in-kernel variant: same w, 1/|k| through the fast reciprocal
+    float km = OW_SQRT(OW_ADD(OW_MUL(kx, kx), OW_MUL(ky, ky)));
+    if (km < 0.00001f) km = 0.00001f;
+    return make_float2(OW_SQRT(OW_MUL(kGravity, km)), OW_RCP(km));
+}
+
+template <bool FAST, bool WK = true>
+OW_HD Sym3 spectrum_folded(const FoldedPair& fp, float ky, float t, const float4* __restrict__ nyq_g /* non-null iff u == 0 */) {
+    const float kx = fp.kx;
+    // tilde_h0_t_cs.glsl:74-79: tabulated at init (WK), or re-derived here with the same operation order - bit-identical either way
+    const float2 wk = WK ? fp.wk : dispersion_fast(kx, ky);
+    const float w = wk.x, ik = wk.y;
     float s, c;
 #if OW_ABLATE & 2
-    s = w * t; c = 1.0f - s; km = 1.0f + kx;
+    s = w * t; c = 1.0f - s;
 #else
     phase_sincos<FAST>(OW_MUL(w, t), &s, &c);                       // :96-97
 #endif
     const float4 f = fp.f;
-    const float ik = OW_RCP(km);
     const float rx = kx * ik, rz = ky * ik;
     Sym3 o;
     o.y = make_float2(f.x * c + f.y * s, f.z * s + f.w * c);
@@ -324,6 +352,7 @@ OW_HD void row_phase0(const Smem& sm, int ft, int p, const Rows& rows, const flo
     }
     const float ky = OW_LDG(ktab + p);
     const float4* prow = rows.pair_row(p);
+    const float2* wrow = rows.wk_row(p);
 #pragma unroll 1
     for (int c = 0; c < P::C0; ++c) {
         const int b = ft + P::T * c;
@@ -331,10 +360,10 @@ OW_HD void row_phase0(const Smem& sm, int ft, int p, const Rows& rows, const flo
         float2 vy[R0], vx[R0], vz[R0];
         FoldedPair fp[R0];
 #pragma unroll
-        for (int d0 = 0; d0 < R0; ++d0) fp[d0] = load_folded(prow, ktab, d0 * P::M + b);
+        for (int d0 = 0; d0 < R0; ++d0) fp[d0] = load_folded<kUseWk<N>>(prow, wrow, ktab, d0 * P::M + b);
 #pragma unroll
         for (int d0 = 0; d0 < R0; ++d0) {
-            const Sym3 s = spectrum_folded<FAST>(fp[d0], ky, t, (d0 == 0 && b == 0) ? rows.nyq_of(p) : nullptr);
+            const Sym3 s = spectrum_folded<FAST, kUseWk<N>>(fp[d0], ky, t, (d0 == 0 && b == 0) ? rows.nyq_of(p) : nullptr);
             vy[d0] = s.y; vx[d0] = s.x; vz[d0] = s.z;
         }
         float2 tw[R0];
@@ -615,6 +644,7 @@ OW_HD void bigrow_phase0(const Smem& sm, int ft, int p, int a, const Rows& rows,
     }
     const float ky = OW_LDG(ktab + p);
     const float4* prow = rows.pair_row(p);
+    const float2* wrow = rows.wk_row(p);
 #pragma unroll 1
     for (int c = 0; c < P::C0; ++c) {
         const int b = ft + P::T * c;
@@ -622,10 +652,10 @@ OW_HD void bigrow_phase0(const Smem& sm, int ft, int p, int a, const Rows& rows,
         float2 vy[R0], vx[R0], vz[R0];
         FoldedPair fp[R0];
 #pragma unroll
-        for (int d0 = 0; d0 < R0; ++d0) fp[d0] = load_folded(prow, ktab, A * (d0 * P::M + b) + a);
+        for (int d0 = 0; d0 < R0; ++d0) fp[d0] = load_folded<false>(prow, wrow, ktab, A * (d0 * P::M + b) + a);
 #pragma unroll
         for (int d0 = 0; d0 < R0; ++d0) {
-            const Sym3 s = spectrum_folded<FAST>(fp[d0], ky, t, (d0 == 0 && b == 0 && a == 0) ? rows.nyq_of(p) : nullptr);
+            const Sym3 s = spectrum_folded<FAST, false>(fp[d0], ky, t, (d0 == 0 && b == 0 && a == 0) ? rows.nyq_of(p) : nullptr);
             vy[d0] = s.y; vx[d0] = s.x; vz[d0] = s.z;
         }
         float2 tw[R0];

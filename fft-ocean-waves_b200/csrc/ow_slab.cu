@@ -114,9 +114,9 @@ int ow_slab_create(int32_t N, int32_t world, int32_t rank, const ow_params* p, i
     OWS_TRY(cudaSetDevice(device));
     OWS_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     OWS_TRY(cudaMalloc(&s->d_h0, (size_t)2 * g.PL * N * sizeof(float4)));
-    OWS_TRY(cudaMalloc(&s->d_hp, (size_t)g.PL * N * sizeof(float4)));
+    OWS_TRY(cudaMalloc(&s->d_hp, hp_block_elems(g.PL, N) * sizeof(float4)));     // [PL][N] float4 + [PL][N] float2 (w, 1/|k|)
     OWS_TRY(cudaMalloc(&s->d_nyq, (size_t)g.PL * sizeof(float4)));
-    OWS_TRY(cudaMemsetAsync(s->d_hp, 0, (size_t)g.PL * N * sizeof(float4), s->stream));
+    OWS_TRY(cudaMemsetAsync(s->d_hp, 0, hp_block_elems(g.PL, N) * sizeof(float4), s->stream));
     OWS_TRY(cudaMemsetAsync(s->d_nyq, 0, (size_t)g.PL * sizeof(float4), s->stream));
     OWS_TRY(cudaMalloc(&s->d_ktab, (size_t)N * sizeof(float)));
     OWS_TRY(cudaMalloc(&s->d_send, block_elems(g) * world * sizeof(float2)));
@@ -155,7 +155,7 @@ int ow_slab_init_spectrum_seeded(ow_slab* s, uint64_t seed) {
     const SlabGeom& g = s->g;
     OWS_CUDA(s, launch_ktab(s->d_ktab, g.N, s->params.L, s->stream));
     OWS_CUDA(s, launch_h0_slab(s->d_h0, g.N, g.rank * g.PL, g.PL, seed, s->casc, s->stream));
-    OWS_CUDA(s, launch_fold_slab(s->d_h0, s->d_hp, s->d_nyq, g.N, g.rank * g.PL, g.PL, s->stream));
+    OWS_CUDA(s, launch_fold_slab(s->d_h0, s->d_hp, s->d_nyq, s->d_ktab, g.N, g.rank * g.PL, g.PL, s->stream));
     OWS_CUDA(s, cudaStreamSynchronize(s->stream));   // like the reference's glFinish after tilde_h0_k (src/main.cpp:582)
     s->spectrum_ready = true;
     return OW_OK;

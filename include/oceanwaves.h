@@ -176,6 +176,13 @@ int ow_set_row_kernel(ow_ctx* ctx, int32_t mode);
 int ow_set_column_kernel(ow_ctx* ctx, int32_t mode, int32_t fused);
 /* The kernels this context will actually run (per-N defaults resolved): row 1..3, column 1..3, fused 0/1. */
 int ow_get_kernel_modes(ow_ctx* ctx, int32_t* row, int32_t* column, int32_t* fused);
+/* Tuning: resident CTAs per SM of the PERSISTENT row (modes 2, 3) and column (modes 2, 3) kernels; 0 = as many as fit. Smaller grids
+ * leave room on every SM for the other kernels of frames in flight on the context's other streams. */
+int ow_set_resident_ctas(ow_ctx* ctx, int32_t row_per_sm, int32_t col_per_sm);
+/* L2 residency of the folded initial spectrum (what every frame of a cascade re-reads): 1 = the context's launch streams carry an
+ * access-policy window over it (hits persist in the device's L2 carve-out, cudaLimitPersistingL2CacheSize - a per-device limit this
+ * call sets), 0 = off (default: measured slower on B200), -1 = on when all cascades' blocks fit two thirds of the carve-out. A hint only. */
+int ow_set_l2_persist(ow_ctx* ctx, int32_t mode);
 int ow_set_discard_intermediate(ow_ctx* ctx, int32_t on);
 
 /* ---- CUDA-GL interop: replaces the renderer's texture binds (src/main.cpp:477-487) ------------------- */

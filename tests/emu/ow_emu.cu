@@ -61,16 +61,21 @@ struct SmemEmu {
     }
 };
 
-// Host restatement of ow_fold_kernel (ow_init_kernels.cu): hp[p][u] = fold_pair(h0[p][u], h0[N-p][(N-u) mod N]).
+// Host restatement of ow_fold_kernel (ow_init_kernels.cu): hp[p][u] = fold_pair(h0[p][u], h0[N-p][(N-u) mod N]), followed by the
+// (w, 1/|k|) table of the same pair texels (second half of the block, hp_block_f4).
 template <int N>
-void fold_full(const std::vector<float4>& h0, std::vector<float4>& hp, std::vector<float4>& nyq) {
-    hp.assign((size_t)(N / 2) * N, make_float4(0, 0, 0, 0));
+void fold_full(const std::vector<float4>& h0, std::vector<float4>& hp, std::vector<float4>& nyq, float L) {
+    hp.assign(hp_block_f4(N / 2, N), make_float4(0, 0, 0, 0));
     nyq.assign(N / 2, make_float4(0, 0, 0, 0));
+    float2* wk = reinterpret_cast<float2*>(hp.data() + (size_t)(N / 2) * N);
+    const float pi = 3.1415926535897932384626433832795f;
+    auto kof = [&](int i) { return (2.0f * pi * ((float)i - (float)N / 2.0f)) / L; };
     for (int p = 1; p < N / 2; ++p)
         for (int u = 0; u < N; ++u) {
             const float4 A = h0[(size_t)p * N + u], B = h0[(size_t)(N - p) * N + ((N - u) & (N - 1))];
             hp[(size_t)p * N + u] = fold_pair(A, B);
             if (u == 0) nyq[p] = fold_pair_nyq(A, B);
+            if (use_wk(N)) wk[(size_t)p * N + u] = dispersion_of(kof(u), kof(p));
         }
 }
 
@@ -153,7 +158,7 @@ int emu_frame_n(const float* h0k, const float* h0minusk, float L, float t, float
     std::vector<float2> inter((size_t)3 * (N / 2) * N);
     Stats st;
     std::vector<float4> hp, nyq;
-    fold_full<N>(h0, hp, nyq);
+    fold_full<N>(h0, hp, nyq, L);
     emu_rows<N>(FullRows<N>{h0.data(), hp.data(), nyq.data()}, ktab.data(), t, FullSink<N>{inter.data()}, 0, N / 2, st);
     emu_cols<N>(inter.data(), (size_t)(N / 2) * N, disp, (size_t)N * N, N, FullColGeom<N>{}, st);
     emu_normals<N>(disp, FullNrmGeom<N>{}, 0, N, reinterpret_cast<float4*>(normal), jac, N, lambda, L);
@@ -243,7 +248,7 @@ int emu_frame_fused_n(const float* h0k, const float* h0minusk, float L, float t,
                       long* stats) {
     std::vector<float4> h0((size_t)N * N), hp, nyq;
     for (size_t i = 0; i < (size_t)N * N; ++i) h0[i] = make_float4(h0k[2 * i], h0k[2 * i + 1], h0minusk[2 * i], h0minusk[2 * i + 1]);
-    fold_full<N>(h0, hp, nyq);
+    fold_full<N>(h0, hp, nyq, L);
     std::vector<float> ktab(N);
     const float pi = 3.1415926535897932384626433832795f;
     for (int i = 0; i < N; ++i) ktab[i] = (2.0f * pi * ((float)i - (float)N / 2.0f)) / L;
@@ -294,13 +299,15 @@ int emu_slab_frame_n(int world, const float* h0k, const float* h0minusk, float L
         }
         rows.h0 = h0.data();
         // ow_fold_kernel on the slab-local layout: primary row pl, mirror row PL + pl
-        std::vector<float4> hp((size_t)PL * N, make_float4(0, 0, 0, 0)), nyq(PL, make_float4(0, 0, 0, 0));
+        std::vector<float4> hp(hp_block_f4(PL, N), make_float4(0, 0, 0, 0)), nyq(PL, make_float4(0, 0, 0, 0));
+        float2* wk = reinterpret_cast<float2*>(hp.data() + (size_t)PL * N);
         for (int pl = 0; pl < PL; ++pl) {
             if (r * PL + pl == 0) continue;
             for (int u = 0; u < N; ++u) {
                 const float4 A = h0[(size_t)pl * N + u], B = h0[(size_t)(PL + pl) * N + ((N - u) & (N - 1))];
                 hp[(size_t)pl * N + u] = fold_pair(A, B);
                 if (u == 0) nyq[pl] = fold_pair_nyq(A, B);
+                if (use_wk(N)) wk[(size_t)pl * N + u] = dispersion_of(ktab[u], ktab[r * PL + pl]);
             }
         }
         rows.hp = hp.data(); rows.nyq = nyq.data();
@@ -351,7 +358,7 @@ int emu_big_frame_n(const float* h0k, const float* h0minusk, float L, float t, f
     using LY = ColLayout<PK, G>;
     std::vector<float4> h0((size_t)N * N), hp, nyq;
     for (size_t i = 0; i < (size_t)N * N; ++i) h0[i] = make_float4(h0k[2 * i], h0k[2 * i + 1], h0minusk[2 * i], h0minusk[2 * i + 1]);
-    fold_full<N>(h0, hp, nyq);
+    fold_full<N>(h0, hp, nyq, L);
     std::vector<float> ktab(N);
     const float pi = 3.1415926535897932384626433832795f;
     for (int i = 0; i < N; ++i) ktab[i] = (2.0f * pi * ((float)i - (float)N / 2.0f)) / L;

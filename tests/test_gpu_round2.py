@@ -203,7 +203,7 @@ def test_n16384_random_spectrum_vs_fp64_dft_of_sampled_lines():
 @pytest.mark.parametrize("N", [256, 512, 1024, 2048])
 def test_row_and_column_kernel_variants_agree(noise, N):
     """Every row kernel (1 = CTA per row-pair group, 2 = persistent + register prefetch, 3 = persistent + cp.async.bulk/mbarrier staging)
-    with every column kernel (1 = ow_col_kernel, 2 = ow_col2_kernel direct loads, 3 = ow_col2_kernel TMA-staged), normal map fused
+    with every column kernel (1 = ow_col_kernel, 2 = ow_col2_kernel direct loads, 3 = ow_col2_kernel TMA-staged, 4 = ow_col_pipe_kernel), normal map fused
     into the column kernel or not. All of them must sit inside the parity tolerance of the oracle; variants differ only by fp32 round-off
     (2e-6 of peak); and for a FIXED (row, column) pair the fused normal map (interior quads out of shared memory + seams by the last
     arriving tile) must be bit-identical to the separate normal kernel's, the Jacobian (ow_jac_kernel) within round-off."""
@@ -214,7 +214,7 @@ def test_row_and_column_kernel_variants_agree(noise, N):
         base = None
         for rm in (1, 2, 3):
             sim.set_row_kernel(rm)
-            for cm in (1, 2, 3):
+            for cm in (1, 2, 3, 4):
                 sim.set_column_kernel(cm, 0)
                 sep = sim.frame(t)
                 assert sim.last_launch_count() == 3
@@ -225,7 +225,7 @@ def test_row_and_column_kernel_variants_agree(noise, N):
                         assert np.abs(sep[k] - base[k]).max() <= 2e-6 * peak, (rm, cm, k)
                 assert np.abs(sep["normal"] - ref["normal"]).max() < 1e-4 and np.abs(sep["jacobian"] - ref["jacobian"]).max() < 1e-4
                 base = base or sep
-                if cm == 1:
+                if cm in (1, 4):
                     continue
                 sim.set_column_kernel(cm, 1)
                 sim.update(0.0)                      # another frame first: stale texels / seam counters would show

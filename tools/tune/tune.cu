@@ -273,9 +273,9 @@ int main(int argc, char** argv) {
     CascadeDev cd{1000.0f, 40.0f, 0.7071f, 0.7071f, 2.0f, 0.1f, 1.0f, 0.0f};
     CK(cudaMemcpy(casc, &cd, sizeof(cd), cudaMemcpyHostToDevice));
     float4 *hp, *nyq;
-    CK(cudaMalloc(&hp, nn / 2 * sizeof(float4)));
+    CK(cudaMalloc(&hp, nn / 2 * 3 / 2 * sizeof(float4)));   // fold coefficients + (w, 1/|k|) table
     CK(cudaMalloc(&nyq, (size_t)(c.N / 2) * sizeof(float4)));
-    fill_h0<<<(unsigned)((nn / 2 + 255) / 256), 256>>>(hp, nn / 2, 777u);     // timing only: any finite coefficients do
+    fill_h0<<<(unsigned)((nn / 2 * 3 / 2 + 255) / 256), 256>>>(hp, nn / 2 * 3 / 2, 777u);     // timing only: any finite coefficients do
     fill_h0<<<(unsigned)((c.N / 2 + 255) / 256), 256>>>(nyq, c.N / 2, 778u);
     c.fb = FrameBuffers{c.N, h0, hp, nyq, ktab, casc, inter, disp, normal, jac, argc > 4 ? atoi(argv[4]) : 1};
     printf("discard_inter = %d\n", c.fb.discard_inter);
