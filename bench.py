@@ -693,6 +693,8 @@ def measure_slab(env, args, n_grid, steps, warmup, full):
     p = fow.OceanParams(L=1000.0, wind_speed=40.0, wind_dir=(1.0, 1.0), amplitude=2.0, suppression=0.1, choppiness=1.0)
     times = [float(np.float32(f / 60.0)) for f in range(frames)]
     sim = fow.SlabOcean(N=N, params=p, device=env.local, jacobian=jac, transport=args.transport)
+    if args.line_clusters != 0 and hasattr(sim.backend, "set_line_clusters"):
+        sim.backend.set_line_clusters(args.line_clusters)
     sim.init(32768)
     stream = env.stream
 
@@ -778,6 +780,9 @@ def measure_slab(env, args, n_grid, steps, warmup, full):
                        "l2": "flushed between timed steps (256 MiB memset outside the event pair); a frame's working set "
                              f"({(16 + 12 + 12 + 20) * N * N / world / 1e6:.0f} MB per GPU) exceeds L2 at world <= 4",
                        "parallelism": f"slab{world}: row pairs -> transpose (peer stores / all-to-all over NVLink) -> column slabs",
+                       "line_clusters": (sim.backend.line_clusters() if hasattr(sim.backend, "line_clusters") else 0),
+                       "line_clusters_note": "N = A*B line decomposition: bit 0 rows, bit 1 columns run as thread-block clusters of A CTAs that combine "
+                                             "their sub-lines through distributed shared memory (no global scratch), bit 2 = 8-column tiles; 0 = two kernels per direction",
                        "slab_vs_single_gpu_check": parity},
             "clocks": clocks, "gpu_launches": int(sim.launches_per_frame() * frames * steps), "roofline": roofline}
     if full:
@@ -874,6 +879,7 @@ def main():
     ap.add_argument("--no-compare", action="store_true", help="skip the cuFFT comparison leg")
     ap.add_argument("--no-slab-check", action="store_true", help="c5: skip the slab-vs-single-GPU agreement check before timing")
     ap.add_argument("--fused-normals", action="store_true", help="experimental OW_FLAG_FUSED_NORMALS (normal map as the column kernel's epilogue)")
+    ap.add_argument("--line-clusters", type=int, default=0, help="c5: ow_slab_set_line_clusters mode (0 = scratch path (default), -1 = clusters wherever possible, 1 / 3 / 7 = bit mask)")
     ap.add_argument("--c4-shard-of", type=int, default=1, help="c4 on one GPU only: run the 64/P cascades one rank of a P-GPU job would get")
     ap.add_argument("--c5-n", type=int, default=32768, help="c5 only: grid size (32768 = BASELINE config C5; 4096 = its down-scaled parity grid)")
     ap.add_argument("--transport", choices=["auto", "peer", "alltoall"], default="auto", help="c5 only: how the transpose crosses GPUs")

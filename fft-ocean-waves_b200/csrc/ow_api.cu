@@ -60,6 +60,8 @@ struct ow_ctx {
     int l2_persist = 0;
     bool l2_window_on = false;
     cudaStream_t l2_user_stream = nullptr;   // last caller stream the window was applied to
+    int line_clusters = 0;        // ow_set_line_clusters: 0 = global scratch (default: the DSMEM exchange measured 3.5x slower on B200), -1 = whatever
+                                  // cluster shapes the device can co-schedule (kcfg.big_cluster), else a bit mask
     int cap_row = 0, cap_col = 0; // ow_set_resident_ctas: CTAs per SM of the persistent row / column kernels (0 = what fits)
     // ow_step (slot i <- cascade i at ONE time t) as a CUDA graph: [exact sincos, fast sincos]; rebuilt when a tuning knob changes
     bool graph_enabled = true;
@@ -136,6 +138,8 @@ FrameBuffers buffers(const ow_ctx* c) {
         if (c->cap_row > 0) { fb.row_pipe_ctas[i] = std::min(fb.row_pipe_ctas[i], c->cap_row); fb.row_bulk_ctas[i] = std::min(fb.row_bulk_ctas[i], c->cap_row); }
         if (c->cap_col > 0) fb.col2_ctas[i] = std::min(fb.col2_ctas[i], c->cap_col);
     }
+    fb.big_cluster = c->line_clusters < 0 ? c->kcfg.big_cluster
+                                          : (c->line_clusters & c->kcfg.big_cluster & 3) | ((c->line_clusters & 2) ? (c->line_clusters & 4) : 0);
     fb.col_pipe_ctas = c->cap_col > 0 ? std::min(c->kcfg.col_pipe_ctas, c->cap_col) : c->kcfg.col_pipe_ctas;
     return fb;
 }
@@ -609,6 +613,14 @@ int ow_set_resident_ctas(ow_ctx* c, int32_t row_per_sm, int32_t col_per_sm) {
     drop_plans(c);
     return OW_OK;
 }
+
+int ow_set_line_clusters(ow_ctx* c, int32_t mode) {
+    if (!c || mode < -1 || mode > 7) return OW_ERR_INVALID;
+    c->line_clusters = mode;
+    return OW_OK;
+}
+
+int ow_get_line_clusters(ow_ctx* c) { return c ? buffers(c).big_cluster : 0; }
 
 int ow_set_l2_persist(ow_ctx* c, int32_t mode) {
     if (!c || mode < -1 || mode > 1) return OW_ERR_INVALID;

@@ -6,6 +6,7 @@
 #include "ow_kernels.cuh"
 #include "ow_config.cuh"
 #include "ow_async.cuh"
+#include <cooperative_groups.h>
 
 namespace ow {
 
@@ -586,6 +587,69 @@ __global__ void __launch_bounds__(256) ow_bigcol_post_kernel(const float2* __res
     const int pair = blockIdx.x * 32 + threadIdx.x, kb = blockIdx.y * 8 + threadIdx.y, c = blockIdx.z;
     if (pair < npairs && kb < B)
         bigcol_post<B, A>(scratch + (size_t)c * N * npairs + pair, (size_t)npairs, kb, dst + (size_t)c * dst_chan + 2 * pair, ds, scale);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Cluster versions (see "THE SAME DECOMPOSITION INSIDE ONE THREAD-BLOCK CLUSTER" in ow_kernels.cuh): launched with cluster dimension
+// (A, 1, 1), so the A CTAs blockIdx.x = A*line + a hold the A sub-lines of one line (row pair / column tile) and cluster rank == a.
+// ---------------------------------------------------------------------------------------------------
+struct ClusterPeers {               // element i of CTA a's dynamic shared memory
+    float2* mine;
+    __device__ __forceinline__ float2 ld(int a, int i) const {
+        return *cooperative_groups::this_cluster().map_shared_rank(mine + i, a);
+    }
+};
+
+template <class P, int A, int MINB, bool FAST, class Rows, class Sink>
+__global__ void __launch_bounds__(P::T, MINB) ow_bigrow_cluster_kernel(Rows rows, const float* __restrict__ ktab, int p_first, float t, Sink sink) {
+    extern __shared__ __align__(16) float2 smem[];
+    constexpr int B = P::N, SLICE = B / A;
+    static_assert(B % A == 0, "kb slices");
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int ft = threadIdx.x;
+    const int pl = blockIdx.x / A, a = blockIdx.x % A;
+    const SmemDirect sm{smem};
+    bigrow_phase0<P, A, FAST>(sm, ft, p_first + pl, a, rows, ktab, t);
+    __syncthreads();
+    row_phase1<P>(sm, ft);
+    __syncthreads();
+    bigrow_phase2_inplace<P>(sm, ft);
+    cluster.sync();                                  // every sub-line's z is in its CTA's shared memory
+    const ClusterPeers peers{smem};
+#pragma unroll 1
+    for (int task = ft; task < 3 * SLICE; task += P::T) {
+        const int c = task / SLICE, kb = a * SLICE + (task - c * SLICE);
+        bigrow_post_dsm<P, A>(peers, c, p_first + pl, kb, sink);
+    }
+    cluster.sync();                                  // nobody retires while a peer may still read its lines
+}
+
+template <class P, int A, int G, int MINB, class Geom>
+__global__ void __launch_bounds__(P::T* G, MINB) ow_bigcol_cluster_kernel(const float2* __restrict__ src, size_t src_chan, float* __restrict__ dst,
+                                                                         size_t dst_chan, float scale, Geom geom) {
+    extern __shared__ __align__(16) float2 smem[];
+    constexpr int B = P::N, SLICE = B / A;
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    using LY = ColLayout<P, G>;
+    const int job = threadIdx.x % G, ft = threadIdx.x / G;
+    const int tile = blockIdx.x / A, a = blockIdx.x % A;
+    const int pair = tile * G + job;
+    const int f = blockIdx.y;
+    const SmemDirect sm{smem};
+    const int base = job * LY::SJ;
+    bigcol_phase0<P, A>(sm, base, ft, a, src + (size_t)f * src_chan + 2 * pair, geom);
+    __syncthreads();
+    col_phase1<P>(sm, base, ft);
+    __syncthreads();
+    bigcol_phase2_inplace<P>(sm, base, ft);
+    cluster.sync();
+    const ClusterPeers peers{smem};
+    float* out = dst + (size_t)f * dst_chan + 2 * pair;
+#pragma unroll 1
+    for (int kl = ft; kl < SLICE; kl += P::T) bigcol_post_dsm<P, A>(peers, base, a * SLICE + kl, out, geom.dst_stride(), scale);
+    cluster.sync();
 }
 
 constexpr int kNormalRows = 8;      // output rows per thread of the normal kernel's walk

@@ -50,6 +50,8 @@ struct FrameBuffers {
     int row_bulk_ctas[2];
     int col2_ctas[2];      // resident CTAs per SM of ow_col2_kernel: [direct loads, TMA staged]
     int col_pipe_ctas;     // resident CTAs per SM of ow_col_pipe_kernel
+    int big_cluster;       // N = A*B decomposition: bit 0 = rows, bit 1 = columns run as thread-block clusters (DSMEM radix-A stage, no scratch),
+                           // bit 2 = the column clusters use 8-column tiles (3 CTAs per SM) instead of 16-column ones (1 CTA per SM)
 };
 
 // What configure_frame_kernels found out about the device the calling context lives on (kept per context: no process-global state).
@@ -59,6 +61,8 @@ struct KernelConfig {
     int row_bulk_ctas[2] = {1, 1};     // ow_row_bulk_kernel, [exact, fast]
     int col2_ctas[2] = {1, 1};         // ow_col2_kernel, [direct loads, TMA staged]
     int col_pipe_ctas = 1;             // ow_col_pipe_kernel
+    int big_cluster = 0;               // what the device can co-schedule (FrameBuffers::big_cluster bits)
+    int big_clusters_rows = 0, big_clusters_cols8 = 0, big_clusters_cols4 = 0;   // cudaOccupancyMaxActiveClusters of the three cluster shapes
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -142,6 +146,17 @@ bool big_supported(int N, bool forced);
 cudaError_t configure_big(int N, bool forced, KernelConfig* cfg);
 int launch_big_frame(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_jacobian, bool fast_phase, cudaStream_t st,
                      cudaEvent_t* ev, bool forced);
+// Launch with cluster dimension (csize, 1, 1) (cudaLaunchKernelEx); the error also lands in the thread's launch-error stash.
+template <class... KArgs, class... Args>
+cudaError_t launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int csize, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 // Launch the three frame kernels for `count` table entries. Returns number of kernels launched (<0: error).
 // ev (optional): 4 events recorded before the row kernel and after each of the three kernels.
 // fast_phase: every |w*t| of this launch is below kFastPhaseLimit, so the SFU sin/cos path is accurate enough.
@@ -174,6 +189,7 @@ struct SlabGeom {
     int PL;   // row pairs per rank   = N / 2 / world
     int XL;   // columns per rank     = N / world
     int XH;   // padded columns       = XL + 2 * kSlabHalo
+    int big_cluster = 0;   // FrameBuffers::big_cluster bits (KernelConfig::big_cluster of the rank's device, or 0 to force the scratch path)
 };
 bool slab_supported(int N, int world);
 // Row kernel for this rank's pairs; block h of the result goes to sink_base[h] ([PL][3][XH] float2 each).

@@ -761,6 +761,79 @@ OW_HD void bigcol_post(const float2* __restrict__ z /* scratch[c] + pair */, siz
 }
 
 // ---------------------------------------------------------------------------------------------------
+// THE SAME DECOMPOSITION INSIDE ONE THREAD-BLOCK CLUSTER (sm_90+; ow_bigrow_cluster_kernel / ow_bigcol_cluster_kernel).
+// The A sub-lines of a line are transformed by the A CTAs of a cluster; instead of leaving through a global scratch array, z_a stays
+// in its CTA's shared memory (stage 2 writes it back IN PLACE: slot (k0,k1,k2) of the line then holds z_a[k0 + R0 k1 + R0 R1 k2]),
+// the cluster synchronises, and the radix-A stage reads the A partial results of each kb straight out of the peers' shared memory
+// (distributed shared memory). CTA a finishes the outputs of kb in [a B/A, (a+1) B/A). No scratch traffic: 24 B/texel less per direction
+// and one kernel instead of two. `Peers::ld(a, i)` loads element i of CTA a's lines (mapa + ld.shared::cluster on the device).
+// ---------------------------------------------------------------------------------------------------
+template <class P, class Smem>
+OW_HD void stage2_inplace(const Smem& sm, int base, int bp) {
+    const int k0 = bp % P::R0, k1 = bp / P::R0;
+    float2 v[P::R2];
+    stage2<P>(sm, base, bp, v);
+#pragma unroll
+    for (int k2 = 0; k2 < P::R2; ++k2) sm.st(base + P::addr(k0, k1, k2), v[k2]);
+}
+
+template <class P>
+OW_HD int slot_of(int kb) { return P::addr(kb % P::R0, (kb / P::R0) % P::R1, kb / (P::R0 * P::R1)); }
+
+// Stage 2 of the three lines of a row pair, in place (task list over the lines, as row_phase2).
+template <class P, class Smem>
+OW_HD void bigrow_phase2_inplace(const Smem& sm, int ft) {
+#pragma unroll 1
+    for (int task = ft; task < 3 * P::B2; task += P::T) {
+        const int f = task / P::B2;
+        stage2_inplace<P>(sm, f * P::LINE, task - f * P::B2);
+    }
+}
+
+// Radix-A stage of (channel c, kb) of row pair p out of the cluster's shared memory, through the sink.
+template <class P, int A, class Peers, class Sink>
+OW_HD void bigrow_post_dsm(const Peers& peers, int c, int p, int kb, const Sink& sink) {
+    constexpr int B = P::N, N = A * B;
+    float2 v[A], tw[A];
+    twiddle_powers<A>(unit_root(kb, N), tw);                      // W_N^{a kb}
+    const int i = c * P::LINE + slot_of<P>(kb);
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        const float2 z = peers.ld(a, i);
+        v[a] = a ? cmul(z, tw[a]) : z;
+    }
+    Dft<A>::run(v);
+#pragma unroll
+    for (int ka = 0; ka < A; ++ka) sink.put(c, p, kb + B * ka, v[ka]);
+}
+
+// Column direction: stage 2 of this job's line in place ...
+template <class P, class Smem>
+OW_HD void bigcol_phase2_inplace(const Smem& sm, int base, int ft) {
+#pragma unroll 1
+    for (int bp = ft; bp < P::B2; bp += P::T) stage2_inplace<P>(sm, base, bp);
+}
+
+// ... and the radix-A stage of (job, kb): output rows y = kb + B*ka of the job's column pair, inversion sign/scale as bigcol_post.
+template <class P, int A, class Peers>
+OW_HD void bigcol_post_dsm(const Peers& peers, int base /* job's line offset */, int kb, float* __restrict__ dst /* out[c] + x */, size_t ds, float scale) {
+    constexpr int B = P::N, N = A * B;
+    float2 v[A], tw[A];
+    twiddle_powers<A>(unit_root(kb, N), tw);
+    const int i = base + slot_of<P>(kb);
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        const float2 q = peers.ld(a, i);
+        v[a] = a ? cmul(q, tw[a]) : q;
+    }
+    Dft<A>::run(v);
+    const float sg = (kb & 1) ? -scale : scale;
+#pragma unroll
+    for (int ka = 0; ka < A; ++ka)
+        *reinterpret_cast<float2*>(dst + (size_t)(kb + B * ka) * ds) = make_float2(sg * v[ka].x, -sg * v[ka].y);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // NORMAL (+ JACOBIAN).  normal_map_cs.glsl:24-54: the eight texture() taps sit on texel corners, so with
 // LINEAR+REPEAT each tap is the mean of a 2x2 block ("box"); the stencil covers columns x-2..x+1 and rows
 // y-2..y+1 with wrap-around. One thread owns FOUR adjacent columns x0..x0+3 and walks down RY output rows with

@@ -33,6 +33,7 @@ struct ow_slab {
     float4* d_h0 = nullptr;       // [2*PL][N]
     float4* d_hp = nullptr;       // [PL][N] folded pairs
     float4* d_nyq = nullptr;      // [PL]
+    int cluster_caps = 0;         // KernelConfig::big_cluster of this rank's device (N = A*B decomposition as thread-block clusters)
     float* d_ktab = nullptr;      // [N]
     float2* d_send = nullptr;     // [world][PL][3][XH]
     float2* d_recv = nullptr;     // [N/2][3][XH] = [world][PL][3][XH]
@@ -127,6 +128,8 @@ int ow_slab_create(int32_t N, int32_t world, int32_t rank, const ow_params* p, i
     if (slab_scratch_elems(g)) OWS_TRY(cudaMalloc(&s->d_scratch, slab_scratch_elems(g) * sizeof(float2)));
     KernelConfig kcfg;
     OWS_TRY(configure_frame_kernels(N, &kcfg));
+    s->cluster_caps = kcfg.big_cluster;
+    s->g.big_cluster = 0;          // scratch path by default (ow_slab_set_line_clusters)
 #undef OWS_TRY
     s->peer_recv[rank] = s->d_recv;
     *out = s;
@@ -226,6 +229,14 @@ int ow_slab_cols(ow_slab* s, void* stream) {
         return scuda(s, cudaGetLastError(), "launch_slab_cols");
     return OW_OK;
 }
+
+int ow_slab_set_line_clusters(ow_slab* s, int32_t mode) {
+    if (!s || mode < -1 || mode > 7) return OW_ERR_INVALID;
+    s->g.big_cluster = mode < 0 ? s->cluster_caps : (mode & s->cluster_caps & 3) | ((mode & 2) ? (mode & 4) : 0);
+    return OW_OK;
+}
+
+int ow_slab_get_line_clusters(const ow_slab* s) { return s ? s->g.big_cluster : 0; }
 
 int ow_slab_sync(ow_slab* s, void* stream) {
     if (!s) return OW_ERR_INVALID;

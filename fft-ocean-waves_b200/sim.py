@@ -31,7 +31,8 @@ EXPORTED_SYMBOLS = [
     "ow_step", "ow_step_multi", "ow_step_multi_timed", "ow_sync", "ow_get_outputs", "ow_download", "ow_download_frame_async",
     "ow_frame_bytes", "ow_set_group_size", "ow_set_streams", "ow_last_launch_count", "ow_gl_register", "ow_gl_step", "ow_gl_unregister",
     "ow_set_noise_seed", "ow_last_group_count", "ow_init_spectrum_cascade", "ow_set_graph", "ow_get_packed", "ow_packed_bytes",
-    "ow_download_packed_async", "ow_set_row_kernel", "ow_set_discard_intermediate", "ow_gl_register_packed", "ow_set_column_kernel", "ow_get_kernel_modes", "ow_set_resident_ctas", "ow_set_l2_persist",
+    "ow_download_packed_async", "ow_set_row_kernel", "ow_set_discard_intermediate", "ow_gl_register_packed", "ow_set_column_kernel", "ow_get_kernel_modes", "ow_set_resident_ctas", "ow_set_l2_persist", "ow_set_line_clusters", "ow_get_line_clusters",
+    "ow_slab_set_line_clusters", "ow_slab_get_line_clusters",
     "ow_slab_create", "ow_slab_destroy", "ow_slab_last_error", "ow_slab_get_info", "ow_slab_init_spectrum_seeded", "ow_slab_ipc_handle",
     "ow_slab_open_peers", "ow_slab_rows", "ow_slab_cols", "ow_slab_local_exchange", "ow_slab_sync", "ow_slab_download",
 ]
@@ -144,6 +145,10 @@ def load_library():
     L.ow_set_column_kernel.argtypes = [vp, i32, i32]
     L.ow_set_resident_ctas.argtypes = [vp, i32, i32]
     L.ow_set_l2_persist.argtypes = [vp, i32]
+    L.ow_set_line_clusters.argtypes = [vp, i32]
+    L.ow_get_line_clusters.argtypes = [vp]
+    L.ow_slab_set_line_clusters.argtypes = [vp, i32]
+    L.ow_slab_get_line_clusters.argtypes = [vp]
     L.ow_get_kernel_modes.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.ow_gl_register_packed.argtypes = [vp, u32, u32]
     L.ow_slab_create.argtypes = [i32, i32, i32, C.POINTER(_Params), i32, u32, C.POINTER(vp)]
@@ -291,6 +296,12 @@ class FFTOceanWaves:
 
     def set_resident_ctas(self, row_per_sm: int = 0, col_per_sm: int = 0):
         self._check(self._lib.ow_set_resident_ctas(self._h, int(row_per_sm), int(col_per_sm)), "ow_set_resident_ctas")
+
+    def set_line_clusters(self, mode: int = -1):
+        self._check(self._lib.ow_set_line_clusters(self._h, int(mode)), "ow_set_line_clusters")
+
+    def line_clusters(self) -> int:
+        return int(self._lib.ow_get_line_clusters(self._h))
 
     def set_l2_persist(self, mode: int = -1):
         self._check(self._lib.ow_set_l2_persist(self._h, int(mode)), "ow_set_l2_persist")

@@ -104,6 +104,12 @@ class LibSlabBackend:
     def sync(self, stream: int = 0):
         self._check(self._lib.ow_slab_sync(self._h, C.c_void_p(stream or None)), "ow_slab_sync")
 
+    def set_line_clusters(self, mode: int = -1):
+        self._check(self._lib.ow_slab_set_line_clusters(self._h, int(mode)), "ow_slab_set_line_clusters")
+
+    def line_clusters(self) -> int:
+        return int(self._lib.ow_slab_get_line_clusters(self._h))
+
     # transports
     def ipc_handle(self) -> bytes:
         buf = (C.c_ubyte * IPC_HANDLE_BYTES)()
@@ -285,8 +291,12 @@ class SlabOcean:
         return np.concatenate(parts, axis=1)
 
     def launches_per_frame(self) -> int:
-        """Kernels this rank launches per frame: row, column, normal; above N = 4096 the line decomposition doubles the first two."""
-        return 5 if self.N > 4096 else 3
+        """Kernels this rank launches per frame: row, column, normal; above N = 4096 the line decomposition doubles the first two
+        unless they run as thread-block clusters (ow_slab_get_line_clusters: bit 0 rows, bit 1 columns)."""
+        if self.N <= 4096:
+            return 3
+        bits = self.backend.line_clusters() if hasattr(self.backend, "line_clusters") else 0
+        return 5 - (bits & 1) - ((bits >> 1) & 1)
 
     def exchange_bytes_per_frame(self) -> int:
         """Bytes this rank sends to OTHER ranks per frame (NVLink traffic per direction)."""

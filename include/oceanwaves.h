@@ -183,6 +183,13 @@ int ow_set_resident_ctas(ow_ctx* ctx, int32_t row_per_sm, int32_t col_per_sm);
  * access-policy window over it (hits persist in the device's L2 carve-out, cudaLimitPersistingL2CacheSize - a per-device limit this
  * call sets), 0 = off (default: measured slower on B200), -1 = on when all cascades' blocks fit two thirds of the carve-out. A hint only. */
 int ow_set_l2_persist(ow_ctx* ctx, int32_t mode);
+/* Lines longer than one CTA's shared memory (N > 4096, or OW_FLAG_FOUR_STEP): N = A*B, the A sub-lines of a line are transformed by the
+ * A CTAs of a thread-block cluster and combined through distributed shared memory (no global scratch). mode: -1 = wherever the device can
+ * co-schedule the cluster, 0 = never (default: two kernels per direction through a global scratch array - measured 3.5x FASTER on B200
+ * at N = 32768, where the exchange through distributed shared memory is bound by its ~20 B/clk per SM), else a bit mask:
+ * 1 = rows, 2 = columns, 4 = columns on 8-column tiles (3 CTAs per SM) instead of 16-column ones. ow_get_line_clusters returns the mask in use. */
+int ow_set_line_clusters(ow_ctx* ctx, int32_t mode);
+int ow_get_line_clusters(ow_ctx* ctx);
 int ow_set_discard_intermediate(ow_ctx* ctx, int32_t on);
 
 /* ---- CUDA-GL interop: replaces the renderer's texture binds (src/main.cpp:477-487) ------------------- */
@@ -243,6 +250,9 @@ int ow_slab_cols(ow_slab* s, void* stream);
 /* world == 1 stand-in for the all-to-all (send -> recv device copy). */
 int ow_slab_local_exchange(ow_slab* s, void* stream);
 int ow_slab_sync(ow_slab* s, void* stream);
+/* As ow_set_line_clusters / ow_get_line_clusters, for a slab rank. */
+int ow_slab_set_line_clusters(ow_slab* s, int32_t mode);
+int ow_slab_get_line_clusters(const ow_slab* s);
 /* which = OW_IMG_DY/DX/DZ ([N][XL] floats, halo stripped), OW_IMG_NORMAL ([N][XL][4]), OW_IMG_JACOBIAN ([N][XL]). */
 int ow_slab_download(ow_slab* s, int32_t which, void* host, size_t bytes, void* stream);
 

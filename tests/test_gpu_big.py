@@ -90,3 +90,27 @@ def test_large_grid_known_answers(N):
             assert np.abs(dy[:, x] - expect).max() < 2e-5 / n2, ("col", x)
         nm = sim.download("normal")
         assert np.isfinite(nm).all() and np.abs(np.linalg.norm(nm[::257, ::263, :3], axis=-1) - 1).max() < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,four", [(1024, True), (2048, True), (8192, False)])
+def test_cluster_line_decomposition_equals_scratch_path(N, four):
+    """The N = A*B decomposition as thread-block clusters (sub-lines combined through distributed shared memory, no global scratch;
+    16-column and 8-column tiles) must give the SAME images as the two-kernel scratch path: identical arithmetic, different plumbing."""
+    with fow.FFTOceanWaves(N=N, cascades=[P], jacobian=True, four_step=four) as sim:
+        sim.set_noise_seed(N)
+        sim.tilde_h0_k()
+        assert sim.line_clusters() == 0          # default: the scratch path
+        sim.set_line_clusters(-1)
+        if sim.line_clusters() == 0:
+            pytest.skip("this device cannot co-schedule the clusters")
+        sim.set_line_clusters(0)
+        ref = sim.frame(1.5)
+        assert sim.last_launch_count() == 5
+        for mode in (1, 3, 7):
+            sim.set_line_clusters(mode)
+            got = sim.frame(1.5)
+            used = sim.line_clusters()
+            assert sim.last_launch_count() == 5 - (used & 1) - ((used >> 1) & 1)
+            for k in ("dy", "dx", "dz", "normal", "jacobian"):
+                assert np.array_equal(got[k], ref[k]), (mode, used, k)
