@@ -7,7 +7,7 @@ rows = list(csv.reader(io.StringIO(out)))
 hdr, units = rows[0], rows[1]
 want = {
     "gpu__time_duration.sum": "duration", "dram__bytes_read.sum": "dram_read", "dram__bytes_write.sum": "dram_write",
-    "dram__throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed": "l2_pct",
+    "dram__throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed": "l2_pct",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed": "sm_pct", "sm__warps_active.avg.pct_of_peak_sustained_active": "occupancy_pct",
     "launch__registers_per_thread": "regs", "launch__grid_size": "grid", "launch__block_size": "block",
     "smsp__inst_executed.sum": "warp_inst", "sm__inst_executed_pipe_fma.sum": "fma_inst",
