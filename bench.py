@@ -674,7 +674,8 @@ def slab_parity_check(env, fow, N, transport):
     t = 1.0
     slab = fow.SlabOcean(N=N, params=p, device=env.local, jacobian=True, transport=transport)
     slab.init(32768)
-    slab.update(t)
+    for tt in (0.25, 0.5, 0.75, t):          # four frames: the pipelined path (rows of f+1 during the columns of f) reuses both receive buffers
+        slab.update(tt)
     slab.sync()
     got = {k: slab.gather(k) for k in ("dy", "dx", "dz", "jacobian")}
     slab.close()
@@ -709,7 +710,9 @@ def measure_slab(env, args, n_grid, steps, warmup, full):
             raise SystemExit(f"bench.py: slab path disagrees with the single-GPU path: {parity}")
     p = fow.OceanParams(L=1000.0, wind_speed=40.0, wind_dir=(1.0, 1.0), amplitude=2.0, suppression=0.1, choppiness=1.0)
     times = [float(np.float32(f / 60.0)) for f in range(frames)]
-    sim = fow.SlabOcean(N=N, params=p, device=env.local, jacobian=jac, transport=args.transport)
+    sim = fow.SlabOcean(N=N, params=p, device=env.local, jacobian=jac, transport=args.transport, pipeline=(False if args.no_pipeline else None))
+    if args.post_ctas >= 0 and hasattr(sim.backend, "set_post_ctas"):
+        sim.backend.set_post_ctas(args.post_ctas)
     if args.line_clusters != 0 and hasattr(sim.backend, "set_line_clusters"):
         sim.backend.set_line_clusters(args.line_clusters)
     sim.init(32768)
@@ -718,6 +721,7 @@ def measure_slab(env, args, n_grid, steps, warmup, full):
     def sweep():
         for t in times:
             sim.update(t)
+        sim.flush()                 # pipelined frames: the caller's stream (and the event recorded on it next) waits for all of them
 
     for _ in range(warmup):
         env.flush_l2()
@@ -797,6 +801,8 @@ def measure_slab(env, args, n_grid, steps, warmup, full):
                        "l2": "flushed between timed steps (256 MiB memset, then a 256 MiB read so the L2 is left clean; both outside the event pair); a frame's working set "
                              f"({(16 + 12 + 12 + 20) * N * N / world / 1e6:.0f} MB per GPU) exceeds L2 at world <= 4",
                        "parallelism": f"slab{world}: row pairs -> transpose (peer stores / all-to-all over NVLink) -> column slabs",
+                       "pipelined": bool(getattr(sim, "pipelined", False)),
+                       "pipelined_note": "frame f+1's row pass (its peer stores are the exchange) overlaps frame f's column pass: two receive buffers, two streams",
                        "line_clusters": (sim.backend.line_clusters() if hasattr(sim.backend, "line_clusters") else 0),
                        "line_clusters_note": "N = A*B line decomposition: bit 0 rows, bit 1 columns run as thread-block clusters of A CTAs that combine "
                                              "their sub-lines through distributed shared memory (no global scratch), bit 2 = 8-column tiles; 0 = two kernels per direction",
@@ -812,6 +818,7 @@ def measure_slab(env, args, n_grid, steps, warmup, full):
             sim.init(32768)
             for t in times:
                 sim.update(t)
+                sim.flush()                      # this frame's outputs are complete on the current stream before they are copied
                 for k, v in outs.items():
                     host[k].copy_(v, non_blocking=True)
             torch.cuda.synchronize()
@@ -896,6 +903,8 @@ def main():
     ap.add_argument("--no-compare", action="store_true", help="skip the cuFFT comparison leg")
     ap.add_argument("--no-slab-check", action="store_true", help="c5: skip the slab-vs-single-GPU agreement check before timing")
     ap.add_argument("--fused-normals", action="store_true", help="experimental OW_FLAG_FUSED_NORMALS (normal map as the column kernel's epilogue)")
+    ap.add_argument("--post-ctas", type=int, default=-1, help="c5: ow_slab_set_post_ctas (CTAs per SM of the row pass's store kernel; -1 = the library's choice)")
+    ap.add_argument("--no-pipeline", action="store_true", help="c5: one frame at a time (no overlap of the next frame's rows with this frame's columns)")
     ap.add_argument("--no-graph", action="store_true", help="c4: submit the step through ow_step_multi (stream launches) instead of ow_step (one graph launch)")
     ap.add_argument("--line-clusters", type=int, default=0, help="c5: ow_slab_set_line_clusters mode (0 = scratch path (default), -1 = clusters wherever possible, 1 / 3 / 7 = bit mask)")
     ap.add_argument("--c4-shard-of", type=int, default=1, help="c4 on one GPU only: run the 64/P cascades one rank of a P-GPU job would get")

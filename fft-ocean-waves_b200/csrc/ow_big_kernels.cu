@@ -97,7 +97,7 @@ struct Big {
 
     template <class Rows, class Sink>
     static void rows_pass(const Rows& rows, const float* ktab, int p_first, int npairs_rows, float t, bool fast, float2* scratch, const Sink& sink,
-                          cudaStream_t st, int cluster_bits) {
+                          cudaStream_t st, int cluster_bits, int post_ctas = 0) {
         if (cluster_bits & 1) {
             cudaError_t e = fast ? launch_cluster(ow_bigrow_cluster_kernel<R, A, RMB, true, Rows, Sink>, dim3(npairs_rows * A), dim3(R::T), row_smem<R, 1>(), st, A,
                                                   rows, ktab, p_first, t, sink)
@@ -108,7 +108,8 @@ struct Big {
         }
         if (fast) ow_bigrow_lines_kernel<R, A, RMB, true, Rows><<<npairs_rows * A, R::T, row_smem<R, 1>(), st>>>(rows, ktab, p_first, t, scratch);
         else ow_bigrow_lines_kernel<R, A, RMB, false, Rows><<<npairs_rows * A, R::T, row_smem<R, 1>(), st>>>(rows, ktab, p_first, t, scratch);
-        ow_bigrow_post_kernel<B, A, Sink><<<dim3((B + 255) / 256, npairs_rows, 3), 256, 0, st>>>(scratch, p_first, sink);
+        if (post_ctas > 0) ow_bigrow_post_slim_kernel<B, A, Sink><<<post_ctas, 256, 0, st>>>(scratch, p_first, npairs_rows, sink);
+        else ow_bigrow_post_kernel<B, A, Sink><<<dim3((B + 255) / 256, npairs_rows, 3), 256, 0, st>>>(scratch, p_first, sink);
     }
 
     template <class Geom>
@@ -162,7 +163,7 @@ struct Big {
         sink.world = g.world; sink.p0 = g.rank * g.PL; sink.XL = g.XL; sink.XH = g.XH;
         sink.xl_shift = 0;
         while ((1 << sink.xl_shift) < g.XL) ++sink.xl_shift;
-        rows_pass(rows, ktab, g.rank * g.PL, g.PL, t, fast, scratch, sink, st, g.big_cluster);
+        rows_pass(rows, ktab, g.rank * g.PL, g.PL, t, fast, scratch, sink, st, g.big_cluster, g.post_ctas);
         return launches_ok() && take_and_restash() ? ((g.big_cluster & 1) ? 1 : 2) : -1;
     }
 

@@ -559,6 +559,21 @@ __global__ void __launch_bounds__(256) ow_bigrow_post_kernel(const float2* __res
     if (kb < B) bigrow_post<B, A>(scratch + (size_t)pl * 3 * N, c, p_first + pl, kb, sink);
 }
 
+// The same work from a SMALL persistent grid (a few CTAs per SM, grid-stride over the (channel, pair, kb block) items). With peer stores the
+// post kernel is bound by NVLink, not by the SMs: a full grid parks 8 stalled CTAs on every SM and keeps the column kernels of the
+// previous frame (which run concurrently on another stream in the frame-pipelined slab path) from being scheduled; a slim one leaves them room.
+template <int B, int A, class Sink>
+__global__ void __launch_bounds__(256) ow_bigrow_post_slim_kernel(const float2* __restrict__ scratch, int p_first, int npairs, Sink sink) {
+    constexpr int N = A * B, KBB = (B + 255) / 256;
+    const int total = KBB * npairs * 3;
+#pragma unroll 1
+    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        const int kbb = item % KBB, r = item / KBB, pl = r % npairs, c = r / npairs;
+        const int kb = kbb * 256 + threadIdx.x;
+        if (kb < B) bigrow_post<B, A>(scratch + (size_t)pl * 3 * N, c, p_first + pl, kb, sink);
+    }
+}
+
 // src: channel-0 base of the Hermitian-packed intermediate; channel c at src + c*src_chan.
 template <class P, int A, int G, int MINB, class Geom>
 __global__ void __launch_bounds__(P::T* G, MINB) ow_bigcol_lines_kernel(const float2* __restrict__ src, size_t src_chan, int npairs,

@@ -190,6 +190,7 @@ struct SlabGeom {
     int XL;   // columns per rank     = N / world
     int XH;   // padded columns       = XL + 2 * kSlabHalo
     int big_cluster = 0;   // FrameBuffers::big_cluster bits (KernelConfig::big_cluster of the rank's device, or 0 to force the scratch path)
+    int post_ctas = 0;     // N > 4096: grid of the row post kernel (0 = one CTA per item; > 0 = slim persistent grid, see ow_bigrow_post_slim_kernel)
 };
 bool slab_supported(int N, int world);
 // Row kernel for this rank's pairs; block h of the result goes to sink_base[h] ([PL][3][XH] float2 each).

@@ -36,7 +36,12 @@ struct ow_slab {
     int cluster_caps = 0;         // KernelConfig::big_cluster of this rank's device (N = A*B decomposition as thread-block clusters)
     float* d_ktab = nullptr;      // [N]
     float2* d_send = nullptr;     // [world][PL][3][XH]
-    float2* d_recv = nullptr;     // [N/2][3][XH] = [world][PL][3][XH]
+    float2* d_recv = nullptr;     // [N/2][3][XH] = [world][PL][3][XH]   (receive buffer 0)
+    int post_ctas_per_sm = 2;     // ow_slab_set_post_ctas
+    float2* d_recv1 = nullptr;    // receive buffer 1 (ow_slab_enable_double_buffer): frame f+1's rows land here while frame f's columns read buffer 0
+    float2* d_scratch_cols = nullptr;   // N > 4096 with two buffers: the column pass gets its own scratch (rows and columns then run concurrently)
+    float2* peer_recv1[kSlabMaxWorld] = {};
+    bool peers_open1 = false;
     float* d_disp = nullptr;      // [3][N][XH]
     float4* d_normal = nullptr;   // [N][XL]
     float* d_jac = nullptr;       // [N][XL]
@@ -72,6 +77,10 @@ void srelease(ow_slab* s) {
     if (s->peers_open)
         for (int h = 0; h < s->g.world; ++h)
             if (h != s->g.rank && s->peer_recv[h]) cudaIpcCloseMemHandle(s->peer_recv[h]);
+    if (s->peers_open1)
+        for (int h = 0; h < s->g.world; ++h)
+            if (h != s->g.rank && s->peer_recv1[h]) cudaIpcCloseMemHandle(s->peer_recv1[h]);
+    cudaFree(s->d_recv1); cudaFree(s->d_scratch_cols);
     cudaFree(s->d_h0); cudaFree(s->d_hp); cudaFree(s->d_nyq); cudaFree(s->d_ktab); cudaFree(s->d_send); cudaFree(s->d_recv); cudaFree(s->d_disp);
     cudaFree(s->d_normal); cudaFree(s->d_jac); cudaFree(s->d_scratch);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -164,21 +173,34 @@ int ow_slab_init_spectrum_seeded(ow_slab* s, uint64_t seed) {
     return OW_OK;
 }
 
-int ow_slab_ipc_handle(ow_slab* s, void* handle, size_t bytes) {
-    if (!s || !handle) return OW_ERR_INVALID;
+int ow_slab_enable_double_buffer(ow_slab* s) {
+    if (!s) return OW_ERR_INVALID;
+    if (s->d_recv1) return OW_OK;
+    OWS_CUDA(s, cudaSetDevice(s->device));
+    const SlabGeom& g = s->g;
+    OWS_CUDA(s, cudaMalloc(&s->d_recv1, block_elems(g) * g.world * sizeof(float2)));
+    if (slab_scratch_elems(g)) OWS_CUDA(s, cudaMalloc(&s->d_scratch_cols, slab_scratch_elems(g) * sizeof(float2)));
+    s->peer_recv1[g.rank] = s->d_recv1;
+    // the row post kernel then shares the SMs with the previous frame's column pass: slim persistent grid (2 CTAs per SM)
+    int sms = 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device) != cudaSuccess) { cudaGetLastError(); sms = 148; }
+    s->g.post_ctas = (g.world > 1 ? s->post_ctas_per_sm : 0) * sms;
+    return OW_OK;
+}
+
+static int ipc_handle_of(ow_slab* s, float2* buf, void* handle, size_t bytes) {
     if (bytes != sizeof(cudaIpcMemHandle_t)) return sfail(s, OW_ERR_INVALID, "ow_slab_ipc_handle: handle buffer must be OW_SLAB_IPC_HANDLE_BYTES");
     OWS_CUDA(s, cudaSetDevice(s->device));
     cudaIpcMemHandle_t h;
-    OWS_CUDA(s, cudaIpcGetMemHandle(&h, s->d_recv));
+    OWS_CUDA(s, cudaIpcGetMemHandle(&h, buf));
     std::memcpy(handle, &h, sizeof(h));
     return OW_OK;
 }
 
-int ow_slab_open_peers(ow_slab* s, const void* handles, size_t bytes) {
-    if (!s || !handles) return OW_ERR_INVALID;
+static int open_peers_of(ow_slab* s, float2** peer, bool* open, const void* handles, size_t bytes) {
     const SlabGeom& g = s->g;
     if (bytes != sizeof(cudaIpcMemHandle_t) * (size_t)g.world) return sfail(s, OW_ERR_INVALID, "ow_slab_open_peers: need world handles");
-    if (s->peers_open) return OW_OK;
+    if (*open) return OW_OK;
     OWS_CUDA(s, cudaSetDevice(s->device));
     const char* hb = static_cast<const char*>(handles);
     for (int h = 0; h < g.world; ++h) {
@@ -188,24 +210,48 @@ int ow_slab_open_peers(ow_slab* s, const void* handles, size_t bytes) {
         void* ptr = nullptr;
         cudaError_t e = cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess) {
-            for (int k = 0; k < h; ++k) if (k != g.rank && s->peer_recv[k]) { cudaIpcCloseMemHandle(s->peer_recv[k]); s->peer_recv[k] = nullptr; }
+            for (int k = 0; k < h; ++k) if (k != g.rank && peer[k]) { cudaIpcCloseMemHandle(peer[k]); peer[k] = nullptr; }
             cudaGetLastError();
             return scuda(s, e, "cudaIpcOpenMemHandle (peer access between the GPUs of this box is required for OW_SLAB_PEER_STORES)");
         }
-        s->peer_recv[h] = static_cast<float2*>(ptr);
+        peer[h] = static_cast<float2*>(ptr);
     }
-    s->peers_open = true;
+    *open = true;
     return OW_OK;
 }
 
-int ow_slab_rows(ow_slab* s, float t, int32_t transport, void* stream) {
-    if (!s) return OW_ERR_INVALID;
+int ow_slab_ipc_handle(ow_slab* s, void* handle, size_t bytes) {
+    if (!s || !handle) return OW_ERR_INVALID;
+    return ipc_handle_of(s, s->d_recv, handle, bytes);
+}
+
+int ow_slab_ipc_handle_buf(ow_slab* s, int32_t buf, void* handle, size_t bytes) {
+    if (!s || !handle || buf < 0 || buf > 1) return OW_ERR_INVALID;
+    if (buf == 1 && !s->d_recv1) return sfail(s, OW_ERR_STATE, "ow_slab_ipc_handle_buf: call ow_slab_enable_double_buffer first");
+    return ipc_handle_of(s, buf ? s->d_recv1 : s->d_recv, handle, bytes);
+}
+
+int ow_slab_open_peers(ow_slab* s, const void* handles, size_t bytes) {
+    if (!s || !handles) return OW_ERR_INVALID;
+    return open_peers_of(s, s->peer_recv, &s->peers_open, handles, bytes);
+}
+
+int ow_slab_open_peers_buf(ow_slab* s, int32_t buf, const void* handles, size_t bytes) {
+    if (!s || !handles || buf < 0 || buf > 1) return OW_ERR_INVALID;
+    if (buf == 1 && !s->d_recv1) return sfail(s, OW_ERR_STATE, "ow_slab_open_peers_buf: call ow_slab_enable_double_buffer first");
+    return buf ? open_peers_of(s, s->peer_recv1, &s->peers_open1, handles, bytes) : open_peers_of(s, s->peer_recv, &s->peers_open, handles, bytes);
+}
+
+int ow_slab_rows_buf(ow_slab* s, float t, int32_t transport, int32_t buf, void* stream) {
+    if (!s || buf < 0 || buf > 1) return OW_ERR_INVALID;
     if (!s->spectrum_ready) return sfail(s, OW_ERR_STATE, "ow_slab_rows: call ow_slab_init_spectrum_seeded first");
+    if (buf == 1 && !s->d_recv1) return sfail(s, OW_ERR_STATE, "ow_slab_rows_buf: call ow_slab_enable_double_buffer first");
     const SlabGeom& g = s->g;
     float2* base[kSlabMaxWorld] = {};
     if (transport == OW_SLAB_PEER_STORES) {
-        if (g.world > 1 && !s->peers_open) return sfail(s, OW_ERR_STATE, "ow_slab_rows: OW_SLAB_PEER_STORES needs ow_slab_open_peers");
-        for (int h = 0; h < g.world; ++h) base[h] = s->peer_recv[h] + (size_t)g.rank * block_elems(g);
+        float2** peer = buf ? s->peer_recv1 : s->peer_recv;
+        if (g.world > 1 && !(buf ? s->peers_open1 : s->peers_open)) return sfail(s, OW_ERR_STATE, "ow_slab_rows: OW_SLAB_PEER_STORES needs ow_slab_open_peers");
+        for (int h = 0; h < g.world; ++h) base[h] = peer[h] + (size_t)g.rank * block_elems(g);
     } else if (transport == OW_SLAB_SEND_BUFFER) {
         for (int h = 0; h < g.world; ++h) base[h] = s->d_send + (size_t)h * block_elems(g);
     } else {
@@ -219,14 +265,37 @@ int ow_slab_rows(ow_slab* s, float t, int32_t transport, void* stream) {
     return OW_OK;
 }
 
-int ow_slab_cols(ow_slab* s, void* stream) {
-    if (!s) return OW_ERR_INVALID;
+int ow_slab_rows(ow_slab* s, float t, int32_t transport, void* stream) { return ow_slab_rows_buf(s, t, transport, 0, stream); }
+
+int ow_slab_cols_buf(ow_slab* s, int32_t buf, void* stream) {
+    if (!s || buf < 0 || buf > 1) return OW_ERR_INVALID;
     if (!s->spectrum_ready) return sfail(s, OW_ERR_STATE, "ow_slab_cols: call ow_slab_init_spectrum_seeded first");
+    if (buf == 1 && !s->d_recv1) return sfail(s, OW_ERR_STATE, "ow_slab_cols_buf: call ow_slab_enable_double_buffer first");
     OWS_CUDA(s, cudaSetDevice(s->device));
     const SlabGeom& g = s->g;
     const float js = s->casc.choppiness * ((float)g.N / (2.0f * s->casc.L));
-    if (launch_slab_cols(g, s->d_recv, s->d_disp, s->d_normal, s->d_jac, js, s->d_scratch, spick(s, stream)) < 0)
+    // with two receive buffers the column pass may overlap the next frame's row pass: it then has its own scratch
+    float2* scratch = s->d_scratch_cols ? s->d_scratch_cols : s->d_scratch;
+    if (launch_slab_cols(g, buf ? s->d_recv1 : s->d_recv, s->d_disp, s->d_normal, s->d_jac, js, scratch, spick(s, stream)) < 0)
         return scuda(s, cudaGetLastError(), "launch_slab_cols");
+    return OW_OK;
+}
+
+int ow_slab_cols(ow_slab* s, void* stream) { return ow_slab_cols_buf(s, 0, stream); }
+
+int ow_slab_recv_buffer(ow_slab* s, int32_t buf, void** ptr) {
+    if (!s || !ptr || buf < 0 || buf > 1) return OW_ERR_INVALID;
+    if (buf == 1 && !s->d_recv1) return sfail(s, OW_ERR_STATE, "ow_slab_recv_buffer: call ow_slab_enable_double_buffer first");
+    *ptr = buf ? s->d_recv1 : s->d_recv;
+    return OW_OK;
+}
+
+int ow_slab_set_post_ctas(ow_slab* s, int32_t per_sm) {
+    if (!s || per_sm < 0 || per_sm > 8) return OW_ERR_INVALID;
+    int sms = 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device) != cudaSuccess) { cudaGetLastError(); sms = 148; }
+    s->post_ctas_per_sm = per_sm;
+    s->g.post_ctas = per_sm * sms;
     return OW_OK;
 }
 

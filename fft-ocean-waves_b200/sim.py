@@ -32,7 +32,8 @@ EXPORTED_SYMBOLS = [
     "ow_frame_bytes", "ow_set_group_size", "ow_set_streams", "ow_last_launch_count", "ow_gl_register", "ow_gl_step", "ow_gl_unregister",
     "ow_set_noise_seed", "ow_last_group_count", "ow_init_spectrum_cascade", "ow_set_graph", "ow_get_packed", "ow_packed_bytes",
     "ow_download_packed_async", "ow_set_row_kernel", "ow_set_discard_intermediate", "ow_gl_register_packed", "ow_set_column_kernel", "ow_get_kernel_modes", "ow_set_resident_ctas", "ow_set_l2_persist", "ow_set_line_clusters", "ow_get_line_clusters",
-    "ow_slab_set_line_clusters", "ow_slab_get_line_clusters",
+    "ow_slab_set_line_clusters", "ow_slab_get_line_clusters", "ow_slab_enable_double_buffer", "ow_slab_ipc_handle_buf", "ow_slab_open_peers_buf",
+    "ow_slab_rows_buf", "ow_slab_cols_buf", "ow_slab_set_post_ctas", "ow_slab_recv_buffer",
     "ow_slab_create", "ow_slab_destroy", "ow_slab_last_error", "ow_slab_get_info", "ow_slab_init_spectrum_seeded", "ow_slab_ipc_handle",
     "ow_slab_open_peers", "ow_slab_rows", "ow_slab_cols", "ow_slab_local_exchange", "ow_slab_sync", "ow_slab_download",
 ]
@@ -161,6 +162,13 @@ def load_library():
     L.ow_slab_ipc_handle.argtypes = [vp, vp, C.c_size_t]
     L.ow_slab_open_peers.argtypes = [vp, vp, C.c_size_t]
     L.ow_slab_rows.argtypes = [vp, f32, i32, vp]
+    L.ow_slab_enable_double_buffer.argtypes = [vp]
+    L.ow_slab_ipc_handle_buf.argtypes = [vp, i32, vp, C.c_size_t]
+    L.ow_slab_open_peers_buf.argtypes = [vp, i32, vp, C.c_size_t]
+    L.ow_slab_rows_buf.argtypes = [vp, f32, i32, i32, vp]
+    L.ow_slab_cols_buf.argtypes = [vp, i32, vp]
+    L.ow_slab_set_post_ctas.argtypes = [vp, i32]
+    L.ow_slab_recv_buffer.argtypes = [vp, i32, C.POINTER(vp)]
     L.ow_slab_cols.argtypes = [vp, vp]
     L.ow_slab_local_exchange.argtypes = [vp, vp]
     L.ow_slab_sync.argtypes = [vp, vp]

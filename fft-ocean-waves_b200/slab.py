@@ -121,16 +121,43 @@ class LibSlabBackend:
         buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
         self._check(self._lib.ow_slab_open_peers(self._h, buf, len(blob)), "ow_slab_open_peers")
 
-    def exchange_tensors(self):
-        """(send, recv) as flat float32 torch tensors aliasing the library's device buffers."""
+    # two receive buffers: frame f+1's row pass (the exchange) overlaps frame f's column pass
+    def enable_double_buffer(self):
+        self._check(self._lib.ow_slab_enable_double_buffer(self._h), "ow_slab_enable_double_buffer")
+
+    def ipc_handle_buf(self, buf: int) -> bytes:
+        out = (C.c_ubyte * IPC_HANDLE_BYTES)()
+        self._check(self._lib.ow_slab_ipc_handle_buf(self._h, int(buf), out, IPC_HANDLE_BYTES), "ow_slab_ipc_handle_buf")
+        return bytes(out)
+
+    def open_peers_buf(self, buf: int, handles):
+        blob = b"".join(handles)
+        arr = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._check(self._lib.ow_slab_open_peers_buf(self._h, int(buf), arr, len(blob)), "ow_slab_open_peers_buf")
+
+    def rows_buf(self, t: float, transport: int, buf: int, stream: int = 0):
+        self._check(self._lib.ow_slab_rows_buf(self._h, float(t), int(transport), int(buf), C.c_void_p(stream or None)), "ow_slab_rows_buf")
+
+    def cols_buf(self, buf: int, stream: int = 0):
+        self._check(self._lib.ow_slab_cols_buf(self._h, int(buf), C.c_void_p(stream or None)), "ow_slab_cols_buf")
+
+    def set_post_ctas(self, per_sm: int):
+        self._check(self._lib.ow_slab_set_post_ctas(self._h, int(per_sm)), "ow_slab_set_post_ctas")
+
+    def exchange_tensors(self, buf: int = 0):
+        """(send, recv) as flat float32 torch tensors aliasing the library's device buffers (recv: receive buffer `buf`)."""
         if self._views is None:
+            self._views = {}
+        if buf not in self._views:
             import torch
             n = int(self.info.block_bytes) * self.info.world
             dev = f"cuda:{self.device}"
             send = torch.as_tensor(_DeviceBytes(self.info.send, n), device=dev).view(torch.float32)
-            recv = torch.as_tensor(_DeviceBytes(self.info.recv, n), device=dev).view(torch.float32)
-            self._views = (send, recv)
-        return self._views
+            ptr = C.c_void_p()
+            self._check(self._lib.ow_slab_recv_buffer(self._h, int(buf), C.byref(ptr)), "ow_slab_recv_buffer")
+            recv = torch.as_tensor(_DeviceBytes(ptr.value, n), device=dev).view(torch.float32)
+            self._views[buf] = (send, recv)
+        return self._views[buf]
 
     def output_tensors(self) -> dict:
         """torch views of this rank's output slabs (halo columns cut off): dy/dx/dz [N][XL] (row stride XH), normal
@@ -175,7 +202,10 @@ class SlabOcean:
     """
 
     def __init__(self, N: int, params: Optional[OceanParams] = None, device: Optional[int] = None, jacobian: bool = False,
-                 exact_sincos: bool = False, transport: str = "auto", group=None, backend=None):
+                 exact_sincos: bool = False, transport: str = "auto", group=None, backend=None, pipeline: Optional[bool] = None):
+        """pipeline: overlap frame f+1's row pass and exchange (peer stores, or the all-to-all) with frame f's column pass, through a second
+        receive buffer and two internal streams. None = whenever it applies (several ranks over NCCL); outputs are then complete after
+        flush() / sync() / download()."""
         self._dist = None
         self.world, self.rank = 1, 0
         try:
@@ -201,6 +231,10 @@ class SlabOcean:
         self._peers_ready = False
         self._token = None
         self.frames = 0
+        self._want_pipeline = pipeline
+        self.pipelined = False
+        self._pipe = None           # (rows stream, columns stream, rows-done events, columns-done events)
+        self._fence_in = True       # the internal streams must first wait for the caller's stream
 
     def close(self):
         self.backend.close()
@@ -233,7 +267,38 @@ class SlabOcean:
                 self.transport = "peer"
         elif self.transport == "auto":
             self.transport = "peer"          # world == 1: the "peer" is this rank's own receive buffer
+        self._setup_pipeline()
         return True
+
+    def _setup_pipeline(self):
+        """Second receive buffer + its peer mappings + two streams; decided identically on every rank."""
+        can = (self.world > 1 and self._want_pipeline is not False and hasattr(self.backend, "rows_buf")
+               and self._dist is not None and self._dist.get_backend(self.group) == "nccl")
+        if not can:
+            if self._want_pipeline:
+                raise OceanWavesError("pipeline=True needs NCCL and more than one rank")
+            return
+        err = None
+        try:
+            self.backend.enable_double_buffer()
+            if self.transport == "peer":
+                handles = [None] * self.world
+                self._dist.all_gather_object(handles, self.backend.ipc_handle_buf(1), group=self.group)
+                self.backend.open_peers_buf(1, handles)
+        except OceanWavesError as e:
+            err = f"rank {self.rank}: {e}"
+        errs = [None] * self.world
+        self._dist.all_gather_object(errs, err, group=self.group)
+        if any(errs):
+            if self._want_pipeline:
+                raise OceanWavesError("pipeline=True: " + "; ".join(e for e in errs if e))
+            return
+        import torch
+        dev = self.backend.device
+        # the ROWS stream has the higher priority: once both passes are eligible, frame f+1's rows must go first, so that their exchange (NVLink-
+        # bound, few SMs) is under way while frame f's columns have the SMs; the other way round the exchange would queue up behind the columns
+        self._pipe = (torch.cuda.Stream(dev, priority=-1), torch.cuda.Stream(dev), [torch.cuda.Event(), torch.cuda.Event()], [torch.cuda.Event(), torch.cuda.Event()])
+        self.pipelined = True
 
     def _open_peers(self):
         handles = [None] * self.world
@@ -256,6 +321,8 @@ class SlabOcean:
 
     # ---- per frame (reference update(): src/main.cpp:240-244) -------------------------------------------------------
     def update(self, t: float):
+        if self.pipelined:
+            return self._update_pipelined(t)
         b = self.backend
         st = b.current_stream()
         if self.transport == "peer":
@@ -273,12 +340,57 @@ class SlabOcean:
         b.cols(st)
         self.frames += 1
 
+    def _update_pipelined(self, t: float):
+        """rows(f) -> receive buffer f % 2 on the rows stream; cols(f) on the columns stream once every rank's rows(f) have landed;
+        rows(f) only after every rank's cols(f-2) has finished reading that buffer. All barriers live on the rows stream, in the same order
+        on every rank, so the columns of frame f run while the rows (and the NVLink stores) of frame f+1 are under way."""
+        import torch
+        b = self.backend
+        R, Cs, ev_rows, ev_cols = self._pipe
+        f, buf = self.frames, self.frames % 2
+        if self._fence_in:                       # first frame after init / flush: order after whatever the caller queued so far
+            e = torch.cuda.Event()
+            e.record(torch.cuda.current_stream(b.device))
+            R.wait_event(e)
+            Cs.wait_event(e)
+            self._fence_in = False
+        with torch.cuda.stream(R):
+            if self.transport == "peer":
+                if f >= 2:
+                    R.wait_event(ev_cols[buf])   # this rank's cols(f-2) ...
+                    self._barrier()              # ... and every other rank's
+                b.rows_buf(t, PEER_STORES, buf, int(R.cuda_stream))
+                self._barrier()                  # every rank's rows(f) have landed
+            else:
+                b.rows_buf(t, SEND_BUFFER, buf, int(R.cuda_stream))      # into the (single) send buffer: the previous all-to-all precedes it on this stream
+                if f >= 2:
+                    R.wait_event(ev_cols[buf])   # the all-to-all overwrites MY receive buffer f % 2: my cols(f-2) must be done with it
+                send, recv = b.exchange_tensors(buf)
+                self._dist.all_to_all_single(recv, send, group=self.group)
+            ev_rows[buf].record(R)
+        with torch.cuda.stream(Cs):
+            Cs.wait_event(ev_rows[buf])
+            b.cols_buf(buf, int(Cs.cuda_stream))
+            ev_cols[buf].record(Cs)
+        self.frames += 1
+
+    def flush(self):
+        """Make the caller's current stream wait for every frame submitted so far (a no-op unless frames are pipelined)."""
+        if self.pipelined and self.frames:
+            import torch
+            cur = torch.cuda.current_stream(self.backend.device)
+            cur.wait_stream(self._pipe[0])
+            cur.wait_stream(self._pipe[1])
+            self._fence_in = True
+
     def sync(self):
+        self.flush()
         self.backend.sync(self.backend.current_stream())
 
     # ---- outputs ---------------------------------------------------------------------------------------------------
     def download(self, name: str) -> np.ndarray:
         """This rank's column slab: [N][XL] (normal: [N][XL][4])."""
+        self.flush()
         return self.backend.download(name, self.backend.current_stream())
 
     def gather(self, name: str) -> np.ndarray:

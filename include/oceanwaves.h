@@ -250,6 +250,20 @@ int ow_slab_cols(ow_slab* s, void* stream);
 /* world == 1 stand-in for the all-to-all (send -> recv device copy). */
 int ow_slab_local_exchange(ow_slab* s, void* stream);
 int ow_slab_sync(ow_slab* s, void* stream);
+/* Frame pipelining over NVLink: a second receive buffer (and, above N = 4096, a second scratch), so that frame f+1's row pass - whose
+ * stores ARE the exchange - runs on one stream while frame f's column pass reads the other buffer on another. The *_buf entry points
+ * take the buffer index (0 or 1); ow_slab_rows / ow_slab_cols / ow_slab_ipc_handle / ow_slab_open_peers are buffer 0. The caller orders
+ * every rank's rows(f) before any rank's cols(f), and every rank's cols(f) before any rank's rows(f+2). */
+int ow_slab_enable_double_buffer(ow_slab* s);
+int ow_slab_ipc_handle_buf(ow_slab* s, int32_t buf, void* handle, size_t bytes);
+int ow_slab_open_peers_buf(ow_slab* s, int32_t buf, const void* handles, size_t bytes);
+int ow_slab_rows_buf(ow_slab* s, float t, int32_t transport, int32_t buf, void* stream);
+int ow_slab_cols_buf(ow_slab* s, int32_t buf, void* stream);
+/* Device pointer of receive buffer `buf` (the all-to-all's destination; info.recv is buffer 0). */
+int ow_slab_recv_buffer(ow_slab* s, int32_t buf, void** ptr);
+/* N > 4096: CTAs per SM of the row pass's store kernel (0 = one CTA per work item; ow_slab_enable_double_buffer sets 2 when world > 1, so that the
+ * NVLink-bound stores leave the SMs to the column pass running beside them). */
+int ow_slab_set_post_ctas(ow_slab* s, int32_t per_sm);
 /* As ow_set_line_clusters / ow_get_line_clusters, for a slab rank. */
 int ow_slab_set_line_clusters(ow_slab* s, int32_t mode);
 int ow_slab_get_line_clusters(const ow_slab* s);

@@ -28,7 +28,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, world = dist.get_rank(), dist.get_world_size()
     p = fow.OceanParams(L=1000.0, wind_speed=40.0, wind_dir=(1.0, 1.0), amplitude=2.0, suppression=0.1, choppiness=1.0)
-    seed, times = 32768, (0.5, 1.0)
+    seed, times = 32768, (0.25, 0.5, 0.75, 1.0)       # four frames: both receive buffers of the pipelined path are reused once
     ref = None
     if rank == 0:
         with fow.FFTOceanWaves(N=N, cascades=[p], jacobian=True, device=local) as one:
@@ -36,13 +36,17 @@ def main():
             one.tilde_h0_k()
             ref = one.frame(times[-1])
     ok = True
-    for transport in (("peer",) if shared else ("peer", "alltoall")):
-        with fow.SlabOcean(N=N, params=p, device=local, jacobian=True, transport=transport) as sim:
+    # (transport, pipeline): over NCCL the peer transport runs frame-pipelined by default (rows of frame f+1 during the columns of frame f)
+    variants = (("peer", None),) if shared else (("peer", None), ("peer", False), ("alltoall", None), ("alltoall", False))
+    for transport, pipeline in variants:
+        with fow.SlabOcean(N=N, params=p, device=local, jacobian=True, transport=transport, pipeline=pipeline) as sim:
             sim.init(seed)
             assert sim.transport == transport
+            assert sim.pipelined == (pipeline is None and not shared and world > 1), (transport, pipeline, sim.pipelined)
+            transport = transport + ("+pipelined" if sim.pipelined else "")
             stream = torch.cuda.Stream()
             with torch.cuda.stream(stream):
-                for t in times:                      # two frames back to back: exercises the buffer-reuse ordering
+                for t in times:                      # frames back to back: exercises the buffer-reuse ordering
                     sim.update(t)
                 sim.sync()
                 full = {k: sim.gather(k) for k in ("dy", "dx", "dz", "normal", "jacobian")}
