@@ -110,6 +110,15 @@ int slab_cols_n(const SlabGeom& g, const float2* recv, float* disp_loc, float4* 
     return launches_ok() ? 2 : -1;
 }
 
+// Grid of a persistent kernel over `items` work items with at most `resident` CTAs on the device: the fewest CTAs that still finish in the
+// same number of rounds (768 items on 444 slots: 384 CTAs x 2 items instead of 444 CTAs of which 120 do one item and wait), which leaves the
+// other SM slots to the kernels of the launch groups running beside this one.
+static int balanced_grid(int items, int resident) {
+    if (items <= resident) return items;
+    const int rounds = (items + resident - 1) / resident;
+    return (items + rounds - 1) / rounds;
+}
+
 template <int N>
 int launch_n(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_jac, bool fast_phase, Launcher& L, cudaEvent_t* ev) {
     using C = Cfg<N>;
@@ -128,13 +137,13 @@ int launch_n(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_
         else L(ow_row_kernel<R, C::ROW_PAIRS, C::ROW_MINB, false>, rgrid, R::T * C::ROW_PAIRS, rs, fb, tab);
     } else if (row_mode == 2) {
         const int resident = fb.sm_count * fb.row_pipe_ctas[fi];
-        const int grid = n_cta_items < resident ? n_cta_items : resident;
+        const int grid = balanced_grid(n_cta_items, resident);
         if (fast_phase) L(ow_row_pipe_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true>, grid, R::T * C::ROW_PAIRS, rs, fb, tab, n_cta_items);
         else L(ow_row_pipe_kernel<R, C::ROW_PAIRS, C::ROW_MINB, false>, grid, R::T * C::ROW_PAIRS, rs, fb, tab, n_cta_items);
     } else {
         constexpr size_t rbs = row_bulk_smem<R, C::ROW_PAIRS>();
         const int resident = fb.sm_count * fb.row_bulk_ctas[fi];
-        const int grid = n_cta_items < resident ? n_cta_items : resident;
+        const int grid = balanced_grid(n_cta_items, resident);
         if (fast_phase) L(ow_row_bulk_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true>, grid, R::T * C::ROW_PAIRS, rbs, fb, tab, n_cta_items);
         else L(ow_row_bulk_kernel<R, C::ROW_PAIRS, C::ROW_MINB, false>, grid, R::T * C::ROW_PAIRS, rbs, fb, tab, n_cta_items);
     }
@@ -148,7 +157,7 @@ int launch_n(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_
     int launches = 1;
     if (col_mode == 4) {
         const int total = 3 * (N / (2 * C::COL_G)) * count, resident = fb.sm_count * fb.col_pipe_ctas;
-        L(ow_col_pipe_kernel<K, C::COL_G, C::COLP_MINB>, total < resident ? total : resident, K::T * C::COL_G, cs, fb, tab, scale, total);
+        L(ow_col_pipe_kernel<K, C::COL_G, C::COLP_MINB>, balanced_grid(total, resident), K::T * C::COL_G, cs, fb, tab, scale, total);
     }
     if constexpr (C::COL_FUSE) {
         if (col_mode == 2 || col_mode == 3) {
@@ -156,7 +165,7 @@ int launch_n(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_
             const int total = 3 * (N / (2 * C::COL_G)) * count;
             if (col_mode == 3) {
                 const int resident = fb.sm_count * fb.col2_ctas[1];
-                L(ow_col2_kernel<K, C::COL_G, C::COL2_MINB, C::NRM_RY, true>, total < resident ? total : resident, K::T * C::COL_G,
+                L(ow_col2_kernel<K, C::COL_G, C::COL2_MINB, C::NRM_RY, true>, balanced_grid(total, resident), K::T * C::COL_G,
                   Col2Smem<K, C::COL_G, true>::BYTES, *static_cast<const CUtensorMap*>(fb.inter_tmap), fb, tab, scale, total, fused ? 1 : 0);
             } else {
                 CUtensorMap none{};
