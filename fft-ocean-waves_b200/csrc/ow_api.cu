@@ -60,6 +60,7 @@ struct ow_ctx {
     int l2_persist = 0;
     bool l2_window_on = false;
     cudaStream_t l2_user_stream = nullptr;   // last caller stream the window was applied to
+    int latency_shapes = 1;       // ow_set_latency_shapes
     int line_clusters = 0;        // ow_set_line_clusters: 0 = global scratch (default: the DSMEM exchange measured 3.5x slower on B200), -1 = whatever
                                   // cluster shapes the device can co-schedule (kcfg.big_cluster), else a bit mask
     int cap_row = 0, cap_col = 0; // ow_set_resident_ctas: CTAs per SM of the persistent row / column kernels (0 = what fits)
@@ -138,6 +139,7 @@ FrameBuffers buffers(const ow_ctx* c) {
         if (c->cap_row > 0) { fb.row_pipe_ctas[i] = std::min(fb.row_pipe_ctas[i], c->cap_row); fb.row_bulk_ctas[i] = std::min(fb.row_bulk_ctas[i], c->cap_row); }
         if (c->cap_col > 0) fb.col2_ctas[i] = std::min(fb.col2_ctas[i], c->cap_col);
     }
+    fb.latency_shapes = c->latency_shapes;
     fb.big_cluster = c->line_clusters < 0 ? c->kcfg.big_cluster
                                           : (c->line_clusters & c->kcfg.big_cluster & 3) | ((c->line_clusters & 2) ? (c->line_clusters & 4) : 0);
     fb.col_pipe_ctas = c->cap_col > 0 ? std::min(c->kcfg.col_pipe_ctas, c->cap_col) : c->kcfg.col_pipe_ctas;
@@ -610,6 +612,13 @@ int ow_set_resident_ctas(ow_ctx* c, int32_t row_per_sm, int32_t col_per_sm) {
     if (!c || row_per_sm < 0 || col_per_sm < 0) return OW_ERR_INVALID;
     c->cap_row = row_per_sm;
     c->cap_col = col_per_sm;
+    drop_plans(c);
+    return OW_OK;
+}
+
+int ow_set_latency_shapes(ow_ctx* c, int32_t on) {
+    if (!c) return OW_ERR_INVALID;
+    c->latency_shapes = on ? 1 : 0;
     drop_plans(c);
     return OW_OK;
 }

@@ -16,6 +16,10 @@ namespace ow {
 // COLP_MINB: resident CTAs per SM the register allocation of ow_col_pipe_kernel (COL_MODE 4) aims at.
 // COL_FUSED: the normal map comes out of the column kernel (no separate normal kernel) by default.
 // Normal kernel: NRM_RY output rows per thread walk, NRM_WARPS warps per CTA, NRM_MINB resident CTAs per SM.
+// LAT: a second, LATENCY-oriented shape for launches of ONE frame (the drop-in ow_step of a single cascade): the throughput shapes above
+// leave most SMs idle there (N = 512: 64 row CTAs on 148 SMs, 5-7 us per kernel), so a single frame runs RowL (the same radices and
+// paddings with LAT_T threads per row pair instead of T, one pair per CTA: identical butterflies, hence identical bits, dealt out over
+// more threads) and a normal-map walk of NRML_RY rows per thread.
 // Column plans interleave G jobs in the lane index, need S0 odd and a job stride == 16/G (mod 16).
 // ---------------------------------------------------------------------------------------------------
 #ifndef OW_C2MB_SMALL
@@ -59,6 +63,9 @@ struct Cfg<256> {
     static constexpr int COL_MODE = 1;
     static constexpr bool COL_FUSED = false;
     static constexpr int NRM_RY = 8, NRM_WARPS = 4, NRM_MINB = 4;
+    static constexpr bool LAT = true;
+    using RowL = Plan<256, 4, 4, 16, 64, 1, 0>;
+    static constexpr int NRML_RY = 2;
 };
 template <>
 struct Cfg<512> {
@@ -73,6 +80,9 @@ struct Cfg<512> {
     static constexpr int COL_MODE = 1;
     static constexpr bool COL_FUSED = false;
     static constexpr int NRM_RY = 8, NRM_WARPS = 4, NRM_MINB = OW_NRM_MINB;
+    static constexpr bool LAT = true;
+    using RowL = Plan<512, 8, 4, 16, 128, 1, 14>;
+    static constexpr int NRML_RY = 2;
 };
 template <>
 struct Cfg<1024> {
@@ -87,6 +97,9 @@ struct Cfg<1024> {
     static constexpr int COL_MODE = 1;
     static constexpr bool COL_FUSED = false;
     static constexpr int NRM_RY = 8, NRM_WARPS = 4, NRM_MINB = 4;
+    static constexpr bool LAT = true;
+    using RowL = Plan<1024, 8, 8, 16, 128, 1, 10>;
+    static constexpr int NRML_RY = 2;
 };
 template <>
 struct Cfg<2048> {
@@ -101,6 +114,9 @@ struct Cfg<2048> {
     static constexpr int COL_MODE = 4;
     static constexpr bool COL_FUSED = false;
     static constexpr int NRM_RY = 8, NRM_WARPS = 4, NRM_MINB = 4;
+    static constexpr bool LAT = false;
+    using RowL = Row;
+    static constexpr int NRML_RY = NRM_RY;
 };
 template <>
 struct Cfg<4096> {
@@ -115,6 +131,9 @@ struct Cfg<4096> {
     static constexpr int COL_MODE = 1;
     static constexpr bool COL_FUSED = false;
     static constexpr int NRM_RY = 8, NRM_WARPS = 4, NRM_MINB = 4;
+    static constexpr bool LAT = false;
+    using RowL = Row;
+    static constexpr int NRML_RY = NRM_RY;
 };
 
 template <class P, int G>

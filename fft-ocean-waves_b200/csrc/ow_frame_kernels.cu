@@ -39,6 +39,11 @@ cudaError_t configure_n(KernelConfig* cfg) {
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ow_col_pipe_kernel<K, C::COL_G, C::COLP_MINB>, K::T * C::COL_G, cs)) != cudaSuccess) return e;
         cfg->col_pipe_ctas = n > 0 ? n : 1;
     }
+    if constexpr (C::LAT) {
+        using RL = typename C::RowL;
+        if ((e = opt_in_smem(ow_row_kernel<RL, 1, 2, false>, row_smem<RL, 1>())) != cudaSuccess) return e;
+        if ((e = opt_in_smem(ow_row_kernel<RL, 1, 2, true>, row_smem<RL, 1>())) != cudaSuccess) return e;
+    }
     constexpr size_t rbs = row_bulk_smem<R, C::ROW_PAIRS>();
     if ((e = opt_in_smem(ow_row_bulk_kernel<R, C::ROW_PAIRS, C::ROW_MINB, false>, rbs)) != cudaSuccess) return e;
     if ((e = opt_in_smem(ow_row_bulk_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true>, rbs)) != cudaSuccess) return e;
@@ -110,14 +115,10 @@ int slab_cols_n(const SlabGeom& g, const float2* recv, float* disp_loc, float4* 
     return launches_ok() ? 2 : -1;
 }
 
-// Grid of a persistent kernel over `items` work items with at most `resident` CTAs on the device: the fewest CTAs that still finish in the
-// same number of rounds (768 items on 444 slots: 384 CTAs x 2 items instead of 444 CTAs of which 120 do one item and wait), which leaves the
-// other SM slots to the kernels of the launch groups running beside this one.
-static int balanced_grid(int items, int resident) {
-    if (items <= resident) return items;
-    const int rounds = (items + resident - 1) / resident;
-    return (items + rounds - 1) / rounds;
-}
+// Grid of a persistent kernel over `items` work items with at most `resident` CTAs on the device. (Sizing it to whole rounds - 384 CTAs x 2 items
+// instead of 444 CTAs for 768 items - was measured and is 3.5 % SLOWER on an 8-cascade C4 step: the extra CTAs' loads in flight are worth more
+// than the slots they take from the neighbouring launch groups; profiles/r02_experiments.md.)
+static int persistent_grid(int items, int resident) { return items < resident ? items : resident; }
 
 template <int N>
 int launch_n(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_jac, bool fast_phase, Launcher& L, cudaEvent_t* ev) {
@@ -131,19 +132,26 @@ int launch_n(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_
     const int row_mode = fb.row_mode ? fb.row_mode : C::ROW_MODE;
     const int n_cta_items = count * (N / 2 / C::ROW_PAIRS);
     L.reads_time = true;
-    if (row_mode == 1) {
+    // one frame, nothing forced: the latency shapes (Cfg<N>::LAT)
+    const bool lat = C::LAT && count == 1 && fb.row_mode == 0 && fb.col_mode == 0 && fb.fuse_mode < 0 && fb.latency_shapes;
+    if (lat) {
+        using RL = typename C::RowL;
+        const dim3 rgrid(N / 2, 1);
+        if (fast_phase) L(ow_row_kernel<RL, 1, 2, true>, rgrid, RL::T, row_smem<RL, 1>(), fb, tab);
+        else L(ow_row_kernel<RL, 1, 2, false>, rgrid, RL::T, row_smem<RL, 1>(), fb, tab);
+    } else if (row_mode == 1) {
         const dim3 rgrid(N / 2 / C::ROW_PAIRS, count);
         if (fast_phase) L(ow_row_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true>, rgrid, R::T * C::ROW_PAIRS, rs, fb, tab);
         else L(ow_row_kernel<R, C::ROW_PAIRS, C::ROW_MINB, false>, rgrid, R::T * C::ROW_PAIRS, rs, fb, tab);
     } else if (row_mode == 2) {
         const int resident = fb.sm_count * fb.row_pipe_ctas[fi];
-        const int grid = balanced_grid(n_cta_items, resident);
+        const int grid = persistent_grid(n_cta_items, resident);
         if (fast_phase) L(ow_row_pipe_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true>, grid, R::T * C::ROW_PAIRS, rs, fb, tab, n_cta_items);
         else L(ow_row_pipe_kernel<R, C::ROW_PAIRS, C::ROW_MINB, false>, grid, R::T * C::ROW_PAIRS, rs, fb, tab, n_cta_items);
     } else {
         constexpr size_t rbs = row_bulk_smem<R, C::ROW_PAIRS>();
         const int resident = fb.sm_count * fb.row_bulk_ctas[fi];
-        const int grid = balanced_grid(n_cta_items, resident);
+        const int grid = persistent_grid(n_cta_items, resident);
         if (fast_phase) L(ow_row_bulk_kernel<R, C::ROW_PAIRS, C::ROW_MINB, true>, grid, R::T * C::ROW_PAIRS, rbs, fb, tab, n_cta_items);
         else L(ow_row_bulk_kernel<R, C::ROW_PAIRS, C::ROW_MINB, false>, grid, R::T * C::ROW_PAIRS, rbs, fb, tab, n_cta_items);
     }
@@ -157,7 +165,7 @@ int launch_n(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_
     int launches = 1;
     if (col_mode == 4) {
         const int total = 3 * (N / (2 * C::COL_G)) * count, resident = fb.sm_count * fb.col_pipe_ctas;
-        L(ow_col_pipe_kernel<K, C::COL_G, C::COLP_MINB>, balanced_grid(total, resident), K::T * C::COL_G, cs, fb, tab, scale, total);
+        L(ow_col_pipe_kernel<K, C::COL_G, C::COLP_MINB>, persistent_grid(total, resident), K::T * C::COL_G, cs, fb, tab, scale, total);
     }
     if constexpr (C::COL_FUSE) {
         if (col_mode == 2 || col_mode == 3) {
@@ -165,7 +173,7 @@ int launch_n(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_
             const int total = 3 * (N / (2 * C::COL_G)) * count;
             if (col_mode == 3) {
                 const int resident = fb.sm_count * fb.col2_ctas[1];
-                L(ow_col2_kernel<K, C::COL_G, C::COL2_MINB, C::NRM_RY, true>, balanced_grid(total, resident), K::T * C::COL_G,
+                L(ow_col2_kernel<K, C::COL_G, C::COL2_MINB, C::NRM_RY, true>, persistent_grid(total, resident), K::T * C::COL_G,
                   Col2Smem<K, C::COL_G, true>::BYTES, *static_cast<const CUtensorMap*>(fb.inter_tmap), fb, tab, scale, total, fused ? 1 : 0);
             } else {
                 CUtensorMap none{};
@@ -178,7 +186,12 @@ int launch_n(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_
     if (ev) cudaEventRecord(ev[2], L.st);
     // ---- normal map (+ Jacobian) ------------------------------------------------------------------------------------------
     const dim3 ngrid(N / 128, N / (C::NRM_WARPS * C::NRM_RY), count);
-    if (!fused) {
+    if (!fused && lat && C::NRML_RY != C::NRM_RY) {
+        const dim3 lgrid(N / 128, N / (C::NRM_WARPS * C::NRML_RY), count);
+        if (with_jac) L(ow_normal_kernel<N, true, C::NRML_RY, C::NRM_WARPS, C::NRM_MINB>, lgrid, dim3(32, C::NRM_WARPS), 0, fb, tab);
+        else L(ow_normal_kernel<N, false, C::NRML_RY, C::NRM_WARPS, C::NRM_MINB>, lgrid, dim3(32, C::NRM_WARPS), 0, fb, tab);
+        ++launches;
+    } else if (!fused) {
         if (with_jac) L(ow_normal_kernel<N, true, C::NRM_RY, C::NRM_WARPS, C::NRM_MINB>, ngrid, dim3(32, C::NRM_WARPS), 0, fb, tab);
         else L(ow_normal_kernel<N, false, C::NRM_RY, C::NRM_WARPS, C::NRM_MINB>, ngrid, dim3(32, C::NRM_WARPS), 0, fb, tab);
         ++launches;

@@ -50,6 +50,7 @@ struct FrameBuffers {
     int row_bulk_ctas[2];
     int col2_ctas[2];      // resident CTAs per SM of ow_col2_kernel: [direct loads, TMA staged]
     int col_pipe_ctas;     // resident CTAs per SM of ow_col_pipe_kernel
+    int latency_shapes;    // launches of ONE frame use the latency-oriented kernel shapes (Cfg<N>::LAT); ow_set_latency_shapes
     int big_cluster;       // N = A*B decomposition: bit 0 = rows, bit 1 = columns run as thread-block clusters (DSMEM radix-A stage, no scratch),
                            // bit 2 = the column clusters use 8-column tiles (3 CTAs per SM) instead of 16-column ones (1 CTA per SM)
 };

@@ -183,6 +183,9 @@ int ow_set_resident_ctas(ow_ctx* ctx, int32_t row_per_sm, int32_t col_per_sm);
  * access-policy window over it (hits persist in the device's L2 carve-out, cudaLimitPersistingL2CacheSize - a per-device limit this
  * call sets), 0 = off (default: measured slower on B200), -1 = on when all cascades' blocks fit two thirds of the carve-out. A hint only. */
 int ow_set_l2_persist(ow_ctx* ctx, int32_t mode);
+/* Launches of ONE frame (ow_step of a single cascade, the reference's update()) use latency-oriented kernel shapes for N <= 1024: the same
+ * butterflies dealt out over more threads and CTAs, bit-identical images. 1 = on (default), 0 = the throughput shapes everywhere. */
+int ow_set_latency_shapes(ow_ctx* ctx, int32_t on);
 /* Lines longer than one CTA's shared memory (N > 4096, or OW_FLAG_FOUR_STEP): N = A*B, the A sub-lines of a line are transformed by the
  * A CTAs of a thread-block cluster and combined through distributed shared memory (no global scratch). mode: -1 = wherever the device can
  * co-schedule the cluster, 0 = never (default: two kernels per direction through a global scratch array - measured 3.5x FASTER on B200

@@ -261,3 +261,30 @@ def test_fused_normals_without_jacobian(noise):
         assert np.abs(fused[k] - sep[k]).max() <= 2e-6 * np.abs(sep[k]).max()
         assert np.array_equal(fused[k], fused2[k])
     assert np.abs(fused["normal"] - sep["normal"]).max() < 2e-6 and np.array_equal(fused["normal"], fused2["normal"])
+
+
+@pytest.mark.parametrize("N", [256, 512, 1024])
+@pytest.mark.parametrize("jac", [False, True])
+def test_single_frame_latency_shapes_agree(noise, N, jac):
+    """ow_step of ONE cascade runs latency-oriented kernel shapes (more threads per row pair, one pair per CTA, shorter normal-map walks;
+    Cfg<N>::LAT): the same butterflies dealt out differently. The images must agree with the throughput shapes' to fp32 round-off (2e-6 of
+    peak: the compiler may contract multiply-adds differently in another instantiation) - through the CUDA graph and through plain
+    launches - and sit inside the parity tolerance of the oracle."""
+    t = 3.25
+    ref_o = OracleSim(N, 1000.0, 40.0, (1.0, 1.0), 2.0, 0.1, noise, threads=8).frame(np.float32(t), choppiness=1.0)
+    with fow.FFTOceanWaves(N=N, cascades=[params()], jacobian=jac, n_slots=2) as sim:
+        sim.init(noise)
+        names = ["dy", "dx", "dz", "normal"] + (["jacobian"] if jac else [])
+        sim.set_latency_shapes(False)
+        ref = sim.frame(t)
+        sim.set_latency_shapes(True)
+        for graph in (True, False):
+            sim.set_graph(graph)
+            sim.update(0.5)                  # another frame first
+            got = sim.frame(t)
+            assert sim.last_launch_count() == 3
+            for k in names:
+                peak = float(np.abs(ref[k]).max())
+                assert np.abs(got[k] - ref[k]).max() <= 2e-6 * max(peak, 1.0), (graph, k)
+            for k in ("dy", "dx", "dz"):
+                assert np.abs(got[k] - ref_o[k]).max() <= 1e-4 * np.abs(ref_o[k]).max(), (graph, k)

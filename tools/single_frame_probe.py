@@ -21,8 +21,9 @@ with fow.FFTOceanWaves(N=N, cascades=[p], device=0) as sim:
             sim.update(f / 60.0, stream=sp)
         sim.sync(stream=sp)
         sys.exit(0)
-    for graph in (True, False):
+    for graph, lat in ((True, True), (False, True), (True, False)):
         sim.set_graph(graph)
+        sim.set_latency_shapes(lat)
         for f in range(20):
             sim.update(f / 60.0, stream=sp)
         sim.sync(stream=sp)
@@ -33,4 +34,4 @@ with fow.FFTOceanWaves(N=N, cascades=[p], device=0) as sim:
             sim.update(f / 60.0, stream=sp)
         b.record(st)
         torch.cuda.synchronize()
-        print("N=%d %s: %.2f us/frame back to back (%.0f fps), %d launches" % (N, "graph" if graph else "launches", a.elapsed_time(b) * 1e3 / n, n / (a.elapsed_time(b) * 1e-3), sim.last_launch_count()))
+        print("N=%d %s %s: %.2f us/frame back to back (%.0f fps), %d launches" % (N, "graph" if graph else "launches", "latency shapes" if lat else "throughput shapes", a.elapsed_time(b) * 1e3 / n, n / (a.elapsed_time(b) * 1e-3), sim.last_launch_count()))
