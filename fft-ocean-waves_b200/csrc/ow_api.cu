@@ -237,7 +237,7 @@ int ow_create(int32_t N, int32_t n_cascades, int32_t n_slots, const ow_params* c
               uint32_t flags, ow_ctx** out) {
     if (!out) return fail(nullptr, OW_ERR_INVALID, "ow_create: out is NULL");
     *out = nullptr;
-    if (!frame_supported(N)) return fail(nullptr, OW_ERR_INVALID, "ow_create: N must be a power of two in [256, 32768]");
+    if (!frame_supported(N)) return fail(nullptr, OW_ERR_INVALID, "ow_create: N must be a power of two in [128, 32768]");
     if ((flags & OW_FLAG_FOUR_STEP) && !big_supported(N, true))
         return fail(nullptr, OW_ERR_INVALID, "ow_create: OW_FLAG_FOUR_STEP is a test mode for N = 1024 or 2048");
     if ((flags & OW_FLAG_PACKED_F32) && (flags & OW_FLAG_PACKED_F16))

@@ -50,6 +50,25 @@ namespace ow {
 template <int N>
 struct Cfg;
 
+// N = 128: the reference's DISPLACEMENT_MAP_SIZE is a free #define (src/main.cpp:17); the smallest grid whose rows still fill the normal kernel's
+// 128-column warp tiles. Not tuned: one warp per row pair, the plain kernels only (no TMA-staged / fused column variant).
+template <>
+struct Cfg<128> {
+    using Row = Plan<128, 2, 4, 16, 32, 1, 0>;
+    static constexpr int ROW_PAIRS = 4, ROW_MINB = 4;
+    static constexpr int ROW_MODE = 1;
+    using Col = Plan<128, 2, 4, 16, 32, 0, 1>;
+    static constexpr int COL_G = 8, COL_MINB = 2;
+    static constexpr int COL2_MINB = 2;
+    static constexpr int COLP_MINB = 2;
+    static constexpr bool COL_FUSE = false;
+    static constexpr int COL_MODE = 1;
+    static constexpr bool COL_FUSED = false;
+    static constexpr int NRM_RY = 8, NRM_WARPS = 4, NRM_MINB = 4;
+    static constexpr bool LAT = false;
+    using RowL = Row;
+    static constexpr int NRML_RY = NRM_RY;
+};
 template <>
 struct Cfg<256> {
     using Row = Plan<256, 4, 4, 16, 32, 1, 0>;

@@ -239,7 +239,7 @@ bool make_inter_tensor_map(void* out, const float2* inter, int N, int n_slots) {
 
 size_t hp_block_elems(int npairs, int N) { return hp_block_f4(npairs, N); }
 
-bool frame_supported(int N) { return N == 256 || N == 512 || N == 1024 || N == 2048 || N == 4096 || big_supported(N, false); }
+bool frame_supported(int N) { return N == 128 || N == 256 || N == 512 || N == 1024 || N == 2048 || N == 4096 || big_supported(N, false); }
 
 cudaError_t configure_frame_kernels(int N, KernelConfig* cfg) {
     int dev = 0;
@@ -251,6 +251,7 @@ cudaError_t configure_frame_kernels(int N, KernelConfig* cfg) {
         if ((e = configure_big(N, true, cfg)) != cudaSuccess) return e;
     }
     switch (N) {
+        case 128: return configure_n<128>(cfg);
         case 256: return configure_n<256>(cfg);
         case 512: return configure_n<512>(cfg);
         case 1024: return configure_n<1024>(cfg);
@@ -321,6 +322,7 @@ void effective_modes(const FrameBuffers& fb, int* row, int* col, int* fused) {
     *fused = 0;
     if (!frame_graphable(fb)) return;
     switch (fb.N) {
+        case 128: return modes_n<128>(fb, row, col, fused);
         case 256: return modes_n<256>(fb, row, col, fused);
         case 512: return modes_n<512>(fb, row, col, fused);
         case 1024: return modes_n<1024>(fb, row, col, fused);
@@ -337,6 +339,7 @@ int launch_frame(const FrameBuffers& fb, const SlotTable& tab, int count, bool w
         return launch_big_frame(fb, tab, count, with_jac, fast_phase, L.st, ev, !big_supported(fb.N, false));
     }
     switch (fb.N) {
+        case 128: return launch_n<128>(fb, tab, count, with_jac, fast_phase, L, ev);
         case 256: return launch_n<256>(fb, tab, count, with_jac, fast_phase, L, ev);
         case 512: return launch_n<512>(fb, tab, count, with_jac, fast_phase, L, ev);
         case 1024: return launch_n<1024>(fb, tab, count, with_jac, fast_phase, L, ev);

@@ -92,7 +92,7 @@ typedef enum ow_image {
 
 /* ---- lifecycle: replaces create_textures() (src/main.cpp:1083-1145) for the sim resources ------------- */
 
-/* n_cascades independent patches of size N x N (N a power of two in [256, 32768]; N > 4096 uses the N = A*B line decomposition); n_slots >= n_cascades
+/* n_cascades independent patches of size N x N (N a power of two in [128, 32768]; N > 4096 uses the N = A*B line decomposition); n_slots >= n_cascades
  * output sets (extra slots let one cascade be evaluated at several times per launch, see ow_step_multi).
  * device = CUDA ordinal. */
 int ow_create(int32_t N, int32_t n_cascades, int32_t n_slots, const ow_params* cascades, int32_t device,

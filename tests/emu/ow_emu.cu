@@ -338,6 +338,7 @@ int emu_slab_frame_n(int world, const float* h0k, const float* h0minusk, float L
 extern "C" int emu_frame(int N, const float* h0k, const float* h0minusk, float L, float t, float lambda, float* inter_out,
                          float* disp, float* normal, float* jac, long* stats) {
     switch (N) {
+        case 128: return emu_frame_n<128>(h0k, h0minusk, L, t, lambda, inter_out, disp, normal, jac, stats);
         case 256: return emu_frame_n<256>(h0k, h0minusk, L, t, lambda, inter_out, disp, normal, jac, stats);
         case 512: return emu_frame_n<512>(h0k, h0minusk, L, t, lambda, inter_out, disp, normal, jac, stats);
         case 1024: return emu_frame_n<1024>(h0k, h0minusk, L, t, lambda, inter_out, disp, normal, jac, stats);

@@ -20,7 +20,7 @@ def test_register_dft(R_):
     assert np.abs(emu.dft(x) - ref).max() < 2e-6 * np.abs(ref).max()
 
 
-@pytest.mark.parametrize("N,t", [(256, 0.0), (256, 1.0), (256, 10.0), (512, 599.0 / 60.0), (1024, 1.0)])
+@pytest.mark.parametrize("N,t", [(128, 1.0), (256, 0.0), (256, 1.0), (256, 10.0), (512, 599.0 / 60.0), (1024, 1.0)])
 def test_emulated_frame_matches_oracle(noise, N, t):
     s = OracleSim(N, 1000.0, 40.0, (1.0, 1.0), 2.0, 0.1, noise, threads=8)
     a, b = s.h0()

@@ -295,7 +295,7 @@ def test_fused_normal_epilogue_equals_separate_normal_kernel(noise, N):
     check_frame(fused, oracle_for(N, noise).frame(2.0), f"fused N={N} ")
 
 
-@pytest.mark.parametrize("N,t", [(256, 1.0), (512, 9.98), (1024, 2.0)])
+@pytest.mark.parametrize("N,t", [(128, 1.5), (256, 1.0), (512, 9.98), (1024, 2.0)])
 def test_cuda_path_vs_the_reference_shaders_themselves(noise, N, t):
     """The CUDA path against oracle/_ref — the reference's OWN compute shaders (GLSL text compiled for the CPU, dispatched in the
     reference's order) — without the hand-written oracle in between. Same tolerance as everywhere: 1e-4 of peak, plus the RMS bound."""
@@ -310,3 +310,19 @@ def test_cuda_path_vs_the_reference_shaders_themselves(noise, N, t):
     ra, _ = refmod.RefSim(N, 1000, 40.0, (1.0, 1.0), 2.0, 0.1, noise).h0()
     assert np.abs(a - ra).max() <= 2e-6 * np.abs(ra).max()
     check_frame(got, ref, f"vs reference shaders N={N} ")
+
+
+def test_smallest_grid_n128(noise):
+    """N = 128 (the reference's DISPLACEMENT_MAP_SIZE is a free #define, src/main.cpp:17): plain kernels, checked against the oracle, with the
+    Jacobian, through the graph and through a multi-slot launch; N = 64 is rejected (the normal kernel's warp tiles are 128 columns wide)."""
+    ref = OracleSim(128, 1000.0, 40.0, (1.0, 1.0), 2.0, 0.1, noise, threads=4).frame(np.float32(2.5), choppiness=1.0)
+    with fow.FFTOceanWaves(N=128, cascades=[params()], jacobian=True, n_slots=3) as sim:
+        sim.init(noise)
+        got = sim.frame(2.5)
+        check_frame(got, ref, "N=128 ")
+        assert np.abs(got["jacobian"] - ref["jacobian"]).max() < 1e-4
+        sim.update_multi([0, 0, 0], [0.0, 2.5, 1.0])
+        sim.sync()
+        assert np.array_equal(sim.download("dy", 1), got["dy"]) and np.array_equal(sim.download("normal", 1), got["normal"])
+    with pytest.raises(fow.OceanWavesError):
+        fow.FFTOceanWaves(N=64, cascades=[params()])
