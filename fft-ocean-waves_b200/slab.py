@@ -237,6 +237,11 @@ class SlabOcean:
         self._fence_in = True       # the internal streams must first wait for the caller's stream
 
     def close(self):
+        if self.pipelined and self._pipe is not None:
+            self._pipe[0].synchronize()          # nothing of ours may still be running on the internal streams when the buffers go
+            self._pipe[1].synchronize()
+            self._pipe = None
+            self.pipelined = False
         self.backend.close()
 
     def __enter__(self):
