@@ -18,6 +18,8 @@ def main():
     ap.add_argument("--caps", default="0:0", help="resident CTAs per SM of the persistent row:column kernels, comma list (0 = what fits)")
     ap.add_argument("--c4-shard-of", type=int, default=1)
     ap.add_argument("--l2", default="0", help="ow_set_l2_persist modes, comma list")
+    ap.add_argument("--discard", action="store_true", help="ow_set_discard_intermediate(1): the column kernel drops the intermediate's lines from L2 after reading them")
+    ap.add_argument("--slots", type=int, default=0)
     ap.add_argument("--graph", action="store_true", help="c4: time ow_step (one CUDA graph launch per step) instead of ow_step_multi")
     ap.add_argument("--check", action="store_true", help="compare every combination's frame with the first combination's")
     args = ap.parse_args()
@@ -32,11 +34,13 @@ def main():
     for name in args.workloads:
         w = bench.workload_setup(name, only=(0, 64 // args.c4_shard_of) if name == "c4" and args.c4_shard_of > 1 else None)
         N, frames = w["N"], w["frames"]
-        slots = min(128 if N <= 512 else 32, frames) if name != "c4" else frames
+        slots = min(args.slots or (300 if N <= 512 else 32), frames) if name != "c4" else frames
         sim = fow.FFTOceanWaves(N=N, cascades=w["cascades"], n_slots=max(slots, len(w["cascades"])), device=0, jacobian=w["jacobian"])
         for i, nz in enumerate(w["noise"]):
             sim.set_noise(nz, cascade=i)
         sim.tilde_h0_k()
+        if args.discard:
+            sim.set_discard_intermediate(True)
 
         def sweep():
             if args.graph:
