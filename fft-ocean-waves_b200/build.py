@@ -21,6 +21,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 SOURCES = [
     ("ow_frame_kernels.cu", []),
     ("ow_big_kernels.cu", []),
+    ("ow_mega_kernels.cu", []),
     ("ow_init_kernels.cu", ["-fmad=false"]),
     ("ow_pack_kernels.cu", []),
     ("ow_api.cu", []),

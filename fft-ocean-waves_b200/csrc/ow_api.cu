@@ -60,6 +60,8 @@ struct ow_ctx {
     int l2_persist = 0;
     bool l2_window_on = false;
     cudaStream_t l2_user_stream = nullptr;   // last caller stream the window was applied to
+    int frame_mode = 0;           // ow_set_frame_kernel
+    int* d_mega_sched = nullptr;  // (kMaxAux + 1) areas of kMegaSchedInts counters: one per auxiliary stream + one for the caller's stream
     int latency_shapes = 1;       // ow_set_latency_shapes
     int line_clusters = 0;        // ow_set_line_clusters: 0 = global scratch (default: the DSMEM exchange measured 3.5x slower on B200), -1 = whatever
                                   // cluster shapes the device can co-schedule (kcfg.big_cluster), else a bit mask
@@ -140,6 +142,9 @@ FrameBuffers buffers(const ow_ctx* c) {
         if (c->cap_col > 0) fb.col2_ctas[i] = std::min(fb.col2_ctas[i], c->cap_col);
     }
     fb.latency_shapes = c->latency_shapes;
+    fb.frame_mode = c->frame_mode;
+    fb.mega_ctas = c->kcfg.mega_ctas;
+    fb.mega_sched = c->d_mega_sched ? c->d_mega_sched + (size_t)ow_ctx::kMaxAux * kMegaSchedInts : nullptr;   // the caller's stream; step_impl re-points it per group
     fb.big_cluster = c->line_clusters < 0 ? c->kcfg.big_cluster
                                           : (c->line_clusters & c->kcfg.big_cluster & 3) | ((c->line_clusters & 2) ? (c->line_clusters & 4) : 0);
     fb.col_pipe_ctas = c->cap_col > 0 ? std::min(c->kcfg.col_pipe_ctas, c->cap_col) : c->kcfg.col_pipe_ctas;
@@ -221,6 +226,7 @@ void release(ow_ctx* c) {
     c->gl_registered = false;
     cudaFree(c->d_noise); cudaFree(c->d_h0); cudaFree(c->d_hp); cudaFree(c->d_nyq); cudaFree(c->d_ktab); cudaFree(c->d_casc); cudaFree(c->d_inter);
     drop_plans(c);
+    cudaFree(c->d_mega_sched);
     cudaFree(c->d_disp); cudaFree(c->d_normal); cudaFree(c->d_jac); cudaFree(c->d_tmp); cudaFree(c->d_scratch); cudaFree(c->d_packed); cudaFree(c->d_seam);
     if (c->stream) cudaStreamDestroy(c->stream);
     for (auto& s : c->aux) if (s) cudaStreamDestroy(s);
@@ -297,6 +303,7 @@ int ow_create(int32_t N, int32_t n_cascades, int32_t n_slots, const ow_params* c
     }
     OW_TRY(cudaMalloc(&c->d_seam, (size_t)n_slots * (N / 16) * sizeof(int)));
     OW_TRY(cudaMemsetAsync(c->d_seam, 0, (size_t)n_slots * (N / 16) * sizeof(int), c->stream));
+    OW_TRY(cudaMalloc(&c->d_mega_sched, (size_t)(ow_ctx::kMaxAux + 1) * kMegaSchedInts * sizeof(int)));
     OW_TRY(configure_frame_kernels(N, &c->kcfg));
     configure_l2(c);
     c->have_tmap = make_inter_tensor_map(c->inter_tmap, c->d_inter, N, n_slots);
@@ -480,7 +487,9 @@ static int step_impl(ow_ctx* c, int32_t count, const int32_t* cascade_of_slot, c
             tab.slot[i] = base + i;
             if (!fast_phase_ok(c, tab.cascade[i], tab.time[i])) fast = false;
         }
-        int k = launch_frame(fb, tab, n, (c->flags & OW_FLAG_JACOBIAN) != 0, fast, L, kernel_ms ? guard.ev : nullptr);
+        FrameBuffers fbg = fb;
+        if (fbg.mega_sched && nfan) fbg.mega_sched = c->d_mega_sched + (size_t)(gi % nfan) * kMegaSchedInts;     // this group's stream's counters
+        int k = launch_frame(fbg, tab, n, (c->flags & OW_FLAG_JACOBIAN) != 0, fast, L, kernel_ms ? guard.ev : nullptr);
         if (k < 0) return launch_failed(c, "launch_frame");
         launches += k;
         if (c->d_packed) {
@@ -616,9 +625,18 @@ int ow_set_resident_ctas(ow_ctx* c, int32_t row_per_sm, int32_t col_per_sm) {
     return OW_OK;
 }
 
+int ow_set_frame_kernel(ow_ctx* c, int32_t mode) {
+    if (!c || mode < 0 || mode > 1) return OW_ERR_INVALID;
+    if (mode == 1 && (!mega_supported(c->N) || c->kcfg.mega_ctas < 1))
+        return fail(c, OW_ERR_INVALID, "ow_set_frame_kernel: the one-kernel frame exists for N = 256, 512 and 1024");
+    c->frame_mode = mode;
+    drop_plans(c);
+    return OW_OK;
+}
+
 int ow_set_latency_shapes(ow_ctx* c, int32_t on) {
     if (!c) return OW_ERR_INVALID;
-    c->latency_shapes = on ? 1 : 0;
+    c->latency_shapes = on < 0 ? 0 : on > 2 ? 2 : on;     // 2 (tuning): the wide row shape for every launch, not only single frames
     drop_plans(c);
     return OW_OK;
 }

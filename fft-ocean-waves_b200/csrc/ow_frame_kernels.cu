@@ -134,9 +134,10 @@ int launch_n(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_
     L.reads_time = true;
     // one frame, nothing forced: the latency shapes (Cfg<N>::LAT)
     const bool lat = C::LAT && count == 1 && fb.row_mode == 0 && fb.col_mode == 0 && fb.fuse_mode < 0 && fb.latency_shapes;
-    if (lat) {
+    const bool wide_rows = C::LAT && fb.latency_shapes == 2 && fb.row_mode == 0;      // tuning: the wide row shape for every launch
+    if (lat || wide_rows) {
         using RL = typename C::RowL;
-        const dim3 rgrid(N / 2, 1);
+        const dim3 rgrid(N / 2, count);
         if (fast_phase) L(ow_row_kernel<RL, 1, 2, true>, rgrid, RL::T, row_smem<RL, 1>(), fb, tab);
         else L(ow_row_kernel<RL, 1, 2, false>, rgrid, RL::T, row_smem<RL, 1>(), fb, tab);
     } else if (row_mode == 1) {
@@ -250,6 +251,9 @@ cudaError_t configure_frame_kernels(int N, KernelConfig* cfg) {
     if (big_supported(N, true)) {
         if ((e = configure_big(N, true, cfg)) != cudaSuccess) return e;
     }
+    if (mega_supported(N)) {
+        if ((e = configure_mega(N, cfg)) != cudaSuccess) return e;
+    }
     switch (N) {
         case 128: return configure_n<128>(cfg);
         case 256: return configure_n<256>(cfg);
@@ -337,6 +341,12 @@ int launch_frame(const FrameBuffers& fb, const SlotTable& tab, int count, bool w
     if (!frame_graphable(fb)) {
         if (L.plan) return -1;                  // the line decomposition launches on a stream only
         return launch_big_frame(fb, tab, count, with_jac, fast_phase, L.st, ev, !big_supported(fb.N, false));
+    }
+    if (fb.frame_mode == 1 && mega_supported(fb.N) && !L.plan && fb.mega_sched && fb.mega_ctas > 0) {
+        if (ev) cudaEventRecord(ev[0], L.st);
+        const int k = launch_mega_frame(fb, tab, count, with_jac, fast_phase, L.st);
+        if (ev) { cudaEventRecord(ev[1], L.st); cudaEventRecord(ev[2], L.st); cudaEventRecord(ev[3], L.st); }   // one kernel: all of it under the first slot
+        return k;
     }
     switch (fb.N) {
         case 128: return launch_n<128>(fb, tab, count, with_jac, fast_phase, L, ev);

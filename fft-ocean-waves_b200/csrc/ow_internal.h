@@ -17,6 +17,8 @@ struct CascadeDev {
 
 constexpr int kMaxGroup = 128;  // slots per launch group (slot table travels by value in the kernel params: 1.5 KB of the 4 KB)
 
+constexpr int kMegaSchedInts = 1 + 2 * kMaxGroup;   // ow_mega_kernel's queue head + per-entry rows-done and columns-done counters
+
 struct SlotTable {
     int32_t cascade[kMaxGroup];
     float time[kMaxGroup];
@@ -50,6 +52,9 @@ struct FrameBuffers {
     int row_bulk_ctas[2];
     int col2_ctas[2];      // resident CTAs per SM of ow_col2_kernel: [direct loads, TMA staged]
     int col_pipe_ctas;     // resident CTAs per SM of ow_col_pipe_kernel
+    int frame_mode;        // 0 = separate row / column / normal kernels, 1 = ow_mega_kernel (one persistent dataflow kernel per launch group; N <= 1024)
+    int* mega_sched;       // kMegaSchedInts counters of the launch group being submitted (one area per stream of the context)
+    int mega_ctas;         // resident CTAs per SM of ow_mega_kernel
     int latency_shapes;    // launches of ONE frame use the latency-oriented kernel shapes (Cfg<N>::LAT); ow_set_latency_shapes
     int big_cluster;       // N = A*B decomposition: bit 0 = rows, bit 1 = columns run as thread-block clusters (DSMEM radix-A stage, no scratch),
                            // bit 2 = the column clusters use 8-column tiles (3 CTAs per SM) instead of 16-column ones (1 CTA per SM)
@@ -62,6 +67,7 @@ struct KernelConfig {
     int row_bulk_ctas[2] = {1, 1};     // ow_row_bulk_kernel, [exact, fast]
     int col2_ctas[2] = {1, 1};         // ow_col2_kernel, [direct loads, TMA staged]
     int col_pipe_ctas = 1;             // ow_col_pipe_kernel
+    int mega_ctas = 0;                 // ow_mega_kernel (0: not available for this N)
     int big_cluster = 0;               // what the device can co-schedule (FrameBuffers::big_cluster bits)
     int big_clusters_rows = 0, big_clusters_cols8 = 0, big_clusters_cols4 = 0;   // cudaOccupancyMaxActiveClusters of the three cluster shapes
 };
@@ -165,6 +171,10 @@ int launch_frame(const FrameBuffers& fb, const SlotTable& tab, int count, bool w
                  Launcher& L, cudaEvent_t* ev = nullptr);
 constexpr float kFastPhaseLimit = 2.0e4f;
 bool frame_graphable(const FrameBuffers& fb);
+// The whole frame as one persistent kernel (ow_mega_kernels.cu).
+bool mega_supported(int N);
+cudaError_t configure_mega(int N, KernelConfig* cfg);
+int launch_mega_frame(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_jacobian, bool fast_phase, cudaStream_t st);
 void effective_modes(const FrameBuffers& fb, int* row, int* col, int* fused);   // launch_frame can build graph nodes for this context (direct kernels, N <= 4096)
 // Tensor map over the row->column intermediate for the TMA-staged column kernel (64 bytes, 64-byte aligned, at `out`).
 // Returns false when the driver entry point is missing or N has no staged kernel; the context then runs without staging.

@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = [
     "ow_step", "ow_step_multi", "ow_step_multi_timed", "ow_sync", "ow_get_outputs", "ow_download", "ow_download_frame_async",
     "ow_frame_bytes", "ow_set_group_size", "ow_set_streams", "ow_last_launch_count", "ow_gl_register", "ow_gl_step", "ow_gl_unregister",
     "ow_set_noise_seed", "ow_last_group_count", "ow_init_spectrum_cascade", "ow_set_graph", "ow_get_packed", "ow_packed_bytes",
-    "ow_download_packed_async", "ow_set_row_kernel", "ow_set_discard_intermediate", "ow_gl_register_packed", "ow_set_column_kernel", "ow_get_kernel_modes", "ow_set_resident_ctas", "ow_set_l2_persist", "ow_set_latency_shapes", "ow_set_line_clusters", "ow_get_line_clusters",
+    "ow_download_packed_async", "ow_set_row_kernel", "ow_set_discard_intermediate", "ow_gl_register_packed", "ow_set_column_kernel", "ow_get_kernel_modes", "ow_set_resident_ctas", "ow_set_l2_persist", "ow_set_latency_shapes", "ow_set_frame_kernel", "ow_set_line_clusters", "ow_get_line_clusters",
     "ow_slab_set_line_clusters", "ow_slab_get_line_clusters", "ow_slab_enable_double_buffer", "ow_slab_ipc_handle_buf", "ow_slab_open_peers_buf",
     "ow_slab_rows_buf", "ow_slab_cols_buf", "ow_slab_set_post_ctas", "ow_slab_recv_buffer",
     "ow_slab_create", "ow_slab_destroy", "ow_slab_last_error", "ow_slab_get_info", "ow_slab_init_spectrum_seeded", "ow_slab_ipc_handle",
@@ -147,6 +147,7 @@ def load_library():
     L.ow_set_resident_ctas.argtypes = [vp, i32, i32]
     L.ow_set_l2_persist.argtypes = [vp, i32]
     L.ow_set_latency_shapes.argtypes = [vp, i32]
+    L.ow_set_frame_kernel.argtypes = [vp, i32]
     L.ow_set_line_clusters.argtypes = [vp, i32]
     L.ow_get_line_clusters.argtypes = [vp]
     L.ow_slab_set_line_clusters.argtypes = [vp, i32]
@@ -311,6 +312,9 @@ class FFTOceanWaves:
 
     def line_clusters(self) -> int:
         return int(self._lib.ow_get_line_clusters(self._h))
+
+    def set_frame_kernel(self, mode: int):
+        self._check(self._lib.ow_set_frame_kernel(self._h, int(mode)), "ow_set_frame_kernel")
 
     def set_latency_shapes(self, on: bool = True):
         self._check(self._lib.ow_set_latency_shapes(self._h, int(bool(on))), "ow_set_latency_shapes")

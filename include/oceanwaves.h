@@ -186,6 +186,10 @@ int ow_set_l2_persist(ow_ctx* ctx, int32_t mode);
 /* Launches of ONE frame (ow_step of a single cascade, the reference's update()) use latency-oriented kernel shapes for N <= 1024: the same
  * butterflies dealt out over more threads and CTAs, bit-identical images. 1 = on (default), 0 = the throughput shapes everywhere. */
 int ow_set_latency_shapes(ow_ctx* ctx, int32_t on);
+/* How ow_step_multi runs a launch group: 0 = three kernels (row, column, normal; default), 1 = ONE persistent kernel that walks row, column and
+ * normal-map work items of consecutive frames behind per-frame dependency counters, so that only two or three frames are in flight and the
+ * intermediate and the displacement planes are consumed out of L2 (N = 256, 512, 1024; ow_step's CUDA graph keeps the three kernels). */
+int ow_set_frame_kernel(ow_ctx* ctx, int32_t mode);
 /* Lines longer than one CTA's shared memory (N > 4096, or OW_FLAG_FOUR_STEP): N = A*B, the A sub-lines of a line are transformed by the
  * A CTAs of a thread-block cluster and combined through distributed shared memory (no global scratch). mode: -1 = wherever the device can
  * co-schedule the cluster, 0 = never (default: two kernels per direction through a global scratch array - measured 3.5x FASTER on B200

@@ -288,3 +288,38 @@ def test_single_frame_latency_shapes_agree(noise, N, jac):
                 assert np.abs(got[k] - ref[k]).max() <= 2e-6 * max(peak, 1.0), (graph, k)
             for k in ("dy", "dx", "dz"):
                 assert np.abs(got[k] - ref_o[k]).max() <= 1e-4 * np.abs(ref_o[k]).max(), (graph, k)
+
+
+@pytest.mark.parametrize("N", [256, 512, 1024])
+@pytest.mark.parametrize("jac", [False, True])
+def test_one_kernel_frame_agrees_with_the_three_kernel_frame(noise, N, jac):
+    """ow_set_frame_kernel(1): a launch group as ONE persistent kernel (ow_mega_kernel) that walks row, column and normal-map work items of
+    consecutive frames behind per-frame dependency counters. Same phase functions as the separate kernels, so every slot of a multi-frame
+    call must agree with the three-kernel path to fp32 round-off (2e-6 of peak), twice in a row (the counters are re-armed per launch), with
+    one frame per call as well as many, and sit inside the parity tolerance of the oracle."""
+    times = [0.0, 0.5, 2.0, 9.98, 2.0, 1.25, 7.5]
+    n = len(times)
+    ref_o = OracleSim(N, 1000.0, 40.0, (1.0, 1.0), 2.0, 0.1, noise, threads=8).frame(np.float32(2.0), choppiness=1.0)
+    names = ["dy", "dx", "dz", "normal"] + (["jacobian"] if jac else [])
+    with fow.FFTOceanWaves(N=N, cascades=[params()], jacobian=jac, n_slots=n) as sim:
+        sim.init(noise)
+        sim.update_multi([0] * n, times)
+        sim.sync()
+        ref = [{k: sim.download(k, s) for k in names} for s in range(n)]
+        sim.set_frame_kernel(1)
+        for rep in range(2):
+            sim.update_multi([0] * n, [t + 1.0 for t in times])     # other frames first: stale outputs would show
+            sim.update_multi([0] * n, times)
+            sim.sync()
+            for s in range(n):
+                for k in names:
+                    got = sim.download(k, s)
+                    peak = float(np.abs(ref[s][k]).max())
+                    assert np.abs(got - ref[s][k]).max() <= 2e-6 * max(peak, 1.0), (rep, s, k)
+        for k in ("dy", "dx", "dz"):
+            assert np.abs(sim.download(k, 2) - ref_o[k]).max() <= 1e-4 * np.abs(ref_o[k]).max(), k
+        sim.update_multi([0], [2.0])                                # a single frame through the same kernel
+        sim.sync()
+        for k in names:
+            assert np.abs(sim.download(k, 0) - ref[2][k]).max() <= 2e-6 * max(float(np.abs(ref[2][k]).max()), 1.0), ("single", k)
+        assert sim.last_launch_count() == 1

@@ -20,6 +20,8 @@ def main():
     ap.add_argument("--l2", default="0", help="ow_set_l2_persist modes, comma list")
     ap.add_argument("--discard", action="store_true", help="ow_set_discard_intermediate(1): the column kernel drops the intermediate's lines from L2 after reading them")
     ap.add_argument("--slots", type=int, default=0)
+    ap.add_argument("--mega", type=int, default=0, help="ow_set_frame_kernel")
+    ap.add_argument("--lat", type=int, default=1, help="ow_set_latency_shapes: 1 = default, 2 = wide row shape for every launch")
     ap.add_argument("--graph", action="store_true", help="c4: time ow_step (one CUDA graph launch per step) instead of ow_step_multi")
     ap.add_argument("--check", action="store_true", help="compare every combination's frame with the first combination's")
     args = ap.parse_args()
@@ -41,6 +43,9 @@ def main():
         sim.tilde_h0_k()
         if args.discard:
             sim.set_discard_intermediate(True)
+        sim._check(sim._lib.ow_set_latency_shapes(sim._h, args.lat), 'ow_set_latency_shapes')
+        if args.mega:
+            sim.set_frame_kernel(args.mega)
 
         def sweep():
             if args.graph:
