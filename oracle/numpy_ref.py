@@ -112,6 +112,33 @@ def jacobian(dx, dz, L, lam):
     return (1 - lam * dxdx) * (1 - lam * dzdz) - (lam * dxdz) * (lam * dzdx)
 
 
+def jacobian_spectral(h0k, h0minusk, N, L, t, lam):
+    """The Jacobian of the horizontal map X = x - lam*Dx, Z = z - lam*Dz (consumer convention, grid_tes.glsl:61-62) with EXACT
+    spectral derivatives (SURVEY.md §8 f1's validation target): D(x) = Re sum_k H(k) e^{+i k.x} on x_n = n L / N, so
+    d/dx D = Re(ifft2(ifftshift(i kx H))). Meaningful for spectra with no energy on the Nyquist row/column (index 0), whose
+    derivative is not defined on the grid; the central-difference Jacobian converges to this one as (|k| L/N)^2 / 6."""
+    kx, ky = wave_vectors(N, L)
+    _, hdx, hdz = spectra(h0k, h0minusk, N, L, t)
+    dxdx, dxdz = displacement(1j * kx * hdx), displacement(1j * ky * hdx)
+    dzdx, dzdz = displacement(1j * kx * hdz), displacement(1j * ky * hdz)
+    return (1 - lam * dxdx) * (1 - lam * dzdz) - (lam * dxdz) * (lam * dzdx)
+
+
+def band_limited_h0(N, m, seed, amplitude=1.0):
+    """A random initial spectrum with energy only on the (2m+1)^2 - 1 lowest non-zero wave vectors (|index - N/2| <= m): the same
+    PHYSICAL waves at every N for a fixed L, which is what a grid-convergence check of the finite-difference Jacobian needs."""
+    rng = np.random.default_rng(seed)
+    a = np.zeros((N, N), np.complex128)
+    b = np.zeros((N, N), np.complex128)
+    c = N // 2
+    # the chain divides by N^2 (inversion_cs.glsl:35): amplitudes in metres per mode need a factor N^2 in the spectrum
+    blk = (rng.standard_normal((2, 2 * m + 1, 2 * m + 1)) + 1j * rng.standard_normal((2, 2 * m + 1, 2 * m + 1))) * (amplitude * N * N / (2 * m + 1))
+    blk[:, m, m] = 0.0
+    a[c - m:c + m + 1, c - m:c + m + 1] = blk[0]
+    b[c - m:c + m + 1, c - m:c + m + 1] = blk[1]
+    return a, b
+
+
 def frame_from_h0(h0k, h0minusk, N, L, t, choppiness=None):
     hdy, hdx, hdz = spectra(h0k, h0minusk, N, L, t)
     dy, dx, dz = displacement(hdy), displacement(hdx), displacement(hdz)

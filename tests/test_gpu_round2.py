@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 import fft_ocean_waves_b200 as fow
+from oracle import numpy_ref as R
 from oracle.oracle import OracleSim
 from tests.conftest import rng_noise
 
@@ -201,6 +202,28 @@ def test_n16384_random_spectrum_vs_fp64_dft_of_sampled_lines():
 
 
 @pytest.mark.parametrize("N", [256, 512, 1024, 2048])
+def test_jacobian_against_spectral_derivatives():
+    """SURVEY.md §8 f1's validation target: the CUDA Jacobian (central differences riding the normal walk) against the Jacobian from
+    EXACT spectral derivatives in fp64 (oracle/numpy_ref.jacobian_spectral), on the same band-limited physical waves at N = 256,
+    512 and 1024: within the discretisation error (|k| L/N)^2/6 of the derivative terms, and that error falls 4x per doubling of N."""
+    L, lam, t, err = 1000.0, 1.0, 1.0, {}
+    for N in (256, 512, 1024):
+        a, b = R.band_limited_h0(N, 5, seed=7, amplitude=2.0)
+        a32 = np.stack([a.real, a.imag], -1).astype(np.float32)
+        b32 = np.stack([b.real, b.imag], -1).astype(np.float32)
+        with fow.FFTOceanWaves(N=N, cascades=[params(L=L, choppiness=lam)], jacobian=True) as sim:
+            sim.set_h0(a32, b32)
+            got = sim.frame(t)
+        a64, b64 = a32[..., 0] + 1j * a32[..., 1].astype(np.float64), b32[..., 0] + 1j * b32[..., 1].astype(np.float64)
+        js = R.jacobian_spectral(a64, b64, N, L, t, lam)
+        ref = R.frame_from_h0(a64, b64, N, L, t, lam)
+        assert js.min() < 0.8 and js.max() > 1.2
+        assert np.abs(got["jacobian"] - ref["jacobian"]).max() < 1e-4           # the same finite differences in fp64
+        err[N] = np.abs(got["jacobian"] - js).max()
+    assert err[256] < 1e-3 and err[512] < 2.5e-4 and err[1024] < 1.5e-4
+    assert 3.0 < err[256] / err[512] < 5.0, err
+
+
 def test_row_and_column_kernel_variants_agree(noise, N):
     """Every row kernel (1 = CTA per row-pair group, 2 = persistent + register prefetch, 3 = persistent + cp.async.bulk/mbarrier staging)
     with every column kernel (1 = ow_col_kernel, 2 = ow_col2_kernel direct loads, 3 = ow_col2_kernel TMA-staged, 4 = ow_col_pipe_kernel), normal map fused
