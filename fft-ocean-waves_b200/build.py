@@ -24,6 +24,7 @@ SOURCES = [
     ("ow_mega_kernels.cu", []),
     ("ow_init_kernels.cu", ["-fmad=false"]),
     ("ow_pack_kernels.cu", []),
+    ("ow_compose_kernels.cu", []),
     ("ow_api.cu", []),
     ("ow_slab.cu", []),
 ]

@@ -78,6 +78,11 @@ struct ow_ctx {
     cudaGraphicsResource* gl_res[4] = {nullptr, nullptr, nullptr, nullptr};
     int gl_count = 0;             // 4 = dy,dx,dz,normal; 2 = packed displacement + normal_xz
     bool gl_registered = false;
+    // multi-cascade composition / the demo's clock
+    std::vector<int> slot_cascade;    // cascade last stepped into each slot (-1: never)
+    float time_scale = 1.0f, time_offset = 0.0f;
+    float* d_query = nullptr;         // staging of ow_sample_points_host: [cap][2] positions + [cap][8] results
+    size_t query_cap = 0;
 };
 
 static thread_local std::string g_create_error;
@@ -227,6 +232,7 @@ void release(ow_ctx* c) {
     cudaFree(c->d_noise); cudaFree(c->d_h0); cudaFree(c->d_hp); cudaFree(c->d_nyq); cudaFree(c->d_ktab); cudaFree(c->d_casc); cudaFree(c->d_inter);
     drop_plans(c);
     cudaFree(c->d_mega_sched);
+    cudaFree(c->d_query);
     cudaFree(c->d_disp); cudaFree(c->d_normal); cudaFree(c->d_jac); cudaFree(c->d_tmp); cudaFree(c->d_scratch); cudaFree(c->d_packed); cudaFree(c->d_seam);
     if (c->stream) cudaStreamDestroy(c->stream);
     for (auto& s : c->aux) if (s) cudaStreamDestroy(s);
@@ -266,6 +272,7 @@ int ow_create(int32_t N, int32_t n_cascades, int32_t n_slots, const ow_params* c
     for (int i = 0; i < n_cascades; ++i) c->ident[i] = i;
     c->tbuf.assign(n_cascades, 0.0f);
     c->casc_host.resize(n_cascades);
+    c->slot_cascade.assign(n_slots, -1);
     const size_t nn = (size_t)N * N;
 #define OW_TRY(call)                                                                 \
     do {                                                                             \
@@ -512,6 +519,7 @@ static int step_impl(ow_ctx* c, int32_t count, const int32_t* cascade_of_slot, c
     }
     c->last_launches = launches;
     c->last_groups = ngroups;
+    for (int i = 0; i < count; ++i) c->slot_cascade[i] = cascade_of_slot[i];
     return OW_OK;
 }
 
@@ -580,6 +588,7 @@ int ow_step(ow_ctx* c, float t, void* stream) {
     OW_CUDA(c, cudaGraphLaunch(plan->exec, pick(c, stream)));
     c->last_launches = plan->launches;
     c->last_groups = plan->groups;
+    for (int i = 0; i < c->n_cascades; ++i) c->slot_cascade[i] = i;
     return OW_OK;
 }
 
@@ -777,6 +786,87 @@ int ow_set_streams(ow_ctx* c, int32_t n) {
 
 int ow_last_launch_count(const ow_ctx* c) { return c ? c->last_launches : 0; }
 int ow_last_group_count(const ow_ctx* c) { return c ? c->last_groups : 0; }
+
+// ---- multi-cascade composition / the demo's clock ----------------------------------
+static int compose_args(ow_ctx* c, int32_t n_terms, const ow_blend_term* terms, float displacement_scale, const char* who, ComposeArgs* A) {
+    if (!terms || n_terms < 1 || n_terms > kMaxComposeTerms)
+        return fail(c, OW_ERR_INVALID, std::string(who) + ": need 1..16 blend terms");
+    A->disp = c->d_disp; A->normal = c->d_normal; A->N = c->N; A->n_terms = n_terms; A->displacement_scale = displacement_scale;
+    for (int i = 0; i < n_terms; ++i) {
+        const int slot = terms[i].slot;
+        if (slot < 0 || slot >= c->n_slots) return fail(c, OW_ERR_INVALID, std::string(who) + ": slot out of range");
+        const int casc = c->slot_cascade[slot];
+        if (casc < 0) return fail(c, OW_ERR_STATE, std::string(who) + ": a referenced slot has not been stepped yet");
+        A->term[i].inv_L = 1.0 / (double)c->params[casc].L;
+        A->term[i].slot = slot;
+        A->term[i].weight = terms[i].weight;
+        A->term[i].choppiness = c->params[casc].choppiness;
+    }
+    return OW_OK;
+}
+
+int ow_sample_points(ow_ctx* c, int32_t n_terms, const ow_blend_term* terms, float displacement_scale, int32_t n_points, const float* xz,
+                     float* out, void* stream) {
+    if (!c) return OW_ERR_INVALID;
+    if (n_points < 0 || (n_points > 0 && (!xz || !out))) return fail(c, OW_ERR_INVALID, "ow_sample_points: bad point arguments");
+    ComposeArgs A{};
+    const int rc = compose_args(c, n_terms, terms, displacement_scale, "ow_sample_points", &A);
+    if (rc != OW_OK) return rc;
+    OW_CUDA(c, cudaSetDevice(c->device));
+    OW_CUDA(c, launch_sample_points(A, n_points, reinterpret_cast<const float2*>(xz), reinterpret_cast<float4*>(out), pick(c, stream)));
+    return OW_OK;
+}
+
+int ow_sample_points_host(ow_ctx* c, int32_t n_terms, const ow_blend_term* terms, float displacement_scale, int32_t n_points, const float* xz,
+                          float* out, void* stream) {
+    if (!c) return OW_ERR_INVALID;
+    if (n_points < 0 || (n_points > 0 && (!xz || !out))) return fail(c, OW_ERR_INVALID, "ow_sample_points_host: bad point arguments");
+    ComposeArgs A{};
+    const int rc = compose_args(c, n_terms, terms, displacement_scale, "ow_sample_points_host", &A);
+    if (rc != OW_OK) return rc;
+    if (n_points == 0) return OW_OK;
+    OW_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = pick(c, stream);
+    if ((size_t)n_points > c->query_cap) {
+        OW_CUDA(c, cudaStreamSynchronize(st));                 // an earlier query on this stream may still use the old buffer
+        cudaFree(c->d_query);
+        c->d_query = nullptr; c->query_cap = 0;
+        OW_CUDA(c, cudaMalloc(&c->d_query, (size_t)n_points * 10 * sizeof(float)));
+        c->query_cap = (size_t)n_points;
+    }
+    float* d_xz = c->d_query + (size_t)c->query_cap * 8;       // results first: they are float4-aligned
+    OW_CUDA(c, cudaMemcpyAsync(d_xz, xz, (size_t)n_points * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+    OW_CUDA(c, launch_sample_points(A, n_points, reinterpret_cast<const float2*>(d_xz), reinterpret_cast<float4*>(c->d_query), st));
+    OW_CUDA(c, cudaMemcpyAsync(out, c->d_query, (size_t)n_points * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    OW_CUDA(c, cudaStreamSynchronize(st));
+    return OW_OK;
+}
+
+int ow_compose_grid(ow_ctx* c, int32_t n_terms, const ow_blend_term* terms, float displacement_scale, int32_t M, float origin_x, float origin_z,
+                    float extent, float* out_offset, float* out_normal, void* stream) {
+    if (!c) return OW_ERR_INVALID;
+    if (M < 1 || M > 32768 || !(extent > 0.0f) || !out_offset || !out_normal) return fail(c, OW_ERR_INVALID, "ow_compose_grid: bad grid arguments");
+    ComposeArgs A{};
+    const int rc = compose_args(c, n_terms, terms, displacement_scale, "ow_compose_grid", &A);
+    if (rc != OW_OK) return rc;
+    OW_CUDA(c, cudaSetDevice(c->device));
+    OW_CUDA(c, launch_compose_grid(A, M, origin_x, origin_z, extent, reinterpret_cast<float4*>(out_offset), reinterpret_cast<float4*>(out_normal),
+                                   pick(c, stream)));
+    return OW_OK;
+}
+
+int ow_set_time_scale(ow_ctx* c, float scale, float offset) {
+    if (!c) return OW_ERR_INVALID;
+    if (!std::isfinite(scale) || !std::isfinite(offset)) return fail(c, OW_ERR_INVALID, "ow_set_time_scale: scale and offset must be finite");
+    c->time_scale = scale;
+    c->time_offset = offset;
+    return OW_OK;
+}
+
+int ow_step_wall_clock(ow_ctx* c, double wall_seconds, void* stream) {
+    if (!c) return OW_ERR_INVALID;
+    return ow_step(c, c->time_offset + c->time_scale * (float)wall_seconds, stream);
+}
 
 // ---- CUDA-GL interop -------------------------------------------------------------------------------
 // The image has no GL headers, so the three cudart entry points are declared here with GL's own scalar

@@ -228,6 +228,24 @@ struct PackedBuffers {
 };
 int launch_pack(const FrameBuffers& fb, const SlotTable& tab, int count, const PackedBuffers& pk, Launcher& L);
 
+// Multi-cascade composition (ow_compose_kernels.cu): term i samples output slot `slot` (whose cascade has patch
+// size 1/inv_L and the given choppiness) and contributes with `weight`.
+constexpr int kMaxComposeTerms = 16;
+struct ComposeTerm {
+    double inv_L;
+    int slot;
+    float weight, choppiness;
+};
+struct ComposeArgs {
+    const float* disp;        // [slot][3][N][N]
+    const float4* normal;     // [slot][N][N]
+    int N, n_terms;
+    float displacement_scale;
+    ComposeTerm term[kMaxComposeTerms];
+};
+cudaError_t launch_sample_points(const ComposeArgs& A, int n_points, const float2* xz, float4* out /* [n_points][2] */, cudaStream_t st);
+cudaError_t launch_compose_grid(const ComposeArgs& A, int M, float ox, float oz, float extent, float4* out_offset, float4* out_normal, cudaStream_t st);
+
 // Init-time kernels (ow_init_kernels.cu)
 cudaError_t launch_noise_seed(uint8_t* noise /* [4][N][N] */, int N, uint64_t seed, cudaStream_t st);
 cudaError_t launch_h0_slab(float4* h0_loc, int N, int p0, int PL, uint64_t seed, const CascadeDev& c, cudaStream_t st);

@@ -36,6 +36,7 @@ EXPORTED_SYMBOLS = [
     "ow_slab_rows_buf", "ow_slab_cols_buf", "ow_slab_set_post_ctas", "ow_slab_recv_buffer",
     "ow_slab_create", "ow_slab_destroy", "ow_slab_last_error", "ow_slab_get_info", "ow_slab_init_spectrum_seeded", "ow_slab_ipc_handle",
     "ow_slab_open_peers", "ow_slab_rows", "ow_slab_cols", "ow_slab_local_exchange", "ow_slab_sync", "ow_slab_download",
+    "ow_sample_points", "ow_sample_points_host", "ow_compose_grid", "ow_set_time_scale", "ow_step_wall_clock",
 ]
 
 OW_FLAG_JACOBIAN = 0x1
@@ -88,6 +89,10 @@ class OceanParams:
         p.wind_dir[0], p.wind_dir[1] = float(self.wind_dir[0]), float(self.wind_dir[1])
         p.amplitude, p.suppression, p.choppiness = float(self.amplitude), float(self.suppression), float(self.choppiness)
         return p
+
+
+class _BlendTerm(C.Structure):
+    _fields_ = [("slot", C.c_int32), ("weight", C.c_float)]
 
 
 def lib_path() -> str:
@@ -154,6 +159,11 @@ def load_library():
     L.ow_slab_get_line_clusters.argtypes = [vp]
     L.ow_get_kernel_modes.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.ow_gl_register_packed.argtypes = [vp, u32, u32]
+    L.ow_sample_points.argtypes = [vp, i32, C.POINTER(_BlendTerm), f32, i32, vp, vp, vp]
+    L.ow_sample_points_host.argtypes = [vp, i32, C.POINTER(_BlendTerm), f32, i32, vp, vp, vp]
+    L.ow_compose_grid.argtypes = [vp, i32, C.POINTER(_BlendTerm), f32, i32, f32, f32, f32, vp, vp, vp]
+    L.ow_set_time_scale.argtypes = [vp, f32, f32]
+    L.ow_step_wall_clock.argtypes = [vp, C.c_double, vp]
     L.ow_slab_create.argtypes = [i32, i32, i32, C.POINTER(_Params), i32, u32, C.POINTER(vp)]
     L.ow_slab_destroy.argtypes = [vp]
     L.ow_slab_destroy.restype = None
@@ -196,6 +206,7 @@ class FFTOceanWaves:
         self.cascades = list(cascades) if cascades is not None else [OceanParams()]
         self.n_slots = int(n_slots) if n_slots is not None else len(self.cascades)
         self.jacobian = bool(jacobian)
+        self.device = int(device)
         if packed not in (None, "f32", "f16"):
             raise ValueError("packed must be None, 'f32' or 'f16'")
         self.packed = packed
@@ -270,6 +281,44 @@ class FFTOceanWaves:
     # ---- per frame (reference update(): src/main.cpp:240-244) ---------------------------------------
     def update(self, t: float, stream: int = 0):
         self._check(self._lib.ow_step(self._h, float(t), C.c_void_p(stream or None)), "ow_step")
+
+    def set_time_scale(self, scale: float = 1.0, offset: float = 0.0):
+        """The demo's clock (src/main.cpp:599, t = glfwGetTime()): update_wall_clock(w) evaluates t = offset + scale * w."""
+        self._check(self._lib.ow_set_time_scale(self._h, float(scale), float(offset)), "ow_set_time_scale")
+
+    def update_wall_clock(self, wall_seconds: float, stream: int = 0):
+        self._check(self._lib.ow_step_wall_clock(self._h, float(wall_seconds), C.c_void_p(stream or None)), "ow_step_wall_clock")
+
+    # ---- multi-cascade composition (SURVEY.md §8 f4; the consumer's sum grid_tes.glsl:60-64 over cascades) ---
+    @staticmethod
+    def _terms(slots: Sequence[int], weights: Sequence[float]):
+        if len(slots) != len(weights):
+            raise ValueError("one weight per slot")
+        arr = (_BlendTerm * max(len(slots), 1))()
+        for i, (s, w) in enumerate(zip(slots, weights)):
+            arr[i].slot, arr[i].weight = int(s), float(w)
+        return arr
+
+    def sample_points(self, xz: np.ndarray, slots: Sequence[int], weights: Sequence[float], displacement_scale: float = 1.0,
+                      stream: int = 0) -> dict:
+        """Blended vertex offset and normal at world positions xz [n][2] (metres): dict(offset [n][4], normal [n][4])."""
+        pts = np.ascontiguousarray(xz, np.float32).reshape(-1, 2)
+        out = np.empty((pts.shape[0], 8), np.float32)
+        self._check(self._lib.ow_sample_points_host(self._h, len(slots), self._terms(slots, weights), float(displacement_scale), pts.shape[0],
+                                                    pts.ctypes.data, out.ctypes.data, C.c_void_p(stream or None)), "ow_sample_points_host")
+        return dict(offset=out[:, :4].copy(), normal=out[:, 4:].copy())
+
+    def compose_grid(self, M: int, origin: Sequence[float], extent: float, slots: Sequence[int], weights: Sequence[float],
+                     displacement_scale: float = 1.0, stream: int = 0) -> dict:
+        """The same sum on M x M world positions origin + (i + 0.5) * extent / M, evaluated into two device images and downloaded."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        off = torch.empty((M, M, 4), dtype=torch.float32, device=dev)
+        nrm = torch.empty((M, M, 4), dtype=torch.float32, device=dev)
+        self._check(self._lib.ow_compose_grid(self._h, len(slots), self._terms(slots, weights), float(displacement_scale), int(M), float(origin[0]),
+                                              float(origin[1]), float(extent), off.data_ptr(), nrm.data_ptr(), C.c_void_p(stream or None)), "ow_compose_grid")
+        self.sync(stream)
+        return dict(offset=off.cpu().numpy(), normal=nrm.cpu().numpy())
 
     def update_multi(self, cascade_of_slot: Sequence[int], time_of_slot: Sequence[float], stream: int = 0):
         n = len(cascade_of_slot)

@@ -199,6 +199,34 @@ int ow_set_line_clusters(ow_ctx* ctx, int32_t mode);
 int ow_get_line_clusters(ow_ctx* ctx);
 int ow_set_discard_intermediate(ow_ctx* ctx, int32_t on);
 
+/* ---- multi-cascade composition and the demo's clock ----------------------------------
+ * The reference renders ONE cascade: grid_tes.glsl:60-64 samples the sim textures (LINEAR/REPEAT: src/main.cpp:1142-1144 for the normal map, the texture class defaults for m_dy/m_dx/m_dz) and
+ * displaces the vertex: pos.y += dy*u_DisplacementScale, pos.x -= dx*u_Choppiness, pos.z -= dz*u_Choppiness, normal = texture(s_NormalMap).
+ * With several cascades the consumer sums these terms over the cascades, cascade c sampled at uv = (x, z)/L_c and scaled by a
+ * blending weight w_c (LOD / distance fades). ow_sample_points / ow_compose_grid evaluate that sum on the device:
+ *   offset = (-sum w_c*choppiness_c*dx_c, displacement_scale * sum w_c*dy_c, -sum w_c*choppiness_c*dz_c, sum w_c)
+ *   normal = normalize(sum w_c*n_c.x/n_c.y, 1, sum w_c*n_c.z/n_c.y), w = 1          (slopes add)
+ * A term names an output SLOT; its cascade (L, choppiness) is the one the last ow_step* put there. Up to 16 terms. Asynchronous on
+ * `stream`, ordered after the steps submitted to the same stream. */
+typedef struct ow_blend_term {
+    int32_t slot;
+    float weight;
+} ow_blend_term;
+/* xz: DEVICE pointer, n_points x (x, z) world positions in metres; out: DEVICE pointer, n_points x 8 floats (offset.xyzw, normal.xyzw). */
+int ow_sample_points(ow_ctx* ctx, int32_t n_terms, const ow_blend_term* terms, float displacement_scale, int32_t n_points,
+                     const float* xz, float* out, void* stream);
+/* The same with HOST pointers (copies in and out on `stream`, then synchronises it): buoyancy / picking queries of a few points. */
+int ow_sample_points_host(ow_ctx* ctx, int32_t n_terms, const ow_blend_term* terms, float displacement_scale, int32_t n_points,
+                          const float* xz, float* out, void* stream);
+/* M x M world positions (origin_x + (i+0.5)*extent/M, origin_z + (j+0.5)*extent/M), row j / column i of two DEVICE images of M*M float4:
+ * the combined offset and normal of one clip-map level. */
+int ow_compose_grid(ow_ctx* ctx, int32_t n_terms, const ow_blend_term* terms, float displacement_scale, int32_t M, float origin_x,
+                    float origin_z, float extent, float* out_offset, float* out_normal, void* stream);
+/* The demo's clock: t = float(glfwGetTime()) (src/main.cpp:599). ow_step_wall_clock(ctx, wall) = ow_step(ctx, offset + scale*wall):
+ * scale 0 pauses, negative runs backwards; offset re-bases (e.g. after a pause). Defaults 1, 0. */
+int ow_set_time_scale(ow_ctx* ctx, float scale, float offset);
+int ow_step_wall_clock(ow_ctx* ctx, double wall_seconds, void* stream);
+
 /* ---- CUDA-GL interop: replaces the renderer's texture binds (src/main.cpp:477-487) ------------------- */
 
 /* Register the caller's GL textures (R32F dy,dx,dz; RGBA32F normal) via cudaGraphicsGLRegisterImage. The

@@ -78,7 +78,15 @@ public:
     // The demo's clock: t = float(glfwGetTime()) (:599). time_scale / time_offset let the app slow, speed up, pause (scale 0) or
     // scrub the sea without touching the sim (the reference has no such control; a GUI slider next to the ones at :348-358 would set them).
     float time_scale = 1.0f, time_offset = 0.0f;
-    bool update_wall_clock(double wall_seconds, void* stream = nullptr) { return update(time_offset + time_scale * float(wall_seconds), stream); }
+    bool update_wall_clock(double wall_seconds, void* stream = nullptr) {
+        return ok(ow_set_time_scale(ctx_, time_scale, time_offset)) && ok(ow_step_wall_clock(ctx_, wall_seconds, stream));
+    }
+    // What grid_tes.glsl:60-64 does to a vertex, evaluated on the device at world positions (x, z) in metres: out[i] = 8 floats
+    // (offset.xyz, weight sum, normal.xyz, 1). HOST pointers; buoyancy / picking queries. displacement_scale = m_displacement_scale (:1644).
+    bool sample_points(int n, const float* xz, float* out, float displacement_scale = 0.5f, void* stream = nullptr) {
+        const ow_blend_term term{0, 1.0f};
+        return ok(ow_sample_points_host(ctx_, 1, &term, displacement_scale, n, xz, out, stream));
+    }
     bool sync(void* stream = nullptr) { return ok(ow_sync(ctx_, stream)); }
 
     // Device pointers (row-major [y][x], the layout of the reference's R32F / RGBA32F textures).

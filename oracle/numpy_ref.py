@@ -139,6 +139,41 @@ def band_limited_h0(N, m, seed, amplitude=1.0):
     return a, b
 
 
+def bilinear_repeat(img, u, v):
+    """GL_LINEAR + GL_REPEAT fetch of img[row][col(, channels)] at normalised coordinates (u along columns, v along rows): texel
+    centres at (i + 0.5)/N, taps floor(u N - 0.5) and the next, wrapped (what texture() does for the reference's sim textures,
+    src/main.cpp:1142-1144 and the texture class defaults, SURVEY.md §8 b1, grid_tes.glsl:60-64)."""
+    img = np.asarray(img, np.float64)
+    n_r, n_c = img.shape[:2]
+    tu = (np.asarray(u, np.float64) % 1.0) * n_c - 0.5
+    tv = (np.asarray(v, np.float64) % 1.0) * n_r - 0.5
+    fu, fv = np.floor(tu), np.floor(tv)
+    a, b = tu - fu, tv - fv
+    i0, j0 = fu.astype(np.int64) % n_c, fv.astype(np.int64) % n_r
+    i1, j1 = (i0 + 1) % n_c, (j0 + 1) % n_r
+    if img.ndim == 3:
+        a, b = a[..., None], b[..., None]
+    return (img[j0, i0] * (1 - a) + img[j0, i1] * a) * (1 - b) + (img[j1, i0] * (1 - a) + img[j1, i1] * a) * b
+
+
+def blend_cascades(frames, Ls, choppiness, weights, displacement_scale, x, z):
+    """the consumer's vertex displacement (grid_tes.glsl:60-64) summed over cascades with blending weights.
+    frames[c] = dict(dy, dx, dz, normal) of cascade c (patch size Ls[c], sampled at uv = (x, z)/L). Returns (offset[...,4], normal[...,4])."""
+    x, z = np.asarray(x, np.float64), np.asarray(z, np.float64)
+    ox, oy, oz, ws, sx, sz = (np.zeros(x.shape) for _ in range(6))
+    for f, L, lam, w in zip(frames, Ls, choppiness, weights):
+        u, v = x / L, z / L
+        oy += w * bilinear_repeat(f["dy"], u, v)
+        ox -= w * lam * bilinear_repeat(f["dx"], u, v)
+        oz -= w * lam * bilinear_repeat(f["dz"], u, v)
+        n = bilinear_repeat(f["normal"], u, v)
+        sx += w * n[..., 0] / n[..., 1]
+        sz += w * n[..., 2] / n[..., 1]
+        ws += w
+    r = 1.0 / np.sqrt(sx * sx + 1.0 + sz * sz)
+    return np.stack([ox, displacement_scale * oy, oz, ws], -1), np.stack([sx * r, r, sz * r, np.ones_like(r)], -1)
+
+
 def frame_from_h0(h0k, h0minusk, N, L, t, choppiness=None):
     hdy, hdx, hdz = spectra(h0k, h0minusk, N, L, t)
     dy, dx, dz = displacement(hdy), displacement(hdx), displacement(hdz)

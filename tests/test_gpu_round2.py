@@ -201,7 +201,6 @@ def test_n16384_random_spectrum_vs_fp64_dft_of_sampled_lines():
         assert np.abs(got[k][:, xs] - cols).max() <= 1e-4 * peak, (k, "columns")
 
 
-@pytest.mark.parametrize("N", [256, 512, 1024, 2048])
 def test_jacobian_against_spectral_derivatives():
     """SURVEY.md §8 f1's validation target: the CUDA Jacobian (central differences riding the normal walk) against the Jacobian from
     EXACT spectral derivatives in fp64 (oracle/numpy_ref.jacobian_spectral), on the same band-limited physical waves at N = 256,
@@ -224,6 +223,63 @@ def test_jacobian_against_spectral_derivatives():
     assert 3.0 < err[256] / err[512] < 5.0, err
 
 
+def test_cascade_blend_matches_the_restatement(noise):
+    """ow_sample_points / ow_compose_grid (the consumer's grid_tes.glsl:60-64 displacement summed over cascades with
+    blending weights, LINEAR/REPEAT taps) against oracle/numpy_ref.blend_cascades on the frames the context itself produced."""
+    N, Ls, lams = 256, (250.0, 1000.0, 4000.0), (0.5, 1.0, 0.75)
+    casc = [params(L=L, choppiness=lam, wind_speed=10.0 + 10.0 * i) for i, (L, lam) in enumerate(zip(Ls, lams))]
+    with fow.FFTOceanWaves(N=N, cascades=casc, n_slots=4) as sim:
+        with pytest.raises(fow.OceanWavesError):
+            sim.sample_points(np.zeros((1, 2)), [0], [1.0])                     # nothing stepped yet
+        sim.init(noise)
+        sim.update_multi([0, 1, 2, 1], [1.0, 1.0, 1.0, 5.0])                     # slot 3: cascade 1 at another time
+        sim.sync()
+        frames = [{k: sim.download(k, s) for k in ("dy", "dx", "dz", "normal")} for s in range(4)]
+        rng = np.random.default_rng(11)
+        pts = rng.uniform(-2.0e4, 2.0e4, (4000, 2)).astype(np.float32)
+        pts[:64, 0] = (np.arange(64) + 0.5) * Ls[1] / N                          # texel centres of cascade 1, row 7
+        pts[:64, 1] = 7.5 * Ls[1] / N
+        slots, w = [0, 1, 2, 3], [0.3, 1.0, 1.5, -0.25]
+        got = sim.sample_points(pts, slots, w, displacement_scale=0.5)
+        off, nrm = R.blend_cascades([frames[s] for s in slots], [Ls[0], Ls[1], Ls[2], Ls[1]], [lams[0], lams[1], lams[2], lams[1]], w, 0.5,
+                                    pts[:, 0].astype(np.float64), pts[:, 1].astype(np.float64))
+        peak = np.abs(off[:, :3]).max()
+        assert np.abs(got["offset"] - off).max() < 2e-5 * peak
+        assert np.abs(got["normal"] - nrm).max() < 2e-5
+        one = sim.sample_points(pts[:64], [1], [1.0], displacement_scale=1.0)      # one cascade at its texel centres = the texels
+        assert np.abs(one["offset"][:, 1] - frames[1]["dy"][7, :64]).max() < 1e-5 * np.abs(frames[1]["dy"]).max()
+        M, origin, extent = 192, (-333.0, 125.0), 1500.0
+        grid = sim.compose_grid(M, origin, extent, slots, w, displacement_scale=0.5)
+        gi, gj = np.meshgrid(np.arange(M), np.arange(M))
+        gx = np.float32(origin[0]) + (gi.astype(np.float32) + np.float32(0.5)) * np.float32(extent / M)
+        gz = np.float32(origin[1]) + (gj.astype(np.float32) + np.float32(0.5)) * np.float32(extent / M)
+        goff, gnrm = R.blend_cascades([frames[s] for s in slots], [Ls[0], Ls[1], Ls[2], Ls[1]], [lams[0], lams[1], lams[2], lams[1]], w, 0.5,
+                                      gx.astype(np.float64), gz.astype(np.float64))
+        assert np.abs(grid["offset"] - goff).max() < 2e-5 * peak and np.abs(grid["normal"] - gnrm).max() < 2e-5
+        for bad_slots, bad_w in (([4], [1.0]), ([0] * 17, [1.0] * 17), ([], [])):
+            with pytest.raises(fow.OceanWavesError):
+                sim.sample_points(pts[:4], bad_slots, bad_w)
+
+
+def test_wall_clock_time_scale(noise):
+    """The demo's clock (src/main.cpp:599): ow_step_wall_clock(w) is ow_step(offset + scale * w), bit for bit; scale 0 pauses."""
+    with fow.FFTOceanWaves(N=256, cascades=[params()]) as sim:
+        sim.init(noise)
+        sim.set_time_scale(0.5, 2.0)
+        sim.update_wall_clock(6.0)
+        sim.sync()
+        a = sim.download("dy")
+        ref = sim.frame(np.float32(2.0) + np.float32(0.5) * np.float32(6.0))
+        assert np.array_equal(a, ref["dy"])
+        sim.set_time_scale(0.0, 5.0)
+        sim.update_wall_clock(123.0)
+        sim.sync()
+        assert np.array_equal(sim.download("dy"), sim.frame(5.0)["dy"])
+        with pytest.raises(fow.OceanWavesError):
+            sim.set_time_scale(float("nan"), 0.0)
+
+
+@pytest.mark.parametrize("N", [256, 512, 1024, 2048])
 def test_row_and_column_kernel_variants_agree(noise, N):
     """Every row kernel (1 = CTA per row-pair group, 2 = persistent + register prefetch, 3 = persistent + cp.async.bulk/mbarrier staging)
     with every column kernel (1 = ow_col_kernel, 2 = ow_col2_kernel direct loads, 3 = ow_col2_kernel TMA-staged, 4 = ow_col_pipe_kernel), normal map fused
