@@ -29,7 +29,7 @@ def test_forced_line_decomposition_equals_direct_kernels(N):
 
 
 def test_n8192_vs_fp64_closed_form():
-    """A = 2, B = 4096 (the production instantiation) against Re(ifft2(ifftshift(H))) in double precision."""
+    """N = 8192 = A * B with A = 4, B = 2048 (the production line decomposition, OW_BIG_B) against Re(ifft2(ifftshift(H))) in double precision."""
     N = 8192
     with fow.FFTOceanWaves(N=N, cascades=[P]) as sim:
         sim.set_noise_seed(8192)
