@@ -462,6 +462,11 @@ def measure_patch(env, args, name, steps, warmup, full):
                        "submission": "ow_step: one CUDA graph launch per step" if whole_step else "ow_step_multi: stream launches, launch groups on the context's auxiliary streams"},
             "clocks": clocks, "gpu_launches": int(timed_launches), "roofline": roofline}
 
+    if name == "c4":
+        try:
+            line["config"]["compose"] = compose_numbers(env, sim, frames)
+        except Exception as e:  # noqa: BLE001 - a side record must never take the bench line down
+            line["config"]["compose"] = {"unavailable": f"{type(e).__name__}: {e}"}
     # ---- the drop-in call itself: ONE frame per ow_step (what FFTOceanWaves::update() does, src/main.cpp:240-244) ---------------
     if name != "c4":
         line["config"]["single_frame"] = single_frame_numbers(env, sim, w)
@@ -517,6 +522,35 @@ def measure_patch(env, args, name, steps, warmup, full):
     if rank == 0 and world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(w)
     return line
+
+
+def compose_numbers(env, sim, n_slots, M=2048, extent=200.0, max_terms=8):
+    """ow_compose_grid - the consumer's displacement (grid_tes.glsl:60-64) summed over the first cascades of this rank with
+    unit blending weights, on an M x M clip-map image. CUDA events on the launching stream, L2 flushed before every repetition."""
+    import ctypes as C
+    torch = env.torch
+    n = min(max_terms, n_slots)
+    terms = sim._terms(list(range(n)), [1.0] * n)
+    off = torch.empty((M, M, 4), dtype=torch.float32, device="cuda")
+    nrm = torch.empty((M, M, 4), dtype=torch.float32, device="cuda")
+    ms = []
+    for i in range(6):
+        env.flush_l2()
+        a, b = env.event(), env.event()
+        a.record(env.stream)
+        rc = sim._lib.ow_compose_grid(sim._h, n, terms, 0.5, M, -100.0, -100.0, float(extent), off.data_ptr(), nrm.data_ptr(), C.c_void_p(env.sp))
+        b.record(env.stream)
+        if rc != 0:
+            raise RuntimeError("ow_compose_grid failed")
+        torch.cuda.synchronize()
+        if i:
+            ms.append(a.elapsed_time(b))
+    t = float(np.median(ms)) * 1e-3
+    src_bytes = n * 28.0 * sim.N * sim.N          # every source texel of every term at most once from DRAM (dy,dx,dz 12 B + normal 16 B)
+    return {"what": f"ow_compose_grid: {n} cascades blended into one {M}x{M} offset + normal image over {extent:.0f} m", "terms": n, "M": M,
+            "ms": t * 1e3, "output_mtexels_per_s": M * M / t / 1e6,
+            "algorithmic_gbs": (32.0 * M * M + min(src_bytes, n * 4 * 28.0 * M * M)) / t / 1e9,
+            "bytes_note": "32 B written per output texel + each term's source texels once (28 B each)"}
 
 
 def single_frame_numbers(env, sim, w):
