@@ -29,6 +29,8 @@ struct ow_ctx {
     float4* d_hp = nullptr;       // [cascade][N/2][N] folded texel pairs (what the row kernel streams)
     float4* d_nyq = nullptr;      // [cascade][N/2]
     float* d_ktab = nullptr;
+    float* d_ktab_sub = nullptr;  // contexts that run the N = A*B line decomposition: the k table sub-line-major (their folded rows d_hp are too)
+    int sub_A = 0;                // A of that decomposition, 0 for the direct kernels
     CascadeDev* d_casc = nullptr;
     float2* d_inter = nullptr;
     float* d_disp = nullptr;
@@ -122,7 +124,7 @@ cudaStream_t pick(ow_ctx* c, void* s) { return s ? static_cast<cudaStream_t>(s) 
 
 FrameBuffers buffers(const ow_ctx* c) {
     FrameBuffers fb{};
-    fb.N = c->N; fb.h0 = c->d_h0; fb.hp = c->d_hp; fb.nyq = c->d_nyq; fb.ktab = c->d_ktab; fb.casc = c->d_casc; fb.inter = c->d_inter;
+    fb.N = c->N; fb.h0 = c->d_h0; fb.hp = c->d_hp; fb.nyq = c->d_nyq; fb.ktab = c->d_ktab; fb.ktab_sub = c->d_ktab_sub; fb.casc = c->d_casc; fb.inter = c->d_inter;
     fb.disp = c->d_disp; fb.normal = c->d_normal; fb.jacobian = c->d_jac;
     // Measured on B200 (profiles/r01d_discard_ab.txt): dropping the consumed intermediate from L2 changed nothing in the
     // multi-stream sweep, so it is off unless ow_set_discard_intermediate turns it on.
@@ -229,7 +231,7 @@ void release(ow_ctx* c) {
     cudaSetDevice(c->device);
     if (c->gl_registered) for (auto& r : c->gl_res) if (r) cudaGraphicsUnregisterResource(r);
     c->gl_registered = false;
-    cudaFree(c->d_noise); cudaFree(c->d_h0); cudaFree(c->d_hp); cudaFree(c->d_nyq); cudaFree(c->d_ktab); cudaFree(c->d_casc); cudaFree(c->d_inter);
+    cudaFree(c->d_noise); cudaFree(c->d_h0); cudaFree(c->d_hp); cudaFree(c->d_nyq); cudaFree(c->d_ktab); cudaFree(c->d_ktab_sub); cudaFree(c->d_casc); cudaFree(c->d_inter);
     drop_plans(c);
     cudaFree(c->d_mega_sched);
     cudaFree(c->d_query);
@@ -300,7 +302,11 @@ int ow_create(int32_t N, int32_t n_cascades, int32_t n_slots, const ow_params* c
     OW_TRY(cudaMalloc(&c->d_normal, nn * n_slots * sizeof(float4)));
     if (flags & OW_FLAG_JACOBIAN) OW_TRY(cudaMalloc(&c->d_jac, nn * n_slots * sizeof(float)));
     OW_TRY(cudaMalloc(&c->d_tmp, nn * 4 * sizeof(float)));
-    if (big_supported(N, false) || (flags & OW_FLAG_FOUR_STEP)) OW_TRY(cudaMalloc(&c->d_scratch, nn / 2 * 3 * sizeof(float2)));
+    if (big_supported(N, false) || (flags & OW_FLAG_FOUR_STEP)) {
+        OW_TRY(cudaMalloc(&c->d_scratch, nn / 2 * 3 * sizeof(float2)));
+        c->sub_A = big_radix(N, (flags & OW_FLAG_FOUR_STEP) != 0);
+        OW_TRY(cudaMalloc(&c->d_ktab_sub, (size_t)N * n_cascades * sizeof(float)));
+    }
     if (flags & (OW_FLAG_PACKED_F32 | OW_FLAG_PACKED_F16)) {
         c->pk.half = (flags & OW_FLAG_PACKED_F16) ? 1 : 0;
         c->pk.normal_offset = nn * (c->pk.half ? 8 : 16);
@@ -398,7 +404,9 @@ static int init_range(ow_ctx* c, int lo, int hi, const char* who) {
         OW_CUDA(c, launch_ktab(c->d_ktab + (size_t)i * c->N, c->N, c->params[i].L, c->stream));
         OW_CUDA(c, launch_h0(c->d_h0 + (size_t)i * nn, c->d_noise + (size_t)i * 4 * plane, c->noise_w, c->noise_h, c->N,
                              c->casc_host[i], c->stream));
-        OW_CUDA(c, launch_fold(c->d_h0 + (size_t)i * nn, c->d_hp + (size_t)i * hp_block_elems(c->N / 2, c->N), c->d_nyq + (size_t)i * (c->N / 2), c->d_ktab + (size_t)i * c->N, c->N, c->stream));
+        if (c->sub_A) OW_CUDA(c, launch_ktab_sub(c->d_ktab + (size_t)i * c->N, c->d_ktab_sub + (size_t)i * c->N, c->N, c->sub_A, c->stream));
+        OW_CUDA(c, launch_fold(c->d_h0 + (size_t)i * nn, c->d_hp + (size_t)i * hp_block_elems(c->N / 2, c->N), c->d_nyq + (size_t)i * (c->N / 2), c->d_ktab + (size_t)i * c->N, c->N,
+                               c->sub_A, c->stream));
     }
     for (int i = 0; i < c->n_cascades; ++i) c->casc_host[i] = to_dev(c->params[i]);
     OW_CUDA(c, cudaMemcpyAsync(c->d_casc, c->casc_host.data(), c->n_cascades * sizeof(CascadeDev), cudaMemcpyHostToDevice, c->stream));
@@ -429,8 +437,9 @@ int ow_set_h0(ow_ctx* c, int32_t cascade, const float* h0k, const float* h0minus
     OW_CUDA(c, launch_merge_h0(c->d_h0 + (size_t)cascade * nn, c->d_tmp, c->d_tmp + nn * 2, (int)nn, c->stream));
     // this cascade's k table and the cascade constants follow the CURRENT parameters (h0 itself is the caller's)
     OW_CUDA(c, launch_ktab(c->d_ktab + (size_t)cascade * c->N, c->N, c->params[cascade].L, c->stream));
+    if (c->sub_A) OW_CUDA(c, launch_ktab_sub(c->d_ktab + (size_t)cascade * c->N, c->d_ktab_sub + (size_t)cascade * c->N, c->N, c->sub_A, c->stream));
     OW_CUDA(c, launch_fold(c->d_h0 + (size_t)cascade * nn, c->d_hp + (size_t)cascade * hp_block_elems(c->N / 2, c->N), c->d_nyq + (size_t)cascade * (c->N / 2),
-                           c->d_ktab + (size_t)cascade * c->N, c->N, c->stream));
+                           c->d_ktab + (size_t)cascade * c->N, c->N, c->sub_A, c->stream));
     for (int i = 0; i < c->n_cascades; ++i) c->casc_host[i] = to_dev(c->params[i]);
     OW_CUDA(c, cudaMemcpyAsync(c->d_casc, c->casc_host.data(), c->n_cascades * sizeof(CascadeDev), cudaMemcpyHostToDevice, c->stream));
     OW_CUDA(c, cudaStreamSynchronize(c->stream));

@@ -96,18 +96,18 @@ struct Big {
     }
 
     template <class Rows, class Sink>
-    static void rows_pass(const Rows& rows, const float* ktab, int p_first, int npairs_rows, float t, bool fast, float2* scratch, const Sink& sink,
-                          cudaStream_t st, int cluster_bits, int post_ctas = 0) {
+    static void rows_pass(const Rows& rows, const float* ktab, const float* ktab_sub, int p_first, int npairs_rows, float t, bool fast, float2* scratch,
+                          const Sink& sink, cudaStream_t st, int cluster_bits, int post_ctas = 0) {
         if (cluster_bits & 1) {
             cudaError_t e = fast ? launch_cluster(ow_bigrow_cluster_kernel<R, A, RMB, true, Rows, Sink>, dim3(npairs_rows * A), dim3(R::T), row_smem<R, 1>(), st, A,
-                                                  rows, ktab, p_first, t, sink)
+                                                  rows, ktab, ktab_sub, p_first, t, sink)
                                  : launch_cluster(ow_bigrow_cluster_kernel<R, A, RMB, false, Rows, Sink>, dim3(npairs_rows * A), dim3(R::T), row_smem<R, 1>(), st, A,
-                                                  rows, ktab, p_first, t, sink);
+                                                  rows, ktab, ktab_sub, p_first, t, sink);
             if (e != cudaSuccess) stash_launch_error(e);
             return;
         }
-        if (fast) ow_bigrow_lines_kernel<R, A, RMB, true, Rows><<<npairs_rows * A, R::T, row_smem<R, 1>(), st>>>(rows, ktab, p_first, t, scratch);
-        else ow_bigrow_lines_kernel<R, A, RMB, false, Rows><<<npairs_rows * A, R::T, row_smem<R, 1>(), st>>>(rows, ktab, p_first, t, scratch);
+        if (fast) ow_bigrow_lines_kernel<R, A, RMB, true, Rows><<<npairs_rows * A, R::T, row_smem<R, 1>(), st>>>(rows, ktab, ktab_sub, p_first, t, scratch);
+        else ow_bigrow_lines_kernel<R, A, RMB, false, Rows><<<npairs_rows * A, R::T, row_smem<R, 1>(), st>>>(rows, ktab, ktab_sub, p_first, t, scratch);
         if (post_ctas > 0) ow_bigrow_post_slim_kernel<B, A, Sink><<<post_ctas, 256, 0, st>>>(scratch, p_first, npairs_rows, sink);
         else ow_bigrow_post_kernel<B, A, Sink><<<dim3((B + 255) / 256, npairs_rows, 3), 256, 0, st>>>(scratch, p_first, sink);
     }
@@ -131,13 +131,14 @@ struct Big {
 
     // One slot entry per call (the scratch holds one frame).
     static int frame(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_jac, bool fast, cudaStream_t st, cudaEvent_t* ev) {
-        if (count != 1 || !fb.scratch) return -1;
+        if (count != 1 || !fb.scratch || !fb.ktab_sub) return -1;
         const int cascade = tab.cascade[0], slot = tab.slot[0];
         const size_t nn = (size_t)N * N;
         if (ev) cudaEventRecord(ev[0], st);
         const FullRows<N> rows{fb.h0 + (size_t)cascade * nn, fb.hp + (size_t)cascade * hp_block_f4(N / 2, N), fb.nyq + (size_t)cascade * (N / 2)};
         float2* inter = fb.inter + (size_t)slot * 3 * (nn / 2);
-        rows_pass(rows, fb.ktab + (size_t)cascade * N, 0, N / 2, tab.time[0], fast, fb.scratch, FullSink<N>{inter}, st, fb.big_cluster);
+        rows_pass(rows, fb.ktab + (size_t)cascade * N, fb.ktab_sub + (size_t)cascade * N, 0, N / 2, tab.time[0], fast, fb.scratch, FullSink<N>{inter}, st,
+                  fb.big_cluster);
         if (ev) cudaEventRecord(ev[1], st);
         cols_pass(inter, nn / 2, N / 2, fb.scratch, fb.disp + (size_t)slot * 3 * nn, nn, FullColGeom<N>{}, st, fb.big_cluster);
         if (ev) cudaEventRecord(ev[2], st);
@@ -155,15 +156,16 @@ struct Big {
         return XH % (2 * G) == 0 && XL % 128 == 0 && (XL & (XL - 1)) == 0;
     }
 
-    static int slab_rows(const SlabGeom& g, const float4* h0_loc, const float4* hp_loc, const float4* nyq_loc, const float* ktab,
+    static int slab_rows(const SlabGeom& g, const float4* h0_loc, const float4* hp_loc, const float4* nyq_loc, const float* ktab, const float* ktab_sub,
                          float2* const sink_base[kSlabMaxWorld], float t, bool fast, float2* scratch, cudaStream_t st) {
+        if (!ktab_sub) return -1;
         SlabRows<N> rows{h0_loc, hp_loc, nyq_loc, g.rank * g.PL, g.PL};
         SlabSink<N> sink{};
         for (int h = 0; h < g.world; ++h) sink.base[h] = sink_base[h];
         sink.world = g.world; sink.p0 = g.rank * g.PL; sink.XL = g.XL; sink.XH = g.XH;
         sink.xl_shift = 0;
         while ((1 << sink.xl_shift) < g.XL) ++sink.xl_shift;
-        rows_pass(rows, ktab, g.rank * g.PL, g.PL, t, fast, scratch, sink, st, g.big_cluster, g.post_ctas);
+        rows_pass(rows, ktab, ktab_sub, g.rank * g.PL, g.PL, t, fast, scratch, sink, st, g.big_cluster, g.post_ctas);
         return launches_ok() && take_and_restash() ? ((g.big_cluster & 1) ? 1 : 2) : -1;
     }
 
@@ -192,6 +194,12 @@ struct Big {
 
 }  // namespace
 
+// Radix A of the line decomposition N = A * B a context of this (N, forced) runs; 0 when it runs the direct kernels.
+int big_radix(int N, bool forced) {
+    if (forced) return (N == 1024 || N == 2048) ? 4 : 0;
+    return (N == 8192 || N == 16384 || N == 32768) ? N / OW_BIG_B : 0;
+}
+
 bool big_supported(int N, bool forced) {
     return forced ? (N == 1024 || N == 2048) : (N == 8192 || N == 16384 || N == 32768);
 }
@@ -212,9 +220,9 @@ bool big_slab_supported(int N, int world, bool forced) {
     return false;
 }
 
-int launch_big_slab_rows(const SlabGeom& g, const float4* h0_loc, const float4* hp_loc, const float4* nyq_loc, const float* ktab,
+int launch_big_slab_rows(const SlabGeom& g, const float4* h0_loc, const float4* hp_loc, const float4* nyq_loc, const float* ktab, const float* ktab_sub,
                          float2* const sink_base[kSlabMaxWorld], float t, bool fast, float2* scratch, cudaStream_t st, bool forced) {
-    OW_BIG_DISPATCH(g.N, forced, slab_rows(g, h0_loc, hp_loc, nyq_loc, ktab, sink_base, t, fast, scratch, st));
+    OW_BIG_DISPATCH(g.N, forced, slab_rows(g, h0_loc, hp_loc, nyq_loc, ktab, ktab_sub, sink_base, t, fast, scratch, st));
     return -1;
 }
 

@@ -277,9 +277,9 @@ bool slab_supported(int N, int world) {
     return false;
 }
 
-int launch_slab_rows(const SlabGeom& g, const float4* h0_loc, const float4* hp_loc, const float4* nyq_loc, const float* ktab,
+int launch_slab_rows(const SlabGeom& g, const float4* h0_loc, const float4* hp_loc, const float4* nyq_loc, const float* ktab, const float* ktab_sub,
                      float2* const sink_base[kSlabMaxWorld], float t, bool fast_phase, float2* scratch, cudaStream_t st) {
-    if (big_supported(g.N, false)) return launch_big_slab_rows(g, h0_loc, hp_loc, nyq_loc, ktab, sink_base, t, fast_phase, scratch, st, false);
+    if (big_supported(g.N, false)) return launch_big_slab_rows(g, h0_loc, hp_loc, nyq_loc, ktab, ktab_sub, sink_base, t, fast_phase, scratch, st, false);
     switch (g.N) {
         case 256: return slab_rows_n<256>(g, h0_loc, hp_loc, nyq_loc, ktab, sink_base, t, fast_phase, st);
         case 512: return slab_rows_n<512>(g, h0_loc, hp_loc, nyq_loc, ktab, sink_base, t, fast_phase, st);

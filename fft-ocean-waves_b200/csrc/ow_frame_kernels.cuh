@@ -534,18 +534,19 @@ __global__ void __launch_bounds__(P::T* G, MINB) ow_col_slab_kernel(const float2
 // N = A * B > 4096 (see "LINES LONGER THAN ONE CTA'S SHARED MEMORY" in ow_kernels.cuh): a lines kernel (one CTA per sub-line
 // of decimated input) and a post kernel (twiddles + radix-A + coalesced final stores) per direction. P is the sub-line
 // plan (P::N = B). Rows is FullRows<N> or SlabRows<N>, Sink FullSink<N> or SlabSink<N>.
+//   folded rows   [pair][A][B] float4  sub-line-major (subline_index), and the k table in the same order (ktab_sub)
 //   row scratch   [pair][3][A][B]      (pair index local to the launch: p - p_first)
 //   col scratch   [3][A][B][npairs]    (npairs = column pairs of the launch: N/2, or XH/2 for a slab)
 // ---------------------------------------------------------------------------------------------------
 template <class P, int A, int MINB, bool FAST, class Rows>
-__global__ void __launch_bounds__(P::T, MINB) ow_bigrow_lines_kernel(Rows rows, const float* __restrict__ ktab, int p_first, float t,
-                                                                     float2* __restrict__ scratch) {
+__global__ void __launch_bounds__(P::T, MINB) ow_bigrow_lines_kernel(Rows rows, const float* __restrict__ ktab, const float* __restrict__ ktab_sub,
+                                                                     int p_first, float t, float2* __restrict__ scratch) {
     extern __shared__ __align__(16) float2 smem[];
     constexpr int N = A * P::N;
     const int ft = threadIdx.x;
     const int pl = blockIdx.x / A, a = blockIdx.x % A;
     const SmemDirect sm{smem};
-    bigrow_phase0<P, A, FAST>(sm, ft, p_first + pl, a, rows, ktab, t);
+    bigrow_phase0<P, A, FAST>(sm, ft, p_first + pl, a, rows, ktab, ktab_sub, t);
     __syncthreads();
     row_phase1<P>(sm, ft);
     __syncthreads();
@@ -616,7 +617,8 @@ struct ClusterPeers {               // element i of CTA a's dynamic shared memor
 };
 
 template <class P, int A, int MINB, bool FAST, class Rows, class Sink>
-__global__ void __launch_bounds__(P::T, MINB) ow_bigrow_cluster_kernel(Rows rows, const float* __restrict__ ktab, int p_first, float t, Sink sink) {
+__global__ void __launch_bounds__(P::T, MINB) ow_bigrow_cluster_kernel(Rows rows, const float* __restrict__ ktab, const float* __restrict__ ktab_sub,
+                                                                       int p_first, float t, Sink sink) {
     extern __shared__ __align__(16) float2 smem[];
     constexpr int B = P::N, SLICE = B / A;
     static_assert(B % A == 0, "kb slices");
@@ -625,7 +627,7 @@ __global__ void __launch_bounds__(P::T, MINB) ow_bigrow_cluster_kernel(Rows rows
     const int ft = threadIdx.x;
     const int pl = blockIdx.x / A, a = blockIdx.x % A;
     const SmemDirect sm{smem};
-    bigrow_phase0<P, A, FAST>(sm, ft, p_first + pl, a, rows, ktab, t);
+    bigrow_phase0<P, A, FAST>(sm, ft, p_first + pl, a, rows, ktab, ktab_sub, t);
     __syncthreads();
     row_phase1<P>(sm, ft);
     __syncthreads();

@@ -106,19 +106,26 @@ __global__ void ow_h0_slab_kernel(float4* __restrict__ h0, int N, int p0, int PL
 
 // hp[pl][u] = fold_pair(h0 at (u, p), h0 at the mirror texel); rowsA/rowsB = first "primary"/"mirror" row of the block,
 // mirror rows advance by mirror_step (-N for the full grid where row N-p follows row N-p+1 downwards, +N in a slab).
+// sub_A > 0: the row is stored sub-line-major (subline_index) for the line decomposition N = sub_A * B.
 __global__ void ow_fold_kernel(const float4* __restrict__ rowsA, const float4* __restrict__ rowsB, long long mirror_step,
-                               float4* __restrict__ hp, float4* __restrict__ nyq, const float* __restrict__ ktab, int N, int npairs, int first_pair) {
+                               float4* __restrict__ hp, float4* __restrict__ nyq, const float* __restrict__ ktab, int N, int npairs, int first_pair,
+                               int sub_A) {
     const int u = blockIdx.x * blockDim.x + threadIdx.x, pl = blockIdx.y;
     if (u >= N || pl >= npairs) return;
     if (first_pair + pl == 0) return;      // pair 0 (rows 0 and N/2) keeps the unfolded path
     const float4 A = rowsA[(size_t)pl * N + u];
     const float4 B = (rowsB + (long long)pl * mirror_step)[(N - u) & (N - 1)];
-    hp[(size_t)pl * N + u] = fold_pair(A, B);
+    hp[(size_t)pl * N + (sub_A > 0 ? subline_index(u, sub_A, N) : u)] = fold_pair(A, B);
     if (u == 0) nyq[pl] = fold_pair_nyq(A, B);
     if (use_wk(N)) {
         float2* wk = reinterpret_cast<float2*>(hp + (size_t)npairs * N);     // second half of the block (hp_block_f4)
         wk[(size_t)pl * N + u] = dispersion_of(ktab[u], ktab[first_pair + pl]);
     }
+}
+
+__global__ void ow_ktab_sub_kernel(const float* __restrict__ ktab, float* __restrict__ ktab_sub, int N, int A) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < N) ktab_sub[subline_index(u, A, N)] = ktab[u];
 }
 
 __global__ void ow_split_h0_kernel(const float4* __restrict__ h0, float2* __restrict__ a, float2* __restrict__ b, int n) {
@@ -141,6 +148,11 @@ cudaError_t launch_ktab(float* ktab, int N, float L, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+cudaError_t launch_ktab_sub(const float* ktab, float* ktab_sub, int N, int A, cudaStream_t st) {
+    ow_ktab_sub_kernel<<<(N + 255) / 256, 256, 0, st>>>(ktab, ktab_sub, N, A);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_h0(float4* h0, const uint8_t* noise, int nw, int nh, int N, const CascadeDev& c, cudaStream_t st) {
     ow_h0_kernel<<<dim3(N / 32, N / 8), dim3(32, 8), 0, st>>>(h0, noise, nw, nh, N, c);
     return cudaGetLastError();
@@ -156,14 +168,15 @@ cudaError_t launch_h0_slab(float4* h0, int N, int p0, int PL, uint64_t seed, con
     return cudaGetLastError();
 }
 
-cudaError_t launch_fold(const float4* h0, float4* hp, float4* nyq, const float* ktab, int N, cudaStream_t st) {
+cudaError_t launch_fold(const float4* h0, float4* hp, float4* nyq, const float* ktab, int N, int sub_A, cudaStream_t st) {
     // pair p: rows p and N-p; block starts at pair 0 (skipped), mirror of pair pl is row N - pl = rowsB - pl*N with rowsB = row N
-    ow_fold_kernel<<<dim3((N + 255) / 256, N / 2), 256, 0, st>>>(h0, h0 + (size_t)N * N, -(long long)N, hp, nyq, ktab, N, N / 2, 0);
+    ow_fold_kernel<<<dim3((N + 255) / 256, N / 2), 256, 0, st>>>(h0, h0 + (size_t)N * N, -(long long)N, hp, nyq, ktab, N, N / 2, 0, sub_A);
     return cudaGetLastError();
 }
 
-cudaError_t launch_fold_slab(const float4* h0_loc, float4* hp_loc, float4* nyq_loc, const float* ktab, int N, int first_pair, int PL, cudaStream_t st) {
-    ow_fold_kernel<<<dim3((N + 255) / 256, PL), 256, 0, st>>>(h0_loc, h0_loc + (size_t)PL * N, (long long)N, hp_loc, nyq_loc, ktab, N, PL, first_pair);
+cudaError_t launch_fold_slab(const float4* h0_loc, float4* hp_loc, float4* nyq_loc, const float* ktab, int N, int first_pair, int PL, int sub_A,
+                             cudaStream_t st) {
+    ow_fold_kernel<<<dim3((N + 255) / 256, PL), 256, 0, st>>>(h0_loc, h0_loc + (size_t)PL * N, (long long)N, hp_loc, nyq_loc, ktab, N, PL, first_pair, sub_A);
     return cudaGetLastError();
 }
 

@@ -32,6 +32,8 @@ struct FrameBuffers {
     const float4* hp;      // [cascade] blocks of [N/2][N] float4 folded texel pairs (fold_pair) + [N/2][N] float2 (w, 1/|k|): what the row kernel streams
     const float4* nyq;     // [cascade][N/2]    Nyquist-column extras (fold_pair_nyq)
     const float* ktab;     // [cascade][N]      k(i) = 2*pi*(i - N/2)/L, computed with the shader's operation order
+    const float* ktab_sub; // [cascade][N]      the same table sub-line-major (subline_index) - contexts that run the N = A*B line decomposition only,
+                           //                   whose folded rows `hp` are stored in that order too; nullptr otherwise
     const CascadeDev* casc;
     float2* inter;         // [slot][3][N/2][N] row-transformed Hermitian half spectra (dy, dx, dz)
     float* disp;           // [slot][3][N][N]   dy, dx, dz
@@ -150,6 +152,7 @@ size_t hp_block_elems(int npairs, int N);
 bool frame_supported(int N);            // direct kernels (N <= 4096) or the N = A*B decomposition (8192 .. 32768)
 // N = A*B line decomposition (ow_big_kernels.cu). forced: the test-only mapping of N = 1024 / 2048 onto it.
 bool big_supported(int N, bool forced);
+int big_radix(int N, bool forced);      // A of N = A*B for such a grid, else 0
 cudaError_t configure_big(int N, bool forced, KernelConfig* cfg);
 int launch_big_frame(const FrameBuffers& fb, const SlotTable& tab, int count, bool with_jacobian, bool fast_phase, cudaStream_t st,
                      cudaEvent_t* ev, bool forced);
@@ -205,7 +208,8 @@ struct SlabGeom {
 };
 bool slab_supported(int N, int world);
 // Row kernel for this rank's pairs; block h of the result goes to sink_base[h] ([PL][3][XH] float2 each).
-int launch_slab_rows(const SlabGeom& g, const float4* h0_loc, const float4* hp_loc, const float4* nyq_loc, const float* ktab,
+// ktab_sub: the sub-line-major k table (N > 4096, where hp_loc is sub-line-major too), else unused.
+int launch_slab_rows(const SlabGeom& g, const float4* h0_loc, const float4* hp_loc, const float4* nyq_loc, const float* ktab, const float* ktab_sub,
                      float2* const sink_base[kSlabMaxWorld], float t, bool fast_phase, float2* scratch, cudaStream_t st);
 // Column kernel on recv[N/2][3][XH] -> disp_loc[3][N][XH], then normals (+ Jacobian when jac != nullptr) for the XL
 // interior columns -> normal_loc[N][XL], jac_loc[N][XL]. jac_scale = choppiness * N / (2 L).
@@ -213,7 +217,7 @@ int launch_slab_cols(const SlabGeom& g, const float2* recv, float* disp_loc, flo
                      float2* scratch, cudaStream_t st);
 
 bool big_slab_supported(int N, int world, bool forced);
-int launch_big_slab_rows(const SlabGeom& g, const float4* h0_loc, const float4* hp_loc, const float4* nyq_loc, const float* ktab,
+int launch_big_slab_rows(const SlabGeom& g, const float4* h0_loc, const float4* hp_loc, const float4* nyq_loc, const float* ktab, const float* ktab_sub,
                          float2* const sink_base[kSlabMaxWorld], float t, bool fast_phase, float2* scratch, cudaStream_t st, bool forced);
 int launch_big_slab_cols(const SlabGeom& g, const float2* recv, float* disp_loc, float4* normal_loc, float* jac_loc, float jac_scale,
                          float2* scratch, cudaStream_t st, bool forced);
@@ -250,13 +254,16 @@ cudaError_t launch_compose_grid(const ComposeArgs& A, int M, float ox, float oz,
 cudaError_t launch_noise_seed(uint8_t* noise /* [4][N][N] */, int N, uint64_t seed, cudaStream_t st);
 cudaError_t launch_h0_slab(float4* h0_loc, int N, int p0, int PL, uint64_t seed, const CascadeDev& c, cudaStream_t st);
 cudaError_t launch_ktab(float* ktab, int N, float L, cudaStream_t st);
+cudaError_t launch_ktab_sub(const float* ktab, float* ktab_sub, int N, int A, cudaStream_t st);    // ktab_sub[subline_index(u, A, N)] = ktab[u]
 cudaError_t launch_h0(float4* h0, const uint8_t* noise, int noise_w, int noise_h, int N, const CascadeDev& c,
                       cudaStream_t st);
 // Fold h0 into the per-pair coefficients the row kernel streams. Full grid: pair p uses rows p and N-p of h0[N][N];
 // slab: local rows pl and PL+pl of h0_loc[2*PL][N] (first_pair = rank*PL; pair 0 is skipped in both).
 // hp / hp_loc are blocks of hp_block_f4(npairs, N) float4: the fold coefficients, then (w, 1/|k|) per pair texel (ktab: this cascade's k table).
-cudaError_t launch_fold(const float4* h0, float4* hp, float4* nyq, const float* ktab, int N, cudaStream_t st);
-cudaError_t launch_fold_slab(const float4* h0_loc, float4* hp_loc, float4* nyq_loc, const float* ktab, int N, int first_pair, int PL, cudaStream_t st);
+// sub_A > 0: every folded row is written sub-line-major for the N = sub_A * B line decomposition (texel u at subline_index(u, sub_A, N)).
+cudaError_t launch_fold(const float4* h0, float4* hp, float4* nyq, const float* ktab, int N, int sub_A, cudaStream_t st);
+cudaError_t launch_fold_slab(const float4* h0_loc, float4* hp_loc, float4* nyq_loc, const float* ktab, int N, int first_pair, int PL, int sub_A,
+                             cudaStream_t st);
 cudaError_t launch_split_h0(const float4* h0, float* h0k, float* h0minusk, int n, cudaStream_t st);
 cudaError_t launch_merge_h0(float4* h0, const float* h0k, const float* h0minusk, int n, cudaStream_t st);
 

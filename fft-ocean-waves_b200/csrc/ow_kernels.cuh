@@ -633,18 +633,27 @@ __host__ __device__ __noinline__ void bigrow_phase0_pair0(const Smem& sm, int ft
     }
 }
 
-// Row lines, stage 0: spectrum at the decimated texels u = A*m + a of pair p — row_phase0 with a strided texel index
-// (all loads of a butterfly in flight before the first use).
+// Contexts that run the line decomposition keep every folded pair row (and a copy of the k table) SUB-LINE-MAJOR: texel u = A*m + a
+// sits at index a*B + m, so the B texels of sub-line a are contiguous. The lines kernel's stage-0 loads are then coalesced 512-byte runs
+// per warp instruction; in the natural order they were 32 separate 16-byte pieces 16*A bytes apart, i.e. 32 L1 wavefronts per load
+// instruction - two thirds of the kernel's L1/shared-memory pipe time at N = 32768.
+OW_HD int subline_index(int u, int A, int N) { return (u % A) * (N / A) + u / A; }
+
+// Row lines, stage 0: spectrum at the decimated texels u = A*m + a of pair p — row_phase0 on the sub-line-major folded row
+// (all loads of a butterfly in flight before the first use). ktab_sub = the k table in the same order (kx of the texels);
+// ktab = the natural one (ky of the pair, pair 0's literal path).
 template <class P, int A, bool FAST, class Smem, class Rows>
-OW_HD void bigrow_phase0(const Smem& sm, int ft, int p, int a, const Rows& rows, const float* __restrict__ ktab, float t) {
+OW_HD void bigrow_phase0(const Smem& sm, int ft, int p, int a, const Rows& rows, const float* __restrict__ ktab, const float* __restrict__ ktab_sub,
+                         float t) {
     constexpr int B = P::N, R0 = P::R0;
     if (p == 0) {
         bigrow_phase0_pair0<P, A, FAST>(sm, ft, a, rows, ktab, t);
         return;
     }
     const float ky = OW_LDG(ktab + p);
-    const float4* prow = rows.pair_row(p);
+    const float4* prow = rows.pair_row(p) + (size_t)a * B;      // sub-line a of the pair's folded row
     const float2* wrow = rows.wk_row(p);
+    const float* ksub = ktab_sub + (size_t)a * B;
 #pragma unroll 1
     for (int c = 0; c < P::C0; ++c) {
         const int b = ft + P::T * c;
@@ -652,7 +661,7 @@ OW_HD void bigrow_phase0(const Smem& sm, int ft, int p, int a, const Rows& rows,
         float2 vy[R0], vx[R0], vz[R0];
         FoldedPair fp[R0];
 #pragma unroll
-        for (int d0 = 0; d0 < R0; ++d0) fp[d0] = load_folded<false>(prow, wrow, ktab, A * (d0 * P::M + b) + a);
+        for (int d0 = 0; d0 < R0; ++d0) fp[d0] = load_folded<false>(prow, wrow, ksub, d0 * P::M + b);
 #pragma unroll
         for (int d0 = 0; d0 < R0; ++d0) {
             const Sym3 s = spectrum_folded<FAST, false>(fp[d0], ky, t, (d0 == 0 && b == 0 && a == 0) ? rows.nyq_of(p) : nullptr);

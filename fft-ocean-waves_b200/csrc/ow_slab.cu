@@ -35,6 +35,8 @@ struct ow_slab {
     float4* d_nyq = nullptr;      // [PL]
     int cluster_caps = 0;         // KernelConfig::big_cluster of this rank's device (N = A*B decomposition as thread-block clusters)
     float* d_ktab = nullptr;      // [N]
+    float* d_ktab_sub = nullptr;  // [N] sub-line-major copy (N > 4096: the folded rows d_hp are stored in that order too)
+    int sub_A = 0;                // A of the line decomposition N = A*B, 0 for the direct kernels
     float2* d_send = nullptr;     // [world][PL][3][XH]
     float2* d_recv = nullptr;     // [N/2][3][XH] = [world][PL][3][XH]   (receive buffer 0)
     int post_ctas_per_sm = 2;     // ow_slab_set_post_ctas
@@ -81,7 +83,7 @@ void srelease(ow_slab* s) {
         for (int h = 0; h < s->g.world; ++h)
             if (h != s->g.rank && s->peer_recv1[h]) cudaIpcCloseMemHandle(s->peer_recv1[h]);
     cudaFree(s->d_recv1); cudaFree(s->d_scratch_cols);
-    cudaFree(s->d_h0); cudaFree(s->d_hp); cudaFree(s->d_nyq); cudaFree(s->d_ktab); cudaFree(s->d_send); cudaFree(s->d_recv); cudaFree(s->d_disp);
+    cudaFree(s->d_h0); cudaFree(s->d_hp); cudaFree(s->d_nyq); cudaFree(s->d_ktab); cudaFree(s->d_ktab_sub); cudaFree(s->d_send); cudaFree(s->d_recv); cudaFree(s->d_disp);
     cudaFree(s->d_normal); cudaFree(s->d_jac); cudaFree(s->d_scratch);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
@@ -129,6 +131,8 @@ int ow_slab_create(int32_t N, int32_t world, int32_t rank, const ow_params* p, i
     OWS_TRY(cudaMemsetAsync(s->d_hp, 0, hp_block_elems(g.PL, N) * sizeof(float4), s->stream));
     OWS_TRY(cudaMemsetAsync(s->d_nyq, 0, (size_t)g.PL * sizeof(float4), s->stream));
     OWS_TRY(cudaMalloc(&s->d_ktab, (size_t)N * sizeof(float)));
+    s->sub_A = big_radix(N, false);
+    if (s->sub_A) OWS_TRY(cudaMalloc(&s->d_ktab_sub, (size_t)N * sizeof(float)));
     OWS_TRY(cudaMalloc(&s->d_send, block_elems(g) * world * sizeof(float2)));
     OWS_TRY(cudaMalloc(&s->d_recv, block_elems(g) * world * sizeof(float2)));
     OWS_TRY(cudaMalloc(&s->d_disp, (size_t)3 * N * g.XH * sizeof(float)));
@@ -167,7 +171,8 @@ int ow_slab_init_spectrum_seeded(ow_slab* s, uint64_t seed) {
     const SlabGeom& g = s->g;
     OWS_CUDA(s, launch_ktab(s->d_ktab, g.N, s->params.L, s->stream));
     OWS_CUDA(s, launch_h0_slab(s->d_h0, g.N, g.rank * g.PL, g.PL, seed, s->casc, s->stream));
-    OWS_CUDA(s, launch_fold_slab(s->d_h0, s->d_hp, s->d_nyq, s->d_ktab, g.N, g.rank * g.PL, g.PL, s->stream));
+    if (s->sub_A) OWS_CUDA(s, launch_ktab_sub(s->d_ktab, s->d_ktab_sub, g.N, s->sub_A, s->stream));
+    OWS_CUDA(s, launch_fold_slab(s->d_h0, s->d_hp, s->d_nyq, s->d_ktab, g.N, g.rank * g.PL, g.PL, s->sub_A, s->stream));
     OWS_CUDA(s, cudaStreamSynchronize(s->stream));   // like the reference's glFinish after tilde_h0_k (src/main.cpp:582)
     s->spectrum_ready = true;
     return OW_OK;
@@ -261,7 +266,7 @@ int ow_slab_rows_buf(ow_slab* s, float t, int32_t transport, int32_t buf, void* 
     bool fast = (s->flags & OW_FLAG_EXACT_SINCOS) == 0;
     const float kmax = 1.41421356f * 3.14159265f * (float)g.N / s->params.L;
     if (!(sqrtf(9.81f * kmax) * fabsf(t) < kFastPhaseLimit)) fast = false;
-    if (launch_slab_rows(g, s->d_h0, s->d_hp, s->d_nyq, s->d_ktab, base, t, fast, s->d_scratch, spick(s, stream)) < 0) return scuda(s, cudaGetLastError(), "launch_slab_rows");
+    if (launch_slab_rows(g, s->d_h0, s->d_hp, s->d_nyq, s->d_ktab, s->d_ktab_sub, base, t, fast, s->d_scratch, spick(s, stream)) < 0) return scuda(s, cudaGetLastError(), "launch_slab_rows");
     return OW_OK;
 }
 

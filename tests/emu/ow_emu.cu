@@ -63,8 +63,9 @@ struct SmemEmu {
 
 // Host restatement of ow_fold_kernel (ow_init_kernels.cu): hp[p][u] = fold_pair(h0[p][u], h0[N-p][(N-u) mod N]), followed by the
 // (w, 1/|k|) table of the same pair texels (second half of the block, hp_block_f4).
+// sub_A > 0: rows stored sub-line-major (subline_index), as the contexts that run the N = sub_A * B line decomposition keep them.
 template <int N>
-void fold_full(const std::vector<float4>& h0, std::vector<float4>& hp, std::vector<float4>& nyq, float L) {
+void fold_full(const std::vector<float4>& h0, std::vector<float4>& hp, std::vector<float4>& nyq, float L, int sub_A = 0) {
     hp.assign(hp_block_f4(N / 2, N), make_float4(0, 0, 0, 0));
     nyq.assign(N / 2, make_float4(0, 0, 0, 0));
     float2* wk = reinterpret_cast<float2*>(hp.data() + (size_t)(N / 2) * N);
@@ -73,7 +74,7 @@ void fold_full(const std::vector<float4>& h0, std::vector<float4>& hp, std::vect
     for (int p = 1; p < N / 2; ++p)
         for (int u = 0; u < N; ++u) {
             const float4 A = h0[(size_t)p * N + u], B = h0[(size_t)(N - p) * N + ((N - u) & (N - 1))];
-            hp[(size_t)p * N + u] = fold_pair(A, B);
+            hp[(size_t)p * N + (sub_A > 0 ? subline_index(u, sub_A, N) : u)] = fold_pair(A, B);
             if (u == 0) nyq[p] = fold_pair_nyq(A, B);
             if (use_wk(N)) wk[(size_t)p * N + u] = dispersion_of(kof(u), kof(p));
         }
@@ -359,10 +360,11 @@ int emu_big_frame_n(const float* h0k, const float* h0minusk, float L, float t, f
     using LY = ColLayout<PK, G>;
     std::vector<float4> h0((size_t)N * N), hp, nyq;
     for (size_t i = 0; i < (size_t)N * N; ++i) h0[i] = make_float4(h0k[2 * i], h0k[2 * i + 1], h0minusk[2 * i], h0minusk[2 * i + 1]);
-    fold_full<N>(h0, hp, nyq, L);
-    std::vector<float> ktab(N);
+    fold_full<N>(h0, hp, nyq, L, A);
+    std::vector<float> ktab(N), ktab_sub(N);
     const float pi = 3.1415926535897932384626433832795f;
     for (int i = 0; i < N; ++i) ktab[i] = (2.0f * pi * ((float)i - (float)N / 2.0f)) / L;
+    for (int i = 0; i < N; ++i) ktab_sub[subline_index(i, A, N)] = ktab[i];
     std::vector<float2> inter((size_t)3 * (N / 2) * N), scratch((size_t)3 * (N / 2) * N);
     const FullRows<N> rows{h0.data(), hp.data(), nyq.data()};
     const FullSink<N> sink{inter.data()};
@@ -373,7 +375,7 @@ int emu_big_frame_n(const float* h0k, const float* h0minusk, float L, float t, f
         const SmemEmu sm{smem.data(), &dummy};
         for (int p = 0; p < N / 2; ++p)
             for (int a = 0; a < A; ++a) {
-                for (int ft = 0; ft < PR::T; ++ft) { dummy.clear(); bigrow_phase0<PR, A, false>(sm, ft, p, a, rows, ktab.data(), t); }
+                for (int ft = 0; ft < PR::T; ++ft) { dummy.clear(); bigrow_phase0<PR, A, false>(sm, ft, p, a, rows, ktab.data(), ktab_sub.data(), t); }
                 for (int ft = 0; ft < PR::T; ++ft) { dummy.clear(); row_phase1<PR>(sm, ft); }
                 for (int ft = 0; ft < PR::T; ++ft) { dummy.clear(); bigrow_phase2<PR, A>(sm, ft, a, scratch.data() + (size_t)p * 3 * N); }
             }
