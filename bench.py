@@ -745,6 +745,8 @@ def measure_slab(env, args, n_grid, steps, warmup, full):
     p = fow.OceanParams(L=1000.0, wind_speed=40.0, wind_dir=(1.0, 1.0), amplitude=2.0, suppression=0.1, choppiness=1.0)
     times = [float(np.float32(f / 60.0)) for f in range(frames)]
     sim = fow.SlabOcean(N=N, params=p, device=env.local, jacobian=jac, transport=args.transport, pipeline=(False if args.no_pipeline else None))
+    if args.col_lines and hasattr(sim.backend, "set_column_lines"):
+        sim.backend.set_column_lines(args.col_lines)
     if args.post_ctas >= 0 and hasattr(sim.backend, "set_post_ctas"):
         sim.backend.set_post_ctas(args.post_ctas)
     if args.line_clusters != 0 and hasattr(sim.backend, "set_line_clusters"):
@@ -937,6 +939,7 @@ def main():
     ap.add_argument("--no-compare", action="store_true", help="skip the cuFFT comparison leg")
     ap.add_argument("--no-slab-check", action="store_true", help="c5: skip the slab-vs-single-GPU agreement check before timing")
     ap.add_argument("--fused-normals", action="store_true", help="experimental OW_FLAG_FUSED_NORMALS (normal map as the column kernel's epilogue)")
+    ap.add_argument("--col-lines", type=int, default=0, help="c5: ow_slab_set_column_lines (0 = default, 2 = 8-column tiles, 4 = persistent pipelined)")
     ap.add_argument("--post-ctas", type=int, default=-1, help="c5: ow_slab_set_post_ctas (CTAs per SM of the row pass's store kernel; -1 = the library's choice)")
     ap.add_argument("--no-pipeline", action="store_true", help="c5: one frame at a time (no overlap of the next frame's rows with this frame's columns)")
     ap.add_argument("--no-graph", action="store_true", help="c4: submit the step through ow_step_multi (stream launches) instead of ow_step (one graph launch)")

@@ -155,6 +155,8 @@ FrameBuffers buffers(const ow_ctx* c) {
     fb.big_cluster = c->line_clusters < 0 ? c->kcfg.big_cluster
                                           : (c->line_clusters & c->kcfg.big_cluster & 3) | ((c->line_clusters & 2) ? (c->line_clusters & 4) : 0);
     fb.col_pipe_ctas = c->cap_col > 0 ? std::min(c->kcfg.col_pipe_ctas, c->cap_col) : c->kcfg.col_pipe_ctas;
+    // line decomposition: the persistent pipelined column lines kernel unless ow_set_column_kernel(1) asks for one CTA per item
+    fb.bigcol_pipe_grid = c->col_mode == 4 ? c->kcfg.sm_count * c->kcfg.bigcol_pipe_ctas : c->col_mode == 2 ? -1 : 0;
     return fb;
 }
 

@@ -64,6 +64,22 @@ struct Big {
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(ow_bigcol_lines_kernel<K, A, G, KMB, SlabColGeom>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ColLayout<K, G>::SMEM);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(ow_bigcol_lines_kernel<K, A, G4, KMB4, FullColGeom<N>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ColLayout<K, G4>::SMEM);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(ow_bigcol_lines_kernel<K, A, G4, KMB4, SlabColGeom>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ColLayout<K, G4>::SMEM);
+        if (e != cudaSuccess) return e;
+        {   // persistent pipelined column lines kernel: how many CTAs of it an SM holds
+            int n = 0, m = 0;
+            e = cudaFuncSetAttribute(ow_bigcol_lines_pipe_kernel<K, A, G, KMB, FullColGeom<N>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ColLayout<K, G>::SMEM);
+            if (e != cudaSuccess) return e;
+            e = cudaFuncSetAttribute(ow_bigcol_lines_pipe_kernel<K, A, G, KMB, SlabColGeom>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ColLayout<K, G>::SMEM);
+            if (e != cudaSuccess) return e;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ow_bigcol_lines_pipe_kernel<K, A, G, KMB, FullColGeom<N>>, K::T * G, ColLayout<K, G>::SMEM);
+            if (e != cudaSuccess) return e;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m, ow_bigcol_lines_pipe_kernel<K, A, G, KMB, SlabColGeom>, K::T * G, ColLayout<K, G>::SMEM);
+            if (e != cudaSuccess) return e;
+            cfg->bigcol_pipe_ctas = n < m ? n : m;
+        }
         // cluster versions: opt in to their shared memory, then ask the device how many clusters it can co-schedule
         const size_t rs = row_smem<R, 1>(), cs8 = ColLayout<K, G>::SMEM, cs4 = ColLayout<K, G4>::SMEM;
 #define OW_OPT(kern, bytes) if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))) != cudaSuccess) return e
@@ -114,7 +130,7 @@ struct Big {
 
     template <class Geom>
     static void cols_pass(const float2* src, size_t src_chan, int npairs, float2* scratch, float* dst, size_t dst_chan, const Geom& geom,
-                          cudaStream_t st, int cluster_bits) {
+                          cudaStream_t st, int cluster_bits, int pipe_grid) {
         const float scale = 0.5f / ((float)N * (float)N);
         if ((cluster_bits & 2) && npairs % ((cluster_bits & 4) ? G4 : G) == 0) {
             cudaError_t e = (cluster_bits & 4)
@@ -125,7 +141,14 @@ struct Big {
             if (e != cudaSuccess) stash_launch_error(e);
             return;
         }
-        ow_bigcol_lines_kernel<K, A, G, KMB, Geom><<<dim3(npairs / G * A, 3), K::T * G, ColLayout<K, G>::SMEM, st>>>(src, src_chan, npairs, scratch, geom);
+        const int total = npairs / G * A * 3;
+        if (pipe_grid < 0 && npairs % G4 == 0)          // 8-column tiles: three 256-thread CTAs per SM instead of one 512-thread CTA
+            ow_bigcol_lines_kernel<K, A, G4, KMB4, Geom><<<dim3(npairs / G4 * A, 3), K::T * G4, ColLayout<K, G4>::SMEM, st>>>(src, src_chan, npairs, scratch, geom);
+        else if (pipe_grid > 0)
+            ow_bigcol_lines_pipe_kernel<K, A, G, KMB, Geom><<<total < pipe_grid ? total : pipe_grid, K::T * G, ColLayout<K, G>::SMEM, st>>>(src, src_chan, npairs, scratch,
+                                                                                                                                 geom, total);
+        else
+            ow_bigcol_lines_kernel<K, A, G, KMB, Geom><<<dim3(npairs / G * A, 3), K::T * G, ColLayout<K, G>::SMEM, st>>>(src, src_chan, npairs, scratch, geom);
         ow_bigcol_post_kernel<B, A><<<dim3((npairs + 31) / 32, B / 8, 3), dim3(32, 8), 0, st>>>(scratch, npairs, dst, dst_chan, geom.dst_stride(), scale);
     }
 
@@ -140,7 +163,7 @@ struct Big {
         rows_pass(rows, fb.ktab + (size_t)cascade * N, fb.ktab_sub + (size_t)cascade * N, 0, N / 2, tab.time[0], fast, fb.scratch, FullSink<N>{inter}, st,
                   fb.big_cluster);
         if (ev) cudaEventRecord(ev[1], st);
-        cols_pass(inter, nn / 2, N / 2, fb.scratch, fb.disp + (size_t)slot * 3 * nn, nn, FullColGeom<N>{}, st, fb.big_cluster);
+        cols_pass(inter, nn / 2, N / 2, fb.scratch, fb.disp + (size_t)slot * 3 * nn, nn, FullColGeom<N>{}, st, fb.big_cluster, fb.bigcol_pipe_grid);
         if (ev) cudaEventRecord(ev[2], st);
         const dim3 ngrid(N / 128, N / (WARPS * RY), 1);
         if (with_jac) ow_normal_kernel<N, true, RY, WARPS, NMINB><<<ngrid, dim3(32, WARPS), 0, st>>>(fb, tab);
@@ -171,7 +194,8 @@ struct Big {
 
     static int slab_cols(const SlabGeom& g, const float2* recv, float* disp_loc, float4* normal_loc, float* jac_loc, float jac_scale,
                          float2* scratch, cudaStream_t st) {
-        cols_pass(recv, (size_t)g.XH, g.XH / 2, scratch, disp_loc, (size_t)N * g.XH, SlabColGeom{(size_t)3 * g.XH, (size_t)g.XH}, st, g.big_cluster);
+        cols_pass(recv, (size_t)g.XH, g.XH / 2, scratch, disp_loc, (size_t)N * g.XH, SlabColGeom{(size_t)3 * g.XH, (size_t)g.XH}, st, g.big_cluster,
+                  g.bigcol_pipe_grid);
         const dim3 ngrid(g.XL / 128, N / (WARPS * RY));
         if (jac_loc) ow_normal_slab_kernel<N, true, RY, WARPS, NMINB><<<ngrid, dim3(32, WARPS), 0, st>>>(disp_loc, normal_loc, jac_loc, g.XL, g.XH, jac_scale);
         else ow_normal_slab_kernel<N, false, RY, WARPS, NMINB><<<ngrid, dim3(32, WARPS), 0, st>>>(disp_loc, normal_loc, nullptr, g.XL, g.XH, 0.f);

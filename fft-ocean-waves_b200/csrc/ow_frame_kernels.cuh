@@ -575,6 +575,15 @@ __global__ void __launch_bounds__(256) ow_bigrow_post_slim_kernel(const float2* 
     }
 }
 
+// Order of the column-lines items of one channel: CTA index -> (tile, sub-line), sub-line fastest, so the CTAs in flight cover all A
+// sub-lines of ~9 adjacent tiles and the rows that sub-lines a and A - a share are read close together (served once from DRAM).
+// (Measured alternative, N = 32768: sub-line PAIRS {a, A-a} x 64 adjacent tiles in flight, for longer contiguous runs of every row:
+// column pass 20.1 ms instead of 18.4 ms - profiles/r02_experiments.md.)
+__host__ __device__ __forceinline__ void bigcol_item(int idx, int A, int* tile, int* a) {
+    *tile = idx / A;
+    *a = idx - (idx / A) * A;
+}
+
 // src: channel-0 base of the Hermitian-packed intermediate; channel c at src + c*src_chan.
 template <class P, int A, int G, int MINB, class Geom>
 __global__ void __launch_bounds__(P::T* G, MINB) ow_bigcol_lines_kernel(const float2* __restrict__ src, size_t src_chan, int npairs,
@@ -583,7 +592,8 @@ __global__ void __launch_bounds__(P::T* G, MINB) ow_bigcol_lines_kernel(const fl
     constexpr int N = A * P::N;
     using LY = ColLayout<P, G>;
     const int job = threadIdx.x % G, ft = threadIdx.x / G;
-    const int tile = blockIdx.x / A, a = blockIdx.x % A;
+    int tile, a;
+    bigcol_item(blockIdx.x, A, &tile, &a);
     const int pair = tile * G + job;
     const int f = blockIdx.y;
     const SmemDirect sm{smem};
@@ -593,6 +603,62 @@ __global__ void __launch_bounds__(P::T* G, MINB) ow_bigcol_lines_kernel(const fl
     col_phase1<P>(sm, base, ft);
     __syncthreads();
     bigcol_phase2<P>(sm, base, ft, scratch + (size_t)f * N * npairs + (size_t)a * P::N * npairs + pair, (size_t)npairs);
+}
+
+// The same kernel, persistent and register-pipelined (the big-grid counterpart of ow_col_pipe_kernel). ow_bigcol_lines_kernel holds ONE
+// 512-thread CTA per SM (a 16-column tile of 2048-point sub-lines is 141 KB of shared memory), and that CTA runs load batch -> wait a DRAM
+// round trip -> transform, four times per tile, then stages 1-2 and the stores with nothing in flight: 3.3 TB/s at N = 32768. Here a CTA walks
+// over the (channel, tile, sub-line) items - sub-line fastest, so the rows sub-lines a and A-a share are read close together - and always has
+// the NEXT batch's R0 row loads in flight in registers: the next batch of this tile during a batch's arithmetic, the first batch of the next
+// tile during stages 1 and 2 and their stores.
+template <class P, int A, int G, int MINB, class Geom>
+__global__ void __launch_bounds__(P::T* G, MINB) ow_bigcol_lines_pipe_kernel(const float2* __restrict__ src, size_t src_chan, int npairs,
+                                                                             float2* __restrict__ scratch, Geom geom, int total) {
+    extern __shared__ __align__(16) float2 smem[];
+    constexpr int N = A * P::N, R0 = P::R0, C0 = P::M / P::T;
+    static_assert(P::M % P::T == 0 && C0 >= 1, "whole stage-0 batches");
+    using LY = ColLayout<P, G>;
+    const int job = threadIdx.x % G, ft = threadIdx.x / G;
+    const SmemDirect sm{smem};
+    const int base = job * LY::SJ;
+    const size_t ss = geom.src_stride();
+    const int per_f = npairs / G * A;                 // items per channel
+    int w = blockIdx.x;
+    if (w >= total) return;
+    auto src_of = [&](int wi, int* a) {
+        const int f = wi / per_f;
+        int tile;
+        bigcol_item(wi - f * per_f, A, &tile, a);
+        return src + (size_t)f * src_chan + 2 * (tile * G + job);
+    };
+    float4 nxt[R0];
+    int a = 0;
+    const float2* s = src_of(w, &a);
+    bigcol_issue<P, A>(ft, a, s, ss, nxt);
+    for (; w < total; w += gridDim.x) {
+        const int f = w / per_f;
+        int tile_w, a_w;
+        bigcol_item(w - f * per_f, A, &tile_w, &a_w);
+        const int pair = tile_w * G + job;
+        const int wn = w + gridDim.x;
+        int an = 0;
+        const float2* sn = wn < total ? src_of(wn, &an) : s;
+#pragma unroll
+        for (int c = 0; c < C0; ++c) {
+            float4 cur[R0];
+#pragma unroll
+            for (int d0 = 0; d0 < R0; ++d0) cur[d0] = nxt[d0];
+            if (c + 1 < C0) bigcol_issue<P, A>(ft + (c + 1) * P::T, a, s, ss, nxt);          // next batch of this tile
+            else if (wn < total) bigcol_issue<P, A>(ft, an, sn, ss, nxt);                      // first batch of the next tile: lands during stages 1-2
+            bigcol_phase0_math<P, A>(sm, base, ft + c * P::T, a, cur);
+        }
+        __syncthreads();
+        col_phase1<P>(sm, base, ft);
+        __syncthreads();
+        bigcol_phase2<P>(sm, base, ft, scratch + (size_t)f * N * npairs + (size_t)a * P::N * npairs + pair, (size_t)npairs);
+        __syncthreads();                               // the next tile's stage-0 stores reuse the lines
+        s = sn; a = an;
+    }
 }
 
 // dst: channel-0 base of the displacement planes; channel c at dst + c*dst_chan, rows ds floats apart.

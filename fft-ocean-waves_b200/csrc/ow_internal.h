@@ -60,6 +60,7 @@ struct FrameBuffers {
     int latency_shapes;    // launches of ONE frame use the latency-oriented kernel shapes (Cfg<N>::LAT); ow_set_latency_shapes
     int big_cluster;       // N = A*B decomposition: bit 0 = rows, bit 1 = columns run as thread-block clusters (DSMEM radix-A stage, no scratch),
                            // bit 2 = the column clusters use 8-column tiles (3 CTAs per SM) instead of 16-column ones (1 CTA per SM)
+    int bigcol_pipe_grid;  // N = A*B decomposition: grid of the persistent column lines kernel (resident CTAs of the device), 0 = one CTA per item
 };
 
 // What configure_frame_kernels found out about the device the calling context lives on (kept per context: no process-global state).
@@ -72,6 +73,7 @@ struct KernelConfig {
     int mega_ctas = 0;                 // ow_mega_kernel (0: not available for this N)
     int big_cluster = 0;               // what the device can co-schedule (FrameBuffers::big_cluster bits)
     int big_clusters_rows = 0, big_clusters_cols8 = 0, big_clusters_cols4 = 0;   // cudaOccupancyMaxActiveClusters of the three cluster shapes
+    int bigcol_pipe_ctas = 0;          // resident CTAs per SM of ow_bigcol_lines_pipe_kernel (0: not a line-decomposition grid)
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -205,6 +207,7 @@ struct SlabGeom {
     int XH;   // padded columns       = XL + 2 * kSlabHalo
     int big_cluster = 0;   // FrameBuffers::big_cluster bits (KernelConfig::big_cluster of the rank's device, or 0 to force the scratch path)
     int post_ctas = 0;     // N > 4096: grid of the row post kernel (0 = one CTA per item; > 0 = slim persistent grid, see ow_bigrow_post_slim_kernel)
+    int bigcol_pipe_grid = 0;   // N > 4096: grid of the persistent column lines kernel (0 = one CTA per item, ow_bigcol_lines_kernel)
 };
 bool slab_supported(int N, int world);
 // Row kernel for this rank's pairs; block h of the result goes to sink_base[h] ([PL][3][XH] float2 each).

@@ -710,29 +710,41 @@ OW_HD void bigrow_post(const float2* __restrict__ zrow /* scratch row of pair p:
     for (int ka = 0; ka < A; ++ka) sink.put(c, p, kb + B * ka, v[ka]);
 }
 
-// Column lines, stage 0: the decimated source rows v = A*m + a of this job's column pair.
+// Column lines, stage 0: the decimated source rows v = A*m + a of this job's column pair. Loading is split from the arithmetic so that
+// the pipelined kernel can keep the next batch's R0 row loads in flight while this batch is transformed.
+// Row of v: v itself below N/2, N - v above (conjugated on unpacking), row 0 for the two packed real rows v = 0 and v = N/2.
+template <class P, int A>
+OW_HD void bigcol_issue(int b, int a, const float2* __restrict__ src /* inter[c] + x */, size_t ss, float4 (&r)[P::R0]) {
+    constexpr int B = P::N, N = A * B, R0 = P::R0;
+#pragma unroll
+    for (int d0 = 0; d0 < R0; ++d0) {
+        const int vv = A * (d0 * P::M + b) + a;
+        const int row = (vv < N / 2 ? vv : N - vv) & (N / 2 - 1);
+        r[d0] = OW_LDG(reinterpret_cast<const float4*>(src + (size_t)row * ss));
+    }
+}
+
+template <class P, int A, class Smem>
+OW_HD void bigcol_phase0_math(const Smem& sm, int base, int b, int a, const float4 (&r)[P::R0]) {
+    constexpr int B = P::N, N = A * B, R0 = P::R0;
+    float2 v[R0], tw[R0];
+#pragma unroll
+    for (int d0 = 0; d0 < R0; ++d0) {
+        const int vv = A * (d0 * P::M + b) + a;
+        v[d0] = vv == 0 ? make_float2(r[d0].x, r[d0].z) : vv == N / 2 ? make_float2(r[d0].y, r[d0].w) : vv < N / 2 ? pack_fwd(r[d0]) : pack_cnj(r[d0]);
+    }
+    twiddle_powers<R0>(unit_root(b, B), tw);
+    stage0_finish<P>(sm, base, b, v, tw);
+}
+
 template <class P, int A, class Smem, class Geom>
 OW_HD void bigcol_phase0(const Smem& sm, int base, int ft, int a, const float2* __restrict__ src /* inter[c] + x */, const Geom& geom) {
-    constexpr int B = P::N, N = A * B, R0 = P::R0;
     const size_t ss = geom.src_stride();
 #pragma unroll 1
     for (int b = ft; b < P::M; b += P::T) {
-        float2 v[R0], tw[R0];
-        float4 r[R0];
-        // all R0 row loads first (row of v: v itself below N/2, N - v above, row 0 for the two packed real rows), then the unpacking
-#pragma unroll
-        for (int d0 = 0; d0 < R0; ++d0) {
-            const int vv = A * (d0 * P::M + b) + a;
-            const int row = (vv < N / 2 ? vv : N - vv) & (N / 2 - 1);
-            r[d0] = OW_LDG(reinterpret_cast<const float4*>(src + (size_t)row * ss));
-        }
-#pragma unroll
-        for (int d0 = 0; d0 < R0; ++d0) {
-            const int vv = A * (d0 * P::M + b) + a;
-            v[d0] = vv == 0 ? make_float2(r[d0].x, r[d0].z) : vv == N / 2 ? make_float2(r[d0].y, r[d0].w) : vv < N / 2 ? pack_fwd(r[d0]) : pack_cnj(r[d0]);
-        }
-        twiddle_powers<R0>(unit_root(b, B), tw);
-        stage0_finish<P>(sm, base, b, v, tw);
+        float4 r[P::R0];
+        bigcol_issue<P, A>(b, a, src, ss, r);
+        bigcol_phase0_math<P, A>(sm, base, b, a, r);
     }
 }
 

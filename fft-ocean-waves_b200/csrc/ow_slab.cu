@@ -40,6 +40,7 @@ struct ow_slab {
     float2* d_send = nullptr;     // [world][PL][3][XH]
     float2* d_recv = nullptr;     // [N/2][3][XH] = [world][PL][3][XH]   (receive buffer 0)
     int post_ctas_per_sm = 2;     // ow_slab_set_post_ctas
+    int bigcol_pipe_full = 0;     // grid of the persistent pipelined column lines kernel on this device (ow_slab_set_column_lines(4))
     float2* d_recv1 = nullptr;    // receive buffer 1 (ow_slab_enable_double_buffer): frame f+1's rows land here while frame f's columns read buffer 0
     float2* d_scratch_cols = nullptr;   // N > 4096 with two buffers: the column pass gets its own scratch (rows and columns then run concurrently)
     float2* peer_recv1[kSlabMaxWorld] = {};
@@ -142,6 +143,8 @@ int ow_slab_create(int32_t N, int32_t world, int32_t rank, const ow_params* p, i
     KernelConfig kcfg;
     OWS_TRY(configure_frame_kernels(N, &kcfg));
     s->cluster_caps = kcfg.big_cluster;
+    s->bigcol_pipe_full = kcfg.sm_count * kcfg.bigcol_pipe_ctas;
+    s->g.bigcol_pipe_grid = 0;      // N > 4096: one CTA per column-lines item (ow_slab_set_column_lines; the persistent pipelined kernel measured slower)
     s->g.big_cluster = 0;          // scratch path by default (ow_slab_set_line_clusters)
 #undef OWS_TRY
     s->peer_recv[rank] = s->d_recv;
@@ -292,6 +295,12 @@ int ow_slab_recv_buffer(ow_slab* s, int32_t buf, void** ptr) {
     if (!s || !ptr || buf < 0 || buf > 1) return OW_ERR_INVALID;
     if (buf == 1 && !s->d_recv1) return sfail(s, OW_ERR_STATE, "ow_slab_recv_buffer: call ow_slab_enable_double_buffer first");
     *ptr = buf ? s->d_recv1 : s->d_recv;
+    return OW_OK;
+}
+
+int ow_slab_set_column_lines(ow_slab* s, int32_t mode) {
+    if (!s || (mode != 0 && mode != 2 && mode != 4)) return OW_ERR_INVALID;
+    s->g.bigcol_pipe_grid = mode == 4 ? s->bigcol_pipe_full : mode == 2 ? -1 : 0;
     return OW_OK;
 }
 

@@ -36,7 +36,7 @@ EXPORTED_SYMBOLS = [
     "ow_slab_rows_buf", "ow_slab_cols_buf", "ow_slab_set_post_ctas", "ow_slab_recv_buffer",
     "ow_slab_create", "ow_slab_destroy", "ow_slab_last_error", "ow_slab_get_info", "ow_slab_init_spectrum_seeded", "ow_slab_ipc_handle",
     "ow_slab_open_peers", "ow_slab_rows", "ow_slab_cols", "ow_slab_local_exchange", "ow_slab_sync", "ow_slab_download",
-    "ow_sample_points", "ow_sample_points_host", "ow_compose_grid", "ow_set_time_scale", "ow_step_wall_clock",
+    "ow_slab_set_column_lines", "ow_sample_points", "ow_sample_points_host", "ow_compose_grid", "ow_set_time_scale", "ow_step_wall_clock",
 ]
 
 OW_FLAG_JACOBIAN = 0x1
@@ -180,6 +180,7 @@ def load_library():
     L.ow_slab_rows_buf.argtypes = [vp, f32, i32, i32, vp]
     L.ow_slab_cols_buf.argtypes = [vp, i32, vp]
     L.ow_slab_set_post_ctas.argtypes = [vp, i32]
+    L.ow_slab_set_column_lines.argtypes = [vp, i32]
     L.ow_slab_recv_buffer.argtypes = [vp, i32, C.POINTER(vp)]
     L.ow_slab_cols.argtypes = [vp, vp]
     L.ow_slab_local_exchange.argtypes = [vp, vp]

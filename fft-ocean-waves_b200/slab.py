@@ -141,6 +141,9 @@ class LibSlabBackend:
     def cols_buf(self, buf: int, stream: int = 0):
         self._check(self._lib.ow_slab_cols_buf(self._h, int(buf), C.c_void_p(stream or None)), "ow_slab_cols_buf")
 
+    def set_column_lines(self, mode: int):
+        self._check(self._lib.ow_slab_set_column_lines(self._h, int(mode)), "ow_slab_set_column_lines")
+
     def set_post_ctas(self, per_sm: int):
         self._check(self._lib.ow_slab_set_post_ctas(self._h, int(per_sm)), "ow_slab_set_post_ctas")
 

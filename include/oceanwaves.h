@@ -299,6 +299,10 @@ int ow_slab_recv_buffer(ow_slab* s, int32_t buf, void** ptr);
 /* N > 4096: CTAs per SM of the row pass's store kernel (0 = one CTA per work item; ow_slab_enable_double_buffer sets 2 when world > 1, so that the
  * NVLink-bound stores leave the SMs to the column pass running beside them). */
 int ow_slab_set_post_ctas(ow_slab* s, int32_t per_sm);
+/* Tuning (N > 4096): shape of the column pass's lines kernel. 0 = one 512-thread CTA per (channel, 16-column tile, sub-line) item (default),
+ * 2 = 8-column tiles (three 256-thread CTAs per SM), 4 = persistent CTAs with the next batch's row loads in flight in registers. Same results.
+ * For a single-GPU context the same shapes are ow_set_column_kernel modes 0/1, 2 and 4. */
+int ow_slab_set_column_lines(ow_slab* s, int32_t mode);
 /* As ow_set_line_clusters / ow_get_line_clusters, for a slab rank. */
 int ow_slab_set_line_clusters(ow_slab* s, int32_t mode);
 int ow_slab_get_line_clusters(const ow_slab* s);
