@@ -169,7 +169,8 @@ int ow_last_group_count(const ow_ctx* ctx);
 /* Tuning / A-B runs (per context; results agree to fp32 round-off): which row kernel runs (0 = the per-N default, 1 = one CTA
  * per row-pair group, 2 = persistent, next row prefetched into registers, 3 = persistent, next row staged by cp.async.bulk behind an
  * mbarrier); which column kernel (0 = per-N default, 1 = ow_col_kernel, 2 = ow_col2_kernel with direct loads, 3 = ow_col2_kernel with
- * TMA-staged tiles) and whether the normal map is its epilogue (fused: -1 = per-N default, 0 = separate normal kernel, 1 = fused;
+ * TMA-staged tiles, 4 = ow_col_pipe_kernel: persistent, next tile's first load batch in flight in registers; on a line-decomposition
+ * grid, N > 4096, modes 2 and 4 select the column LINES kernel's 8-column-tile and persistent shapes instead) and whether the normal map is its epilogue (fused: -1 = per-N default, 0 = separate normal kernel, 1 = fused;
  * needs mode 2 or 3 and N <= 2048); and whether the column kernel drops the consumed intermediate from L2 without writing it back
  * (discard.global.L2). */
 int ow_set_row_kernel(ow_ctx* ctx, int32_t mode);
