@@ -81,7 +81,8 @@ struct ow_ctx {
     int gl_count = 0;             // 4 = dy,dx,dz,normal; 2 = packed displacement + normal_xz
     bool gl_registered = false;
     // multi-cascade composition / the demo's clock
-    std::vector<int> slot_cascade;    // cascade last stepped into each slot (-1: never)
+    struct SlotPatch { float L = 0.0f, choppiness = 0.0f; };     // patch size / choppiness the frame in a slot was computed with (L = 0: never stepped);
+    std::vector<SlotPatch> slot_patch;                           // NOT the cascade index: ow_set_params may change the cascade before its next step
     float time_scale = 1.0f, time_offset = 0.0f;
     float* d_query = nullptr;         // staging of ow_sample_points_host: [cap][2] positions + [cap][8] results
     size_t query_cap = 0;
@@ -276,7 +277,7 @@ int ow_create(int32_t N, int32_t n_cascades, int32_t n_slots, const ow_params* c
     for (int i = 0; i < n_cascades; ++i) c->ident[i] = i;
     c->tbuf.assign(n_cascades, 0.0f);
     c->casc_host.resize(n_cascades);
-    c->slot_cascade.assign(n_slots, -1);
+    c->slot_patch.assign(n_slots, ow_ctx::SlotPatch{});
     const size_t nn = (size_t)N * N;
 #define OW_TRY(call)                                                                 \
     do {                                                                             \
@@ -530,7 +531,7 @@ static int step_impl(ow_ctx* c, int32_t count, const int32_t* cascade_of_slot, c
     }
     c->last_launches = launches;
     c->last_groups = ngroups;
-    for (int i = 0; i < count; ++i) c->slot_cascade[i] = cascade_of_slot[i];
+    for (int i = 0; i < count; ++i) c->slot_patch[i] = {c->casc_host[cascade_of_slot[i]].L, c->casc_host[cascade_of_slot[i]].choppiness};
     return OW_OK;
 }
 
@@ -599,7 +600,7 @@ int ow_step(ow_ctx* c, float t, void* stream) {
     OW_CUDA(c, cudaGraphLaunch(plan->exec, pick(c, stream)));
     c->last_launches = plan->launches;
     c->last_groups = plan->groups;
-    for (int i = 0; i < c->n_cascades; ++i) c->slot_cascade[i] = i;
+    for (int i = 0; i < c->n_cascades; ++i) c->slot_patch[i] = {c->casc_host[i].L, c->casc_host[i].choppiness};
     return OW_OK;
 }
 
@@ -806,12 +807,12 @@ static int compose_args(ow_ctx* c, int32_t n_terms, const ow_blend_term* terms, 
     for (int i = 0; i < n_terms; ++i) {
         const int slot = terms[i].slot;
         if (slot < 0 || slot >= c->n_slots) return fail(c, OW_ERR_INVALID, std::string(who) + ": slot out of range");
-        const int casc = c->slot_cascade[slot];
-        if (casc < 0) return fail(c, OW_ERR_STATE, std::string(who) + ": a referenced slot has not been stepped yet");
-        A->term[i].inv_L = 1.0 / (double)c->params[casc].L;
+        const ow_ctx::SlotPatch& sp = c->slot_patch[slot];
+        if (!(sp.L > 0.0f)) return fail(c, OW_ERR_STATE, std::string(who) + ": a referenced slot has not been stepped yet");
+        A->term[i].inv_L = 1.0 / (double)sp.L;
         A->term[i].slot = slot;
         A->term[i].weight = terms[i].weight;
-        A->term[i].choppiness = c->params[casc].choppiness;
+        A->term[i].choppiness = sp.choppiness;
     }
     return OW_OK;
 }
