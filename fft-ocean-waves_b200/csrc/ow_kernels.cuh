@@ -737,9 +737,25 @@ OW_HD void bigcol_phase0_math(const Smem& sm, int base, int b, int a, const floa
     stage0_finish<P>(sm, base, b, v, tw);
 }
 
+// Two batches of row loads (2*R0 float4 per thread) are put in flight together when the sub-line has an even number of batches: a CTA
+// of this kernel is alone on its SM (N = 32768: 141 KB of shared memory), so every load round trip it waits for is exposed.
+#ifndef OW_BIGCOL_BATCH2
+#define OW_BIGCOL_BATCH2 1
+#endif
 template <class P, int A, class Smem, class Geom>
 OW_HD void bigcol_phase0(const Smem& sm, int base, int ft, int a, const float2* __restrict__ src /* inter[c] + x */, const Geom& geom) {
     const size_t ss = geom.src_stride();
+    if (OW_BIGCOL_BATCH2 && (P::M / P::T) % 2 == 0 && P::M % P::T == 0) {
+#pragma unroll 1
+        for (int b = ft; b < P::M; b += 2 * P::T) {
+            float4 r0[P::R0], r1[P::R0];
+            bigcol_issue<P, A>(b, a, src, ss, r0);
+            bigcol_issue<P, A>(b + P::T, a, src, ss, r1);
+            bigcol_phase0_math<P, A>(sm, base, b, a, r0);
+            bigcol_phase0_math<P, A>(sm, base, b + P::T, a, r1);
+        }
+        return;
+    }
 #pragma unroll 1
     for (int b = ft; b < P::M; b += P::T) {
         float4 r[P::R0];
