@@ -53,6 +53,12 @@ def test_invalid_arguments_are_rejected_without_a_gpu():
     assert b"N must be" in lib.ow_last_error(None)
     assert lib.ow_create(256, 2, 1, C.byref(p), 0, 0, C.byref(h)) == 1          # n_slots < n_cascades
     assert lib.ow_step(None, 0.0, None) == 1
+    # the composition / clock entry points reject a NULL context the same way
+    assert lib.ow_sample_points(None, 0, None, 1.0, 0, None, None, None) == 1
+    assert lib.ow_sample_points_host(None, 0, None, 1.0, 0, None, None, None) == 1
+    assert lib.ow_compose_grid(None, 0, None, 1.0, 16, 0.0, 0.0, 1.0, None, None, None) == 1
+    assert lib.ow_set_time_scale(None, 1.0, 0.0) == 1 and lib.ow_step_wall_clock(None, 0.0, None) == 1
+    assert lib.ow_slab_set_column_lines(None, 0) == 1
 
 
 def test_no_cpu_fallback():
